@@ -1,0 +1,139 @@
+/*
+ * rtk_cuda.h -- batched, data-parallel extension of the rtk.h C ABI.
+ *
+ * The reference offers only a single-ray query (rtk.h:129, rtk.c:543-577) that
+ * the user calls in a loop from their own threads.  On a GPU the unit of work
+ * is a batch, so this header adds the entry points the benchmark and any
+ * throughput-minded caller drive.  Everything is extern "C", plain pointers and
+ * sizes; CUDA streams cross the boundary as void* (a cudaStream_t / CUstream).
+ *
+ * Each function names the reference code it replaces.  All of them return 0 on
+ * success and a negative rtk_cuda_status on failure unless stated otherwise;
+ * rtk_cuda_last_error() returns a thread-local, human-readable reason.
+ */
+#ifndef RTK_B200_RTK_CUDA_H
+#define RTK_B200_RTK_CUDA_H
+
+#include "rtk.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rtk_cuda_status {
+	RTK_CUDA_OK            =  0,
+	RTK_CUDA_ERR_NO_DEVICE = -1,  /* no CUDA device / driver: there is NO CPU fallback */
+	RTK_CUDA_ERR_CUDA      = -2,  /* a CUDA runtime call failed */
+	RTK_CUDA_ERR_ARGUMENT  = -3,
+	RTK_CUDA_ERR_SCENE     = -4,  /* blob is not a scene written by this library */
+	RTK_CUDA_ERR_MEMORY    = -5,
+	RTK_CUDA_ERR_OVERFLOW  = -6,  /* traversal stack exhausted (never seen; reported, not ignored) */
+} rtk_cuda_status;
+
+/* 16-byte compact hit record produced by the traversal kernel and consumed by
+ * the resolve kernel; prim is the global triangle number (meshes concatenated
+ * in rtk_scene_desc order, the numbering of rtk.c:1131-1170) or RTK_CUDA_MISS. */
+#define RTK_CUDA_MISS 0xffffffffu
+typedef struct rtk_cuda_hit16 {
+	float    t, u, v;
+	uint32_t prim;
+} rtk_cuda_hit16;
+
+/* Builder selection for rtk_cuda_set_build_mode(). */
+typedef enum rtk_cuda_build_mode {
+	RTK_CUDA_BUILD_LBVH = 0,      /* Morton radix sort + Karras hierarchy */
+	RTK_CUDA_BUILD_SAH  = 1,      /* binned SAH (32 bins x 3 axes, rtk.c:867-1019) on top of the Morton order */
+} rtk_cuda_build_mode;
+
+/* What a built scene looks like on the device (rtk_cuda_get_scene_info). */
+typedef struct rtk_cuda_scene_info {
+	uint64_t num_triangles;
+	uint64_t num_meshes;
+	uint64_t num_wide_nodes;      /* 256-byte 8-wide nodes */
+	uint64_t num_leaves;
+	uint32_t wide_depth;          /* levels of 8-wide nodes */
+	uint32_t build_mode;
+	uint64_t device_bytes;        /* resident bytes of the scene on one GPU */
+	double   build_device_ms;     /* CUDA-event time of the device build (no H2D) */
+	double   build_total_ms;      /* wall time of ingest + H2D + build */
+	double   sah_cost;            /* SAH cost of the wide BVH (node cost 1, leaf cost ceil(n/8)) */
+	float    bounds_min[3];
+	float    bounds_max[3];
+} rtk_cuda_scene_info;
+
+/* Per-batch traversal counters (rtk_cuda_trace_stats_device). */
+typedef struct rtk_cuda_trace_stats {
+	uint64_t rays;
+	uint64_t hits;
+	uint64_t node_visits;         /* 256-byte wide-node fetches */
+	uint64_t leaf_visits;         /* leaf records opened */
+	uint64_t tri_tests;           /* triangles pushed through the watertight test */
+	uint64_t stack_max;           /* deepest traversal stack seen */
+} rtk_cuda_trace_stats;
+
+/* ---- device selection ------------------------------------------------- */
+
+/* Bind the calling process to one CUDA device (one process per GPU).  Called
+ * implicitly with device 0 by the first entry point that needs a device. */
+int  rtk_cuda_init(int device);
+void rtk_cuda_shutdown(void);
+const char *rtk_cuda_last_error(void);
+int  rtk_cuda_set_build_mode(int mode);
+/* SM count, L2 bytes, resident CTAs of the traversal kernel... for the bench. */
+int  rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *trace_ctas_per_sm, int *trace_threads_per_cta);
+
+/* ---- batched closest hit (replaces a user loop over rtk_trace_ray) ----- */
+
+/* Host buffers.  rays[n] in, hits[n] / hit_mask[n] out; hits[i] is written
+ * only where hit_mask[i] != 0 (the miss rule of rtk.c:571-576).  hit_mask may
+ * be NULL.  Returns the number of hits, or (size_t)-1 on error. */
+size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits, uint8_t *hit_mask, size_t n);
+
+/* Device buffers, asynchronous on `stream`.  d_hits / d_hit_mask as above. */
+int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hits, void *d_hit_mask, size_t n, void *stream);
+
+/* The two halves of the call above: traversal to compact records
+ * (rtk.c:390-539 + 181-388), then expansion to rtk_hit (rtk.c:371-381). */
+int rtk_trace_rays_compact_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream);
+int rtk_resolve_hits_device(const rtk_scene *scene, const void *d_hit16, void *d_hits, void *d_hit_mask, size_t n, void *stream);
+
+/* Exhaustive ray x triangle kernel with the same arithmetic: the GPU-side
+ * check used by the parity tests and by the bench's self-check. */
+int rtk_trace_rays_bruteforce_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream);
+
+/* Counter-instrumented traversal (slow; for the algorithmic-bytes figure). */
+int rtk_trace_stats_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, rtk_cuda_trace_stats *stats, void *stream);
+
+/* ---- build with inputs already resident in HBM ------------------------ */
+
+/* A mesh whose buffers live on the device: float xyz positions (tightly
+ * packed) and optional uint32 index triples (NULL => 3i,3i+1,3i+2).
+ * num_vertices is needed because the device cannot infer it. */
+typedef struct rtk_cuda_mesh {
+	const void *d_positions;
+	const void *d_indices;
+	size_t      num_vertices;
+	size_t      num_triangles;
+} rtk_cuda_mesh;
+
+/* Device-to-device counterpart of rtk_build_scene (rtk.c:1788-1792): builds on
+ * `stream`, returns a library-owned scene (free with rtk_free_scene). */
+rtk_scene *rtk_cuda_build_scene(const rtk_cuda_mesh *meshes, size_t num_meshes, void *stream);
+
+/* Re-run the device build of an existing scene from its resident decoded
+ * triangles (bench loop for build Mtris/s; also refits after nothing moved). */
+int rtk_cuda_rebuild_scene(const rtk_scene *scene, void *stream);
+
+int rtk_cuda_get_scene_info(const rtk_scene *scene, rtk_cuda_scene_info *info);
+
+/* Upload a relocated / reloaded blob (written by rtk_finish_build_to) so that
+ * later queries on this address hit the device directly.  Queries do this
+ * lazily themselves; the explicit call lets the caller pay the cost up front. */
+int rtk_cuda_attach_scene(const rtk_scene *scene);
+int rtk_cuda_detach_scene(const rtk_scene *scene);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RTK_B200_RTK_CUDA_H */

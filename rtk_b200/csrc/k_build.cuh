@@ -1,0 +1,472 @@
+// k_build.cuh -- BVH construction kernels (sm_100a).
+//
+// Replaces the reference's CPU build (rtk.c:1116-1182 triangle setup, :867-1019 binned-SAH
+// recursion, :1570-1622 2->4 collapse) with a data-parallel pipeline:
+//
+//   k_decode_mesh     strided U16/U32/implicit indices + F32/F64 positions -> 48-byte corner
+//                     records (rtk.c:1028-1114, 1150-1171)
+//   k_scene_bounds    scene AABB, warp-shuffle + shared-memory reduction (rtk.c:1398-1404)
+//   k_morton          63-bit Morton code of each triangle's AABB centre
+//   k_radix_*         LSD radix sort, 8-bit digits, 64-bit keys + 32-bit payload
+//   k_hierarchy       binary radix tree over the sorted codes (Karras 2012)
+//   k_refit           bottom-up bounds with per-node arrival counters
+//   k_collapse        binary tree -> 8-wide nodes + leaves of <= 8 triangles
+//   k_emit_tris       leaf-ordered SoA triangle copy for traversal
+//
+// All kernels are memory-streaming integer/fp32 work; none is GEMM-shaped.
+#pragma once
+#include "rtk_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// mesh decode
+// ---------------------------------------------------------------------------------------------
+
+struct rtkd_decode_args {
+	const unsigned char *pos;     // device copy of the position buffer
+	const unsigned char *idx;     // device copy of the index buffer or NULL
+	unsigned long long pos_stride, idx_stride;
+	int pos_f64;                  // positions are doubles (RTK_TYPE_F64), else floats
+	int idx_bytes;                // 0 implicit, 2 uint16, 4 uint32
+	int pregathered;              // positions are stored per corner (3 per triangle, in order)
+	uint32_t ntris, first_prim;
+};
+
+RTK_DEV float4 rtk_fetch_corner(const rtkd_decode_args &a, unsigned long long slot, uint32_t index)
+{
+	const unsigned char *p = a.pos + slot * a.pos_stride;
+	float x, y, z;
+	if (a.pos_f64) {
+		const double *d = (const double*)p;
+		// the reference reads floats out of the f64 buffer here (defect D12, rtk.c:1098-1110);
+		// the intended conversion is a round-to-nearest narrowing
+		x = __double2float_rn(d[0]); y = __double2float_rn(d[1]); z = __double2float_rn(d[2]);
+	} else {
+		const float *f = (const float*)p;
+		x = f[0]; y = f[1]; z = f[2];
+	}
+	return make_float4(x, y, z, __uint_as_float(index));
+}
+
+__global__ void k_decode_mesh(rtkd_decode_args a, float4 *tri_orig)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a.ntris) return;
+	uint32_t i0, i1, i2;
+	if (a.idx_bytes == 2) {
+		const unsigned short *s = (const unsigned short*)(a.idx + (unsigned long long)i * a.idx_stride);
+		i0 = s[0]; i1 = s[1]; i2 = s[2];
+	} else if (a.idx_bytes == 4) {
+		const uint32_t *s = (const uint32_t*)(a.idx + (unsigned long long)i * a.idx_stride);
+		i0 = s[0]; i1 = s[1]; i2 = s[2];
+	} else {
+		i0 = 3u * i; i1 = i0 + 1u; i2 = i0 + 2u;          // rtk.c:1062-1068
+	}
+	unsigned long long s0 = a.pregathered ? 3ull * i : i0;
+	unsigned long long s1 = a.pregathered ? 3ull * i + 1 : i1;
+	unsigned long long s2 = a.pregathered ? 3ull * i + 2 : i2;
+	float4 *dst = tri_orig + 3ull * (a.first_prim + i);
+	dst[0] = rtk_fetch_corner(a, s0, i0);
+	dst[1] = rtk_fetch_corner(a, s1, i1);
+	dst[2] = rtk_fetch_corner(a, s2, i2);
+}
+
+// largest index of an index buffer (the reference never needs the vertex count; the upload does)
+__global__ void k_max_index(const unsigned char *idx, unsigned long long stride, int idx_bytes, uint32_t ntris, uint32_t *out)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t m = 0;
+	if (i < ntris) {
+		if (idx_bytes == 2) {
+			const unsigned short *s = (const unsigned short*)(idx + (unsigned long long)i * stride);
+			m = rtk_umax(rtk_umax(s[0], s[1]), s[2]);
+		} else {
+			const uint32_t *s = (const uint32_t*)(idx + (unsigned long long)i * stride);
+			m = rtk_umax(rtk_umax(s[0], s[1]), s[2]);
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) m = rtk_umax(m, __shfl_xor_sync(0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene bounds: bounds[0..2] = min (ordered-uint encoded), bounds[3..5] = max
+// ---------------------------------------------------------------------------------------------
+
+__global__ void k_scene_bounds(const float4 *tri_orig, uint32_t ntris, uint32_t *bounds)
+{
+	__shared__ float s_red[6][8];
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	float mn[3] = { +RTK_INF_F, +RTK_INF_F, +RTK_INF_F }, mx[3] = { -RTK_INF_F, -RTK_INF_F, -RTK_INF_F };
+	if (i < ntris) {
+		float4 a = tri_orig[3ull * i], b = tri_orig[3ull * i + 1], c = tri_orig[3ull * i + 2];
+		mn[0] = rtk_fmin(rtk_fmin(a.x, b.x), c.x); mx[0] = rtk_fmax(rtk_fmax(a.x, b.x), c.x);
+		mn[1] = rtk_fmin(rtk_fmin(a.y, b.y), c.y); mx[1] = rtk_fmax(rtk_fmax(a.y, b.y), c.y);
+		mn[2] = rtk_fmin(rtk_fmin(a.z, b.z), c.z); mx[2] = rtk_fmax(rtk_fmax(a.z, b.z), c.z);
+	}
+	for (int k = 0; k < 3; k++)
+		for (int o = 16; o > 0; o >>= 1) {
+			mn[k] = rtk_fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+			mx[k] = rtk_fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+		}
+	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0) for (int k = 0; k < 3; k++) { s_red[k][warp] = mn[k]; s_red[3 + k][warp] = mx[k]; }
+	__syncthreads();
+	if (threadIdx.x < 6) {
+		int k = threadIdx.x;
+		int nw = blockDim.x >> 5;
+		float v = s_red[k][0];
+		for (int w = 1; w < nw; w++) v = k < 3 ? rtk_fmin(v, s_red[k][w]) : rtk_fmax(v, s_red[k][w]);
+		if (k < 3) atomicMin(&bounds[k], rtk_f2ord(v)); else atomicMax(&bounds[k], rtk_f2ord(v));
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Morton codes
+// ---------------------------------------------------------------------------------------------
+
+RTK_DEV unsigned long long rtk_expand21(unsigned long long x)
+{
+	x &= 0x1fffffull;
+	x = (x | x << 32) & 0x1f00000000ffffull;
+	x = (x | x << 16) & 0x1f0000ff0000ffull;
+	x = (x | x << 8) & 0x100f00f00f00f00full;
+	x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+	x = (x | x << 2) & 0x1249249249249249ull;
+	return x;
+}
+
+__global__ void k_morton(const float4 *tri_orig, uint32_t ntris, const uint32_t *bounds,
+                         unsigned long long *keys, uint32_t *vals)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= ntris) return;
+	float4 a = tri_orig[3ull * i], b = tri_orig[3ull * i + 1], c = tri_orig[3ull * i + 2];
+	float lo[3], ext[3], cen[3];
+	for (int k = 0; k < 3; k++) {
+		lo[k] = rtk_ord2f(bounds[k]);
+		ext[k] = rtk_ord2f(bounds[3 + k]) - lo[k];
+	}
+	// AABB centre, the quantity the reference bins on (rtk.c:899)
+	cen[0] = 0.5f * (rtk_fmin(rtk_fmin(a.x, b.x), c.x) + rtk_fmax(rtk_fmax(a.x, b.x), c.x));
+	cen[1] = 0.5f * (rtk_fmin(rtk_fmin(a.y, b.y), c.y) + rtk_fmax(rtk_fmax(a.y, b.y), c.y));
+	cen[2] = 0.5f * (rtk_fmin(rtk_fmin(a.z, b.z), c.z) + rtk_fmax(rtk_fmax(a.z, b.z), c.z));
+	unsigned long long q[3];
+	for (int k = 0; k < 3; k++) {
+		float f = ext[k] > 0.0f ? (cen[k] - lo[k]) / ext[k] : 0.0f;
+		f = rtk_fmin(rtk_fmax(f, 0.0f), 1.0f);
+		// 21 bits per axis; double keeps all of them
+		double s = (double)f * 2097151.0;
+		q[k] = (unsigned long long)s;
+	}
+	keys[i] = (rtk_expand21(q[0]) << 2) | (rtk_expand21(q[1]) << 1) | rtk_expand21(q[2]);
+	vals[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort: 8-bit digits, 64-bit keys, 32-bit payload.
+// One pass = k_radix_hist (per-block digit counts) + k_radix_scan (per-digit exclusive scan
+// over blocks) + k_radix_scatter (stable ranking with warp match, then scatter).
+// ---------------------------------------------------------------------------------------------
+
+#define RTK_SORT_WARPS 8
+#define RTK_SORT_THREADS (RTK_SORT_WARPS * 32)
+#define RTK_SORT_ITEMS 16
+#define RTK_SORT_TILE (RTK_SORT_THREADS * RTK_SORT_ITEMS)
+
+__global__ void __launch_bounds__(RTK_SORT_THREADS) k_radix_hist(const unsigned long long *keys, uint32_t n, int shift,
+                                                                uint32_t *counts, uint32_t nblocks)
+{
+	__shared__ uint32_t s_cnt[256];
+	s_cnt[threadIdx.x] = 0;
+	__syncthreads();
+	uint32_t base = blockIdx.x * RTK_SORT_TILE;
+	for (int r = 0; r < RTK_SORT_ITEMS; r++) {
+		uint32_t i = base + r * RTK_SORT_THREADS + threadIdx.x;
+		if (i < n) atomicAdd(&s_cnt[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+	}
+	__syncthreads();
+	counts[(size_t)threadIdx.x * nblocks + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// block d scans row d (nblocks entries) in place to exclusive offsets and writes the row total
+__global__ void __launch_bounds__(256) k_radix_scan(uint32_t *counts, uint32_t nblocks, uint32_t *totals)
+{
+	__shared__ uint32_t s_warp[8];
+	__shared__ uint32_t s_carry;
+	uint32_t *row = counts + (size_t)blockIdx.x * nblocks;
+	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < nblocks; base += 256) {
+		uint32_t i = base + threadIdx.x;
+		uint32_t v = i < nblocks ? row[i] : 0;
+		uint32_t x = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31) s_warp[warp] = x;
+		__syncthreads();
+		uint32_t woff = 0;
+		for (int w = 0; w < warp; w++) woff += s_warp[w];
+		uint32_t carry = s_carry;
+		if (i < nblocks) row[i] = carry + woff + x - v;
+		__syncthreads();
+		if (threadIdx.x == 255) s_carry = carry + woff + x;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) totals[blockIdx.x] = s_carry;
+}
+
+__global__ void __launch_bounds__(RTK_SORT_THREADS) k_radix_scatter(
+	const unsigned long long *keys_in, const uint32_t *vals_in,
+	unsigned long long *keys_out, uint32_t *vals_out, uint32_t n, int shift,
+	const uint32_t *offsets, const uint32_t *totals, uint32_t nblocks)
+{
+	__shared__ uint32_t s_cnt[RTK_SORT_WARPS][256];
+	__shared__ uint32_t s_base[256];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int w = 0; w < RTK_SORT_WARPS; w++) s_cnt[w][threadIdx.x] = 0;
+	s_base[threadIdx.x] = totals[threadIdx.x];
+	__syncthreads();
+	// global start of each digit = exclusive scan of the 256 totals
+	if (threadIdx.x == 0) {
+		uint32_t run = 0;
+		for (int d = 0; d < 256; d++) { uint32_t c = s_base[d]; s_base[d] = run; run += c; }
+	}
+
+	unsigned long long key[RTK_SORT_ITEMS];
+	uint32_t rank[RTK_SORT_ITEMS];
+	const uint32_t base = blockIdx.x * RTK_SORT_TILE + warp * (32 * RTK_SORT_ITEMS);
+	const uint32_t lt = (1u << lane) - 1u;
+	// phase 1: rank inside the warp, in key order (round r holds keys base + 32 r + lane)
+#pragma unroll
+	for (int r = 0; r < RTK_SORT_ITEMS; r++) {
+		uint32_t i = base + r * 32 + lane;
+		bool valid = i < n;
+		key[r] = valid ? keys_in[i] : 0xffffffffffffffffull;
+		uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;
+		uint32_t peers = __match_any_sync(0xffffffffu, d);
+		uint32_t before = __popc(peers & lt);
+		uint32_t old = 0;
+		if (valid && before == 0) {
+			old = s_cnt[warp][d];
+			s_cnt[warp][d] = old + __popc(peers);
+		}
+		old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
+		rank[r] = old + before;
+		__syncwarp();
+	}
+	__syncthreads();
+	// phase 2: per digit, exclusive scan over the warps, seeded with this block's global offset
+	{
+		uint32_t d = threadIdx.x;
+		uint32_t run = s_base[d] + offsets[(size_t)d * nblocks + blockIdx.x];
+		for (int w = 0; w < RTK_SORT_WARPS; w++) { uint32_t c = s_cnt[w][d]; s_cnt[w][d] = run; run += c; }
+	}
+	__syncthreads();
+	// phase 3: scatter
+#pragma unroll
+	for (int r = 0; r < RTK_SORT_ITEMS; r++) {
+		uint32_t i = base + r * 32 + lane;
+		if (i < n) {
+			uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+			uint32_t pos = s_cnt[warp][d] + rank[r];
+			keys_out[pos] = key[r];
+			vals_out[pos] = vals_in[i];
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Binary radix tree (Karras 2012).  Internal nodes 0..n-2, node 0 is the root.  A child id
+// >= 0 is an internal node, < 0 is ~position of a sorted triangle.  Bounds are stored for
+// internal node i at [i] and for sorted triangle j at [n-1+j].
+// ---------------------------------------------------------------------------------------------
+
+struct rtkd_bvh2 {
+	int *left, *right;           // [n-1]
+	int *parent;                 // [2n-1] parent internal node of node / leaf (n-1+j); root: -1
+	int *first, *last;           // [n-1] covered range of sorted positions
+	float4 *blo, *bhi;           // [2n-1]
+	int *flags;                  // [n-1] arrival counters for the refit
+};
+
+RTK_DEV int rtk_delta(const unsigned long long *keys, int n, int i, int j)
+{
+	if (j < 0 || j >= n) return -1;
+	unsigned long long a = keys[i], b = keys[j];
+	if (a != b) return __clzll((long long)(a ^ b));
+	return 64 + __clz(i ^ j);
+}
+
+__global__ void k_hierarchy(const unsigned long long *keys, int n, rtkd_bvh2 t)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n - 1) return;
+	int d = rtk_delta(keys, n, i, i + 1) - rtk_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+	int dmin = rtk_delta(keys, n, i, i - d);
+	int lmax = 2;
+	while (rtk_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+	int l = 0;
+	for (int s = lmax >> 1; s >= 1; s >>= 1)
+		if (rtk_delta(keys, n, i, i + (l + s) * d) > dmin) l += s;
+	int j = i + l * d;
+	int dnode = rtk_delta(keys, n, i, j);
+	int s = 0;
+	int div = 2;
+	for (;;) {
+		int step = (l + div - 1) / div;
+		if (rtk_delta(keys, n, i, i + (s + step) * d) > dnode) s += step;
+		if (step <= 1) break;
+		div <<= 1;
+	}
+	int gamma = i + s * d + rtk_imin(d, 0);
+	int lo = rtk_imin(i, j), hi = rtk_imax(i, j);
+	int lc = (lo == gamma) ? ~gamma : gamma;
+	int rc = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+	t.left[i] = lc; t.right[i] = rc;
+	t.first[i] = lo; t.last[i] = hi;
+	t.parent[lc >= 0 ? lc : (n - 1) + ~lc] = i;
+	t.parent[rc >= 0 ? rc : (n - 1) + ~rc] = i;
+	if (i == 0) t.parent[0] = -1;
+}
+
+__global__ void k_refit(const float4 *tri_orig, const uint32_t *vals, int n, rtkd_bvh2 t)
+{
+	int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	uint32_t prim = vals[j];
+	float4 a = tri_orig[3ull * prim], b = tri_orig[3ull * prim + 1], c = tri_orig[3ull * prim + 2];
+	float4 lo = make_float4(rtk_fmin(rtk_fmin(a.x, b.x), c.x), rtk_fmin(rtk_fmin(a.y, b.y), c.y), rtk_fmin(rtk_fmin(a.z, b.z), c.z), 0.0f);
+	float4 hi = make_float4(rtk_fmax(rtk_fmax(a.x, b.x), c.x), rtk_fmax(rtk_fmax(a.y, b.y), c.y), rtk_fmax(rtk_fmax(a.z, b.z), c.z), 0.0f);
+	int self = (n - 1) + j;
+	t.blo[self] = lo; t.bhi[self] = hi;
+	int cur = t.parent[self];
+	while (cur >= 0) {
+		__threadfence();
+		if (atomicAdd(&t.flags[cur], 1) == 0) return;      // first arrival: the sibling finishes
+		__threadfence();
+		int l = t.left[cur], r = t.right[cur];
+		int li = l >= 0 ? l : (n - 1) + ~l, ri = r >= 0 ? r : (n - 1) + ~r;
+		int other = (li == self) ? ri : li;
+		float4 olo = __ldcg(&t.blo[other]), ohi = __ldcg(&t.bhi[other]);
+		lo.x = rtk_fmin(lo.x, olo.x); lo.y = rtk_fmin(lo.y, olo.y); lo.z = rtk_fmin(lo.z, olo.z);
+		hi.x = rtk_fmax(hi.x, ohi.x); hi.y = rtk_fmax(hi.y, ohi.y); hi.z = rtk_fmax(hi.z, ohi.z);
+		t.blo[cur] = lo; t.bhi[cur] = hi;
+		self = cur;
+		cur = t.parent[cur];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Collapse to 8-wide nodes.  One thread per wide node, one launch per level of wide nodes.
+// A binary subtree covering <= RTK_LEAF_MAX triangles becomes a leaf (its triangles are
+// contiguous in sorted order); otherwise the child with the largest surface area is opened
+// until 8 slots are filled (the reference's 2->4 collapse, rtk.c:1570-1622, takes fixed
+// grandchildren instead).
+// ---------------------------------------------------------------------------------------------
+
+RTK_DEV float rtk_half_area(float4 lo, float4 hi)
+{
+	float x = hi.x - lo.x, y = hi.y - lo.y, z = hi.z - lo.z;
+	return x * y + y * z + z * x;
+}
+
+struct rtkd_collapse_args {
+	const uint2 *work_in; uint32_t n_in;
+	uint2 *work_out; uint32_t *n_out;
+	uint32_t *node_alloc; uint32_t node_cap;
+	uint32_t *leaf_count;
+	double *sah_cost;            // accumulates area-weighted cost (divide by root area on host)
+	float4 *nodes;
+	int n;                       // triangles
+	uint32_t *err;
+};
+
+__global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
+{
+	uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= a.n_in) return;
+	const int n = a.n;
+	int root = (int)a.work_in[w].x;
+	uint32_t dst = a.work_in[w].y;
+	int slot[RTK_WIDE];
+	float area[RTK_WIDE];
+	int ns = 2;
+	slot[0] = t.left[root]; slot[1] = t.right[root];
+#define RTK_OPENABLE(c) ((c) >= 0 && (t.last[c] - t.first[c] + 1) > RTK_LEAF_MAX)
+#define RTK_BIDX(c) ((c) >= 0 ? (c) : (n - 1) + ~(c))
+	for (int k = 0; k < 2; k++)
+		area[k] = RTK_OPENABLE(slot[k]) ? rtk_half_area(t.blo[slot[k]], t.bhi[slot[k]]) : -1.0f;
+	while (ns < RTK_WIDE) {
+		int best = -1; float ba = -1.0f;
+		for (int k = 0; k < ns; k++) if (area[k] > ba) { ba = area[k]; best = k; }
+		if (best < 0) break;
+		int c = slot[best];
+		int l = t.left[c], r = t.right[c];
+		slot[best] = l; slot[ns] = r;
+		area[best] = RTK_OPENABLE(l) ? rtk_half_area(t.blo[l], t.bhi[l]) : -1.0f;
+		area[ns] = RTK_OPENABLE(r) ? rtk_half_area(t.blo[r], t.bhi[r]) : -1.0f;
+		ns++;
+	}
+	float4 *node = a.nodes + 16ull * dst;
+	double cost = 0.0;
+	uint32_t leaves = 0;
+	for (int k = 0; k < RTK_WIDE; k++) {
+		if (k >= ns) {
+			node[k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, __uint_as_float(RTK_REF_EMPTY));
+			node[8 + k] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
+			continue;
+		}
+		int c = slot[k];
+		float4 lo = t.blo[RTK_BIDX(c)], hi = t.bhi[RTK_BIDX(c)];
+		uint32_t ref;
+		if (RTK_OPENABLE(c)) {
+			uint32_t idx = atomicAdd(a.node_alloc, 1u);
+			if (idx >= a.node_cap) { atomicOr(a.err, 1u); idx = 0; }
+			uint32_t o = atomicAdd(a.n_out, 1u);
+			a.work_out[o] = make_uint2((uint32_t)c, idx);
+			ref = idx;
+		} else {
+			uint32_t first = c >= 0 ? (uint32_t)t.first[c] : (uint32_t)~c;
+			uint32_t count = c >= 0 ? (uint32_t)(t.last[c] - t.first[c] + 1) : 1u;
+			ref = rtk_leaf_ref(first, count);
+			leaves++;
+		}
+		cost += (double)rtk_half_area(lo, hi);       // node step or one 8-lane triangle round: cost 1
+		lo.w = __uint_as_float(ref); hi.w = 0.0f;
+		node[k] = lo; node[8 + k] = hi;
+	}
+#undef RTK_OPENABLE
+#undef RTK_BIDX
+	atomicAdd(a.sah_cost, cost);
+	if (leaves) atomicAdd(a.leaf_count, leaves);
+}
+
+// scene with a single triangle: a root node with one leaf child
+__global__ void k_single_root(const float4 *tri_orig, const uint32_t *vals, float4 *nodes)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	uint32_t prim = vals[0];
+	float4 a = tri_orig[3ull * prim], b = tri_orig[3ull * prim + 1], c = tri_orig[3ull * prim + 2];
+	for (int k = 0; k < RTK_WIDE; k++) {
+		nodes[k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, __uint_as_float(RTK_REF_EMPTY));
+		nodes[8 + k] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
+	}
+	nodes[0] = make_float4(rtk_fmin(rtk_fmin(a.x, b.x), c.x), rtk_fmin(rtk_fmin(a.y, b.y), c.y), rtk_fmin(rtk_fmin(a.z, b.z), c.z),
+	                       __uint_as_float(rtk_leaf_ref(0, 1)));
+	nodes[8] = make_float4(rtk_fmax(rtk_fmax(a.x, b.x), c.x), rtk_fmax(rtk_fmax(a.y, b.y), c.y), rtk_fmax(rtk_fmax(a.z, b.z), c.z), 0.0f);
+}
+
+// leaf-ordered SoA triangles: tv0[i].w = global triangle number
+__global__ void k_emit_tris(const float4 *tri_orig, const uint32_t *vals, uint32_t n,
+                            float4 *tv0, float4 *tv1, float4 *tv2)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t prim = vals[i];
+	float4 a = tri_orig[3ull * prim], b = tri_orig[3ull * prim + 1], c = tri_orig[3ull * prim + 2];
+	a.w = __uint_as_float(prim);
+	tv0[i] = a; tv1[i] = b; tv2[i] = c;
+}

@@ -1,0 +1,377 @@
+// k_trace.cuh -- closest-hit traversal, brute-force check kernel and hit expansion (sm_100a).
+//
+// k_trace replaces the reference's per-ray rtk_trace_ray (rtk.c:543-577) with a persistent,
+// warp-cooperative kernel:
+//   * one ray per group of 8 lanes, four rays per warp.  Lane c of a group owns child c of the
+//     current 8-wide node and triangle c of the current leaf, so a node visit is two coalesced
+//     128-byte requests and a leaf visit three, instead of 8 scattered fetches per thread;
+//   * persistent CTAs pull batches of 32 rays per warp from a global counter and stage them in
+//     shared memory with asynchronous copies, double buffered (the next batch is in flight
+//     while the current one is traced);
+//   * the traversal stack (distance key + reference, 8 bytes) lives in shared memory,
+//     interleaved across groups, and spills to a per-group slab in global memory when a ray
+//     needs more than RTK_STACK_SMEM entries;
+//   * node order: nearest hit child first, the others are pushed with their entry distance so
+//     they can be culled when popped (the reference sorts all four, rtk.c:489-536);
+//   * exact ties in t go to the lowest triangle number, which makes the result independent
+//     of traversal order (the reference keeps whichever it met first, rtk.c:371).
+//
+// CULL selects the distance used to cull a box against the current best hit:
+//   CULL = 1 (default, provable): entry/exit of the slab of the ray's dominant axis only.  A
+//            triangle accepted by the fp32 watertight test always has its computed t inside
+//            that (padded) slab interval of every box containing it, even when the triangle is
+//            seen edge-on and t is numerically ill-conditioned.
+//   CULL = 0: entry/exit of the full box (tighter, not provable for edge-on triangles).
+#pragma once
+#include "rtk_common.cuh"
+#include "rtk_math.cuh"
+
+#define RTK_TRACE_WARPS 8
+#define RTK_TRACE_THREADS (RTK_TRACE_WARPS * 32)
+#define RTK_GROUPS_PER_CTA (RTK_TRACE_WARPS * 4)
+#define RTK_STACK_SMEM 16
+#define RTK_RAY_BATCH 32
+
+struct rtkd_hit16 { float t, u, v; uint32_t prim; };
+
+struct rtkd_trace_args {
+	rtkd_arrays sc;
+	const float4 *rays;          // rtk_ray = 2 x float4: (o.xyz, d.x) (d.yz, min_t, max_t)
+	float4 *out;                 // rtkd_hit16 per ray
+	uint32_t nrays;
+	uint32_t *counter;           // global ray cursor (zeroed before launch)
+	uint2 *overflow;             // [groups_in_grid * ovf_entries] stack spill
+	uint32_t ovf_entries;
+	uint32_t *err;               // bit 1: stack exhausted
+	unsigned long long *stats;   // [6] when STATS
+};
+
+template <int CULL, bool STATS>
+__global__ void __launch_bounds__(RTK_TRACE_THREADS, 3) k_trace(rtkd_trace_args p)
+{
+	__shared__ float4 s_rays[RTK_TRACE_WARPS][2][RTK_RAY_BATCH * 2];
+	__shared__ uint2 s_stack[RTK_STACK_SMEM][RTK_GROUPS_PER_CTA];
+
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int c = lane & 7, g = lane >> 3;
+	const int gcta = warp * 4 + g;
+	const unsigned long long gglobal = (unsigned long long)blockIdx.x * RTK_GROUPS_PER_CTA + gcta;
+	const uint32_t FULL = 0xffffffffu;
+	const float4 *__restrict__ nodes = p.sc.nodes;
+
+	// ---- warp-level ray batches ------------------------------------------------------------
+	uint32_t cur_base = 0, cur_cnt = 0, cur_pos = 0, next_base = 0, next_cnt = 0;
+	int cur_buf = 0;
+	{
+		// first batch into buffer 0, second into buffer 1
+		uint32_t b = 0;
+		if (lane == 0) b = atomicAdd(p.counter, (uint32_t)RTK_RAY_BATCH);
+		b = __shfl_sync(FULL, b, 0);
+		cur_base = b;
+		cur_cnt = b < p.nrays ? rtk_umin(RTK_RAY_BATCH, p.nrays - b) : 0u;
+		if ((uint32_t)lane < cur_cnt) {
+			rtk_cp_async16(&s_rays[warp][0][lane * 2], p.rays + 2ull * (b + lane));
+			rtk_cp_async16(&s_rays[warp][0][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
+		}
+		rtk_cp_async_commit();
+		if (cur_cnt == RTK_RAY_BATCH) {
+			if (lane == 0) b = atomicAdd(p.counter, (uint32_t)RTK_RAY_BATCH);
+			b = __shfl_sync(FULL, b, 0);
+			next_base = b;
+			next_cnt = b < p.nrays ? rtk_umin(RTK_RAY_BATCH, p.nrays - b) : 0u;
+			if ((uint32_t)lane < next_cnt) {
+				rtk_cp_async16(&s_rays[warp][1][lane * 2], p.rays + 2ull * (b + lane));
+				rtk_cp_async16(&s_rays[warp][1][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
+			}
+			rtk_cp_async_commit();
+		}
+		rtk_cp_async_wait_all();
+		__syncwarp();
+	}
+
+	// ---- per-ray state (identical in the 8 lanes of a group) -------------------------------
+	rtk_ray_ctx rc;
+	bool has_ray = false;
+	uint32_t ray_index = 0;
+	float ray_max_t = 0.0f;
+	float best_t = 0.0f, best_u = 0.0f, best_v = 0.0f;
+	uint32_t best_prim = RTK_MISS;
+	uint32_t cur_ref = RTK_REF_EMPTY;
+	int sp = 0;
+	uint32_t st_nodes = 0, st_leaves = 0, st_tris = 0, st_stack = 0;
+
+#define RTK_STACK_WRITE(pos, val) do { \
+		int _p = (pos); \
+		if (_p < RTK_STACK_SMEM) s_stack[_p][gcta] = (val); \
+		else if ((uint32_t)(_p - RTK_STACK_SMEM) < p.ovf_entries) p.overflow[gglobal * p.ovf_entries + (uint32_t)(_p - RTK_STACK_SMEM)] = (val); \
+		else atomicOr(p.err, 2u); \
+	} while (0)
+#define RTK_STACK_POP() do { \
+		cur_ref = RTK_REF_EMPTY; \
+		while (sp > 0) { \
+			--sp; \
+			uint2 _e; \
+			if (sp < RTK_STACK_SMEM) _e = s_stack[sp][gcta]; \
+			else if ((uint32_t)(sp - RTK_STACK_SMEM) < p.ovf_entries) _e = __ldcg(&p.overflow[gglobal * p.ovf_entries + (uint32_t)(sp - RTK_STACK_SMEM)]); \
+			else continue; \
+			if (__uint_as_float(_e.x) <= best_t) { cur_ref = _e.y; break; } \
+		} \
+	} while (0)
+
+	for (;;) {
+		// ---- (1) hand rays to idle groups --------------------------------------------------
+		uint32_t need_mask = __ballot_sync(FULL, !has_ray && c == 0);
+		while (need_mask) {
+			uint32_t avail = cur_cnt - cur_pos;
+			if (avail == 0) {
+				if (next_cnt == 0) break;                     // input exhausted
+				rtk_cp_async_wait_all();
+				__syncwarp();
+				cur_buf ^= 1; cur_base = next_base; cur_cnt = next_cnt; cur_pos = 0;
+				next_cnt = 0;
+				if (cur_cnt == RTK_RAY_BATCH) {
+					uint32_t b = 0;
+					if (lane == 0) b = atomicAdd(p.counter, (uint32_t)RTK_RAY_BATCH);
+					b = __shfl_sync(FULL, b, 0);
+					next_base = b;
+					next_cnt = b < p.nrays ? rtk_umin(RTK_RAY_BATCH, p.nrays - b) : 0u;
+					if ((uint32_t)lane < next_cnt) {
+						rtk_cp_async16(&s_rays[warp][cur_buf ^ 1][lane * 2], p.rays + 2ull * (b + lane));
+						rtk_cp_async16(&s_rays[warp][cur_buf ^ 1][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
+					}
+					rtk_cp_async_commit();
+				}
+				continue;
+			}
+			uint32_t rank = __popc(need_mask & ((1u << (g * 8)) - 1u));
+			if (!has_ray && rank < avail) {
+				uint32_t slot = cur_pos + rank;
+				float4 r0 = s_rays[warp][cur_buf][slot * 2], r1 = s_rays[warp][cur_buf][slot * 2 + 1];
+				rtk_ray_setup(rc, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, p.sc.abs_max);
+				ray_index = cur_base + slot;
+				ray_max_t = r1.w;
+				best_t = r1.w; best_u = 0.0f; best_v = 0.0f; best_prim = RTK_MISS;   // rtk.c:548
+				sp = 0;
+				cur_ref = p.sc.num_nodes ? 0u : RTK_REF_EMPTY;                        // root = node 0
+				has_ray = true;
+			}
+			cur_pos += rtk_umin((uint32_t)__popc(need_mask), avail);
+			need_mask = __ballot_sync(FULL, !has_ray && c == 0);
+		}
+		if (!__any_sync(FULL, has_ray)) break;
+
+		// ---- (2) leaf: 8 lanes test up to 8 triangles (rtk.c:181-388) ------------------------
+		const bool is_leaf = has_ray && cur_ref != RTK_REF_EMPTY && rtk_ref_is_leaf(cur_ref);
+		if (__any_sync(FULL, is_leaf)) {
+			float t = INFINITY, u = 0.0f, v = 0.0f;
+			uint32_t prim = RTK_MISS;
+			if (is_leaf) {
+				uint32_t first = rtk_leaf_first(cur_ref), cnt = rtk_leaf_count(cur_ref);
+				if ((uint32_t)c < cnt) {
+					float4 p0 = __ldg(&p.sc.tv0[first + c]);
+					float4 p1 = __ldg(&p.sc.tv1[first + c]);
+					float4 p2 = __ldg(&p.sc.tv2[first + c]);
+					uint32_t id = __float_as_uint(p0.w);
+					float tt, uu, vv;
+					if (rtk_tri_test(rc, p0, p1, p2, best_t, tt, uu, vv)) {
+						// strict '<' against the running best (rtk.c:354, 371); an exact tie is
+						// taken only from a lower triangle number than the recorded hit
+						if (tt < best_t || (best_prim != RTK_MISS && id < best_prim)) { t = tt; u = uu; v = vv; prim = id; }
+					}
+				}
+				if (STATS) { st_leaves++; st_tris += cnt; }
+			}
+			float tmin = t;
+			tmin = rtk_fmin(tmin, __shfl_xor_sync(FULL, tmin, 1));
+			tmin = rtk_fmin(tmin, __shfl_xor_sync(FULL, tmin, 2));
+			tmin = rtk_fmin(tmin, __shfl_xor_sync(FULL, tmin, 4));
+			uint32_t pmin = (t == tmin) ? prim : RTK_MISS;
+			pmin = rtk_umin(pmin, __shfl_xor_sync(FULL, pmin, 1));
+			pmin = rtk_umin(pmin, __shfl_xor_sync(FULL, pmin, 2));
+			pmin = rtk_umin(pmin, __shfl_xor_sync(FULL, pmin, 4));
+			const bool winner = prim != RTK_MISS && t == tmin && prim == pmin;
+			uint32_t wm = (__ballot_sync(FULL, winner) >> (g * 8)) & 0xffu;
+			int src = wm ? __ffs(wm) - 1 : 0;
+			float wu = __shfl_sync(FULL, u, src, 8), wv = __shfl_sync(FULL, v, src, 8);
+			if (is_leaf) {
+				if (wm) { best_t = tmin; best_prim = pmin; best_u = wu; best_v = wv; }
+				RTK_STACK_POP();
+			}
+			__syncwarp();
+		}
+
+		// ---- (3) node: 8 lanes test the 8 children (rtk.c:457-473) ---------------------------
+		const bool is_node = has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref);
+		if (__any_sync(FULL, is_node)) {
+			bool hit = false;
+			float key = 0.0f, tn = 0.0f;
+			uint32_t ref = RTK_REF_EMPTY;
+			if (is_node) {
+				const float4 *np = nodes + 16ull * cur_ref;
+				float4 lo = __ldg(np + c), hi = __ldg(np + 8 + c);
+				ref = __float_as_uint(lo.w);
+				const bool nx = rc.sgn & 1u, ny = rc.sgn & 2u, nz = rc.sgn & 4u;
+				float tnx = fmaf(nx ? hi.x : lo.x, rc.idx, rc.cnx), tfx = fmaf(nx ? lo.x : hi.x, rc.idx, rc.cfx);
+				float tny = fmaf(ny ? hi.y : lo.y, rc.idy, rc.cny), tfy = fmaf(ny ? lo.y : hi.y, rc.idy, rc.cfy);
+				float tnz = fmaf(nz ? hi.z : lo.z, rc.idz, rc.cnz), tfz = fmaf(nz ? lo.z : hi.z, rc.idz, rc.cfz);
+				tn = rtk_fmax(rtk_fmax(tnx, tny), tnz);
+				float tf = rtk_fmin(rtk_fmin(tfx, tfy), tfz);
+				float kn, kf;
+				if (CULL == 1) {
+					kn = rc.kz == 0 ? tnx : (rc.kz == 1 ? tny : tnz);
+					kf = rc.kz == 0 ? tfx : (rc.kz == 1 ? tfy : tfz);
+				} else { kn = tn; kf = tf; }
+				hit = ref != RTK_REF_EMPTY && tn <= tf && kn <= best_t && kf >= rc.min_t;
+				key = kn;
+				if (STATS) st_nodes++;
+			}
+			// nearest hit child: order-preserving key with the lane number in the low 3 bits
+			// (the reference tags 2 bits the same way, rtk.c:496)
+			uint32_t ok = hit ? ((rtk_f2ord(tn) & ~7u) | (uint32_t)c) : 0xffffffffu;
+			uint32_t om = ok;
+			om = rtk_umin(om, __shfl_xor_sync(FULL, om, 1));
+			om = rtk_umin(om, __shfl_xor_sync(FULL, om, 2));
+			om = rtk_umin(om, __shfl_xor_sync(FULL, om, 4));
+			const uint32_t gm = (__ballot_sync(FULL, hit) >> (g * 8)) & 0xffu;
+			const int cmin = (int)(om & 7u);
+			const uint32_t nref = __shfl_sync(FULL, ref, cmin, 8);
+			if (is_node) {
+				const uint32_t others = gm & ~(1u << cmin);
+				if (hit && c != cmin) {
+					int pos = sp + __popc(others & ((1u << c) - 1u));
+					RTK_STACK_WRITE(pos, make_uint2(__float_as_uint(key), ref));
+				}
+				sp += __popc(others);
+				if (STATS) st_stack = rtk_umax(st_stack, (uint32_t)sp);
+			}
+			__syncwarp();
+			if (is_node) {
+				if (gm) cur_ref = nref;
+				else RTK_STACK_POP();
+			}
+			__syncwarp();
+		}
+
+		// ---- (4) finished rays --------------------------------------------------------------
+		if (has_ray && cur_ref == RTK_REF_EMPTY) {
+			if (c == 0) {
+				const bool got = best_t < ray_max_t;                    // rtk.c:571
+				float4 o = got ? make_float4(best_t, best_u, best_v, __uint_as_float(best_prim))
+				               : make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RTK_MISS));
+				p.out[ray_index] = o;
+				if (STATS) {
+					atomicAdd(&p.stats[1], (unsigned long long)(got ? 1 : 0));
+					atomicAdd(&p.stats[2], (unsigned long long)st_nodes);
+					atomicAdd(&p.stats[3], (unsigned long long)st_leaves);
+					atomicAdd(&p.stats[4], (unsigned long long)st_tris);
+					atomicMax(&p.stats[5], (unsigned long long)st_stack);
+				}
+			}
+			st_nodes = st_leaves = st_tris = st_stack = 0;
+			has_ray = false;
+		}
+	}
+#undef RTK_STACK_WRITE
+#undef RTK_STACK_POP
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exhaustive check kernel: every ray against every triangle, same arithmetic, same tie rule.
+// One ray per thread; triangles are staged through shared memory 128 at a time.
+// ---------------------------------------------------------------------------------------------
+
+#define RTK_BRUTE_TILE 128
+
+__global__ void __launch_bounds__(128) k_trace_brute(rtkd_arrays sc, const float4 *rays, float4 *out, uint32_t nrays)
+{
+	__shared__ float4 s_v0[RTK_BRUTE_TILE], s_v1[RTK_BRUTE_TILE], s_v2[RTK_BRUTE_TILE];
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	rtk_ray_ctx rc;
+	float best_t = 0.0f, best_u = 0.0f, best_v = 0.0f, max_t = 0.0f;
+	uint32_t best_prim = RTK_MISS;
+	bool live = i < nrays;
+	if (live) {
+		float4 r0 = rays[2ull * i], r1 = rays[2ull * i + 1];
+		rtk_ray_setup(rc, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, sc.abs_max);
+		best_t = max_t = r1.w;
+	}
+	for (uint32_t base = 0; base < sc.num_tris; base += RTK_BRUTE_TILE) {
+		uint32_t k = base + threadIdx.x;
+		__syncthreads();
+		if (threadIdx.x < RTK_BRUTE_TILE && k < sc.num_tris) {
+			s_v0[threadIdx.x] = sc.tv0[k]; s_v1[threadIdx.x] = sc.tv1[k]; s_v2[threadIdx.x] = sc.tv2[k];
+		}
+		__syncthreads();
+		uint32_t cnt = rtk_umin(RTK_BRUTE_TILE, sc.num_tris - base);
+		if (live) {
+			for (uint32_t j = 0; j < cnt; j++) {
+				float t, u, v;
+				if (rtk_tri_test(rc, s_v0[j], s_v1[j], s_v2[j], best_t, t, u, v)) {
+					uint32_t id = __float_as_uint(s_v0[j].w);
+					if (t < best_t || (best_prim != RTK_MISS && id < best_prim)) {
+						best_t = t; best_u = u; best_v = v; best_prim = id;
+					}
+				}
+			}
+		}
+	}
+	if (live) {
+		bool got = best_t < max_t;
+		out[i] = got ? make_float4(best_t, best_u, best_v, __uint_as_float(best_prim))
+		             : make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RTK_MISS));
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Hit expansion: compact record -> rtk_hit (68 bytes), reference rtk.c:371-381.  A block stages
+// its 128 hits in shared memory and writes the 17 words of each with coalesced stores; rows of
+// rays that missed are left untouched (rtk.c:571-576).
+// ---------------------------------------------------------------------------------------------
+
+#define RTK_RESOLVE_THREADS 128
+
+__global__ void __launch_bounds__(RTK_RESOLVE_THREADS) k_resolve(rtkd_arrays sc, const float4 *hit16, uint32_t *hits,
+                                                                 unsigned char *mask, uint32_t nrays,
+                                                                 unsigned long long *hit_count)
+{
+	__shared__ uint32_t s_row[RTK_RESOLVE_THREADS][17];
+	__shared__ unsigned char s_hit[RTK_RESOLVE_THREADS];
+	const uint32_t base = blockIdx.x * RTK_RESOLVE_THREADS;
+	const uint32_t i = base + threadIdx.x;
+	bool got = false;
+	if (i < nrays) {
+		float4 h = hit16[i];
+		uint32_t prim = __float_as_uint(h.w);
+		got = prim != RTK_MISS;
+		if (got) {
+			// mesh of the triangle: mesh_first is a short sorted table
+			uint32_t lo = 0, hi = sc.num_meshes;
+			while (hi - lo > 1) {
+				uint32_t mid = (lo + hi) >> 1;
+				if (sc.mesh_first[mid] <= prim) lo = mid; else hi = mid;
+			}
+			const float4 *tv = sc.tri_orig + 3ull * prim;
+			float4 a = __ldg(tv), b = __ldg(tv + 1), cc = __ldg(tv + 2);
+			uint32_t *r = s_row[threadIdx.x];
+			r[0] = __float_as_uint(h.x); r[1] = __float_as_uint(h.y); r[2] = __float_as_uint(h.z);
+			r[3] = __float_as_uint(a.x); r[4] = __float_as_uint(a.y); r[5] = __float_as_uint(a.z); r[6] = __float_as_uint(a.w);
+			r[7] = __float_as_uint(b.x); r[8] = __float_as_uint(b.y); r[9] = __float_as_uint(b.z); r[10] = __float_as_uint(b.w);
+			r[11] = __float_as_uint(cc.x); r[12] = __float_as_uint(cc.y); r[13] = __float_as_uint(cc.z); r[14] = __float_as_uint(cc.w);
+			r[15] = lo;
+			r[16] = prim - sc.mesh_first[lo];
+		}
+		if (mask) mask[i] = got ? 1 : 0;
+	}
+	s_hit[threadIdx.x] = got ? 1 : 0;
+	{
+		uint32_t m = __ballot_sync(0xffffffffu, got);
+		if (hit_count && (threadIdx.x & 31) == 0 && m) atomicAdd(hit_count, (unsigned long long)__popc(m));
+	}
+	__syncthreads();
+	uint32_t rows = rtk_umin(RTK_RESOLVE_THREADS, nrays > base ? nrays - base : 0u);
+	uint32_t *dst = hits + 17ull * base;
+	for (uint32_t w = threadIdx.x; w < rows * 17u; w += RTK_RESOLVE_THREADS) {
+		uint32_t row = w / 17u;
+		if (s_hit[row]) dst[w] = s_row[row][w - row * 17u];
+	}
+}

@@ -1,0 +1,100 @@
+// rtk_common.cuh -- shared definitions of the device code: launch macro, device data layout,
+// small helpers.  Compiled by nvcc for sm_100a; the test suite additionally compiles the very
+// same sources with g++ against tests/emu/simt.h (RTK_SIMT_EMU) to execute them on the CPU.
+#pragma once
+
+#ifndef RTK_SIMT_EMU
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#define RTK_LAUNCH(kernel, grid, block, stream, ...) \
+	kernel<<<dim3(grid), dim3(block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+
+#define RTK_DEV __device__ __forceinline__
+
+#define RTK_MISS 0xffffffffu
+#define RTK_INF_F 3.402823e+38f          // RTK_INF, reference rtk.h:11
+
+// ---------------------------------------------------------------------------------------------
+// Device scene layout (all arrays in HBM, 256-byte aligned by cudaMalloc)
+//
+//   tri_orig   [3*N] float4  original-order triangles, one rtk_vertex (xyz + mesh vertex index)
+//                            per corner: exactly the 48 bytes rtk_hit::vertex[3] wants
+//                            (reference rtk.c:1162-1167, 376-378).  Read by the resolve kernel.
+//   tv0,tv1,tv2 [N] float4   leaf-ordered SoA copy for traversal: corner k of the i-th triangle in
+//                            BVH leaf order; tv0[i].w carries the global triangle number.  A leaf
+//                            is a contiguous run of <= 8 entries, so the 8 lanes of a ray group
+//                            fetch 3 x 128 contiguous bytes.
+//   nodes      [16*M] float4 8-wide nodes, 256 bytes each, two 128-byte lines:
+//                              line 0: child c -> (lo.x, lo.y, lo.z, ref)
+//                              line 1: child c -> (hi.x, hi.y, hi.z, unused)
+//                            ref: 0xffffffff empty | bit31 set: leaf, bits[30:3] first triangle
+//                            (leaf order), bits[2:0] count-1 | else index of an 8-wide node.
+//                            Lane c of a ray group loads float4 c of each line: one coalesced
+//                            128-byte request per line per ray.
+//   mesh_first [num_meshes+1] first global triangle number of each mesh.
+// ---------------------------------------------------------------------------------------------
+
+#define RTK_WIDE 8                       // children per node == lanes per ray
+#define RTK_LEAF_MAX 8                   // triangles per leaf (one per lane)
+#define RTK_REF_EMPTY 0xffffffffu
+#define RTK_REF_LEAF 0x80000000u
+
+struct rtkd_arrays {
+	const float4 *tri_orig;
+	const float4 *tv0, *tv1, *tv2;
+	const float4 *nodes;
+	const uint32_t *mesh_first;
+	uint32_t num_tris, num_meshes, num_nodes;
+	float abs_max;                       // largest |coordinate| of the scene bounds
+};
+
+RTK_DEV uint32_t rtk_leaf_ref(uint32_t first, uint32_t count) { return RTK_REF_LEAF | (first << 3) | (count - 1u); }
+RTK_DEV bool     rtk_ref_is_leaf(uint32_t ref) { return (ref & RTK_REF_LEAF) != 0; }
+RTK_DEV uint32_t rtk_leaf_first(uint32_t ref) { return (ref & 0x7fffffffu) >> 3; }
+RTK_DEV uint32_t rtk_leaf_count(uint32_t ref) { return (ref & 7u) + 1u; }
+
+RTK_DEV float rtk_fmin(float a, float b) { return fminf(a, b); }
+RTK_DEV float rtk_fmax(float a, float b) { return fmaxf(a, b); }
+RTK_DEV uint32_t rtk_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+RTK_DEV uint32_t rtk_umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+RTK_DEV int rtk_imin(int a, int b) { return a < b ? a : b; }
+RTK_DEV int rtk_imax(int a, int b) { return a > b ? a : b; }
+
+// order-preserving float <-> uint32 map (for atomicMin/Max on floats)
+RTK_DEV uint32_t rtk_f2ord(float f)
+{
+	uint32_t u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+RTK_DEV float rtk_ord2f(uint32_t u)
+{
+	return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// asynchronous 16-byte global->shared copy (LDGSTS); the emulator copies synchronously
+RTK_DEV void rtk_cp_async16(void *smem_dst, const void *gmem_src)
+{
+#ifdef RTK_SIMT_EMU
+	memcpy(smem_dst, gmem_src, 16);
+#else
+	unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gmem_src) : "memory");
+#endif
+}
+RTK_DEV void rtk_cp_async_commit()
+{
+#ifndef RTK_SIMT_EMU
+	asm volatile("cp.async.commit_group;\n" ::: "memory");
+#endif
+}
+RTK_DEV void rtk_cp_async_wait_all()
+{
+#ifndef RTK_SIMT_EMU
+	asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#endif
+}

@@ -1,0 +1,79 @@
+/*
+ * rtk_device.h -- the thin C-ABI layer between the C host code (rtk_host.c) and the CUDA
+ * translation unit (rtk_device.cu).  Internal: not installed, not part of the public ABI.
+ * Plain C types only.
+ */
+#ifndef RTK_DEVICE_H
+#define RTK_DEVICE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* A scene resident on the current device.  Pointers are device pointers. */
+typedef struct rtkd_scene {
+	uint64_t id;                 /* unique per process, also stored in serialised blobs */
+	uint32_t num_tris, num_meshes, num_nodes, num_leaves, depth, build_mode;
+	void *tri_orig;              /* float4[3*num_tris] */
+	void *tv0, *tv1, *tv2;       /* float4[num_tris] each */
+	void *nodes;                 /* float4[16*num_nodes] */
+	void *mesh_first;            /* uint32[num_meshes+1] */
+	uint32_t *h_mesh_first;      /* host copy */
+	float bounds_min[3], bounds_max[3], abs_max;
+	double build_device_ms, build_total_ms, sah_cost;
+	/* traversal scratch, created on first use */
+	void *scratch;               /* counter, err, stats */
+	void *overflow; size_t overflow_entries, overflow_groups;
+	void *hit16; size_t hit16_cap;   /* compact hits of rtk_trace_rays_device */
+} rtkd_scene;
+
+typedef struct rtkd_trace_stats {
+	uint64_t rays, hits, node_visits, leaf_visits, tri_tests, stack_max;
+} rtkd_trace_stats;
+
+int         rtkd_init(int device);           /* 0 or negative rtk_cuda_status */
+void        rtkd_shutdown(void);
+const char *rtkd_last_error(void);
+void        rtkd_set_error(const char *fmt, ...);
+int         rtkd_device_info(int *sm_count, size_t *l2_bytes, int *ctas_per_sm, int *threads_per_cta);
+
+rtkd_scene *rtkd_scene_new(uint32_t num_tris, uint32_t num_meshes, const uint32_t *mesh_first);
+void        rtkd_scene_free(rtkd_scene *s);
+
+/* staging helpers for the host ingest */
+void *rtkd_upload(const void *host, size_t bytes, void *stream);
+void  rtkd_free_async(void *dev, void *stream);
+int   rtkd_sync(void *stream);
+int   rtkd_max_index(const void *d_idx, size_t stride, int idx_bytes, uint32_t ntris, uint32_t *out, void *stream);
+
+/* decode one mesh (device buffers) into the scene's corner records */
+int rtkd_decode_mesh(rtkd_scene *s, uint32_t first_prim, uint32_t ntris,
+                     const void *d_pos, size_t pos_stride, int pos_f64,
+                     const void *d_idx, size_t idx_stride, int idx_bytes, int pregathered, void *stream);
+
+/* build the BVH from the decoded triangles; synchronous with respect to `stream` on return */
+int rtkd_build(rtkd_scene *s, int mode, void *stream);
+
+/* queries: device pointers, asynchronous on stream */
+int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, int cull_mode,
+               rtkd_trace_stats *stats, void *stream);
+int rtkd_trace_brute(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, void *stream);
+int rtkd_resolve(rtkd_scene *s, const void *d_hit16, void *d_hits, void *d_mask, size_t n, void *stream);
+void *rtkd_scene_hit16(rtkd_scene *s, size_t n);   /* scene-owned compact hit buffer of >= n records */
+
+/* host-buffer batch: H2D, trace, resolve, D2H; returns hits or -1 */
+long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n);
+
+/* serialisation of the device layout into a relocatable blob (payload after the 128-byte
+ * header block that rtk_host.c writes) */
+size_t      rtkd_blob_payload_size(const rtkd_scene *s);
+int         rtkd_blob_write(const rtkd_scene *s, void *payload);          /* device -> host */
+rtkd_scene *rtkd_blob_read(const void *payload, size_t payload_size);     /* host -> device */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

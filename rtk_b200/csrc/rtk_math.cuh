@@ -1,0 +1,124 @@
+// rtk_math.cuh -- per-ray constants, the watertight ray/triangle test and the conservative
+// ray/box slab test.  The triangle arithmetic reproduces the reference bit for bit
+// (rtk.c:543-567 setup, :256-354 test); every multiply/add is an explicit round-to-nearest
+// intrinsic so nvcc cannot contract them into FMAs (the reference's SSE code has none).
+#pragma once
+#include "rtk_common.cuh"
+
+struct rtk_ray_ctx {
+	// triangle test (reference rtk.c:550-566)
+	float ox, oy, oz;        // origin permuted to (kx,ky,kz)
+	float sx, sy, sz;        // shear constants
+	int   kz;                // dominant axis; kx=(kz+1)%3, ky=(kz+2)%3
+	// box test: t = fma(plane, id, c) with padded near/far origins folded into c
+	float idx, idy, idz;
+	float cnx, cny, cnz;
+	float cfx, cfy, cfz;
+	uint32_t sgn;            // bit a: direction component a is negative (near plane = hi)
+	float min_t;
+};
+
+// select component k of (x,y,z)
+RTK_DEV float rtk_sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+
+RTK_DEV void rtk_ray_setup(rtk_ray_ctx &r, float ox, float oy, float oz, float dx, float dy, float dz,
+                           float min_t, float scene_abs_max)
+{
+	// rtk.c:550-555: kz = argmax |d|, x wins ties, then y
+	float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+	float mx = ax > ay ? ax : ay;
+	mx = mx > az ? mx : az;
+	int kz = (ax == mx) ? 0 : ((ay == mx) ? 1 : 2);
+	int kx = kz == 2 ? 0 : kz + 1;
+	int ky = kx == 2 ? 0 : kx + 1;
+	float dkx = rtk_sel3(dx, dy, dz, kx), dky = rtk_sel3(dx, dy, dz, ky), dkz = rtk_sel3(dx, dy, dz, kz);
+	r.kz = kz;
+	r.sx = __fdiv_rn(-dkx, dkz);      // rtk.c:561
+	r.sy = __fdiv_rn(-dky, dkz);      // rtk.c:562
+	r.sz = __fdiv_rn(1.0f, dkz);      // rtk.c:563
+	r.ox = rtk_sel3(ox, oy, oz, kx);  // rtk.c:564-566
+	r.oy = rtk_sel3(ox, oy, oz, ky);
+	r.oz = rtk_sel3(ox, oy, oz, kz);
+	r.min_t = min_t;
+
+	// Conservative box test (DESIGN.md "node test").  The triangle test rounds in fp32, so it
+	// can accept a triangle whose exact geometry the exact ray misses by a few ulps of the
+	// origin-to-vertex distance.  Every box is therefore padded by 64 ulps of S = max(|o|, |scene|)
+	// and direction components below 2^-24 |d|max are raised to that value (the ray moves by
+	// less than one ulp of S inside the scene), which also keeps 1/d finite.
+	float thr = mx * 5.9604645e-08f;                       // 2^-24
+	float ddx = copysignf(fmaxf(ax, thr), dx);
+	float ddy = copysignf(fmaxf(ay, thr), dy);
+	float ddz = copysignf(fmaxf(az, thr), dz);
+	r.idx = 1.0f / ddx; r.idy = 1.0f / ddy; r.idz = 1.0f / ddz;
+	float S = fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), scene_abs_max));
+	float pad = S * 3.8146973e-06f;                        // 64 * 2^-24
+	r.cnx = -((ox + copysignf(pad, dx)) * r.idx);
+	r.cny = -((oy + copysignf(pad, dy)) * r.idy);
+	r.cnz = -((oz + copysignf(pad, dz)) * r.idz);
+	r.cfx = -((ox - copysignf(pad, dx)) * r.idx);
+	r.cfy = -((oy - copysignf(pad, dy)) * r.idy);
+	r.cfz = -((oz - copysignf(pad, dz)) * r.idz);
+	r.sgn = (__float_as_uint(dx) >> 31) | ((__float_as_uint(dy) >> 31) << 1) | ((__float_as_uint(dz) >> 31) << 2);
+}
+
+// One triangle, reference rtk.c:256-354 for a single lane with the own-lane fp64 rule
+// (SURVEY 8(c)): returns true and t,u,v when min_t < t <= max_t_incl.  The upper bound is
+// inclusive so that the caller can resolve exact ties towards the lowest triangle number; the
+// caller rejects t == max_t_incl when no hit has been recorded yet (rtk.c:354 is strict).
+RTK_DEV bool rtk_tri_test(const rtk_ray_ctx &r, float4 p0, float4 p1, float4 p2, float max_t_incl,
+                          float &t_out, float &u_out, float &v_out)
+{
+	const int kz = r.kz;
+	// axis permutation (the reference's pshufb, rtk.c:232-243)
+	float a0x = kz == 0 ? p0.y : (kz == 1 ? p0.z : p0.x);
+	float a0y = kz == 0 ? p0.z : (kz == 1 ? p0.x : p0.y);
+	float a0z = kz == 0 ? p0.x : (kz == 1 ? p0.y : p0.z);
+	float a1x = kz == 0 ? p1.y : (kz == 1 ? p1.z : p1.x);
+	float a1y = kz == 0 ? p1.z : (kz == 1 ? p1.x : p1.y);
+	float a1z = kz == 0 ? p1.x : (kz == 1 ? p1.y : p1.z);
+	float a2x = kz == 0 ? p2.y : (kz == 1 ? p2.z : p2.x);
+	float a2y = kz == 0 ? p2.z : (kz == 1 ? p2.x : p2.y);
+	float a2z = kz == 0 ? p2.x : (kz == 1 ? p2.y : p2.z);
+	// translate, rtk.c:256-280
+	a0x = __fsub_rn(a0x, r.ox); a0y = __fsub_rn(a0y, r.oy); a0z = __fsub_rn(a0z, r.oz);
+	a1x = __fsub_rn(a1x, r.ox); a1y = __fsub_rn(a1y, r.oy); a1z = __fsub_rn(a1z, r.oz);
+	a2x = __fsub_rn(a2x, r.ox); a2y = __fsub_rn(a2y, r.oy); a2z = __fsub_rn(a2z, r.oz);
+	// shear, rtk.c:284-292 (separate multiply and add)
+	float x0 = __fadd_rn(a0x, __fmul_rn(r.sx, a0z));
+	float y0 = __fadd_rn(a0y, __fmul_rn(r.sy, a0z));
+	float z0 = __fmul_rn(r.sz, a0z);
+	float x1 = __fadd_rn(a1x, __fmul_rn(r.sx, a1z));
+	float y1 = __fadd_rn(a1y, __fmul_rn(r.sy, a1z));
+	float z1 = __fmul_rn(r.sz, a1z);
+	float x2 = __fadd_rn(a2x, __fmul_rn(r.sx, a2z));
+	float y2 = __fadd_rn(a2y, __fmul_rn(r.sy, a2z));
+	float z2 = __fmul_rn(r.sz, a2z);
+	// edge functions, rtk.c:298-300
+	float u = __fsub_rn(__fmul_rn(x1, y2), __fmul_rn(y1, x2));
+	float v = __fsub_rn(__fmul_rn(x2, y0), __fmul_rn(y2, x0));
+	float w = __fsub_rn(__fmul_rn(x0, y1), __fmul_rn(y0, x1));
+	// exact-zero fallback in double, rtk.c:301-336
+	if (u == 0.0f || v == 0.0f || w == 0.0f) {
+		double ud = __dsub_rn(__dmul_rn((double)x1, (double)y2), __dmul_rn((double)y1, (double)x2));
+		double vd = __dsub_rn(__dmul_rn((double)x2, (double)y0), __dmul_rn((double)y2, (double)x0));
+		double wd = __dsub_rn(__dmul_rn((double)x0, (double)y1), __dmul_rn((double)y0, (double)x1));
+		u = __double2float_rn(ud); v = __double2float_rn(vd); w = __double2float_rn(wd);
+	}
+	// sign test, rtk.c:340-344
+	bool neg = (u < 0.0f) || (v < 0.0f) || (w < 0.0f);
+	bool pos = (u > 0.0f) || (v > 0.0f) || (w > 0.0f);
+	if (neg && pos) return false;
+	// rtk.c:346-353
+	float det = __fadd_rn(__fadd_rn(u, v), w);
+	float rcp = __fdiv_rn(1.0f, det);
+	float z = __fmul_rn(u, z0);
+	z = __fadd_rn(z, __fmul_rn(v, z1));
+	z = __fadd_rn(z, __fmul_rn(w, z2));
+	float t = __fmul_rn(z, rcp);
+	if (!(t > r.min_t && t <= max_t_incl)) return false;  // rtk.c:354
+	t_out = t;
+	u_out = __fmul_rn(u, rcp);                            // rtk.c:363
+	v_out = __fmul_rn(v, rcp);                            // rtk.c:364
+	return true;
+}

@@ -1,0 +1,450 @@
+// simt.h -- a small SIMT emulator so that the product's .cu sources can be compiled with g++ and
+// EXECUTED ON THE CPU BY THE TEST SUITE ONLY (there is no GPU in the authoring container).
+//
+// TEST INFRASTRUCTURE ONLY.  This header is force-included (g++ -x c++ -include simt.h
+// -DRTK_SIMT_EMU) when tests/emu/build_emu.py compiles rtk_b200/csrc/*.cu into
+// tests/emu/librtk_emu.so.  The product library librtk_b200.so is compiled by nvcc for sm_100a
+// and contains none of this; rtk_b200/api.py never loads the emulated library.
+//
+// Model: every CUDA thread of a block is a fiber (hand-rolled x86-64 context switch).  Blocks
+// run one after another; inside a block, warps are scheduled round-robin and a fiber yields
+// whenever it reaches a warp collective (__shfl_*_sync, __ballot_sync, __match_any_sync,
+// __syncwarp ...) or __syncthreads().  Atomics are plain operations (one OS thread).  Floating
+// point follows IEEE with -ffp-contract=off, fmaf() is a true fused multiply-add, so device
+// arithmetic is reproduced bit-for-bit.
+#pragma once
+#ifndef RTK_SIMT_EMU
+#define RTK_SIMT_EMU 1
+#endif
+
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <functional>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// qualifiers
+// ------------------------------------------------------------------------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
+#define __restrict__ __restrict
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __constant__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+// ------------------------------------------------------------------------------------------
+// vector types
+// ------------------------------------------------------------------------------------------
+struct uint3_ { unsigned x, y, z; };
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+struct __attribute__((aligned(8))) float2 { float x, y; };
+struct float3 { float x, y, z; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
+struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
+struct __attribute__((aligned(8))) int2 { int x, y; };
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r = {x, y, z, w}; return r; }
+static inline float3 make_float3(float x, float y, float z) { float3 r = {x, y, z}; return r; }
+static inline float2 make_float2(float x, float y) { float2 r = {x, y}; return r; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r = {x, y, z, w}; return r; }
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r = {x, y}; return r; }
+static inline int2 make_int2(int x, int y) { int2 r = {x, y}; return r; }
+
+// ------------------------------------------------------------------------------------------
+// fibers
+// ------------------------------------------------------------------------------------------
+namespace simt {
+
+struct Warp;
+struct Fiber {
+	void *sp;
+	char *stack;
+	uint3_ tid;
+	int lane, warp;
+	bool done, at_block_barrier;
+	Warp *w;
+};
+struct Warp {
+	unsigned gen, count, live_mask;
+	uint64_t slot[32];
+	uint64_t slot2[32];
+};
+struct Block {
+	unsigned gen, count, live;
+};
+
+extern Fiber *cur;
+extern Block blk;
+extern void *sched_sp;
+extern uint3_ g_blockIdx;
+extern dim3 g_blockDim, g_gridDim;
+extern std::function<void()> *g_body;
+extern unsigned long long g_switches, g_progress;
+
+extern "C" void simt_switch(void **save_sp, void *load_sp);
+
+static inline void yield() { g_switches++; simt_switch(&cur->sp, sched_sp); }
+
+void launch(dim3 grid, dim3 block, const std::function<void()> &body);
+
+// all lanes named in mask rendezvous here
+static inline void warp_barrier(unsigned mask)
+{
+	Warp *w = cur->w;
+	unsigned expect = (unsigned)__builtin_popcount(mask & w->live_mask);
+	unsigned gen = w->gen;
+	g_progress++;
+	if (++w->count >= expect) { w->count = 0; w->gen++; }
+	else while (w->gen == gen) yield();
+}
+
+} // namespace simt
+
+#define threadIdx (simt::cur->tid)
+#define blockIdx (simt::g_blockIdx)
+#define blockDim (simt::g_blockDim)
+#define gridDim (simt::g_gridDim)
+#define warpSize 32
+
+static inline void __syncthreads()
+{
+	simt::Fiber *f = simt::cur;
+	unsigned gen = simt::blk.gen;
+	f->at_block_barrier = true;
+	simt::blk.count++;
+	simt::g_progress++;
+	while (simt::blk.gen == gen) simt::yield();
+}
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { simt::warp_barrier(mask); }
+static inline void __threadfence() {}
+static inline void __threadfence_block() {}
+
+template <typename T> static inline T simt_exchange(unsigned mask, T v, int src_lane)
+{
+	static_assert(sizeof(T) <= 8, "shuffle payload");
+	simt::Warp *w = simt::cur->w;
+	uint64_t raw = 0;
+	memcpy(&raw, &v, sizeof(T));
+	w->slot[simt::cur->lane] = raw;
+	simt::warp_barrier(mask);
+	uint64_t got = w->slot[src_lane & 31];
+	simt::warp_barrier(mask);
+	T r;
+	memcpy(&r, &got, sizeof(T));
+	return r;
+}
+template <typename T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
+{
+	int lane = simt::cur->lane;
+	int base = lane & ~(width - 1);
+	return simt_exchange(mask, v, base + (src & (width - 1)));
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int width = 32)
+{
+	int lane = simt::cur->lane;
+	int src = lane ^ lanemask;
+	if ((src & ~(width - 1)) != (lane & ~(width - 1))) src = lane;
+	return simt_exchange(mask, v, src);
+}
+template <typename T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+	int lane = simt::cur->lane;
+	int src = lane - (int)delta;
+	if (src < (lane & ~(width - 1))) src = lane;
+	return simt_exchange(mask, v, src);
+}
+template <typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned delta, int width = 32)
+{
+	int lane = simt::cur->lane;
+	int src = lane + (int)delta;
+	if (src > (lane | (width - 1))) src = lane;
+	return simt_exchange(mask, v, src);
+}
+static inline unsigned __ballot_sync(unsigned mask, int pred)
+{
+	simt::Warp *w = simt::cur->w;
+	w->slot[simt::cur->lane] = pred ? 1 : 0;
+	simt::warp_barrier(mask);
+	unsigned r = 0;
+	for (int i = 0; i < 32; i++) if (((mask & w->live_mask) >> i & 1) && w->slot[i]) r |= 1u << i;
+	simt::warp_barrier(mask);
+	return r;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
+static inline unsigned __match_any_sync(unsigned mask, unsigned v)
+{
+	simt::Warp *w = simt::cur->w;
+	w->slot[simt::cur->lane] = v;
+	simt::warp_barrier(mask);
+	unsigned r = 0;
+	for (int i = 0; i < 32; i++) if (((mask & w->live_mask) >> i & 1) && w->slot[i] == (uint64_t)v) r |= 1u << i;
+	simt::warp_barrier(mask);
+	return r;
+}
+static inline unsigned __activemask() { return simt::cur->w->live_mask; }
+
+// ------------------------------------------------------------------------------------------
+// intrinsics
+// ------------------------------------------------------------------------------------------
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
+static inline int __clzll(long long v) { return v == 0 ? 64 : __builtin_clzll((unsigned long long)v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __brev(unsigned v)
+{
+	v = (v >> 16) | (v << 16);
+	v = ((v & 0xff00ff00u) >> 8) | ((v & 0x00ff00ffu) << 8);
+	v = ((v & 0xf0f0f0f0u) >> 4) | ((v & 0x0f0f0f0fu) << 4);
+	v = ((v & 0xccccccccu) >> 2) | ((v & 0x33333333u) << 2);
+	v = ((v & 0xaaaaaaaau) >> 1) | ((v & 0x55555555u) << 1);
+	return v;
+}
+static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline int __float_as_int(float f) { int u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline float __double2float_rn(double a) { return (float)a; }
+static inline float __int2float_rn(int a) { return (float)a; }
+static inline float __uint2float_rn(unsigned a) { return (float)a; }
+static inline int __float2int_rd(float a) { return (int)floorf(a); }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+template <typename T> static inline void __stcg(T *p, T v) { *p = v; }
+template <typename T> static inline void __stcs(T *p, T v) { *p = v; }
+static inline float __saturatef(float x) { return x < 0 ? 0 : x > 1 ? 1 : x; }
+static inline unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
+#ifndef __CUDACC__
+template <typename T> static inline T min(T a, T b) { return a < b ? a : b; }
+template <typename T> static inline T max(T a, T b) { return a > b ? a : b; }
+#endif
+
+template <typename T> static inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> static inline T atomicSub(T *p, T v) { T o = *p; *p = o - v; return o; }
+template <typename T> static inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <typename T> static inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
+template <typename T> static inline T atomicOr(T *p, T v) { T o = *p; *p = o | v; return o; }
+template <typename T> static inline T atomicAnd(T *p, T v) { T o = *p; *p = o & v; return o; }
+template <typename T> static inline T atomicExch(T *p, T v) { T o = *p; *p = v; return o; }
+template <typename T> static inline T atomicCAS(T *p, T cmp, T v) { T o = *p; if (o == cmp) *p = v; return o; }
+
+// ------------------------------------------------------------------------------------------
+// a fake CUDA runtime: device memory is host memory
+// ------------------------------------------------------------------------------------------
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+typedef struct simt_event { double t; } *cudaEvent_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+struct cudaDeviceProp { char name[256]; int multiProcessorCount; int l2CacheSize; size_t totalGlobalMem; int major, minor; };
+static inline const char *cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : "emulated CUDA error"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
+{
+	memset(p, 0, sizeof(*p));
+	strcpy(p->name, "SIMT-EMU (CPU, tests only)");
+	p->multiProcessorCount = 2; p->l2CacheSize = 1 << 20; p->totalGlobalMem = (size_t)8 << 30; p->major = 10;
+	return cudaSuccess;
+}
+template <typename T> static inline cudaError_t cudaMalloc(T **p, size_t n)
+{
+	void *q = NULL;
+	if (posix_memalign(&q, 256, n ? n : 256)) return cudaErrorMemoryAllocation;
+	memset(q, 0xCD, n);   // poison: device memory is uninitialised
+	*p = (T*)q;
+	return cudaSuccess;
+}
+template <typename T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMallocAsync(T **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
+static inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = 0) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+static inline cudaError_t cudaStreamCreate(cudaStream_t *s) { *s = NULL; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = NULL; return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+#define cudaStreamNonBlocking 1
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)malloc(sizeof(simt_event)); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0)
+{
+	struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+	e->t = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+	return cudaSuccess;
+}
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
+#define cudaFuncAttributeMaxDynamicSharedMemorySize 8
+#define cudaFuncAttributePreferredSharedMemoryCarveout 9
+struct cudaPointerAttributes { int type; };
+#define cudaMemoryTypeHost 1
+#define cudaMemoryTypeDevice 2
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = 0; return cudaSuccess; }
+
+// kernel launch: RTK_LAUNCH(kernel, grid, block, stream, args...)
+#define RTK_LAUNCH(kernel, grid, block, stream, ...) \
+	simt::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); })
+
+// ------------------------------------------------------------------------------------------
+// implementation (one translation unit defines SIMT_IMPL)
+// ------------------------------------------------------------------------------------------
+#ifdef SIMT_IMPL
+namespace simt {
+Fiber *cur = NULL;
+Block blk;
+void *sched_sp = NULL;
+uint3_ g_blockIdx;
+dim3 g_blockDim, g_gridDim;
+std::function<void()> *g_body = NULL;
+unsigned long long g_switches = 0, g_progress = 0;
+
+asm(R"(
+.text
+.globl simt_switch
+.type simt_switch,@function
+simt_switch:
+	pushq %rbp
+	pushq %rbx
+	pushq %r12
+	pushq %r13
+	pushq %r14
+	pushq %r15
+	movq %rsp, (%rdi)
+	movq %rsi, %rsp
+	popq %r15
+	popq %r14
+	popq %r13
+	popq %r12
+	popq %rbx
+	popq %rbp
+	ret
+.size simt_switch,.-simt_switch
+)");
+
+static void fiber_entry()
+{
+	(*g_body)();
+	cur->done = true;
+	for (;;) simt_switch(&cur->sp, sched_sp);
+}
+
+static const size_t STACK = 256 * 1024;
+static std::vector<Fiber> fibers;
+static std::vector<Warp> warps;
+
+static void prepare(Fiber *f)
+{
+	if (!f->stack) f->stack = (char*)malloc(STACK);
+	uintptr_t top = ((uintptr_t)f->stack + STACK) & ~(uintptr_t)15;
+	void **sp = (void**)(top - 64);
+	for (int i = 0; i < 6; i++) sp[i] = 0;
+	sp[6] = (void*)&fiber_entry;
+	sp[7] = 0;
+	f->sp = sp;
+	f->done = false;
+	f->at_block_barrier = false;
+}
+
+void launch(dim3 grid, dim3 block, const std::function<void()> &body)
+{
+	std::function<void()> b = body;
+	std::function<void()> *saved_body = g_body;
+	g_body = &b;
+	g_blockDim = block; g_gridDim = grid;
+	unsigned nthreads = block.x * block.y * block.z;
+	unsigned nwarps = (nthreads + 31) / 32;
+	if (fibers.size() < nthreads) { fibers.resize(nthreads); }
+	if (warps.size() < nwarps) warps.resize(nwarps);
+	for (unsigned bz = 0; bz < grid.z; bz++)
+	for (unsigned by = 0; by < grid.y; by++)
+	for (unsigned bx = 0; bx < grid.x; bx++) {
+		g_blockIdx.x = bx; g_blockIdx.y = by; g_blockIdx.z = bz;
+		blk.gen = 0; blk.count = 0; blk.live = nthreads;
+		for (unsigned w = 0; w < nwarps; w++) {
+			warps[w].gen = 0; warps[w].count = 0;
+			unsigned n = nthreads - w * 32 < 32 ? nthreads - w * 32 : 32;
+			warps[w].live_mask = n == 32 ? 0xffffffffu : ((1u << n) - 1);
+		}
+		for (unsigned t = 0; t < nthreads; t++) {
+			Fiber *f = &fibers[t];
+			prepare(f);
+			f->tid.x = t % block.x; f->tid.y = (t / block.x) % block.y; f->tid.z = t / (block.x * block.y);
+			f->lane = t & 31; f->warp = t >> 5; f->w = &warps[t >> 5];
+		}
+		unsigned done = 0;
+		while (done < nthreads) {
+			unsigned long long p0 = g_progress;
+			for (unsigned w = 0; w < nwarps; w++) {
+				// run this warp until no lane can move (all finished, parked at __syncthreads,
+				// or polling a warp barrier that cannot complete yet)
+				unsigned base = w * 32, end = base + 32 < nthreads ? base + 32 : nthreads;
+				for (;;) {
+					unsigned long long p1 = g_progress;
+					for (unsigned t = base; t < end; t++) {
+						Fiber *f = &fibers[t];
+						if (f->done || f->at_block_barrier) continue;
+						cur = f;
+						simt_switch(&sched_sp, f->sp);
+						if (f->done) {
+							done++;
+							blk.live--;
+							g_progress++;
+							f->w->live_mask &= ~(1u << f->lane);
+							// lanes waiting on a warp barrier that named this lane are released
+							unsigned expect = (unsigned)__builtin_popcount(f->w->live_mask);
+							if (f->w->count && f->w->count >= expect) { f->w->count = 0; f->w->gen++; }
+						}
+					}
+					if (g_progress == p1) break;
+				}
+			}
+			if (blk.live && blk.count >= blk.live) {
+				blk.count = 0; blk.gen++; g_progress++;
+				for (unsigned t = 0; t < nthreads; t++) fibers[t].at_block_barrier = false;
+			}
+			if (g_progress == p0 && done < nthreads) {
+				fprintf(stderr, "simt: deadlock in block (%u,%u,%u): %u of %u threads finished, %u at __syncthreads\n",
+				        bx, by, bz, done, nthreads, blk.count);
+				abort();
+			}
+		}
+	}
+	g_body = saved_body;
+	cur = NULL;
+}
+} // namespace simt
+#endif

@@ -1,0 +1,388 @@
+"""Parity cases shared by the CPU tier (emulated kernels, tests/emu) and the GPU tier (-m gpu).
+Every case goes through the C ABI of `lib` and is checked against the CPU oracle bit for bit
+(hit index, t, u, v) -- the north star allows 1e-5 relative on t/u/v, the tests demand equality."""
+import ctypes as C
+import json
+import os
+import struct
+
+import numpy as np
+
+from rtk_b200 import api, scenes
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "kat.json")
+
+
+def unhex(h):
+    return struct.unpack("<f", struct.pack("<I", int(h, 16)))[0]
+
+
+def load_kats():
+    with open(GOLDEN) as f:
+        g = json.load(f)
+    kats = []
+    for k in g["kats"]:
+        tris = np.array([[unhex(c) for c in t] for t in k["tris"]], dtype=np.float32).reshape(-1, 3, 3)
+        ray = np.zeros(1, dtype=api.RAY_DTYPE)
+        ray["o"] = [unhex(x) for x in k["ray"]["o"]]
+        ray["d"] = [unhex(x) for x in k["ray"]["d"]]
+        ray["min_t"] = unhex(k["ray"]["min_t"])
+        ray["max_t"] = unhex(k["ray"]["max_t"])
+        kats.append((k["name"], tris, ray, k["expect"], k["literal"], k["num_real_tris"]))
+    r = g["random"]
+    rnd = (np.array(r["tris"], dtype=np.uint32).view(np.float32).reshape(-1, 3, 3),
+           np.array(r["rays"], dtype=np.uint32).view(api.RAY_DTYPE),
+           np.array(r["hits"], dtype=np.uint32).view(api.HIT16_DTYPE))
+    return kats, rnd
+
+
+def expect_hit16(expect):
+    h = np.zeros(1, dtype=api.HIT16_DTYPE)
+    h["prim"] = api.RTK_CUDA_MISS
+    if expect["hit"]:
+        h["t"], h["u"], h["v"] = unhex(expect["t"]), unhex(expect["u"]), unhex(expect["v"])
+        h["prim"] = expect["prim"]
+    return h
+
+
+def soup_mesh(tris):
+    return [{"positions": np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 3), "indices": None}]
+
+
+def trace_hit16(lib, scene_dict_or_meshes, rays, mesh_first=None, mode=None):
+    """build through rtk_build_scene, trace through rtk_trace_rays, return compact records."""
+    meshes = scene_dict_or_meshes["meshes"] if isinstance(scene_dict_or_meshes, dict) else scene_dict_or_meshes
+    if mesh_first is None:
+        mesh_first = scene_dict_or_meshes["mesh_first"] if isinstance(scene_dict_or_meshes, dict) else \
+            np.cumsum([0] + [len(m["indices"]) if m.get("indices") is not None else len(m["positions"]) // 3 for m in meshes])
+    sc = lib.build_scene(meshes, mode=mode)
+    try:
+        hits, mask, nh = sc.trace_rays(rays)
+        assert nh == int(mask.sum())
+        return api.hits_to_hit16(hits, mask, mesh_first), hits, mask
+    finally:
+        sc.free()
+
+
+def assert_same(got, want, what=""):
+    if got.tobytes() == want.tobytes():
+        return
+    bad = np.nonzero((got["prim"] != want["prim"]) | (got["t"].view(np.uint32) != want["t"].view(np.uint32)) |
+                     (got["u"].view(np.uint32) != want["u"].view(np.uint32)) |
+                     (got["v"].view(np.uint32) != want["v"].view(np.uint32)))[0]
+    i = bad[0]
+    raise AssertionError(f"{what}: {len(bad)} of {len(got)} rays differ; first ray {i}: got {got[i]} want {want[i]}")
+
+
+# ---------------------------------------------------------------------------------------------
+
+def case_kats(lib, orc):
+    kats, (rt, rr, rh) = load_kats()
+    for name, tris, ray, expect, literal, nreal in kats:
+        got, hits, mask = trace_hit16(lib, soup_mesh(tris), ray)
+        assert_same(got, expect_hit16(expect), name)
+        # the bare scene (what rtk.c literally sees) stays within the north star's tolerance
+        got2, _, _ = trace_hit16(lib, soup_mesh(tris[:nreal]), ray)
+        lit = expect_hit16(literal)
+        assert got2["prim"][0] == lit["prim"][0], name
+        if literal["hit"]:
+            for f in ("t", "u", "v"):
+                assert abs(float(got2[f][0]) - float(lit[f][0])) <= 1e-5 * max(abs(float(lit[f][0])), 1e-30) + 1e-7, (name, f)
+    got, _, _ = trace_hit16(lib, soup_mesh(rt), rr)
+    assert_same(got, rh, "golden random soup")
+
+
+def case_config(lib, orc, name, scale, nrays, mode=None):
+    s = scenes.config_scene(name, scale)
+    if name == "C1":
+        rays = scenes.config_rays("C1", s)
+        if nrays:
+            rays = rays[:: max(1, len(rays) // nrays)][:nrays]
+    elif name == "C2":
+        side = max(4, int(np.sqrt(nrays)))
+        rays = scenes.soup_primary_rays(side * 16 // 9, side)
+    elif name == "C3":
+        rays = scenes.bounce_rays(s, nrays)
+    else:
+        rays = scenes.mixed_rays(s, nrays, block=max(64, nrays // 12))
+    got, hits, mask = trace_hit16(lib, s, rays, mode=mode)
+    want = orc.trace_brute(s["tris"], rays)
+    assert_same(got, want, f"{name} x{scale}")
+    m = mask.astype(bool)
+    prim = want["prim"][m].astype(np.int64)
+    # payload: the three rtk_vertex of the hit triangle, mesh and per-mesh triangle number
+    assert np.array_equal(hits["vertex"]["position"][m], s["tris"][prim])
+    mesh = np.searchsorted(s["mesh_first"], prim, side="right") - 1
+    assert np.array_equal(hits["mesh_index"][m], mesh)
+    assert np.array_equal(hits["triangle_index"][m], prim - s["mesh_first"][mesh])
+    vidx = []
+    for k, me in enumerate(s["meshes"]):
+        nt = int(s["mesh_first"][k + 1] - s["mesh_first"][k])
+        vidx.append(me["indices"].astype(np.uint32) if me["indices"] is not None else np.arange(3 * nt, dtype=np.uint32).reshape(-1, 3))
+    vidx = np.concatenate(vidx)
+    assert np.array_equal(hits["vertex"]["index"][m], vidx[prim])
+    return int(m.sum())
+
+
+def case_edge_scenes(lib, orc):
+    ray = np.zeros(4, dtype=api.RAY_DTYPE)
+    ray["o"] = [(0.25, 0.25, 0), (0.25, 0.25, 0), (5, 5, 0), (0.25, 0.25, 2)]
+    ray["d"] = [(0, 0, 1), (0, 0, -1), (0, 0, 1), (0, 0, -1)]
+    ray["max_t"] = api.RTK_INF
+    # empty scene
+    sc = lib.build_scene([])
+    hits, mask, nh = sc.trace_rays(ray)
+    assert nh == 0 and not mask.any()
+    sc.free()
+    sc = lib.build_scene([{"positions": np.zeros((0, 3), np.float32), "indices": None}])
+    assert sc.trace_rays(ray)[2] == 0
+    sc.free()
+    # one triangle, then 2..20 triangles (leaf / node boundary cases)
+    rng = np.random.default_rng(7)
+    for n in list(range(1, 21)) + [63, 64, 65]:
+        tris = rng.random((n, 3, 3)).astype(np.float32)
+        tris[0] = [(0, 0, 1), (1, 0, 1), (0, 1, 1)]
+        got, _, _ = trace_hit16(lib, soup_mesh(tris), ray)
+        assert_same(got, orc.trace_brute(tris, ray), f"{n} triangles")
+    # zero rays
+    sc = lib.build_scene(soup_mesh(tris))
+    assert sc.trace_rays(ray[:0])[2] == 0
+    sc.free()
+
+
+def case_ties(lib, orc):
+    """duplicates and shared edges: exact ties go to the lowest triangle number, whatever the
+    order the BVH presents them in"""
+    rng = np.random.default_rng(11)
+    base = rng.random((40, 3, 3)).astype(np.float32)
+    tris = np.concatenate([base, base[::-1], base])            # every triangle three times
+    rays = np.zeros(600, dtype=api.RAY_DTYPE)
+    rays["o"] = (rng.random((600, 3)) * 2 - 0.5).astype(np.float32)
+    tgt = base[rng.integers(0, 40, 600)].mean(axis=1)
+    rays["d"] = tgt - rays["o"]
+    rays["max_t"] = api.RTK_INF
+    got, _, _ = trace_hit16(lib, soup_mesh(tris), rays)
+    want = orc.trace_brute(tris, rays)
+    assert_same(got, want, "duplicated triangles")
+    assert (want["prim"][want["prim"] != api.RTK_CUDA_MISS] < 80).all()
+    # coplanar grid, rays through grid vertices and edges (exact zeros -> fp64 path)
+    g = scenes._quad_grid((0, 0, 1), (1, 0, 0), (0, 1, 0), 8, 8)
+    grid = g[0][g[1].astype(np.int64)]
+    gx, gy = np.meshgrid(np.arange(0, 17) / 16.0, np.arange(0, 17) / 16.0)
+    r2 = np.zeros(gx.size, dtype=api.RAY_DTYPE)
+    r2["o"] = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], -1)
+    r2["d"] = (0, 0, 1)
+    r2["max_t"] = api.RTK_INF
+    got, _, _ = trace_hit16(lib, soup_mesh(grid), r2)
+    want = orc.trace_brute(grid, r2)
+    assert_same(got, want, "coplanar grid")
+    assert (want["prim"] != api.RTK_CUDA_MISS).all()          # watertight: no ray slips through an edge
+
+
+def case_ray_limits(lib, orc):
+    """min_t / max_t strictness, unnormalised directions, zero direction components, -0.0"""
+    rng = np.random.default_rng(13)
+    tris = (rng.random((300, 1, 3)) + 0.1 * (rng.random((300, 3, 3)) * 2 - 1)).astype(np.float32)
+    n = 1500
+    rays = np.zeros(n, dtype=api.RAY_DTYPE)
+    rays["o"] = (rng.random((n, 3)) * 1.4 - 0.2).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32) * rng.choice([1e-3, 1.0, 1e3], size=(n, 1)).astype(np.float32)
+    d[::7, 0] = 0.0
+    d[::11, 1] = -0.0
+    d[::13, 2] = 0.0
+    d[(np.abs(d).max(axis=1) == 0)] = (0, 0, 1)
+    rays["d"] = d
+    rays["min_t"] = rng.choice([0.0, 0.0, 1e-3, 0.3], size=n).astype(np.float32)
+    rays["max_t"] = rng.choice([api.RTK_INF, api.RTK_INF, 0.5, 2.0], size=n).astype(np.float32)
+    got, _, _ = trace_hit16(lib, soup_mesh(tris), rays)
+    want = orc.trace_brute(tris, rays)
+    assert_same(got, want, "ray limits")
+    # a second pass whose limits sit exactly on the found t: both ends are strict (rtk.c:354)
+    hit = want["prim"] != api.RTK_CUDA_MISS
+    r2 = rays[hit].copy()
+    r2["max_t"] = want["t"][hit]
+    r3 = rays[hit].copy()
+    r3["min_t"] = want["t"][hit]
+    for rr in (r2, r3):
+        g2, _, _ = trace_hit16(lib, soup_mesh(tris), rr)
+        w2 = orc.trace_brute(tris, rr)
+        assert_same(g2, w2, "limits on t")
+        assert (g2["prim"][:] != want["prim"][hit]).all()
+
+
+def case_invariances(lib, orc):
+    """triangle order permutes ids but not t; ray order permutes results only"""
+    s = scenes.config_scene("C3", 0.004)
+    rays = scenes.bounce_rays(s, 1500)
+    a, _, _ = trace_hit16(lib, s, rays)
+    perm = np.random.default_rng(5).permutation(len(s["tris"]))
+    tp = s["tris"][perm]
+    b, _, _ = trace_hit16(lib, soup_mesh(tp), rays)
+    assert np.array_equal(a["t"].view(np.uint32), b["t"].view(np.uint32))
+    hit = a["prim"] != api.RTK_CUDA_MISS
+    # ids map back unless an exact tie picked another of the tied triangles
+    same = perm[b["prim"][hit].astype(np.int64)] == a["prim"][hit]
+    assert same.mean() > 0.98
+    rp = np.random.default_rng(6).permutation(len(rays))
+    c, _, _ = trace_hit16(lib, s, rays[rp])
+    assert_same(c, a[rp], "ray order")
+
+
+def case_mesh_formats(lib, orc):
+    """U16 / U32 / implicit indices, F32 / F64 positions, strides, callbacks, DEFAULT types
+    (reference rtk.c:1028-1114)"""
+    s = scenes.config_scene("C1")
+    m = s["meshes"][0]
+    rays = scenes.config_rays("C1", s)[::131]
+    want = orc.trace_brute(s["tris"], rays)
+    pos, idx = m["positions"], m["indices"]
+    variants = []
+    variants.append(("u16", {"positions": pos, "indices": idx}))
+    variants.append(("u32", {"positions": pos, "indices": idx.astype(np.uint32)}))
+    variants.append(("default types", {"positions": pos, "indices": idx.astype(np.uint32),
+                                       "position_type": api.RTK_TYPE_DEFAULT, "index_type": api.RTK_TYPE_DEFAULT}))
+    variants.append(("real", {"positions": pos, "indices": idx, "position_type": api.RTK_TYPE_REAL}))
+    variants.append(("f64", {"positions": pos.astype(np.float64), "indices": idx}))
+    pad = np.zeros((len(pos), 5), dtype=np.float32)
+    pad[:, :3] = pos
+    pad[:, 3:] = 777.0
+    variants.append(("position stride 20", {"positions": pad, "indices": idx, "position_stride": 20}))
+    ipad = np.full((len(idx), 4), 65535, dtype=np.uint16)
+    ipad[:, :3] = idx
+    variants.append(("index stride 8", {"positions": pos, "indices": ipad, "index_stride": 8}))
+    variants.append(("implicit", {"positions": np.ascontiguousarray(s["tris"].reshape(-1, 3)), "indices": None}))
+    for name, mesh in variants:
+        if name == "index stride 8":
+            desc, keep = lib.make_desc([{"positions": pos, "indices": idx}])
+            desc.meshes[0].index.data = ipad.ctypes.data
+            desc.meshes[0].index.stride = 8
+            ptr = lib.rtk_build_scene(C.byref(desc))
+            assert ptr, lib.last_error()
+            sc = api.Scene(lib, ptr)
+            hits, mask, _ = sc.trace_rays(rays)
+            got = api.hits_to_hit16(hits, mask, s["mesh_first"])
+            sc.free()
+        else:
+            got, hits, mask = trace_hit16(lib, [mesh], rays, mesh_first=s["mesh_first"])
+        assert_same(got, want, name)
+        if name in ("u16", "u32", "f64", "position stride 20"):
+            mm = mask.astype(bool)
+            assert np.array_equal(hits["vertex"]["index"][mm], idx[want["prim"][mm].astype(np.int64)].astype(np.uint32)), name
+
+    # callbacks (rtk.h:61-62): positions and indices pulled through user functions
+    calls = {"pos": 0, "idx": 0, "max": 0}
+    idx32 = idx.astype(np.uint32)
+
+    def pos_cb(user, mesh, dst, indices, count):
+        calls["pos"] += 1
+        calls["max"] = max(calls["max"], count)
+        ii = np.ctypeslib.as_array(indices, shape=(3 * count,))
+        out = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_float)), shape=(3 * count, 3))
+        out[:] = pos[ii]
+
+    def idx_cb(user, mesh, dst, offset, count):
+        calls["idx"] += 1
+        out = np.ctypeslib.as_array(dst, shape=(3 * count,))
+        out[:] = idx32[offset:offset + count].reshape(-1)
+    pcb, icb = api.rtk_position_callback_fn(pos_cb), api.rtk_index_callback_fn(idx_cb)
+    mesh = api.rtk_mesh()
+    mesh.num_triangles = len(idx)
+    mesh.position_cb = pcb
+    mesh.index_cb = icb
+    desc = api.rtk_scene_desc()
+    desc.meshes = C.pointer(mesh)
+    desc.num_meshes = 1
+    ptr = lib.rtk_build_scene(C.byref(desc))
+    assert ptr, lib.last_error()
+    sc = api.Scene(lib, ptr)
+    hits, mask, _ = sc.trace_rays(rays)
+    assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want, "callbacks")
+    assert calls["pos"] > 0 and calls["idx"] > 0 and calls["max"] <= 128       # rtk.c:1143
+    sc.free()
+
+
+def case_api_semantics(lib, orc):
+    """rtk_trace_ray miss rule, filter, split-phase build, relocatable blob, log callback"""
+    s = scenes.config_scene("C1")
+    rays = scenes.config_rays("C1", s)[::997]
+    want = orc.trace_brute(s["tris"], rays)
+    logs = []
+    log = api.rtk_log_fn(lambda user, build, msg: logs.append(msg.decode()))
+    desc, keep = lib.make_desc(s["meshes"], log_fn=log)
+    ptr = lib.rtk_build_scene(C.byref(desc))
+    assert ptr
+    assert any("Starting build" in m for m in logs)
+    sc = api.Scene(lib, ptr)
+    hdr = sc.header()
+    assert hdr.magic == b"\x00RTK\r\n\x1a\n"[:len(hdr.magic)] or bytes(hdr.magic) == b""  # c_char stops at NUL
+    assert hdr.endian == 0xAABB and hdr.sizeof_real == 4 and hdr.size_in_bytes >= 128
+    # single-ray entry point: *hit untouched on a miss (rtk.c:571-576)
+    nh = nm = 0
+    for i in range(0, len(rays), 5):
+        r = rays[i:i + 1]
+        h = np.zeros(1, dtype=api.HIT_DTYPE)
+        h.view(np.uint8)[:] = 0xAB
+        ok = lib.rtk_trace_ray(sc.ptr, C.cast(r.ctypes.data, C.POINTER(api.rtk_ray)), C.cast(h.ctypes.data, C.POINTER(api.rtk_hit)))
+        if want["prim"][i] == api.RTK_CUDA_MISS:
+            assert not ok and (h.view(np.uint8) == 0xAB).all()
+            nm += 1
+        else:
+            assert ok and h["t"][0] == want["t"][i] and h["triangle_index"][0] == want["prim"][i]
+            nh += 1
+    assert nh > 0
+    # filter: rejecting everything reports misses, accepting everything equals rtk_trace_ray
+    i = int(np.nonzero(want["prim"] != api.RTK_CUDA_MISS)[0][0])
+    r = rays[i:i + 1]
+    h = np.zeros(1, dtype=api.HIT_DTYPE)
+    rej = api.rtk_filter_fn(lambda u, ray, hit: False)
+    acc = api.rtk_filter_fn(lambda u, ray, hit: True)
+    rp, hp = C.cast(r.ctypes.data, C.POINTER(api.rtk_ray)), C.cast(h.ctypes.data, C.POINTER(api.rtk_hit))
+    assert not lib.rtk_trace_ray_filter(sc.ptr, rp, hp, rej, None)
+    assert lib.rtk_trace_ray_filter(sc.ptr, rp, hp, acc, None) and h["t"][0] == want["t"][i]
+    sc.free()
+
+    # split-phase build into a caller buffer; too-small buffer -> NULL and the build survives
+    desc, keep = lib.make_desc(s["meshes"])
+    first = api.rtk_task()
+    b = lib.rtk_start_build(C.byref(desc), C.byref(first))
+    assert b and first.fn
+    queue = (api.rtk_task * 4)()
+    assert lib.rtk_run_task(C.byref(first), queue, 4) == 0
+    size = lib.rtk_get_build_size(b)
+    assert size > 128 and size % 128 == 0
+    small = np.zeros(size - 128, dtype=np.uint8)
+    assert not lib.rtk_finish_build_to(b, small.ctypes.data, small.nbytes)
+    buf = np.zeros(size + 128, dtype=np.uint8)
+    off = (-buf.ctypes.data) % 128
+    p = lib.rtk_finish_build_to(b, buf.ctypes.data + off, size)
+    assert p == buf.ctypes.data + off
+    sc = api.Scene(lib, p, owner=buf)
+    assert sc.header().size_in_bytes == size
+    hits, mask, _ = sc.trace_rays(rays)
+    assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want, "finish_build_to")
+    # relocate: copy the blob elsewhere, drop the original, trace the copy
+    blob = buf[off:off + size].copy()
+    moved = np.zeros(size + 128, dtype=np.uint8)
+    off2 = (-moved.ctypes.data) % 128
+    moved[off2:off2 + size] = blob
+    sc.free()
+    buf[:] = 0
+    sc2 = api.Scene(lib, moved.ctypes.data + off2, owner=moved)
+    hits, mask, _ = sc2.trace_rays(rays)
+    assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want, "relocated blob")
+    assert lib.rtk_cuda_detach_scene(sc2.ptr) == 0
+    sc2.ptr = None
+    # a foreign blob is refused, loudly
+    junk = np.zeros(256, dtype=np.uint8)
+    assert lib.rtk_trace_rays(junk.ctypes.data, rays.ctypes.data, hits.ctypes.data, mask.ctypes.data, 1) == C.c_size_t(-1).value
+    assert "magic" in lib.last_error()
+    # rtk_finish_build (library-allocated blob)
+    desc, keep = lib.make_desc(s["meshes"])
+    b = lib.rtk_start_build(C.byref(desc), None)
+    p = lib.rtk_finish_build(b)
+    assert p
+    sc = api.Scene(lib, p)
+    assert sc.header().size_in_bytes == size
+    hits, mask, _ = sc.trace_rays(rays)
+    assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want, "finish_build")
+    sc.free()

@@ -1,0 +1,39 @@
+"""CPU tier: the product's own CUDA sources and host layer, compiled against the SIMT emulator
+(tests/emu) and driven through the C ABI, against the CPU oracle.  Small sizes only -- the GPU
+tier (test_gpu_parity.py, -m gpu) runs the same cases on the real library."""
+import pytest
+
+import parity_cases as pc
+
+
+def test_known_answer_vectors(emu_lib, orc):
+    pc.case_kats(emu_lib, orc)
+
+
+@pytest.mark.parametrize("name,scale,nrays", [("C1", 1.0, 1500), ("C2", 0.004, 1200), ("C3", 0.008, 1500), ("C4", 0.001, 1500)])
+def test_configs_small(emu_lib, orc, name, scale, nrays):
+    assert pc.case_config(emu_lib, orc, name, scale, nrays) > 0
+
+
+def test_edge_scenes(emu_lib, orc):
+    pc.case_edge_scenes(emu_lib, orc)
+
+
+def test_ties_and_watertightness(emu_lib, orc):
+    pc.case_ties(emu_lib, orc)
+
+
+def test_ray_limits(emu_lib, orc):
+    pc.case_ray_limits(emu_lib, orc)
+
+
+def test_invariances(emu_lib, orc):
+    pc.case_invariances(emu_lib, orc)
+
+
+def test_mesh_formats(emu_lib, orc):
+    pc.case_mesh_formats(emu_lib, orc)
+
+
+def test_api_semantics(emu_lib, orc):
+    pc.case_api_semantics(emu_lib, orc)

@@ -1,0 +1,133 @@
+"""GPU tier (-m gpu): the product library librtk_b200.so on a real B200, through the C ABI,
+against the CPU oracle (bit-exact) and against size-independent properties at full size."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from rtk_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_known_answer_vectors(gpu_lib, orc):
+    pc.case_kats(gpu_lib, orc)
+
+
+def test_c1_all_rays(gpu_lib, orc):
+    """config 1 in full: 992 triangles, 512x512 primary rays, every ray against the oracle"""
+    assert pc.case_config(gpu_lib, orc, "C1", 1.0, 0) > 200000
+
+
+@pytest.mark.parametrize("name,scale,nrays", [("C2", 0.02, 20000), ("C3", 0.02, 20000), ("C4", 0.004, 20000)])
+def test_configs_reduced(gpu_lib, orc, name, scale, nrays):
+    assert pc.case_config(gpu_lib, orc, name, scale, nrays) > 0
+
+
+@pytest.mark.parametrize("mode", [api.RTK_CUDA_BUILD_LBVH, api.RTK_CUDA_BUILD_SAH])
+def test_build_modes(gpu_lib, orc, mode):
+    assert pc.case_config(gpu_lib, orc, "C3", 0.01, 8000, mode=mode) > 0
+    gpu_lib.rtk_cuda_set_build_mode(api.RTK_CUDA_BUILD_LBVH)
+
+
+def test_edge_scenes(gpu_lib, orc):
+    pc.case_edge_scenes(gpu_lib, orc)
+
+
+def test_ties_and_watertightness(gpu_lib, orc):
+    pc.case_ties(gpu_lib, orc)
+
+
+def test_ray_limits(gpu_lib, orc):
+    pc.case_ray_limits(gpu_lib, orc)
+
+
+def test_invariances(gpu_lib, orc):
+    pc.case_invariances(gpu_lib, orc)
+
+
+def test_mesh_formats(gpu_lib, orc):
+    pc.case_mesh_formats(gpu_lib, orc)
+
+
+def test_api_semantics(gpu_lib, orc):
+    pc.case_api_semantics(gpu_lib, orc)
+
+
+def _device_trace(lib, sc, rays_np, brute=False, stats=False):
+    import torch
+    rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1, 32)).cuda()
+    out = torch.zeros((len(rays_np), 16), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    res = None
+    if brute:
+        r = lib.rtk_trace_rays_bruteforce_device(sc.ptr, rays.data_ptr(), out.data_ptr(), len(rays_np), st)
+    elif stats:
+        res = api.rtk_cuda_trace_stats()
+        r = lib.rtk_trace_stats_device(sc.ptr, rays.data_ptr(), out.data_ptr(), len(rays_np), C.byref(res), st)
+    else:
+        r = lib.rtk_trace_rays_compact_device(sc.ptr, rays.data_ptr(), out.data_ptr(), len(rays_np), st)
+    assert r == 0, lib.last_error()
+    torch.cuda.synchronize()
+    h = out.cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)
+    return (h, res) if stats else h
+
+
+def test_full_size_c3_sampled_oracle_and_gpu_bruteforce(gpu_lib, orc):
+    """1M-triangle terrain at full size: (a) 2048 sampled rays against the CPU oracle,
+    (b) 262144 rays against the exhaustive GPU kernel (same arithmetic, no BVH), (c) device and
+    host entry points agree, (d) statistics kernel returns the same hits."""
+    s = scenes.config_scene("C3")
+    sc = gpu_lib.build_scene(s["meshes"])
+    info = sc.info()
+    assert info.num_triangles == 1_000_000
+    rays = scenes.bounce_rays(s, 1 << 18)
+    trav = _device_trace(gpu_lib, sc, rays)
+    brute = _device_trace(gpu_lib, sc, rays, brute=True)
+    pc.assert_same(trav, brute, "traversal vs exhaustive GPU kernel")
+    sub = rays[:2048]
+    pc.assert_same(trav[:2048], orc.trace_brute(s["tris"], sub), "traversal vs CPU oracle")
+    hits, mask, nh = sc.trace_rays(rays[:50000])
+    pc.assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), trav[:50000], "host vs device entry point")
+    sh, st = _device_trace(gpu_lib, sc, rays[:65536], stats=True)
+    pc.assert_same(sh, trav[:65536], "stats kernel")
+    assert st.rays == 65536 and st.hits == int((trav[:65536]["prim"] != api.RTK_CUDA_MISS).sum())
+    assert st.node_visits > 0 and st.tri_tests > 0
+    sc.free()
+
+
+def test_full_size_c2_coherent(gpu_lib, orc):
+    s = scenes.config_scene("C2")
+    sc = gpu_lib.build_scene(s["meshes"])
+    rays = scenes.config_rays("C2", s)
+    trav = _device_trace(gpu_lib, sc, rays)
+    idx = np.random.default_rng(3).choice(len(rays), 1024, replace=False)
+    pc.assert_same(trav[idx], orc.trace_brute(s["tris"], rays[idx]), "C2 sampled vs oracle")
+    sub = rays[:: 16]
+    pc.assert_same(trav[::16], _device_trace(gpu_lib, sc, sub, brute=True), "C2 vs exhaustive GPU kernel")
+    sc.free()
+
+
+def test_rebuild_and_device_mesh_build(gpu_lib, orc):
+    import torch
+    s = scenes.config_scene("C4", 0.02)
+    rays = scenes.mixed_rays(s, 30000, block=2048)
+    want = orc.trace_brute(s["tris"], rays[:3000])
+    keep, meshes = [], (api.rtk_cuda_mesh * len(s["meshes"]))()
+    for i, m in enumerate(s["meshes"]):
+        p = torch.from_numpy(m["positions"]).cuda()
+        ix = torch.from_numpy(m["indices"].astype(np.int64)).to(torch.int32).cuda()
+        keep += [p, ix]
+        meshes[i].d_positions, meshes[i].d_indices = p.data_ptr(), ix.data_ptr()
+        meshes[i].num_vertices, meshes[i].num_triangles = len(m["positions"]), len(m["indices"])
+    torch.cuda.synchronize()
+    ptr = gpu_lib.rtk_cuda_build_scene(meshes, len(s["meshes"]), None)
+    assert ptr, gpu_lib.last_error()
+    sc = api.Scene(gpu_lib, ptr)
+    a = _device_trace(gpu_lib, sc, rays)
+    pc.assert_same(a[:3000], want, "device-mesh build")
+    assert gpu_lib.rtk_cuda_rebuild_scene(sc.ptr, None) == 0
+    b = _device_trace(gpu_lib, sc, rays)
+    pc.assert_same(b, a, "rebuild")
+    sc.free()

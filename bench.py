@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- closest-hit Mrays/s (incoherent) on the BASELINE.json workload, plus BVH build Mtris/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rays R] [--scale S]
+
+A step is one pass of the hot path over one batch of synthetic rays: the traversal kernel
+(k_trace) followed by the hit-expansion kernel (k_resolve), inputs already resident in HBM.
+N=1 workload: BASELINE.json configs[2] -- 1M-triangle procedural terrain, 16 777 216 incoherent
+diffuse-bounce rays (the configuration the headline "incoherent Mrays/s" metric is quoted on).
+N>1 (torchrun): scene replicated per GPU, every rank traces its own 16 777 216 rays (weak
+scaling), compact hit records are gathered on rank 0 with NCCL inside the timed region.
+
+`--impl reference` times the reference's own CPU path instead: the patched rtk.c traversal
+(oracle/_ref, built from /root/reference/rtk.c) over a reference-format blob packed by the
+oracle's binned-SAH restatement, all host threads, on a bounded sample of the same rays.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rtk_b200 import scenes  # noqa: E402
+
+METRIC = "closest-hit Mrays/s (incoherent)"
+UNIT = "Mrays/s"
+FULL_RAYS = 16_777_216
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def gen_rays(scene, n, rank=0):
+    out = np.empty(n, dtype=scenes.RAY_DTYPE)
+    step = 1 << 21
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        out[lo:hi] = scenes.bounce_rays(scene, hi - lo, seed=0xD3, first=rank * n + lo)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def mark(self):
+        """samples from here on belong to the timed region"""
+        self.first = len(self.rows)
+
+    def start(self):
+        self.first = 0
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        rows = self.rows[self.first:] if len(self.rows) - self.first >= 3 else self.rows
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline (the one place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_run(scene, rays, sample, steps, warmup):
+    """Patched rtk.c traversal (oracle/_ref) over a blob from the oracle's binned-SAH packer."""
+    from oracle import orc
+    cores = orc.num_cores()
+    blob = orc.ReferenceBlob(scene["tris"])
+    build_s = blob.stats.build_seconds
+    kind = "reference" if orc.have_reference(patched=True) else None
+    if kind is None:
+        raise RuntimeError("oracle/_ref/librtk_ref_patched.so is missing (build it where /root/reference exists)")
+    sub = rays[:sample]
+    times = []
+    for i in range(warmup + steps):
+        _, sec = blob.trace(sub, patched=True, threads=cores, want_hits=False)
+        if i >= warmup:
+            times.append(sec)
+    blob.close()
+    sec = float(np.mean(times))
+    return {"value": sample / sec / 1e6, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {sample} of the {len(rays)} rays of the workload, {cores} threads, "
+                      f"rtk.c traversal (6-line stack fix) over a binned-SAH BVH4 blob from the oracle packer",
+            "ms_per_step": sec * 1e3,
+            "build": {"value": len(scene["tris"]) / build_s / 1e6, "unit": "Mtris/s", "cores": 1,
+                      "kind": "port", "what": "rtk.c binned-SAH algorithm restated (oracle), blob packing included"}}
+
+
+def run_reference(args, workload, scene, rays):
+    sample = min(len(rays), args.ref_sample)
+    cb = cpu_reference_run(scene, rays, sample, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload,
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_build_baseline": cb["build"],
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=FULL_RAYS)
+    ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale of the terrain (1.0 = 1M)")
+    ap.add_argument("--ref-sample", type=int, default=1 << 22)
+    ap.add_argument("--cpu-sample", type=int, default=1 << 22)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--build-mode", default="lbvh", choices=["lbvh", "sah"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-rays", type=int, default=1024)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    workload = {"workload": "C3: 1M-triangle procedural terrain (1001x501 value-noise heightfield), "
+                            "16777216 incoherent diffuse-bounce rays per GPU",
+                "triangles": None, "rays_per_gpu": args.rays, "ray_bytes": 32, "hit_bytes": 68,
+                "l2_policy": "ray and hit buffers (0.5 GB in, 1.4 GB out per step) are far larger than the "
+                             "126 MB L2 and stream through it every step; the scene (BVH + triangles) is the "
+                             "reused working set",
+                "parallelism": f"rays sharded over {world} GPU(s), scene replicated"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        scene = scenes.config_scene("C3", args.scale)
+        workload["triangles"] = int(len(scene["tris"]))
+        rays = gen_rays(scene, min(args.rays, args.ref_sample))
+        workload["rays_per_gpu"] = args.rays
+        run_reference(args, workload, scene, rays)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from rtk_b200 import api
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = api.load()
+    r = lib.rtk_cuda_init(local_rank)
+    if r != 0:
+        raise RuntimeError("rtk_cuda_init failed (no CPU fallback): " + lib.last_error())
+    lib.rtk_cuda_set_build_mode(api.RTK_CUDA_BUILD_SAH if args.build_mode == "sah" else api.RTK_CUDA_BUILD_LBVH)
+
+    scene = scenes.config_scene("C3", args.scale)
+    ntris = int(len(scene["tris"]))
+    workload["triangles"] = ntris
+    n = args.rays
+    rays_np = gen_rays(scene, n, rank)
+
+    # ---- build: end to end from host buffers, then device-only rebuilds ------------------------
+    t0 = time.perf_counter()
+    sc = lib.build_scene(scene["meshes"])
+    build_e2e_s = time.perf_counter() - t0
+    build_ms = []
+    for i in range(5):
+        assert lib.rtk_cuda_rebuild_scene(sc.ptr, None) == 0, lib.last_error()
+        build_ms.append(sc.info().build_device_ms)
+    info = sc.info()
+    build_dev_ms = float(np.median(build_ms[1:]))
+
+    # ---- device buffers ------------------------------------------------------------------------
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    d_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1, 32)).cuda()
+    d_h16 = torch.zeros((n, 16), dtype=torch.uint8, device="cuda")
+    d_hits = torch.zeros((n, 68), dtype=torch.uint8, device="cuda")
+    d_mask = torch.zeros((n,), dtype=torch.uint8, device="cuda")
+    gather_list = None
+    if world > 1:
+        gather_list = [torch.empty_like(d_h16) for _ in range(world)] if rank == 0 else None
+
+    def step(ev=None):
+        if ev:
+            ev[0].record(stream)
+        rc = lib.rtk_trace_rays_compact_device(sc.ptr, d_rays.data_ptr(), d_h16.data_ptr(), n, sh)
+        if ev:
+            ev[1].record(stream)
+        rc |= lib.rtk_resolve_hits_device(sc.ptr, d_h16.data_ptr(), d_hits.data_ptr(), d_mask.data_ptr(), n, sh)
+        if ev:
+            ev[2].record(stream)
+        if rc:
+            raise RuntimeError(lib.last_error())
+        if world > 1:
+            dist.gather(d_h16, gather_list, dst=0)
+
+    # ---- parity self-check against the CPU oracle (outside the timed region) -------------------
+    parity = None
+    if rank == 0 and args.parity_rays > 0:
+        from oracle import orc
+        step()
+        torch.cuda.synchronize()
+        k = min(args.parity_rays, n)
+        got = d_h16[:k].cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)
+        want = orc.trace_brute(scene["tris"], rays_np[:k])
+        parity = {"rays_checked": k, "index_mismatches": int((got["prim"] != want["prim"]).sum()),
+                  "bit_exact": bool(got.tobytes() == want.tobytes()), "against": "oracle (CPU brute force)"}
+
+    # ---- algorithmic bytes per ray from the counter-instrumented kernel ------------------------
+    st = api.rtk_cuda_trace_stats()
+    ns = min(n, 1 << 20)
+    assert lib.rtk_trace_stats_device(sc.ptr, d_rays.data_ptr(), d_h16.data_ptr(), ns, C.byref(st), sh) == 0, lib.last_error()
+    nodes_per_ray = st.node_visits / ns
+    tris_per_ray = st.tri_tests / ns
+    leaves_per_ray = st.leaf_visits / ns
+    hit_frac = st.hits / ns
+    bytes_per_ray = 32 + 16 + 256 * nodes_per_ray + 48 * tris_per_ray
+
+    # ---- timed region --------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.mark()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    for i in range(args.steps):
+        step(evs[i])
+    e_end.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = e_start.elapsed_time(e_end)
+    trace_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    resolve_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end through the host API (pinned host buffers, H2D + D2H inside) ---------------
+    e2e = None
+    h_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1, 32)).pin_memory()
+    h_hits = torch.empty((n, 68), dtype=torch.uint8).pin_memory()
+    h_mask = torch.empty((n,), dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        got = lib.rtk_trace_rays(sc.ptr, h_rays.data_ptr(), h_hits.data_ptr(), h_mask.data_ptr(), n)
+        if got == C.c_size_t(-1).value:
+            raise RuntimeError(lib.last_error())
+        return got
+    e2e_step()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        nh = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": world * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 69 * n,
+           "ms_per_step": e2e_s * 1e3, "api": "rtk_trace_rays (host rtk_ray[] in, rtk_hit[] + mask out, pinned)",
+           "hits_per_step": int(nh)}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peaks()
+    achieved = bytes_per_ray * n / (trace_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload,
+        "e2e": e2e, "gpu_launches": 2 * args.steps,
+        "kernels_ms": {"k_trace": trace_ms, "k_resolve": resolve_ms},
+        "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_ray": bytes_per_ray,
+                     "per_ray": {"wide_node_visits": nodes_per_ray, "leaf_visits": leaves_per_ray,
+                                 "triangle_tests": tris_per_ray, "hit_fraction": hit_frac},
+                     "note": "algorithmic bytes = 32 (ray) + 16 (compact hit) + 256 per wide-node visit + 48 per "
+                             "triangle tested, counted by the instrumented kernel on the first 2^20 rays; the 1M-"
+                             "triangle scene (about 107 MB) is L2-resident, so DRAM traffic is far below this"},
+        "build": {"metric": "BVH build Mtris/s", "value": ntris / (build_dev_ms * 1e-3) / 1e6, "unit": "Mtris/s",
+                  "device_ms": build_dev_ms, "mode": args.build_mode,
+                  "e2e": {"value": ntris / build_e2e_s / 1e6, "unit": "Mtris/s", "ms": build_e2e_s * 1e3,
+                          "api": "rtk_build_scene (host mesh buffers in, first call, includes CUDA context warm-up)"},
+                  "wide_nodes": int(info.num_wide_nodes), "leaves": int(info.num_leaves), "depth": int(info.wide_depth),
+                  "sah_cost": info.sah_cost, "scene_bytes": int(info.device_bytes)},
+        "parity": parity, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_reference_run(scene, rays_np, min(n, args.cpu_sample), 1, 0)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_build_baseline"] = cb["build"]
+        except Exception as ex:  # the checker is missing: say so instead of inventing a number
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
+    print(json.dumps(line))
+    sc.free()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,511 @@
+// k_sah.cuh -- binned-SAH BVH builder (sm_100a), the GPU re-design of the reference's top-down
+// build (rtk.c:867-1019 _rtk_build_node_sah, :1421-1453 dispatcher, :813-865 equal split).
+//
+// Same algorithm: 32 bins on each of the 3 axes, triangles binned by the centre of their AABB
+// relative to the node's AABB (rtk.c:892-902), suffix/prefix sweep for the cheapest split
+// (rtk.c:910-945), partition by bin index (rtk.c:968-986), depth cap with forced equal splits
+// (rtk.c:1429-1443).  The cost counts SIMD batches of the leaf test, ceil(n/8) for the 8-lane
+// ray groups of k_trace where the reference uses ceil(n/4) for SSE (rtk.c:934-935); a node with
+// more than RTK_LEAF_MAX triangles is always split and one with at most RTK_LEAF_MAX never is
+// (one leaf visit tests up to 8 triangles at once), which is what rtk.c:948-949 reduces to when
+// max_leaf_items equals the SIMD width.
+//
+// Parallel structure:
+//   * triangles start in Morton order (k_morton + radix sort), their AABBs are stored in that
+//     order, so the members of any subtree are close in memory;
+//   * LARGE nodes (> RTK_SAH_SMALL triangles) are processed level by level: k_sah_bin_large
+//     reduces 2048-triangle chunks into shared-memory bins and merges them into the node's global
+//     bins with atomics, k_sah_split_large evaluates the sweep with one warp per node (warp
+//     prefix scans), k_sah_partition_large scatters triangle indices with block-aggregated
+//     cursors;
+//   * every SMALL node (<= RTK_SAH_SMALL) is finished by ONE CTA entirely in shared memory
+//     (k_sah_small): AABBs and the index permutation stay on chip for all remaining levels.
+#pragma once
+#include "rtk_common.cuh"
+#include "k_build.cuh"
+
+#define RTK_SAH_BINS 32
+#define RTK_SAH_SMALL 512
+#define RTK_SAH_CHUNK 2048
+#define RTK_SAH_MAX_DEPTH 64          // RTK_BVH_MAX_DEPTH, rtk.c:5
+#define RTK_SAH_BINWORDS 8            // lo xyz, hi xyz, count, pad
+#define RTK_SAH_NODEBINS (3 * RTK_SAH_BINS * RTK_SAH_BINWORDS)
+
+struct rtkd_sah {
+	const float4 *pb;             // [2n] AABBs in Morton order: pb[2j] = lo, pb[2j+1] = hi
+	uint32_t *idx0, *idx1;        // ping-pong permutation of Morton positions
+	uint32_t *idx_final;          // final leaf order (Morton positions)
+	int *left, *right, *first, *last;
+	float4 *blo, *bhi;
+	uint32_t *ndepth;
+	uint32_t *counters;           // [0] node_alloc [1] n_act_out [2] n_small [3] err [4] max depth
+	uint32_t *act_in, *act_out;   // large nodes of this / the next level
+	uint32_t *small_list;         // node id | (buffer << 31)
+	uint32_t *chunk_base;         // [n_act + 1] exclusive scan of chunk counts
+	uint32_t *bins;               // [n_act][3][32][8]
+	int4 *split;                  // per active node: axis (-1: equal split), bin, n_left, first child
+	uint32_t *cursor;             // per active node: left / right write cursors
+	uint32_t node_cap;
+};
+
+// bin of a triangle on one axis, rtk.c:892-902
+RTK_DEV int rtk_sah_bin(float lo, float hi, float nmin, float nmax)
+{
+	float min_2x = nmin + nmin;
+	float rcp_scale_2x = (0.5f * (float)RTK_SAH_BINS) / (nmax - nmin);
+	float f = ((lo + hi) - min_2x) * rcp_scale_2x;
+	if (!(f >= 0.0f)) return 0;
+	if (f >= (float)RTK_SAH_BINS) return RTK_SAH_BINS - 1;
+	return (int)f;
+}
+
+RTK_DEV void rtk_sah_bins_clear(uint32_t *bins, int tid, int nthreads)
+{
+	const uint32_t pinf = rtk_f2ord(+RTK_INF_F), ninf = rtk_f2ord(-RTK_INF_F);
+	for (int i = tid; i < RTK_SAH_NODEBINS; i += nthreads) {
+		int w = i & 7;
+		bins[i] = w < 3 ? pinf : (w < 6 ? ninf : 0u);
+	}
+}
+
+// add one AABB to the three axes' bins (shared or global memory)
+RTK_DEV void rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi)
+{
+	int b[3];
+	b[0] = rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x);
+	b[1] = rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y);
+	b[2] = rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z);
+	uint32_t ol[3] = { rtk_f2ord(lo.x), rtk_f2ord(lo.y), rtk_f2ord(lo.z) };
+	uint32_t oh[3] = { rtk_f2ord(hi.x), rtk_f2ord(hi.y), rtk_f2ord(hi.z) };
+	for (int a = 0; a < 3; a++) {
+		uint32_t *p = bins + (a * RTK_SAH_BINS + b[a]) * RTK_SAH_BINWORDS;
+		atomicMin(p + 0, ol[0]); atomicMin(p + 1, ol[1]); atomicMin(p + 2, ol[2]);
+		atomicMax(p + 3, oh[0]); atomicMax(p + 4, oh[1]); atomicMax(p + 5, oh[2]);
+		atomicAdd(p + 6, 1u);
+	}
+}
+
+struct rtk_sah_choice {
+	int axis, bin;               // axis < 0: no valid split
+	uint32_t n_left;
+	float llo[3], lhi[3], rlo[3], rhi[3];
+};
+
+// The sweep of rtk.c:909-945 with one warp: lane i owns bin i.  Returns the same choice in
+// every lane.  Ties go to the lower axis, then the lower bin (the reference's strict '<' in
+// axis-major, bin-minor order, rtk.c:938).
+RTK_DEV rtk_sah_choice rtk_sah_sweep_warp(const uint32_t *bins, float4 plo, float4 phi, uint32_t count)
+{
+	const uint32_t FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	float px = phi.x - plo.x, py = phi.y - plo.y, pz = phi.z - plo.z;
+	float rcp_parent = 1.0f / (2.0f * (px * py + py * pz + pz * px));          // rtk.c:880
+	float best_cost = RTK_INF_F;
+	int best_axis = -1;
+	uint32_t best_nl = 0;
+	float bl[6] = { 0, 0, 0, 0, 0, 0 }, br[6] = { 0, 0, 0, 0, 0, 0 };
+	for (int axis = 0; axis < 3; axis++) {
+		const uint32_t *p = bins + (axis * RTK_SAH_BINS + lane) * RTK_SAH_BINWORDS;
+		float lo[3] = { rtk_ord2f(p[0]), rtk_ord2f(p[1]), rtk_ord2f(p[2]) };
+		float hi[3] = { rtk_ord2f(p[3]), rtk_ord2f(p[4]), rtk_ord2f(p[5]) };
+		uint32_t cnt = p[6];
+		float Llo[3] = { lo[0], lo[1], lo[2] }, Lhi[3] = { hi[0], hi[1], hi[2] };
+		float Rlo[3] = { lo[0], lo[1], lo[2] }, Rhi[3] = { hi[0], hi[1], hi[2] };
+		uint32_t nl = cnt;
+		for (int o = 1; o < 32; o <<= 1) {
+			for (int k = 0; k < 3; k++) {
+				float a = __shfl_up_sync(FULL, Llo[k], o), b = __shfl_up_sync(FULL, Lhi[k], o);
+				float c = __shfl_down_sync(FULL, Rlo[k], o), d = __shfl_down_sync(FULL, Rhi[k], o);
+				if (lane >= o) { Llo[k] = rtk_fmin(Llo[k], a); Lhi[k] = rtk_fmax(Lhi[k], b); }
+				if (lane + o < 32) { Rlo[k] = rtk_fmin(Rlo[k], c); Rhi[k] = rtk_fmax(Rhi[k], d); }
+			}
+			uint32_t e = __shfl_up_sync(FULL, nl, o);
+			if (lane >= o) nl += e;
+		}
+		// split after bin `lane`: left = bins 0..lane (mine), right = bins lane+1..31 (neighbour's suffix)
+		float r[6];
+		for (int k = 0; k < 3; k++) {
+			r[k] = __shfl_down_sync(FULL, Rlo[k], 1);
+			r[3 + k] = __shfl_down_sync(FULL, Rhi[k], 1);
+		}
+		uint32_t nr = count - nl;
+		if (lane < RTK_SAH_BINS - 1 && nl > 0 && nr > 0) {
+			float lx = Lhi[0] - Llo[0], ly = Lhi[1] - Llo[1], lz = Lhi[2] - Llo[2];
+			float rx = r[3] - r[0], ry = r[4] - r[1], rz = r[5] - r[2];
+			float area_l = 2.0f * (lx * ly + ly * lz + lz * lx);                // rtk.c:729-733
+			float area_r = 2.0f * (rx * ry + ry * rz + rz * rx);
+			float cost_l = (float)((nl + 7u) / 8u), cost_r = (float)((nr + 7u) / 8u);  // rtk.c:934-935, 8-wide
+			float cost = 1.0f + (area_l * cost_l + area_r * cost_r) * rcp_parent;     // rtk.c:936, split cost 1
+			if (cost < best_cost) {
+				best_cost = cost; best_axis = axis; best_nl = nl;
+				for (int k = 0; k < 3; k++) { bl[k] = Llo[k]; bl[3 + k] = Lhi[k]; br[k] = r[k]; br[3 + k] = r[3 + k]; }
+			}
+		}
+	}
+	// warp argmin over (cost, axis, bin)
+	float m = best_cost;
+	for (int o = 16; o > 0; o >>= 1) m = rtk_fmin(m, __shfl_xor_sync(FULL, m, o));
+	uint32_t key = (best_axis >= 0 && best_cost == m) ? (uint32_t)(best_axis * 32 + lane) : 0xffffffffu;
+	for (int o = 16; o > 0; o >>= 1) key = rtk_umin(key, __shfl_xor_sync(FULL, key, o));
+	rtk_sah_choice c;
+	if (key == 0xffffffffu) {
+		c.axis = -1; c.bin = 0; c.n_left = count / 2;
+		for (int k = 0; k < 3; k++) { c.llo[k] = c.rlo[k] = k == 0 ? plo.x : (k == 1 ? plo.y : plo.z); c.lhi[k] = c.rhi[k] = k == 0 ? phi.x : (k == 1 ? phi.y : phi.z); }
+		return c;
+	}
+	int src = (int)(key & 31u);
+	c.axis = (int)(key >> 5); c.bin = src;
+	// the winning lane may hold a different axis as its own best: only `src` is read
+	c.n_left = __shfl_sync(FULL, best_nl, src);
+	for (int k = 0; k < 3; k++) {
+		c.llo[k] = __shfl_sync(FULL, bl[k], src); c.lhi[k] = __shfl_sync(FULL, bl[3 + k], src);
+		c.rlo[k] = __shfl_sync(FULL, br[k], src); c.rhi[k] = __shfl_sync(FULL, br[3 + k], src);
+	}
+	return c;
+}
+
+// depth rule of rtk.c:1429-1443: if the remaining levels cannot bring the node down to
+// RTK_LEAF_MAX by halving, split it evenly now
+RTK_DEV bool rtk_sah_must_halve(uint32_t count, uint32_t depth)
+{
+	uint32_t left = RTK_SAH_MAX_DEPTH - 1 - rtk_umin(depth, RTK_SAH_MAX_DEPTH - 1);
+	if (left > 31) return false;
+	return (count >> left) > RTK_LEAF_MAX;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-triangle AABBs in Morton order
+// ---------------------------------------------------------------------------------------------
+
+__global__ void k_sah_prim_bounds(const float4 *tri_orig, const uint32_t *svals, uint32_t n, float4 *pb, uint32_t *idx0)
+{
+	uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	uint32_t prim = svals[j];
+	float4 a = tri_orig[3ull * prim], b = tri_orig[3ull * prim + 1], c = tri_orig[3ull * prim + 2];
+	pb[2ull * j] = make_float4(rtk_fmin(rtk_fmin(a.x, b.x), c.x), rtk_fmin(rtk_fmin(a.y, b.y), c.y), rtk_fmin(rtk_fmin(a.z, b.z), c.z), 0.0f);
+	pb[2ull * j + 1] = make_float4(rtk_fmax(rtk_fmax(a.x, b.x), c.x), rtk_fmax(rtk_fmax(a.y, b.y), c.y), rtk_fmax(rtk_fmax(a.z, b.z), c.z), 0.0f);
+	idx0[j] = j;
+}
+
+// root node from the scene bounds
+__global__ void k_sah_root(rtkd_sah s, const uint32_t *bounds, uint32_t n)
+{
+	if (threadIdx.x || blockIdx.x) return;
+	s.first[0] = 0; s.last[0] = (int)n - 1; s.left[0] = -1; s.right[0] = -1; s.ndepth[0] = 0;
+	s.blo[0] = make_float4(rtk_ord2f(bounds[0]), rtk_ord2f(bounds[1]), rtk_ord2f(bounds[2]), 0.0f);
+	s.bhi[0] = make_float4(rtk_ord2f(bounds[3]), rtk_ord2f(bounds[4]), rtk_ord2f(bounds[5]), 0.0f);
+	s.counters[0] = 1; s.counters[1] = 0; s.counters[2] = 0; s.counters[3] = 0; s.counters[4] = 0;
+	if (n > RTK_SAH_SMALL) { s.act_in[0] = 0; s.counters[1] = 1; }
+	else { s.small_list[0] = 0; s.counters[2] = 1; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// large nodes, one level
+// ---------------------------------------------------------------------------------------------
+
+// chunk table: chunk_base[a] = first chunk of active node a (single block)
+__global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, uint32_t n_act)
+{
+	__shared__ uint32_t s_warp[32];
+	__shared__ uint32_t s_carry;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	for (uint32_t base = 0; base < n_act; base += 1024) {
+		uint32_t a = base + threadIdx.x;
+		uint32_t v = 0;
+		if (a < n_act) {
+			uint32_t node = s.act_in[a];
+			uint32_t cnt = (uint32_t)(s.last[node] - s.first[node] + 1);
+			v = (cnt + RTK_SAH_CHUNK - 1) / RTK_SAH_CHUNK;
+		}
+		uint32_t x = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+			if (lane >= o) x += y;
+		}
+		if (lane == 31) s_warp[warp] = x;
+		__syncthreads();
+		uint32_t woff = 0;
+		for (int w = 0; w < warp; w++) woff += s_warp[w];
+		uint32_t carry = s_carry;
+		if (a < n_act) s.chunk_base[a] = carry + woff + x - v;
+		__syncthreads();
+		if (threadIdx.x == 1023) s_carry = carry + woff + x;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) s.chunk_base[n_act] = s_carry;
+}
+
+RTK_DEV uint32_t rtk_sah_find_node(const uint32_t *chunk_base, uint32_t n_act, uint32_t chunk)
+{
+	uint32_t lo = 0, hi = n_act;          // largest a with chunk_base[a] <= chunk
+	while (hi - lo > 1) {
+		uint32_t mid = (lo + hi) >> 1;
+		if (chunk_base[mid] <= chunk) lo = mid; else hi = mid;
+	}
+	return lo;
+}
+
+__global__ void k_sah_bins_clear(rtkd_sah s, uint32_t n_act)
+{
+	rtk_sah_bins_clear(s.bins + (size_t)blockIdx.x * RTK_SAH_NODEBINS, threadIdx.x, blockDim.x);
+}
+
+__global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, uint32_t n_act, int src_buf)
+{
+	__shared__ uint32_t s_bins[RTK_SAH_NODEBINS];
+	__shared__ uint32_t s_a;
+	if (threadIdx.x == 0) s_a = rtk_sah_find_node(s.chunk_base, n_act, blockIdx.x);
+	rtk_sah_bins_clear(s_bins, threadIdx.x, 256);
+	__syncthreads();
+	const uint32_t a = s_a;
+	const uint32_t node = s.act_in[a];
+	const uint32_t first = (uint32_t)s.first[node], last = (uint32_t)s.last[node];
+	const uint32_t begin = first + (blockIdx.x - s.chunk_base[a]) * RTK_SAH_CHUNK;
+	const uint32_t end = rtk_umin(begin + RTK_SAH_CHUNK, last + 1);
+	const float4 nlo = s.blo[node], nhi = s.bhi[node];
+	const uint32_t *idx = src_buf ? s.idx1 : s.idx0;
+	for (uint32_t p = begin + threadIdx.x; p < end; p += 256) {
+		uint32_t j = idx[p];
+		rtk_sah_bin_add(s_bins, s.pb[2ull * j], s.pb[2ull * j + 1], nlo, nhi);
+	}
+	__syncthreads();
+	uint32_t *g = s.bins + (size_t)a * RTK_SAH_NODEBINS;
+	for (int i = threadIdx.x; i < RTK_SAH_NODEBINS; i += 256) {
+		int w = i & 7;
+		uint32_t v = s_bins[i];
+		if (w < 3) { if (v != rtk_f2ord(+RTK_INF_F)) atomicMin(g + i, v); }
+		else if (w < 6) { if (v != rtk_f2ord(-RTK_INF_F)) atomicMax(g + i, v); }
+		else if (w == 6 && v) atomicAdd(g + i, v);
+	}
+}
+
+// children of a split node: allocate, fill, classify for the next step
+RTK_DEV void rtk_sah_emit_children(rtkd_sah &s, uint32_t node, const rtk_sah_choice &c, uint32_t depth,
+                                   int child_buf, uint32_t &child0)
+{
+	uint32_t ch = atomicAdd(&s.counters[0], 2u);
+	if (ch + 2 > s.node_cap) { atomicOr(&s.counters[3], 1u); ch = 0; }
+	child0 = ch;
+	const uint32_t first = (uint32_t)s.first[node], last = (uint32_t)s.last[node];
+	s.left[node] = (int)ch; s.right[node] = (int)ch + 1;
+	s.first[ch] = (int)first; s.last[ch] = (int)(first + c.n_left) - 1;
+	s.first[ch + 1] = (int)(first + c.n_left); s.last[ch + 1] = (int)last;
+	s.blo[ch] = make_float4(c.llo[0], c.llo[1], c.llo[2], 0.0f); s.bhi[ch] = make_float4(c.lhi[0], c.lhi[1], c.lhi[2], 0.0f);
+	s.blo[ch + 1] = make_float4(c.rlo[0], c.rlo[1], c.rlo[2], 0.0f); s.bhi[ch + 1] = make_float4(c.rhi[0], c.rhi[1], c.rhi[2], 0.0f);
+	for (uint32_t k = 0; k < 2; k++) {
+		uint32_t id = ch + k;
+		uint32_t cnt = k == 0 ? c.n_left : (last - first + 1) - c.n_left;
+		s.left[id] = -1; s.right[id] = -1; s.ndepth[id] = depth + 1;
+		if (child_buf >= 0) {
+			if (cnt > RTK_SAH_SMALL) s.act_out[atomicAdd(&s.counters[1], 1u)] = id;
+			else s.small_list[atomicAdd(&s.counters[2], 1u)] = id | ((uint32_t)child_buf << 31);
+		}
+	}
+	atomicMax(&s.counters[4], depth + 1);
+}
+
+// one warp per active large node
+__global__ void __launch_bounds__(128) k_sah_split_large(rtkd_sah s, uint32_t n_act, uint32_t depth, int dst_buf)
+{
+	const uint32_t a = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (a >= n_act) return;
+	const int lane = threadIdx.x & 31;
+	const uint32_t node = s.act_in[a];
+	const uint32_t count = (uint32_t)(s.last[node] - s.first[node] + 1);
+	rtk_sah_choice c = rtk_sah_sweep_warp(s.bins + (size_t)a * RTK_SAH_NODEBINS, s.blo[node], s.bhi[node], count);
+	if (rtk_sah_must_halve(count, depth) && c.axis >= 0) {
+		// forced equal split (rtk.c:1440-1443): position halves, children keep the parent's box
+		float4 plo = s.blo[node], phi = s.bhi[node];
+		c.axis = -1; c.n_left = count / 2;
+		c.llo[0] = c.rlo[0] = plo.x; c.llo[1] = c.rlo[1] = plo.y; c.llo[2] = c.rlo[2] = plo.z;
+		c.lhi[0] = c.rhi[0] = phi.x; c.lhi[1] = c.rhi[1] = phi.y; c.lhi[2] = c.rhi[2] = phi.z;
+	}
+	if (lane == 0) {
+		uint32_t ch;
+		rtk_sah_emit_children(s, node, c, depth, dst_buf, ch);
+		s.split[a] = make_int4(c.axis, c.bin, (int)c.n_left, (int)ch);
+		s.cursor[2 * a] = 0; s.cursor[2 * a + 1] = 0;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, uint32_t n_act, int src_buf)
+{
+	__shared__ uint32_t s_a, s_cntl[8], s_cntr[8], s_basel, s_baser;
+	if (threadIdx.x == 0) s_a = rtk_sah_find_node(s.chunk_base, n_act, blockIdx.x);
+	__syncthreads();
+	const uint32_t a = s_a;
+	const uint32_t node = s.act_in[a];
+	const int4 sp = s.split[a];
+	const uint32_t first = (uint32_t)s.first[node], last = (uint32_t)s.last[node];
+	const uint32_t begin = first + (blockIdx.x - s.chunk_base[a]) * RTK_SAH_CHUNK;
+	const uint32_t end = rtk_umin(begin + RTK_SAH_CHUNK, last + 1);
+	const float4 nlo = s.blo[node], nhi = s.bhi[node];
+	const uint32_t *src = src_buf ? s.idx1 : s.idx0;
+	uint32_t *dst = src_buf ? s.idx0 : s.idx1;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const float amin = sp.x == 0 ? nlo.x : (sp.x == 1 ? nlo.y : nlo.z);
+	const float amax = sp.x == 0 ? nhi.x : (sp.x == 1 ? nhi.y : nhi.z);
+	for (uint32_t base = begin; base < end; base += 256) {
+		uint32_t p = base + threadIdx.x;
+		bool valid = p < end;
+		uint32_t j = valid ? src[p] : 0;
+		bool goes_left = false;
+		if (valid) {
+			if (sp.x < 0) goes_left = (p - first) < (uint32_t)sp.z;           // equal split by position
+			else {
+				float4 lo = s.pb[2ull * j], hi = s.pb[2ull * j + 1];
+				float l = sp.x == 0 ? lo.x : (sp.x == 1 ? lo.y : lo.z);
+				float h = sp.x == 0 ? hi.x : (sp.x == 1 ? hi.y : hi.z);
+				goes_left = rtk_sah_bin(l, h, amin, amax) <= sp.y;            // rtk.c:973-977
+			}
+		}
+		uint32_t ml = __ballot_sync(0xffffffffu, valid && goes_left);
+		uint32_t mr = __ballot_sync(0xffffffffu, valid && !goes_left);
+		if (lane == 0) { s_cntl[warp] = __popc(ml); s_cntr[warp] = __popc(mr); }
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			uint32_t tl = 0, tr = 0;
+			for (int w = 0; w < 8; w++) { uint32_t x = s_cntl[w]; s_cntl[w] = tl; tl += x; uint32_t y = s_cntr[w]; s_cntr[w] = tr; tr += y; }
+			s_basel = tl ? atomicAdd(&s.cursor[2 * a], tl) : 0;
+			s_baser = tr ? atomicAdd(&s.cursor[2 * a + 1], tr) : 0;
+		}
+		__syncthreads();
+		if (valid) {
+			uint32_t lt = (1u << lane) - 1u;
+			uint32_t pos = goes_left ? first + s_basel + s_cntl[warp] + __popc(ml & lt)
+			                         : first + (uint32_t)sp.z + s_baser + s_cntr[warp] + __popc(mr & lt);
+			dst[pos] = j;
+		}
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// small subtrees: one CTA, everything in shared memory
+// ---------------------------------------------------------------------------------------------
+
+#define RTK_SAH_SMALL_THREADS 128
+
+struct rtk_sah_task { uint32_t node, begin, count, depth; float lo[3], hi[3]; };
+
+__global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s, uint32_t n_small)
+{
+	__shared__ float4 s_lo[RTK_SAH_SMALL], s_hi[RTK_SAH_SMALL];
+	__shared__ uint32_t s_gid[RTK_SAH_SMALL];
+	__shared__ unsigned short s_perm[2][RTK_SAH_SMALL];
+	__shared__ uint32_t s_bins[RTK_SAH_NODEBINS];
+	__shared__ rtk_sah_task s_stack[24];
+	__shared__ int s_sp;
+	__shared__ rtk_sah_choice s_choice;
+	__shared__ uint32_t s_child, s_wl[4], s_wr[4];
+
+	if (blockIdx.x >= n_small) return;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t entry = s.small_list[blockIdx.x];
+	const uint32_t root = entry & 0x7fffffffu;
+	const uint32_t *src = (entry >> 31) ? s.idx1 : s.idx0;
+	const uint32_t gfirst = (uint32_t)s.first[root];
+	const uint32_t total = (uint32_t)(s.last[root] - s.first[root] + 1);
+	for (uint32_t i = tid; i < total; i += RTK_SAH_SMALL_THREADS) {
+		uint32_t j = src[gfirst + i];
+		s_gid[i] = j;
+		s_lo[i] = s.pb[2ull * j]; s_hi[i] = s.pb[2ull * j + 1];
+		s_perm[0][i] = (unsigned short)i;
+	}
+	if (tid == 0) {
+		rtk_sah_task t;
+		float4 lo = s.blo[root], hi = s.bhi[root];
+		t.node = root; t.begin = 0; t.count = total; t.depth = s.ndepth[root];
+		t.lo[0] = lo.x; t.lo[1] = lo.y; t.lo[2] = lo.z; t.hi[0] = hi.x; t.hi[1] = hi.y; t.hi[2] = hi.z;
+		s_stack[0] = t;
+		s_sp = 1;
+	}
+	__syncthreads();
+
+	while (s_sp > 0) {
+		const rtk_sah_task t = s_stack[s_sp - 1];
+		__syncthreads();
+		if (tid == 0) s_sp--;
+		if (t.count <= RTK_LEAF_MAX) { __syncthreads(); continue; }         // a leaf: nothing to do
+		const float4 nlo = make_float4(t.lo[0], t.lo[1], t.lo[2], 0.0f), nhi = make_float4(t.hi[0], t.hi[1], t.hi[2], 0.0f);
+		rtk_sah_bins_clear(s_bins, tid, RTK_SAH_SMALL_THREADS);
+		__syncthreads();
+		for (uint32_t i = tid; i < t.count; i += RTK_SAH_SMALL_THREADS) {
+			uint32_t k = s_perm[0][t.begin + i];
+			rtk_sah_bin_add(s_bins, s_lo[k], s_hi[k], nlo, nhi);
+		}
+		__syncthreads();
+		if (warp == 0) {
+			rtk_sah_choice c = rtk_sah_sweep_warp(s_bins, nlo, nhi, t.count);
+			if (rtk_sah_must_halve(t.count, t.depth) && c.axis >= 0) {
+				c.axis = -1; c.n_left = t.count / 2;
+				for (int k = 0; k < 3; k++) { c.llo[k] = c.rlo[k] = t.lo[k]; c.lhi[k] = c.rhi[k] = t.hi[k]; }
+			}
+			if (lane == 0) {
+				uint32_t ch;
+				rtk_sah_emit_children(s, t.node, c, t.depth, -1, ch);
+				s_choice = c; s_child = ch;
+			}
+		}
+		__syncthreads();
+		const rtk_sah_choice c = s_choice;
+		// stable partition of s_perm[0][begin, begin+count) into s_perm[1], then copy back
+		const float amin = c.axis <= 0 ? nlo.x : (c.axis == 1 ? nlo.y : nlo.z);
+		const float amax = c.axis <= 0 ? nhi.x : (c.axis == 1 ? nhi.y : nhi.z);
+		uint32_t run_l = 0, run_r = 0;
+		for (uint32_t base = 0; base < t.count; base += RTK_SAH_SMALL_THREADS) {
+			uint32_t i = base + tid;
+			bool valid = i < t.count;
+			unsigned short k = valid ? s_perm[0][t.begin + i] : (unsigned short)0;
+			bool goes_left = false;
+			if (valid) {
+				if (c.axis < 0) goes_left = i < c.n_left;
+				else {
+					float l = c.axis == 0 ? s_lo[k].x : (c.axis == 1 ? s_lo[k].y : s_lo[k].z);
+					float h = c.axis == 0 ? s_hi[k].x : (c.axis == 1 ? s_hi[k].y : s_hi[k].z);
+					goes_left = rtk_sah_bin(l, h, amin, amax) <= c.bin;
+				}
+			}
+			uint32_t ml = __ballot_sync(0xffffffffu, valid && goes_left);
+			uint32_t mr = __ballot_sync(0xffffffffu, valid && !goes_left);
+			if (lane == 0) { s_wl[warp] = __popc(ml); s_wr[warp] = __popc(mr); }
+			__syncthreads();
+			uint32_t offl = run_l, offr = run_r, totl = 0, totr = 0;
+			for (int w = 0; w < RTK_SAH_SMALL_THREADS / 32; w++) {
+				if (w < warp) { offl += s_wl[w]; offr += s_wr[w]; }
+				totl += s_wl[w]; totr += s_wr[w];
+			}
+			if (valid) {
+				uint32_t lt = (1u << lane) - 1u;
+				uint32_t pos = goes_left ? offl + __popc(ml & lt) : c.n_left + offr + __popc(mr & lt);
+				s_perm[1][t.begin + pos] = k;
+			}
+			run_l += totl; run_r += totr;
+			__syncthreads();
+		}
+		for (uint32_t i = tid; i < t.count; i += RTK_SAH_SMALL_THREADS) s_perm[0][t.begin + i] = s_perm[1][t.begin + i];
+		if (tid == 0) {
+			// push the larger child first so that the stack stays logarithmic
+			rtk_sah_task a, b;
+			a.node = s_child; a.begin = t.begin; a.count = c.n_left; a.depth = t.depth + 1;
+			b.node = s_child + 1; b.begin = t.begin + c.n_left; b.count = t.count - c.n_left; b.depth = t.depth + 1;
+			for (int k = 0; k < 3; k++) { a.lo[k] = c.llo[k]; a.hi[k] = c.lhi[k]; b.lo[k] = c.rlo[k]; b.hi[k] = c.rhi[k]; }
+			int sp = s_sp;
+			if (a.count >= b.count) { s_stack[sp] = a; s_stack[sp + 1] = b; }
+			else { s_stack[sp] = b; s_stack[sp + 1] = a; }
+			s_sp = sp + 2;
+		}
+		__syncthreads();
+	}
+	for (uint32_t i = tid; i < total; i += RTK_SAH_SMALL_THREADS) s.idx_final[gfirst + i] = s_gid[s_perm[0][i]];
+}
+
+// final leaf order as original triangle numbers
+__global__ void k_sah_compose(const uint32_t *idx_final, const uint32_t *svals, uint32_t n, uint32_t *out)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = svals[idx_final[i]];
+}

@@ -5,6 +5,7 @@
 // fails with RTK_CUDA_ERR_NO_DEVICE.
 #include "rtk_device.h"
 #include "k_build.cuh"
+#include "k_sah.cuh"
 #include "k_trace.cuh"
 #include <stdarg.h>
 
@@ -178,6 +179,76 @@ template <typename T> static cudaError_t tmp_alloc(T **p, size_t count, cudaStre
 	return cudaMallocAsync(p, sizeof(T) * (count ? count : 1), st);
 }
 
+// ---- binned-SAH binary tree (k_sah.cuh) -------------------------------------------------------
+
+static void free_sah(rtkd_sah &h, uint32_t *order, cudaStream_t st)
+{
+	cudaFreeAsync((void*)h.pb, st); cudaFreeAsync(h.idx0, st); cudaFreeAsync(h.idx1, st); cudaFreeAsync(h.idx_final, st);
+	cudaFreeAsync(h.left, st); cudaFreeAsync(h.right, st); cudaFreeAsync(h.first, st); cudaFreeAsync(h.last, st);
+	cudaFreeAsync(h.blo, st); cudaFreeAsync(h.bhi, st); cudaFreeAsync(h.ndepth, st); cudaFreeAsync(h.counters, st);
+	cudaFreeAsync(h.act_in, st); cudaFreeAsync(h.act_out, st); cudaFreeAsync(h.small_list, st);
+	cudaFreeAsync(h.chunk_base, st); cudaFreeAsync(h.bins, st); cudaFreeAsync(h.split, st); cudaFreeAsync(h.cursor, st);
+	cudaFreeAsync(order, st);
+}
+
+static int build_sah(rtkd_scene *s, cudaStream_t st, const float4 *tri, const uint32_t *svals, const uint32_t *d_bounds,
+                     uint32_t n, rtkd_sah &h, uint32_t **order_out)
+{
+	(void)s;
+	const size_t cap = 2 * (size_t)n + 2;
+	const size_t act_cap = n / RTK_SAH_SMALL + 4;
+	const size_t small_cap = 4 * (size_t)(n / RTK_SAH_SMALL) + 8;
+	float4 *pb = NULL;
+	uint32_t *order = NULL;
+	CK(tmp_alloc(&pb, 2 * (size_t)n, st)); h.pb = pb;
+	CK(tmp_alloc(&h.idx0, n, st)); CK(tmp_alloc(&h.idx1, n, st)); CK(tmp_alloc(&h.idx_final, n, st));
+	CK(tmp_alloc(&h.left, cap, st)); CK(tmp_alloc(&h.right, cap, st)); CK(tmp_alloc(&h.first, cap, st)); CK(tmp_alloc(&h.last, cap, st));
+	CK(tmp_alloc(&h.blo, cap, st)); CK(tmp_alloc(&h.bhi, cap, st)); CK(tmp_alloc(&h.ndepth, cap, st));
+	CK(tmp_alloc(&h.counters, 8, st));
+	CK(tmp_alloc(&h.act_in, act_cap, st)); CK(tmp_alloc(&h.act_out, act_cap, st)); CK(tmp_alloc(&h.small_list, small_cap, st));
+	CK(tmp_alloc(&h.chunk_base, act_cap + 1, st));
+	CK(tmp_alloc(&h.bins, act_cap * RTK_SAH_NODEBINS, st));
+	CK(tmp_alloc(&h.split, act_cap, st)); CK(tmp_alloc(&h.cursor, 2 * act_cap, st));
+	CK(tmp_alloc(&order, n, st));
+	h.node_cap = (uint32_t)cap;
+
+	RTK_LAUNCH(k_sah_prim_bounds, (n + 255) / 256, 256, st, tri, svals, n, pb, h.idx0); CK_LAUNCH();
+	RTK_LAUNCH(k_sah_root, 1, 32, st, h, d_bounds, n); CK_LAUNCH();
+	uint32_t hc[8];
+	CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	uint32_t n_act = hc[1], depth = 0;
+	int src_buf = 0;
+	while (n_act) {
+		if (n_act > act_cap) { rtkd_set_error("SAH active list overflow"); return RTKD_ERR_MEMORY; }
+		RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, n_act); CK_LAUNCH();
+		uint32_t chunks = 0;
+		CK(cudaMemcpyAsync(&chunks, h.chunk_base + n_act, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemsetAsync(h.counters + 1, 0, sizeof(uint32_t), st));
+		RTK_LAUNCH(k_sah_bins_clear, n_act, 128, st, h, n_act); CK_LAUNCH();
+		CK(cudaStreamSynchronize(st));
+		RTK_LAUNCH(k_sah_bin_large, chunks, 256, st, h, n_act, src_buf); CK_LAUNCH();
+		RTK_LAUNCH(k_sah_split_large, (n_act + 3) / 4, 128, st, h, n_act, depth, src_buf ^ 1); CK_LAUNCH();
+		RTK_LAUNCH(k_sah_partition_large, chunks, 256, st, h, n_act, src_buf); CK_LAUNCH();
+		CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		uint32_t *tmp = h.act_in; h.act_in = h.act_out; h.act_out = tmp;
+		n_act = hc[1];
+		src_buf ^= 1;
+		depth++;
+	}
+	CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (hc[2] > small_cap) { rtkd_set_error("SAH small-subtree list overflow"); return RTKD_ERR_MEMORY; }
+	if (hc[2]) { RTK_LAUNCH(k_sah_small, hc[2], RTK_SAH_SMALL_THREADS, st, h, hc[2]); CK_LAUNCH(); }
+	RTK_LAUNCH(k_sah_compose, (n + 255) / 256, 256, st, (const uint32_t*)h.idx_final, svals, n, order); CK_LAUNCH();
+	CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	if (hc[3]) { rtkd_set_error("SAH node pool exhausted"); return RTKD_ERR_MEMORY; }
+	*order_out = order;
+	return RTKD_OK;
+}
+
 extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 {
 	cudaStream_t st = (cudaStream_t)stream;
@@ -231,14 +302,28 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	const unsigned long long *skeys = keys[src];
 	const uint32_t *svals = vals[src];
 
-	// traversal triangles in leaf (= sorted) order
 	CK(cudaMalloc((float4**)&s->tv0, sizeof(float4) * (size_t)n));
 	CK(cudaMalloc((float4**)&s->tv1, sizeof(float4) * (size_t)n));
 	CK(cudaMalloc((float4**)&s->tv2, sizeof(float4) * (size_t)n));
-	RTK_LAUNCH(k_emit_tris, (n + 255) / 256, 256, st, tri, svals, n, (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
 
 	uint32_t h_bounds[6];
 	CK(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, st));
+
+	// binary tree: binned SAH over the Morton-ordered triangles, or the radix tree itself
+	const bool use_sah = mode == 1 && n > RTK_LEAF_MAX;
+	rtkd_bvh2 t;
+	memset(&t, 0, sizeof(t));
+	rtkd_sah sah;
+	memset(&sah, 0, sizeof(sah));
+	uint32_t *order = NULL;          // leaf order as triangle numbers (SAH mode)
+	if (use_sah) {
+		int r = build_sah(s, st, tri, svals, d_bounds, n, sah, &order);
+		if (r) return r;
+		t.left = sah.left; t.right = sah.right; t.first = sah.first; t.last = sah.last; t.blo = sah.blo; t.bhi = sah.bhi;
+		svals = order;
+	}
+	// traversal triangles in leaf order
+	RTK_LAUNCH(k_emit_tris, (n + 255) / 256, 256, st, tri, svals, n, (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
 
 	float4 *wide = NULL;
 	uint32_t num_nodes = 0, num_leaves = 0, depth = 0;
@@ -248,15 +333,16 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		RTK_LAUNCH(k_single_root, 1, 32, st, tri, svals, wide); CK_LAUNCH();
 		num_nodes = 1; num_leaves = 1; depth = 1;
 	} else {
-		rtkd_bvh2 t;
-		CK(tmp_alloc(&t.left, n - 1, st)); CK(tmp_alloc(&t.right, n - 1, st));
-		CK(tmp_alloc(&t.parent, 2 * (size_t)n - 1, st));
-		CK(tmp_alloc(&t.first, n - 1, st)); CK(tmp_alloc(&t.last, n - 1, st));
-		CK(tmp_alloc(&t.blo, 2 * (size_t)n - 1, st)); CK(tmp_alloc(&t.bhi, 2 * (size_t)n - 1, st));
-		CK(tmp_alloc(&t.flags, n - 1, st));
-		CK(cudaMemsetAsync(t.flags, 0, sizeof(int) * (size_t)(n - 1), st));
-		RTK_LAUNCH(k_hierarchy, (n - 1 + 255) / 256, 256, st, skeys, (int)n, t); CK_LAUNCH();
-		RTK_LAUNCH(k_refit, (n + 255) / 256, 256, st, tri, svals, (int)n, t); CK_LAUNCH();
+		if (!use_sah) {
+			CK(tmp_alloc(&t.left, n - 1, st)); CK(tmp_alloc(&t.right, n - 1, st));
+			CK(tmp_alloc(&t.parent, 2 * (size_t)n - 1, st));
+			CK(tmp_alloc(&t.first, n - 1, st)); CK(tmp_alloc(&t.last, n - 1, st));
+			CK(tmp_alloc(&t.blo, 2 * (size_t)n - 1, st)); CK(tmp_alloc(&t.bhi, 2 * (size_t)n - 1, st));
+			CK(tmp_alloc(&t.flags, n - 1, st));
+			CK(cudaMemsetAsync(t.flags, 0, sizeof(int) * (size_t)(n - 1), st));
+			RTK_LAUNCH(k_hierarchy, (n - 1 + 255) / 256, 256, st, skeys, (int)n, t); CK_LAUNCH();
+			RTK_LAUNCH(k_refit, (n + 255) / 256, 256, st, tri, svals, (int)n, t); CK_LAUNCH();
+		}
 
 		const uint32_t cap = (uint32_t)(((unsigned long long)n * 4) / 7 + 16);
 		uint2 *work[2] = { NULL, NULL };
@@ -288,11 +374,16 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		num_nodes = h_ctr[1]; num_leaves = h_ctr[2];
 		if (h_ctr[3]) { rtkd_set_error("wide-node pool exhausted (cap %u)", cap); return RTKD_ERR_MEMORY; }
 		CK(cudaMemcpyAsync(&h_cost, d_cost, sizeof(double), cudaMemcpyDeviceToHost, st));
-		cudaFreeAsync(t.left, st); cudaFreeAsync(t.right, st); cudaFreeAsync(t.parent, st);
-		cudaFreeAsync(t.first, st); cudaFreeAsync(t.last, st); cudaFreeAsync(t.blo, st); cudaFreeAsync(t.bhi, st);
-		cudaFreeAsync(t.flags, st); cudaFreeAsync(work[0], st); cudaFreeAsync(work[1], st);
+		if (!use_sah) {
+			cudaFreeAsync(t.left, st); cudaFreeAsync(t.right, st); cudaFreeAsync(t.parent, st);
+			cudaFreeAsync(t.first, st); cudaFreeAsync(t.last, st); cudaFreeAsync(t.blo, st); cudaFreeAsync(t.bhi, st);
+			cudaFreeAsync(t.flags, st);
+		}
+		cudaFreeAsync(work[0], st); cudaFreeAsync(work[1], st);
 		cudaFreeAsync(ctr, st); cudaFreeAsync(d_cost, st);
 	}
+
+	if (use_sah) free_sah(sah, order, st);
 
 	// exact-size node array
 	CK(cudaMalloc((float4**)&s->nodes, sizeof(float4) * 16 * (size_t)num_nodes));

@@ -58,6 +58,7 @@ static inline float2 make_float2(float x, float y) { float2 r = {x, y}; return r
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r = {x, y, z, w}; return r; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r = {x, y}; return r; }
 static inline int2 make_int2(int x, int y) { int2 r = {x, y}; return r; }
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
 
 // ------------------------------------------------------------------------------------------
 // fibers

@@ -57,6 +57,7 @@ def test_api_semantics(gpu_lib, orc):
 
 def _device_trace(lib, sc, rays_np, brute=False, stats=False):
     import torch
+    rays_np = np.ascontiguousarray(rays_np)
     rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1, 32)).cuda()
     out = torch.zeros((len(rays_np), 16), dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
@@ -104,7 +105,7 @@ def test_full_size_c2_coherent(gpu_lib, orc):
     trav = _device_trace(gpu_lib, sc, rays)
     idx = np.random.default_rng(3).choice(len(rays), 1024, replace=False)
     pc.assert_same(trav[idx], orc.trace_brute(s["tris"], rays[idx]), "C2 sampled vs oracle")
-    sub = rays[:: 16]
+    sub = np.ascontiguousarray(rays[:: 16])
     pc.assert_same(trav[::16], _device_trace(gpu_lib, sc, sub, brute=True), "C2 vs exhaustive GPU kernel")
     sc.free()
 

@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--build-mode", default="lbvh", choices=["lbvh", "sah"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-rays", type=int, default=1024)
+    ap.add_argument("--cull", type=int, default=1, help="1 provable dominant-axis culling (default), 0 full-box culling")
+    ap.add_argument("--lib", default=None, help="experiment: alternative build of librtk_b200 (same ABI)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -193,10 +195,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = api.load()
+    lib = api.load() if not args.lib else api.Library(os.path.abspath(args.lib))
     r = lib.rtk_cuda_init(local_rank)
     if r != 0:
         raise RuntimeError("rtk_cuda_init failed (no CPU fallback): " + lib.last_error())
+    lib.rtk_cuda_set_cull_mode(args.cull)
     lib.rtk_cuda_set_build_mode(api.RTK_CUDA_BUILD_SAH if args.build_mode == "sah" else api.RTK_CUDA_BUILD_LBVH)
 
     scene = scenes.config_scene("C3", args.scale)
@@ -247,11 +250,22 @@ def main():
         from oracle import orc
         step()
         torch.cuda.synchronize()
-        k = min(args.parity_rays, n)
+        k = min(args.parity_rays, n, 2048)       # CPU brute force: 1M triangles per ray
         got = d_h16[:k].cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)
         want = orc.trace_brute(scene["tris"], rays_np[:k])
         parity = {"rays_checked": k, "index_mismatches": int((got["prim"] != want["prim"]).sum()),
                   "bit_exact": bool(got.tobytes() == want.tobytes()), "against": "oracle (CPU brute force)"}
+        if args.parity_rays >= 65536:
+            # wide check against the exhaustive GPU kernel (same arithmetic, no BVH)
+            kb = min(n, args.parity_rays)
+            d_b = torch.zeros((kb, 16), dtype=torch.uint8, device="cuda")
+            assert lib.rtk_trace_rays_bruteforce_device(sc.ptr, d_rays.data_ptr(), d_b.data_ptr(), kb, sh) == 0
+            torch.cuda.synchronize()
+            a = d_h16[:kb].cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)
+            b = d_b.cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)
+            parity["gpu_bruteforce_rays"] = kb
+            parity["gpu_bruteforce_index_mismatches"] = int((a["prim"] != b["prim"]).sum())
+            parity["gpu_bruteforce_bit_exact"] = bool(a.tobytes() == b.tobytes())
 
     # ---- algorithmic bytes per ray from the counter-instrumented kernel ------------------------
     st = api.rtk_cuda_trace_stats()

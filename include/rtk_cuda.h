@@ -79,6 +79,10 @@ int  rtk_cuda_init(int device);
 void rtk_cuda_shutdown(void);
 const char *rtk_cuda_last_error(void);
 int  rtk_cuda_set_build_mode(int mode);
+/* Distance used to cull a box against the current best hit: 1 (default) = slab of the ray's
+ * dominant axis only, provably consistent with the fp32 watertight test; 0 = full box entry,
+ * tighter but not provable for triangles seen exactly edge-on. */
+int  rtk_cuda_set_cull_mode(int mode);
 /* SM count, L2 bytes, resident CTAs of the traversal kernel... for the bench. */
 int  rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *trace_ctas_per_sm, int *trace_threads_per_cta);
 

@@ -119,6 +119,7 @@ SYMBOLS = {
     "rtk_cuda_shutdown": (None, []),
     "rtk_cuda_last_error": (C.c_char_p, []),
     "rtk_cuda_set_build_mode": (C.c_int, [C.c_int]),
+    "rtk_cuda_set_cull_mode": (C.c_int, [C.c_int]),
     "rtk_cuda_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rtk_trace_rays": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),
     "rtk_trace_rays_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),

@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librtk_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SOURCES = ["rtk_device.cu", "rtk_host.c", "rtk_common.cuh", "rtk_math.cuh", "k_build.cuh", "k_trace.cuh", "rtk_device.h"]
+SOURCES = ["k_sah.cuh", "rtk_device.cu", "rtk_host.c", "rtk_common.cuh", "rtk_math.cuh", "k_build.cuh", "k_trace.cuh", "rtk_device.h"]
 
 
 def _newer(target, deps):
@@ -19,16 +19,30 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: experiment variants, e.g. build(defines=["-DRTK_TRACE_MINB=4"], out="librtk_b200_m4.so")"""
+    global OUT
+    saved = OUT
+    if out:
+        OUT = os.path.join(HERE, out)
+        force = True
+    try:
+        return _build(force, verbose, list(defines))
+    finally:
+        OUT = saved
+
+
+def _build(force, verbose, defines):
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(HERE, "..", "include", h) for h in ("rtk.h", "rtk_cuda.h")]
     if not force and not _newer(OUT, deps):
         return OUT
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
-    dev_o = os.path.join(bdir, "rtk_device.o")
-    host_o = os.path.join(bdir, "rtk_host.o")
+    tag = os.path.basename(OUT).replace(".so", "")
+    dev_o = os.path.join(bdir, tag + "_device.o")
+    host_o = os.path.join(bdir, tag + "_host.o")
     cmds = [
-        [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+        [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", *defines,
          "-c", os.path.join(CSRC, "rtk_device.cu"), "-o", dev_o],
         ["gcc", "-O2", "-fPIC", "-Wall", "-std=gnu11", "-c", os.path.join(CSRC, "rtk_host.c"), "-o", host_o],
         [NVCC, *ARCH, "-shared", "-o", OUT, dev_o, host_o, "-lpthread"],

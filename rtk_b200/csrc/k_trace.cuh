@@ -31,6 +31,22 @@
 #define RTK_GROUPS_PER_CTA (RTK_TRACE_WARPS * 4)
 #define RTK_STACK_SMEM 16
 #define RTK_RAY_BATCH 32
+#ifndef RTK_TRACE_MINB
+#define RTK_TRACE_MINB 4                 // resident CTAs per SM the register allocation must allow
+#endif
+#ifndef RTK_TRACE_BATCH
+#define RTK_TRACE_BATCH 0                // 1: a phase runs when >= 2 of the warp's 4 rays need it (or nothing else can run)
+#endif
+#ifndef RTK_TRACE_PREFETCH
+#define RTK_TRACE_PREFETCH 0             // 1: L1 prefetch of the next node / leaf as soon as it is known
+#endif
+
+RTK_DEV void rtk_prefetch_l1(const void *p)
+{
+#ifndef RTK_SIMT_EMU
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#endif
+}
 
 struct rtkd_hit16 { float t, u, v; uint32_t prim; };
 
@@ -47,7 +63,7 @@ struct rtkd_trace_args {
 };
 
 template <int CULL, bool STATS>
-__global__ void __launch_bounds__(RTK_TRACE_THREADS, 3) k_trace(rtkd_trace_args p)
+__global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtkd_trace_args p)
 {
 	__shared__ float4 s_rays[RTK_TRACE_WARPS][2][RTK_RAY_BATCH * 2];
 	__shared__ uint2 s_stack[RTK_STACK_SMEM][RTK_GROUPS_PER_CTA];
@@ -118,6 +134,19 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, 3) k_trace(rtkd_trace_args 
 		} \
 	} while (0)
 
+#if RTK_TRACE_PREFETCH
+#define RTK_PREFETCH_CUR() do { \
+		if (cur_ref != RTK_REF_EMPTY) { \
+			if (rtk_ref_is_leaf(cur_ref)) { \
+				uint32_t _f = rtk_leaf_first(cur_ref) + (uint32_t)c; \
+				if ((uint32_t)c < rtk_leaf_count(cur_ref)) { rtk_prefetch_l1(&p.sc.tv0[_f]); rtk_prefetch_l1(&p.sc.tv1[_f]); rtk_prefetch_l1(&p.sc.tv2[_f]); } \
+			} else { rtk_prefetch_l1(nodes + 16ull * cur_ref + c); rtk_prefetch_l1(nodes + 16ull * cur_ref + 8 + c); } \
+		} \
+	} while (0)
+#else
+#define RTK_PREFETCH_CUR() do { } while (0)
+#endif
+
 	for (;;) {
 		// ---- (1) hand rays to idle groups --------------------------------------------------
 		uint32_t need_mask = __ballot_sync(FULL, !has_ray && c == 0);
@@ -162,7 +191,19 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, 3) k_trace(rtkd_trace_args 
 
 		// ---- (2) leaf: 8 lanes test up to 8 triangles (rtk.c:181-388) ------------------------
 		const bool is_leaf = has_ray && cur_ref != RTK_REF_EMPTY && rtk_ref_is_leaf(cur_ref);
+#if RTK_TRACE_BATCH
+		// Both phases cost a full warp instruction stream however many of the four rays take part,
+		// so a ray whose next entry is a leaf waits (idle lanes, no extra issue slots) until a
+		// second ray reaches a leaf too, unless no ray has node work left; likewise for nodes.
+		const uint32_t leaf_groups = __ballot_sync(FULL, is_leaf && c == 0);
+		const uint32_t node_groups = __ballot_sync(FULL, has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref) && c == 0);
+		const int n_leaf = __popc(leaf_groups), n_node0 = __popc(node_groups);
+		const bool run_tri = n_leaf >= 2 || (n_leaf == 1 && n_node0 <= 1);
+		if (run_tri) {
+#else
+		const bool run_tri = true;
 		if (__any_sync(FULL, is_leaf)) {
+#endif
 			float t = INFINITY, u = 0.0f, v = 0.0f;
 			uint32_t prim = RTK_MISS;
 			if (is_leaf) {
@@ -196,13 +237,22 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, 3) k_trace(rtkd_trace_args 
 			if (is_leaf) {
 				if (wm) { best_t = tmin; best_prim = pmin; best_u = wu; best_v = wv; }
 				RTK_STACK_POP();
+				RTK_PREFETCH_CUR();
 			}
 			__syncwarp();
 		}
 
 		// ---- (3) node: 8 lanes test the 8 children (rtk.c:457-473) ---------------------------
 		const bool is_node = has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref);
+#if RTK_TRACE_BATCH
+		const uint32_t node_groups2 = __ballot_sync(FULL, is_node && c == 0);
+		const uint32_t leaf_groups2 = __ballot_sync(FULL, has_ray && cur_ref != RTK_REF_EMPTY && rtk_ref_is_leaf(cur_ref) && c == 0);
+		const int n_node = __popc(node_groups2);
+		// progress: if the leaf phase did not run this iteration, a lone node must
+		if (n_node >= 2 || (n_node == 1 && (leaf_groups2 == 0 || !run_tri))) {
+#else
 		if (__any_sync(FULL, is_node)) {
+#endif
 			bool hit = false;
 			float key = 0.0f, tn = 0.0f;
 			uint32_t ref = RTK_REF_EMPTY;
@@ -227,7 +277,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, 3) k_trace(rtkd_trace_args 
 			}
 			// nearest hit child: order-preserving key with the lane number in the low 3 bits
 			// (the reference tags 2 bits the same way, rtk.c:496)
-			uint32_t ok = hit ? ((rtk_f2ord(tn) & ~7u) | (uint32_t)c) : 0xffffffffu;
+			uint32_t ok = hit ? ((__float_as_uint(rtk_fmax(tn, 0.0f)) & ~7u) | (uint32_t)c) : 0xffffffffu;
 			uint32_t om = ok;
 			om = rtk_umin(om, __shfl_xor_sync(FULL, om, 1));
 			om = rtk_umin(om, __shfl_xor_sync(FULL, om, 2));
@@ -248,6 +298,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, 3) k_trace(rtkd_trace_args 
 			if (is_node) {
 				if (gm) cur_ref = nref;
 				else RTK_STACK_POP();
+				RTK_PREFETCH_CUR();
 			}
 			__syncwarp();
 		}
@@ -273,6 +324,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, 3) k_trace(rtkd_trace_args 
 	}
 #undef RTK_STACK_WRITE
 #undef RTK_STACK_POP
+#undef RTK_PREFETCH_CUR
 }
 
 // ---------------------------------------------------------------------------------------------

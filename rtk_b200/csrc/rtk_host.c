@@ -55,6 +55,14 @@ int rtk_cuda_set_build_mode(int mode)
 	return RTK_CUDA_OK;
 }
 
+static int g_cull_mode = 1;
+int rtk_cuda_set_cull_mode(int mode)
+{
+	if (mode != 0 && mode != 1) { rtkd_set_error("unknown cull mode %d", mode); return RTK_CUDA_ERR_ARGUMENT; }
+	g_cull_mode = mode;
+	return RTK_CUDA_OK;
+}
+
 int rtk_cuda_init(int device)
 {
 	int r = rtkd_init(device);
@@ -553,7 +561,7 @@ int rtk_trace_rays_compact_device(const rtk_scene *scene, const void *d_rays, vo
 {
 	rtkd_scene *dev = scene_device(scene);
 	if (!dev) return RTK_CUDA_ERR_SCENE;
-	return rtkd_trace(dev, d_rays, d_hit16, n, 1, NULL, stream);
+	return rtkd_trace(dev, d_rays, d_hit16, n, g_cull_mode, NULL, stream);
 }
 
 int rtk_resolve_hits_device(const rtk_scene *scene, const void *d_hit16, void *d_hits, void *d_hit_mask, size_t n, void *stream)
@@ -569,7 +577,7 @@ int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hi
 	if (!dev) return RTK_CUDA_ERR_SCENE;
 	void *h16 = rtkd_scene_hit16(dev, n);
 	if (!h16 && n) return RTK_CUDA_ERR_MEMORY;
-	int r = rtkd_trace(dev, d_rays, h16, n, 1, NULL, stream);
+	int r = rtkd_trace(dev, d_rays, h16, n, g_cull_mode, NULL, stream);
 	if (r) return r;
 	return rtkd_resolve(dev, h16, d_hits, d_hit_mask, n, stream);
 }
@@ -586,7 +594,7 @@ int rtk_trace_stats_device(const rtk_scene *scene, const void *d_rays, void *d_h
 	rtkd_scene *dev = scene_device(scene);
 	if (!dev || !stats) return RTK_CUDA_ERR_SCENE;
 	rtkd_trace_stats st;
-	int r = rtkd_trace(dev, d_rays, d_hit16, n, 1, &st, stream);
+	int r = rtkd_trace(dev, d_rays, d_hit16, n, g_cull_mode, &st, stream);
 	stats->rays = st.rays; stats->hits = st.hits; stats->node_visits = st.node_visits;
 	stats->leaf_visits = st.leaf_visits; stats->tri_tests = st.tri_tests; stats->stack_max = st.stack_max;
 	return r;

@@ -18,6 +18,15 @@ struct rtk_ray_ctx {
 	float min_t;
 };
 
+RTK_DEV float rtk_fast_rcp(float x)
+{
+#ifdef RTK_SIMT_EMU
+	return 1.0f / x;
+#else
+	return __fdividef(1.0f, x);
+#endif
+}
+
 // select component k of (x,y,z)
 RTK_DEV float rtk_sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
 
@@ -50,7 +59,8 @@ RTK_DEV void rtk_ray_setup(rtk_ray_ctx &r, float ox, float oy, float oz, float d
 	float ddx = copysignf(fmaxf(ax, thr), dx);
 	float ddy = copysignf(fmaxf(ay, thr), dy);
 	float ddz = copysignf(fmaxf(az, thr), dz);
-	r.idx = 1.0f / ddx; r.idy = 1.0f / ddy; r.idz = 1.0f / ddz;
+	// approximate reciprocals (2 ulp) are enough here: the error is covered by the padding
+	r.idx = rtk_fast_rcp(ddx); r.idy = rtk_fast_rcp(ddy); r.idz = rtk_fast_rcp(ddz);
 	float S = fmaxf(fmaxf(fabsf(ox), fabsf(oy)), fmaxf(fabsf(oz), scene_abs_max));
 	float pad = S * 3.8146973e-06f;                        // 64 * 2^-24
 	r.cnx = -((ox + copysignf(pad, dx)) * r.idx);

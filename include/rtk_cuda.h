@@ -88,12 +88,16 @@ int  rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *trace_ctas_per_s
 
 /* ---- batched closest hit (replaces a user loop over rtk_trace_ray) ----- */
 
-/* Host buffers.  rays[n] in, hits[n] / hit_mask[n] out; hits[i] is written
- * only where hit_mask[i] != 0 (the miss rule of rtk.c:571-576).  hit_mask may
- * be NULL.  Returns the number of hits, or (size_t)-1 on error. */
+/* Host buffers.  rays[n] in, hits[n] / hit_mask[n] out.  hits[i] is meaningful
+ * only where hit_mask[i] != 0; rows of rays that missed come back zero-filled
+ * (the device variant below leaves them untouched, the miss rule of
+ * rtk.c:571-576).  hit_mask may be NULL.  Pinned (page-locked) buffers let the
+ * H2D copy, the kernels and the D2H copy of consecutive 2M-ray chunks overlap.
+ * Returns the number of hits, or (size_t)-1 on error. */
 size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits, uint8_t *hit_mask, size_t n);
 
-/* Device buffers, asynchronous on `stream`.  d_hits / d_hit_mask as above. */
+/* Device buffers (16-byte aligned), asynchronous on `stream`.  d_hits[i] is
+ * written only where d_hit_mask[i] != 0.  One batch per scene may be in flight. */
 int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hits, void *d_hit_mask, size_t n, void *stream);
 
 /* The two halves of the call above: traversal to compact records

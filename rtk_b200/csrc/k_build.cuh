@@ -374,7 +374,7 @@ RTK_DEV float rtk_half_area(float4 lo, float4 hi)
 }
 
 struct rtkd_collapse_args {
-	const uint2 *work_in; uint32_t n_in;
+	const uint2 *work_in; const uint32_t *n_in;    // the level's item count lives on the device
 	uint2 *work_out; uint32_t *n_out;
 	uint32_t *node_alloc; uint32_t node_cap;
 	uint32_t *leaf_count;
@@ -387,7 +387,7 @@ struct rtkd_collapse_args {
 __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 {
 	uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= a.n_in) return;
+	if (w >= *a.n_in) return;
 	const int n = a.n;
 	int root = (int)a.work_in[w].x;
 	uint32_t dst = a.work_in[w].y;

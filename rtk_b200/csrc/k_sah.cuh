@@ -196,6 +196,7 @@ __global__ void k_sah_root(rtkd_sah s, const uint32_t *bounds, uint32_t n)
 	s.blo[0] = make_float4(rtk_ord2f(bounds[0]), rtk_ord2f(bounds[1]), rtk_ord2f(bounds[2]), 0.0f);
 	s.bhi[0] = make_float4(rtk_ord2f(bounds[3]), rtk_ord2f(bounds[4]), rtk_ord2f(bounds[5]), 0.0f);
 	s.counters[0] = 1; s.counters[1] = 0; s.counters[2] = 0; s.counters[3] = 0; s.counters[4] = 0;
+	s.counters[5] = 0;
 	if (n > RTK_SAH_SMALL) { s.act_in[0] = 0; s.counters[1] = 1; }
 	else { s.small_list[0] = 0; s.counters[2] = 1; }
 }
@@ -204,19 +205,22 @@ __global__ void k_sah_root(rtkd_sah s, const uint32_t *bounds, uint32_t n)
 // large nodes, one level
 // ---------------------------------------------------------------------------------------------
 
-// chunk table: chunk_base[a] = first chunk of active node a (single block)
-__global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, uint32_t n_act)
+// chunk table of the level about to run: chunk_base[a] = first chunk of active node a.  Single
+// block; reads the number of active nodes from counters[1] and leaves the chunk total in
+// counters[5] so that the host needs one read-back per level.
+__global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, const uint32_t *act)
 {
 	__shared__ uint32_t s_warp[32];
 	__shared__ uint32_t s_carry;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t n_act = s.counters[1];
 	if (threadIdx.x == 0) s_carry = 0;
 	__syncthreads();
 	for (uint32_t base = 0; base < n_act; base += 1024) {
 		uint32_t a = base + threadIdx.x;
 		uint32_t v = 0;
 		if (a < n_act) {
-			uint32_t node = s.act_in[a];
+			uint32_t node = act[a];
 			uint32_t cnt = (uint32_t)(s.last[node] - s.first[node] + 1);
 			v = (cnt + RTK_SAH_CHUNK - 1) / RTK_SAH_CHUNK;
 		}
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, uint32_t n_act)
 		if (threadIdx.x == 1023) s_carry = carry + woff + x;
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) s.chunk_base[n_act] = s_carry;
+	if (threadIdx.x == 0) { s.chunk_base[n_act] = s_carry; s.counters[5] = s_carry; }
 }
 
 RTK_DEV uint32_t rtk_sah_find_node(const uint32_t *chunk_base, uint32_t n_act, uint32_t chunk)

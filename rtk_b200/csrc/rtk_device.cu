@@ -8,6 +8,7 @@
 #include "k_sah.cuh"
 #include "k_trace.cuh"
 #include <stdarg.h>
+#include <pthread.h>
 
 #define RTKD_OK 0
 #define RTKD_ERR_NO_DEVICE (-1)
@@ -174,78 +175,106 @@ extern "C" int rtkd_decode_mesh(rtkd_scene *s, uint32_t first_prim, uint32_t ntr
 // build
 // ---------------------------------------------------------------------------------------------
 
-template <typename T> static cudaError_t tmp_alloc(T **p, size_t count, cudaStream_t st)
+// All temporaries of one build come from ONE stream-ordered allocation (the pool keeps it cached
+// between rebuilds); sub-buffers are carved out with 256-byte alignment.
+struct build_arena {
+	unsigned char *base; size_t size, used;
+	template <typename T> T *take(size_t count)
+	{
+		size_t bytes = (sizeof(T) * (count ? count : 1) + 255) & ~(size_t)255;
+		if (!base) { used += bytes; return NULL; }            // sizing pass
+		T *p = (T*)(base + used);
+		used += bytes;
+		return p;
+	}
+};
+
+struct build_bufs {
+	uint32_t *d_bounds;
+	unsigned long long *keys[2];
+	uint32_t *vals[2], *counts, *totals;
+	rtkd_bvh2 t;
+	rtkd_sah h;
+	uint32_t *order;
+	float4 *wide;
+	uint2 *work[2];
+	uint32_t *ctr;
+	double *d_cost;
+	uint32_t cap, nblocks;
+	size_t act_cap, small_cap;
+};
+
+#define RTKD_COLLAPSE_LEVELS 80
+
+static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 {
-	return cudaMallocAsync(p, sizeof(T) * (count ? count : 1), st);
+	memset(&B.t, 0, sizeof(B.t));
+	memset(&B.h, 0, sizeof(B.h));
+	B.nblocks = (n + RTK_SORT_TILE - 1) / RTK_SORT_TILE;
+	B.cap = (uint32_t)(((unsigned long long)n * 4) / 7 + 16);
+	B.d_bounds = A.take<uint32_t>(8);
+	B.keys[0] = A.take<unsigned long long>(n); B.keys[1] = A.take<unsigned long long>(n);
+	B.vals[0] = A.take<uint32_t>(n); B.vals[1] = A.take<uint32_t>(n);
+	B.counts = A.take<uint32_t>(256 * (size_t)B.nblocks); B.totals = A.take<uint32_t>(256);
+	if (use_sah) {
+		const size_t cap2 = 2 * (size_t)n + 2;
+		B.act_cap = n / RTK_SAH_SMALL + 4;
+		B.small_cap = 4 * (size_t)(n / RTK_SAH_SMALL) + 8;
+		B.h.pb = A.take<float4>(2 * (size_t)n);
+		B.h.idx0 = A.take<uint32_t>(n); B.h.idx1 = A.take<uint32_t>(n); B.h.idx_final = A.take<uint32_t>(n);
+		B.h.left = A.take<int>(cap2); B.h.right = A.take<int>(cap2); B.h.first = A.take<int>(cap2); B.h.last = A.take<int>(cap2);
+		B.h.blo = A.take<float4>(cap2); B.h.bhi = A.take<float4>(cap2); B.h.ndepth = A.take<uint32_t>(cap2);
+		B.h.counters = A.take<uint32_t>(8);
+		B.h.act_in = A.take<uint32_t>(B.act_cap); B.h.act_out = A.take<uint32_t>(B.act_cap);
+		B.h.small_list = A.take<uint32_t>(B.small_cap);
+		B.h.chunk_base = A.take<uint32_t>(B.act_cap + 1);
+		B.h.bins = A.take<uint32_t>(B.act_cap * RTK_SAH_NODEBINS);
+		B.h.split = A.take<int4>(B.act_cap); B.h.cursor = A.take<uint32_t>(2 * B.act_cap);
+		B.h.node_cap = (uint32_t)cap2;
+		B.order = A.take<uint32_t>(n);
+	} else if (n > 1) {
+		B.t.left = A.take<int>(n - 1); B.t.right = A.take<int>(n - 1);
+		B.t.parent = A.take<int>(2 * (size_t)n - 1);
+		B.t.first = A.take<int>(n - 1); B.t.last = A.take<int>(n - 1);
+		B.t.blo = A.take<float4>(2 * (size_t)n - 1); B.t.bhi = A.take<float4>(2 * (size_t)n - 1);
+		B.t.flags = A.take<int>(n - 1);
+	}
+	B.wide = A.take<float4>(16 * (size_t)B.cap);
+	B.work[0] = A.take<uint2>(B.cap); B.work[1] = A.take<uint2>(B.cap);
+	B.ctr = A.take<uint32_t>(8 + RTKD_COLLAPSE_LEVELS);
+	B.d_cost = A.take<double>(1);
 }
 
-// ---- binned-SAH binary tree (k_sah.cuh) -------------------------------------------------------
-
-static void free_sah(rtkd_sah &h, uint32_t *order, cudaStream_t st)
+// binned-SAH binary tree (k_sah.cuh): one host synchronisation per level of large nodes
+static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, build_bufs &B, uint32_t n)
 {
-	cudaFreeAsync((void*)h.pb, st); cudaFreeAsync(h.idx0, st); cudaFreeAsync(h.idx1, st); cudaFreeAsync(h.idx_final, st);
-	cudaFreeAsync(h.left, st); cudaFreeAsync(h.right, st); cudaFreeAsync(h.first, st); cudaFreeAsync(h.last, st);
-	cudaFreeAsync(h.blo, st); cudaFreeAsync(h.bhi, st); cudaFreeAsync(h.ndepth, st); cudaFreeAsync(h.counters, st);
-	cudaFreeAsync(h.act_in, st); cudaFreeAsync(h.act_out, st); cudaFreeAsync(h.small_list, st);
-	cudaFreeAsync(h.chunk_base, st); cudaFreeAsync(h.bins, st); cudaFreeAsync(h.split, st); cudaFreeAsync(h.cursor, st);
-	cudaFreeAsync(order, st);
-}
-
-static int build_sah(rtkd_scene *s, cudaStream_t st, const float4 *tri, const uint32_t *svals, const uint32_t *d_bounds,
-                     uint32_t n, rtkd_sah &h, uint32_t **order_out)
-{
-	(void)s;
-	const size_t cap = 2 * (size_t)n + 2;
-	const size_t act_cap = n / RTK_SAH_SMALL + 4;
-	const size_t small_cap = 4 * (size_t)(n / RTK_SAH_SMALL) + 8;
-	float4 *pb = NULL;
-	uint32_t *order = NULL;
-	CK(tmp_alloc(&pb, 2 * (size_t)n, st)); h.pb = pb;
-	CK(tmp_alloc(&h.idx0, n, st)); CK(tmp_alloc(&h.idx1, n, st)); CK(tmp_alloc(&h.idx_final, n, st));
-	CK(tmp_alloc(&h.left, cap, st)); CK(tmp_alloc(&h.right, cap, st)); CK(tmp_alloc(&h.first, cap, st)); CK(tmp_alloc(&h.last, cap, st));
-	CK(tmp_alloc(&h.blo, cap, st)); CK(tmp_alloc(&h.bhi, cap, st)); CK(tmp_alloc(&h.ndepth, cap, st));
-	CK(tmp_alloc(&h.counters, 8, st));
-	CK(tmp_alloc(&h.act_in, act_cap, st)); CK(tmp_alloc(&h.act_out, act_cap, st)); CK(tmp_alloc(&h.small_list, small_cap, st));
-	CK(tmp_alloc(&h.chunk_base, act_cap + 1, st));
-	CK(tmp_alloc(&h.bins, act_cap * RTK_SAH_NODEBINS, st));
-	CK(tmp_alloc(&h.split, act_cap, st)); CK(tmp_alloc(&h.cursor, 2 * act_cap, st));
-	CK(tmp_alloc(&order, n, st));
-	h.node_cap = (uint32_t)cap;
-
-	RTK_LAUNCH(k_sah_prim_bounds, (n + 255) / 256, 256, st, tri, svals, n, pb, h.idx0); CK_LAUNCH();
-	RTK_LAUNCH(k_sah_root, 1, 32, st, h, d_bounds, n); CK_LAUNCH();
+	rtkd_sah &h = B.h;
+	RTK_LAUNCH(k_sah_prim_bounds, (n + 255) / 256, 256, st, tri, svals, n, (float4*)h.pb, h.idx0); CK_LAUNCH();
+	RTK_LAUNCH(k_sah_root, 1, 32, st, h, (const uint32_t*)B.d_bounds, n); CK_LAUNCH();
+	RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();
 	uint32_t hc[8];
 	CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
 	CK(cudaStreamSynchronize(st));
-	uint32_t n_act = hc[1], depth = 0;
+	uint32_t n_act = hc[1], chunks = hc[5], depth = 0;
 	int src_buf = 0;
 	while (n_act) {
-		if (n_act > act_cap) { rtkd_set_error("SAH active list overflow"); return RTKD_ERR_MEMORY; }
-		RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, n_act); CK_LAUNCH();
-		uint32_t chunks = 0;
-		CK(cudaMemcpyAsync(&chunks, h.chunk_base + n_act, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+		if (n_act > B.act_cap) { rtkd_set_error("SAH active list overflow"); return RTKD_ERR_MEMORY; }
 		CK(cudaMemsetAsync(h.counters + 1, 0, sizeof(uint32_t), st));
 		RTK_LAUNCH(k_sah_bins_clear, n_act, 128, st, h, n_act); CK_LAUNCH();
-		CK(cudaStreamSynchronize(st));
 		RTK_LAUNCH(k_sah_bin_large, chunks, 256, st, h, n_act, src_buf); CK_LAUNCH();
 		RTK_LAUNCH(k_sah_split_large, (n_act + 3) / 4, 128, st, h, n_act, depth, src_buf ^ 1); CK_LAUNCH();
 		RTK_LAUNCH(k_sah_partition_large, chunks, 256, st, h, n_act, src_buf); CK_LAUNCH();
+		uint32_t *tmp = h.act_in; h.act_in = h.act_out; h.act_out = tmp;
+		RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();
 		CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
 		CK(cudaStreamSynchronize(st));
-		uint32_t *tmp = h.act_in; h.act_in = h.act_out; h.act_out = tmp;
-		n_act = hc[1];
+		n_act = hc[1]; chunks = hc[5];
 		src_buf ^= 1;
 		depth++;
 	}
-	CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
-	if (hc[2] > small_cap) { rtkd_set_error("SAH small-subtree list overflow"); return RTKD_ERR_MEMORY; }
+	if (hc[2] > B.small_cap) { rtkd_set_error("SAH small-subtree list overflow"); return RTKD_ERR_MEMORY; }
 	if (hc[2]) { RTK_LAUNCH(k_sah_small, hc[2], RTK_SAH_SMALL_THREADS, st, h, hc[2]); CK_LAUNCH(); }
-	RTK_LAUNCH(k_sah_compose, (n + 255) / 256, 256, st, (const uint32_t*)h.idx_final, svals, n, order); CK_LAUNCH();
-	CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
-	if (hc[3]) { rtkd_set_error("SAH node pool exhausted"); return RTKD_ERR_MEMORY; }
-	*order_out = order;
+	RTK_LAUNCH(k_sah_compose, (n + 255) / 256, 256, st, (const uint32_t*)h.idx_final, svals, n, B.order); CK_LAUNCH();
 	return RTKD_OK;
 }
 
@@ -258,11 +287,6 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 	CK(cudaEventRecord(e0, st));
 
-	// (re)build: drop the previous traversal arrays
-	if (s->tv0) { cudaFree(s->tv0); s->tv0 = NULL; }
-	if (s->tv1) { cudaFree(s->tv1); s->tv1 = NULL; }
-	if (s->tv2) { cudaFree(s->tv2); s->tv2 = NULL; }
-	if (s->nodes) { cudaFree(s->nodes); s->nodes = NULL; }
 	s->num_nodes = 0; s->num_leaves = 0; s->depth = 0; s->sah_cost = 0.0;
 	for (int k = 0; k < 3; k++) { s->bounds_min[k] = 0.0f; s->bounds_max[k] = 0.0f; }
 	s->abs_max = 0.0f;
@@ -272,125 +296,111 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		cudaEventDestroy(e0); cudaEventDestroy(e1);
 		return RTKD_OK;
 	}
+	// traversal triangle arrays depend on n only: allocated once, reused by rebuilds
+	if (!s->tv0) {
+		CK(cudaMalloc((float4**)&s->tv0, sizeof(float4) * (size_t)n));
+		CK(cudaMalloc((float4**)&s->tv1, sizeof(float4) * (size_t)n));
+		CK(cudaMalloc((float4**)&s->tv2, sizeof(float4) * (size_t)n));
+	}
+
+	const bool use_sah = mode == 1 && n > RTK_LEAF_MAX;
+	build_arena A = { NULL, 0, 0 };
+	build_bufs B;
+	carve(A, B, n, use_sah);                               // sizing pass
+	A.size = A.used; A.used = 0;
+	CK(cudaMallocAsync(&A.base, A.size, st));
+	carve(A, B, n, use_sah);
 
 	const float4 *tri = (const float4*)s->tri_orig;
-	uint32_t *d_bounds = NULL;
-	unsigned long long *keys[2] = { NULL, NULL };
-	uint32_t *vals[2] = { NULL, NULL };
-	uint32_t *counts = NULL, *totals = NULL;
-	const uint32_t nblocks = (n + RTK_SORT_TILE - 1) / RTK_SORT_TILE;
-	CK(tmp_alloc(&d_bounds, 8, st));
-	CK(tmp_alloc(&keys[0], n, st)); CK(tmp_alloc(&keys[1], n, st));
-	CK(tmp_alloc(&vals[0], n, st)); CK(tmp_alloc(&vals[1], n, st));
-	CK(tmp_alloc(&counts, 256 * (size_t)nblocks, st)); CK(tmp_alloc(&totals, 256, st));
-
 	// scene bounds (ordered-uint encoded: min starts at 0xffffffff, max at 0)
-	CK(cudaMemsetAsync(d_bounds, 0xff, 3 * sizeof(uint32_t), st));
-	CK(cudaMemsetAsync(d_bounds + 3, 0x00, 3 * sizeof(uint32_t), st));
-	RTK_LAUNCH(k_scene_bounds, (n + 255) / 256, 256, st, tri, n, d_bounds); CK_LAUNCH();
-	RTK_LAUNCH(k_morton, (n + 255) / 256, 256, st, tri, n, (const uint32_t*)d_bounds, keys[0], vals[0]); CK_LAUNCH();
+	CK(cudaMemsetAsync(B.d_bounds, 0xff, 3 * sizeof(uint32_t), st));
+	CK(cudaMemsetAsync(B.d_bounds + 3, 0x00, 3 * sizeof(uint32_t), st));
+	RTK_LAUNCH(k_scene_bounds, (n + 255) / 256, 256, st, tri, n, B.d_bounds); CK_LAUNCH();
+	RTK_LAUNCH(k_morton, (n + 255) / 256, 256, st, tri, n, (const uint32_t*)B.d_bounds, B.keys[0], B.vals[0]); CK_LAUNCH();
 
 	// LSD radix sort over the 63 code bits
 	int src = 0;
 	for (int shift = 0; shift < 64; shift += 8) {
-		RTK_LAUNCH(k_radix_hist, nblocks, RTK_SORT_THREADS, st, (const unsigned long long*)keys[src], n, shift, counts, nblocks); CK_LAUNCH();
-		RTK_LAUNCH(k_radix_scan, 256, 256, st, counts, nblocks, totals); CK_LAUNCH();
-		RTK_LAUNCH(k_radix_scatter, nblocks, RTK_SORT_THREADS, st, (const unsigned long long*)keys[src], (const uint32_t*)vals[src],
-		           keys[src ^ 1], vals[src ^ 1], n, shift, (const uint32_t*)counts, (const uint32_t*)totals, nblocks); CK_LAUNCH();
+		RTK_LAUNCH(k_radix_hist, B.nblocks, RTK_SORT_THREADS, st, (const unsigned long long*)B.keys[src], n, shift, B.counts, B.nblocks); CK_LAUNCH();
+		RTK_LAUNCH(k_radix_scan, 256, 256, st, B.counts, B.nblocks, B.totals); CK_LAUNCH();
+		RTK_LAUNCH(k_radix_scatter, B.nblocks, RTK_SORT_THREADS, st, (const unsigned long long*)B.keys[src], (const uint32_t*)B.vals[src],
+		           B.keys[src ^ 1], B.vals[src ^ 1], n, shift, (const uint32_t*)B.counts, (const uint32_t*)B.totals, B.nblocks); CK_LAUNCH();
 		src ^= 1;
 	}
-	const unsigned long long *skeys = keys[src];
-	const uint32_t *svals = vals[src];
-
-	CK(cudaMalloc((float4**)&s->tv0, sizeof(float4) * (size_t)n));
-	CK(cudaMalloc((float4**)&s->tv1, sizeof(float4) * (size_t)n));
-	CK(cudaMalloc((float4**)&s->tv2, sizeof(float4) * (size_t)n));
+	const unsigned long long *skeys = B.keys[src];
+	const uint32_t *svals = B.vals[src];
 
 	uint32_t h_bounds[6];
-	CK(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(h_bounds, B.d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, st));
 
 	// binary tree: binned SAH over the Morton-ordered triangles, or the radix tree itself
-	const bool use_sah = mode == 1 && n > RTK_LEAF_MAX;
-	rtkd_bvh2 t;
-	memset(&t, 0, sizeof(t));
-	rtkd_sah sah;
-	memset(&sah, 0, sizeof(sah));
-	uint32_t *order = NULL;          // leaf order as triangle numbers (SAH mode)
+	rtkd_bvh2 t = B.t;
 	if (use_sah) {
-		int r = build_sah(s, st, tri, svals, d_bounds, n, sah, &order);
-		if (r) return r;
-		t.left = sah.left; t.right = sah.right; t.first = sah.first; t.last = sah.last; t.blo = sah.blo; t.bhi = sah.bhi;
-		svals = order;
+		int r = build_sah(st, tri, svals, B, n);
+		if (r) { cudaFreeAsync(A.base, st); return r; }
+		t.left = B.h.left; t.right = B.h.right; t.first = B.h.first; t.last = B.h.last; t.blo = B.h.blo; t.bhi = B.h.bhi;
+		svals = B.order;
+	} else if (n > 1) {
+		CK(cudaMemsetAsync(t.flags, 0, sizeof(int) * (size_t)(n - 1), st));
+		RTK_LAUNCH(k_hierarchy, (n - 1 + 255) / 256, 256, st, skeys, (int)n, t); CK_LAUNCH();
+		RTK_LAUNCH(k_refit, (n + 255) / 256, 256, st, tri, svals, (int)n, t); CK_LAUNCH();
 	}
 	// traversal triangles in leaf order
 	RTK_LAUNCH(k_emit_tris, (n + 255) / 256, 256, st, tri, svals, n, (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
 
-	float4 *wide = NULL;
 	uint32_t num_nodes = 0, num_leaves = 0, depth = 0;
 	double h_cost = 0.0;
 	if (n == 1) {
-		CK(tmp_alloc(&wide, 16, st));
-		RTK_LAUNCH(k_single_root, 1, 32, st, tri, svals, wide); CK_LAUNCH();
+		RTK_LAUNCH(k_single_root, 1, 32, st, tri, svals, B.wide); CK_LAUNCH();
 		num_nodes = 1; num_leaves = 1; depth = 1;
 	} else {
-		if (!use_sah) {
-			CK(tmp_alloc(&t.left, n - 1, st)); CK(tmp_alloc(&t.right, n - 1, st));
-			CK(tmp_alloc(&t.parent, 2 * (size_t)n - 1, st));
-			CK(tmp_alloc(&t.first, n - 1, st)); CK(tmp_alloc(&t.last, n - 1, st));
-			CK(tmp_alloc(&t.blo, 2 * (size_t)n - 1, st)); CK(tmp_alloc(&t.bhi, 2 * (size_t)n - 1, st));
-			CK(tmp_alloc(&t.flags, n - 1, st));
-			CK(cudaMemsetAsync(t.flags, 0, sizeof(int) * (size_t)(n - 1), st));
-			RTK_LAUNCH(k_hierarchy, (n - 1 + 255) / 256, 256, st, skeys, (int)n, t); CK_LAUNCH();
-			RTK_LAUNCH(k_refit, (n + 255) / 256, 256, st, tri, svals, (int)n, t); CK_LAUNCH();
-		}
-
-		const uint32_t cap = (uint32_t)(((unsigned long long)n * 4) / 7 + 16);
-		uint2 *work[2] = { NULL, NULL };
-		uint32_t *ctr = NULL;          // [0] n_out, [1] node_alloc, [2] leaf_count, [3] err
-		double *d_cost = NULL;
-		CK(tmp_alloc(&wide, 16 * (size_t)cap, st));
-		CK(tmp_alloc(&work[0], cap, st)); CK(tmp_alloc(&work[1], cap, st));
-		CK(tmp_alloc(&ctr, 4, st)); CK(tmp_alloc(&d_cost, 1, st));
-		uint32_t h_ctr[4] = { 0, 1, 0, 0 };
+		// ctr: [0] node_alloc [1] leaf_count [2] err [8 + L] items queued for level L
+		uint32_t h_ctr[8 + RTKD_COLLAPSE_LEVELS];
+		memset(h_ctr, 0, sizeof(h_ctr));
+		h_ctr[0] = 1; h_ctr[8] = 1;
 		uint2 w0 = make_uint2(0u, 0u);
-		CK(cudaMemcpyAsync(ctr, h_ctr, sizeof(h_ctr), cudaMemcpyHostToDevice, st));
-		CK(cudaMemcpyAsync(work[0], &w0, sizeof(w0), cudaMemcpyHostToDevice, st));
-		CK(cudaMemsetAsync(d_cost, 0, sizeof(double), st));
-		uint32_t n_in = 1;
-		int wi = 0;
-		while (n_in) {
-			rtkd_collapse_args a;
-			a.work_in = work[wi]; a.n_in = n_in; a.work_out = work[wi ^ 1]; a.n_out = ctr;
-			a.node_alloc = ctr + 1; a.node_cap = cap; a.leaf_count = ctr + 2; a.sah_cost = d_cost;
-			a.nodes = wide; a.n = (int)n; a.err = ctr + 3;
-			RTK_LAUNCH(k_collapse, (n_in + 127) / 128, 128, st, a, t); CK_LAUNCH();
-			CK(cudaMemcpyAsync(h_ctr, ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
+		CK(cudaMemcpyAsync(B.ctr, h_ctr, sizeof(h_ctr), cudaMemcpyHostToDevice, st));
+		CK(cudaMemcpyAsync(B.work[0], &w0, sizeof(w0), cudaMemcpyHostToDevice, st));
+		CK(cudaMemsetAsync(B.d_cost, 0, sizeof(double), st));
+		// levels are launched with an upper bound on their width (8^L, capped) and read their
+		// true item count on the device; the host looks at the counters every 4 levels
+		unsigned long long bound = 1;
+		int level = 0;
+		bool done = false;
+		while (!done) {
+			for (int k = 0; k < 4 && level < RTKD_COLLAPSE_LEVELS - 1; k++, level++) {
+				rtkd_collapse_args a;
+				a.work_in = B.work[level & 1]; a.n_in = B.ctr + 8 + level;
+				a.work_out = B.work[(level & 1) ^ 1]; a.n_out = B.ctr + 8 + level + 1;
+				a.node_alloc = B.ctr; a.node_cap = B.cap; a.leaf_count = B.ctr + 1; a.sah_cost = B.d_cost;
+				a.nodes = B.wide; a.n = (int)n; a.err = B.ctr + 2;
+				uint32_t width = (uint32_t)(bound < B.cap ? bound : B.cap);
+				RTK_LAUNCH(k_collapse, (width + 127) / 128, 128, st, a, t); CK_LAUNCH();
+				bound = bound * 8 < B.cap ? bound * 8 : B.cap;
+			}
+			CK(cudaMemcpyAsync(h_ctr, B.ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
-			n_in = h_ctr[0];
-			CK(cudaMemsetAsync(ctr, 0, sizeof(uint32_t), st));
-			wi ^= 1;
-			depth++;
+			done = h_ctr[8 + level] == 0 || level >= RTKD_COLLAPSE_LEVELS - 1;
 		}
-		num_nodes = h_ctr[1]; num_leaves = h_ctr[2];
-		if (h_ctr[3]) { rtkd_set_error("wide-node pool exhausted (cap %u)", cap); return RTKD_ERR_MEMORY; }
-		CK(cudaMemcpyAsync(&h_cost, d_cost, sizeof(double), cudaMemcpyDeviceToHost, st));
-		if (!use_sah) {
-			cudaFreeAsync(t.left, st); cudaFreeAsync(t.right, st); cudaFreeAsync(t.parent, st);
-			cudaFreeAsync(t.first, st); cudaFreeAsync(t.last, st); cudaFreeAsync(t.blo, st); cudaFreeAsync(t.bhi, st);
-			cudaFreeAsync(t.flags, st);
+		for (depth = 0; depth < RTKD_COLLAPSE_LEVELS && h_ctr[8 + depth]; depth++) { }
+		num_nodes = h_ctr[0]; num_leaves = h_ctr[1];
+		if (h_ctr[2] || h_ctr[8 + RTKD_COLLAPSE_LEVELS - 1]) {
+			rtkd_set_error("wide-node pool exhausted (cap %u) or tree deeper than %d", B.cap, RTKD_COLLAPSE_LEVELS);
+			cudaFreeAsync(A.base, st);
+			return RTKD_ERR_MEMORY;
 		}
-		cudaFreeAsync(work[0], st); cudaFreeAsync(work[1], st);
-		cudaFreeAsync(ctr, st); cudaFreeAsync(d_cost, st);
+		CK(cudaMemcpyAsync(&h_cost, B.d_cost, sizeof(double), cudaMemcpyDeviceToHost, st));
 	}
 
-	if (use_sah) free_sah(sah, order, st);
-
-	// exact-size node array
-	CK(cudaMalloc((float4**)&s->nodes, sizeof(float4) * 16 * (size_t)num_nodes));
-	CK(cudaMemcpyAsync(s->nodes, wide, sizeof(float4) * 16 * (size_t)num_nodes, cudaMemcpyDeviceToDevice, st));
-	cudaFreeAsync(wide, st);
-	cudaFreeAsync(d_bounds, st); cudaFreeAsync(keys[0], st); cudaFreeAsync(keys[1], st);
-	cudaFreeAsync(vals[0], st); cudaFreeAsync(vals[1], st); cudaFreeAsync(counts, st); cudaFreeAsync(totals, st);
+	// node array: reuse the previous allocation when it is large enough
+	if (!s->nodes || s->nodes_cap < num_nodes) {
+		if (s->nodes) cudaFree(s->nodes);
+		s->nodes = NULL;
+		CK(cudaMalloc((float4**)&s->nodes, sizeof(float4) * 16 * (size_t)num_nodes));
+		s->nodes_cap = num_nodes;
+	}
+	CK(cudaMemcpyAsync(s->nodes, B.wide, sizeof(float4) * 16 * (size_t)num_nodes, cudaMemcpyDeviceToDevice, st));
+	cudaFreeAsync(A.base, st);
 
 	CK(cudaEventRecord(e1, st));
 	CK(cudaEventSynchronize(e1));
@@ -415,8 +425,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		double ra = (double)x * y + (double)y * z + (double)z * x;
 		s->sah_cost = ra > 0.0 ? 1.0 + h_cost / ra : 0.0;
 	}
-	// stack scratch depends on the depth: force re-creation
-	if (s->overflow) { cudaFree(s->overflow); s->overflow = NULL; s->overflow_entries = 0; }
+	// the stack scratch depends on the depth: re-created on the next query if too small
 	return RTKD_OK;
 }
 
@@ -534,63 +543,89 @@ extern "C" void *rtkd_scene_hit16(rtkd_scene *s, size_t n)
 }
 
 // Host-buffer batch.  Rays go up and hits come back in chunks on two streams so that the
-// H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap.
+// H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap.  The
+// device staging buffers and streams are created once per process and reused.
+struct host_stage {
+	size_t chunk;
+	cudaStream_t st[2];
+	cudaEvent_t done[2];
+	float4 *d_rays[2], *d_h16[2];
+	uint32_t *d_hits[2];
+	unsigned char *d_mask[2];
+	bool ready;
+};
+static host_stage g_stage;
+static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static int stage_prepare(size_t want)
+{
+	const size_t CH = (size_t)1 << 21;            // 2 Mi rays = 64 MiB up, 136 MiB down per chunk
+	size_t chunk = want < CH ? want : CH;
+	if (chunk < 4096) chunk = 4096;
+	if (g_stage.ready && g_stage.chunk >= chunk) return RTKD_OK;
+	if (g_stage.ready) {
+		for (int k = 0; k < 2; k++) { cudaFree(g_stage.d_rays[k]); cudaFree(g_stage.d_h16[k]); cudaFree(g_stage.d_hits[k]); cudaFree(g_stage.d_mask[k]); }
+	} else {
+		for (int k = 0; k < 2; k++) {
+			CK(cudaStreamCreateWithFlags(&g_stage.st[k], cudaStreamNonBlocking));
+			CK(cudaEventCreate(&g_stage.done[k]));
+		}
+	}
+	g_stage.ready = false;
+	for (int k = 0; k < 2; k++) {
+		CK(cudaMalloc(&g_stage.d_rays[k], 32 * chunk));
+		CK(cudaMalloc(&g_stage.d_h16[k], 16 * chunk));
+		CK(cudaMalloc(&g_stage.d_hits[k], 68 * chunk));
+		CK(cudaMalloc(&g_stage.d_mask[k], chunk));
+	}
+	g_stage.chunk = chunk;
+	g_stage.ready = true;
+	return RTKD_OK;
+}
+
 extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n)
 {
 	if (!n) return 0;
-	const size_t CH = (size_t)1 << 21;            // 2 Mi rays = 64 MiB up, 136 MiB down
-	const size_t chunk = n < CH ? n : CH;
-	cudaStream_t st[2];
-	float4 *d_rays[2] = { NULL, NULL }, *d_h16[2] = { NULL, NULL };
-	uint32_t *d_hits[2] = { NULL, NULL };
-	unsigned char *d_mask[2] = { NULL, NULL };
-	long long total = 0;
-	int rc = RTKD_OK;
-	for (int k = 0; k < 2; k++) {
-		if (cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking) != cudaSuccess) { rtkd_set_error("stream creation failed"); return -1; }
-	}
-	for (int k = 0; k < 2 && rc == RTKD_OK; k++) {
-		cudaError_t e = cudaMalloc(&d_rays[k], 32 * chunk);
-		if (e == cudaSuccess) e = cudaMalloc(&d_h16[k], 16 * chunk);
-		if (e == cudaSuccess) e = cudaMalloc(&d_hits[k], 68 * chunk);
-		if (e == cudaSuccess) e = cudaMalloc(&d_mask[k], chunk);
-		if (e != cudaSuccess) { rtkd_set_error("batch staging allocation failed: %s", cudaGetErrorString(e)); rc = RTKD_ERR_MEMORY; }
-	}
-	// The traversal scratch (ray cursor, overflow slab) belongs to the scene, so the kernels of
-	// consecutive chunks are serialised on purpose: chunk k+1's kernels wait for chunk k's, while
-	// its H2D copy and chunk k's D2H copy run beside them (pinned caller buffers overlap fully).
-	cudaEvent_t done[2];
-	cudaEventCreate(&done[0]); cudaEventCreate(&done[1]);
-	unsigned long long *d_count = NULL;
+	pthread_mutex_lock(&g_stage_lock);
+	long long total = -1;
+	int rc = stage_prepare(n);
 	if (rc == RTKD_OK) rc = ensure_scratch(s);
+	host_stage &G = g_stage;
+	unsigned long long *d_count = NULL;
 	if (rc == RTKD_OK) {
 		d_count = (unsigned long long*)((unsigned char*)s->scratch + 128);
 		if (cudaMemset(d_count, 0, sizeof(unsigned long long)) != cudaSuccess) rc = RTKD_ERR_CUDA;
 	}
-	size_t nchunks = (n + chunk - 1) / chunk;
+	// The traversal scratch (ray cursor, overflow slab) belongs to the scene, so the kernels of
+	// consecutive chunks are serialised on purpose: chunk k+1's kernels wait for chunk k's, while
+	// its H2D copy and chunk k's D2H copy run beside them (pinned caller buffers overlap fully).
+	const size_t chunk = G.chunk;
+	const size_t nchunks = (n + chunk - 1) / chunk;
 	for (size_t ci = 0; ci < nchunks && rc == RTKD_OK; ci++) {
 		int k = (int)(ci & 1);
 		size_t off = ci * chunk, cnt = n - off < chunk ? n - off : chunk;
-		cudaStream_t q = st[k];
-		if (cudaMemcpyAsync(d_rays[k], (const char*)rays + 32 * off, 32 * cnt, cudaMemcpyHostToDevice, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
+		cudaStream_t q = G.st[k];
+		if (cudaMemcpyAsync(G.d_rays[k], (const char*)rays + 32 * off, 32 * cnt, cudaMemcpyHostToDevice, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
 		// rows of rays that miss come back zero-filled (see rtk_cuda.h)
-		if (cudaMemsetAsync(d_hits[k], 0, 68 * cnt, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
-		if (ci > 0) cudaStreamWaitEvent(q, done[k ^ 1], 0);
-		rc = rtkd_trace(s, d_rays[k], d_h16[k], cnt, 1, NULL, q);
+		if (cudaMemsetAsync(G.d_hits[k], 0, 68 * cnt, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
+		if (ci > 0) cudaStreamWaitEvent(q, G.done[k ^ 1], 0);
+		rc = rtkd_trace(s, G.d_rays[k], G.d_h16[k], cnt, 1, NULL, q);
 		if (rc) break;
 		{
 			rtkd_arrays a;
 			fill_arrays(s, a);
 			RTK_LAUNCH(k_resolve, (unsigned)((cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, q,
-			           a, (const float4*)d_h16[k], d_hits[k], d_mask[k], (uint32_t)cnt, d_count);
+			           a, (const float4*)G.d_h16[k], G.d_hits[k], G.d_mask[k], (uint32_t)cnt, d_count);
 		}
-		cudaEventRecord(done[k], q);
-		if (cudaMemcpyAsync((char*)hits + 68 * off, d_hits[k], 68 * cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
-		if (mask && cudaMemcpyAsync(mask + off, d_mask[k], cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
+		cudaEventRecord(G.done[k], q);
+		if (cudaMemcpyAsync((char*)hits + 68 * off, G.d_hits[k], 68 * cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
+		if (mask && cudaMemcpyAsync(mask + off, G.d_mask[k], cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
 	}
-	for (int k = 0; k < 2; k++) {
-		if (cudaStreamSynchronize(st[k]) != cudaSuccess && rc == RTKD_OK) {
-			rtkd_set_error("batch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = RTKD_ERR_CUDA;
+	if (G.ready) {
+		for (int k = 0; k < 2; k++) {
+			if (cudaStreamSynchronize(G.st[k]) != cudaSuccess && rc == RTKD_OK) {
+				rtkd_set_error("batch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = RTKD_ERR_CUDA;
+			}
 		}
 	}
 	if (rc == RTKD_OK) {
@@ -601,12 +636,8 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 		total = (long long)hc;
 		if (herr & 2u) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
 	}
-	cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
-	for (int k = 0; k < 2; k++) {
-		cudaFree(d_rays[k]); cudaFree(d_h16[k]); cudaFree(d_hits[k]); cudaFree(d_mask[k]);
-		cudaStreamDestroy(st[k]);
-	}
 	if (rc == RTKD_ERR_CUDA && !g_err[0]) rtkd_set_error("CUDA failure in rtk_trace_rays");
+	pthread_mutex_unlock(&g_stage_lock);
 	return rc == RTKD_OK ? total : -1;
 }
 
@@ -697,6 +728,7 @@ extern "C" rtkd_scene *rtkd_blob_read(const void *payload, size_t payload_size)
 	}
 	if (e == cudaSuccess && b.num_nodes) {
 		e = cudaMalloc((float4**)&s->nodes, 256 * (size_t)b.num_nodes);
+		s->nodes_cap = b.num_nodes;
 		if (e == cudaSuccess) e = cudaMemcpy(s->nodes, p + b.off_nodes, 256 * (size_t)b.num_nodes, cudaMemcpyHostToDevice);
 	}
 	if (e != cudaSuccess) {

@@ -20,6 +20,7 @@ typedef struct rtkd_scene {
 	void *tri_orig;              /* float4[3*num_tris] */
 	void *tv0, *tv1, *tv2;       /* float4[num_tris] each */
 	void *nodes;                 /* float4[16*num_nodes] */
+	uint32_t nodes_cap;
 	void *mesh_first;            /* uint32[num_meshes+1] */
 	uint32_t *h_mesh_first;      /* host copy */
 	float bounds_min[3], bounds_max[3], abs_max;

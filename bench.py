@@ -150,7 +150,7 @@ def run_reference(args, workload, scene, rays):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=FULL_RAYS)
@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1 << 22)
     ap.add_argument("--cpu-sample", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--build-mode", default="lbvh", choices=["lbvh", "sah"])
+    ap.add_argument("--build-mode", default="sah", choices=["lbvh", "sah"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-rays", type=int, default=1024)
     ap.add_argument("--cull", type=int, default=1, help="1 provable dominant-axis culling (default), 0 full-box culling")
@@ -230,7 +230,7 @@ def main():
     if world > 1:
         gather_list = [torch.empty_like(d_h16) for _ in range(world)] if rank == 0 else None
 
-    def step(ev=None):
+    def step(ev=None, exchange=True):
         if ev:
             ev[0].record(stream)
         rc = lib.rtk_trace_rays_compact_device(sc.ptr, d_rays.data_ptr(), d_h16.data_ptr(), n, sh)
@@ -241,14 +241,14 @@ def main():
             ev[2].record(stream)
         if rc:
             raise RuntimeError(lib.last_error())
-        if world > 1:
+        if world > 1 and exchange:
             dist.gather(d_h16, gather_list, dst=0)
 
     # ---- parity self-check against the CPU oracle (outside the timed region) -------------------
     parity = None
     if rank == 0 and args.parity_rays > 0:
         from oracle import orc
-        step()
+        step(exchange=False)                 # rank-local: no collective outside the common path
         torch.cuda.synchronize()
         k = min(args.parity_rays, n, 2048)       # CPU brute force: 1M triangles per ray
         got = d_h16[:k].cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)

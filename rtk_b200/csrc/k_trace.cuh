@@ -28,25 +28,15 @@
 
 #define RTK_TRACE_WARPS 8
 #define RTK_TRACE_THREADS (RTK_TRACE_WARPS * 32)
-#define RTK_GROUPS_PER_CTA (RTK_TRACE_WARPS * 4)
+#define RTK_GROUPS_PER_CTA_MAX (RTK_TRACE_WARPS * 16)   // 2 lanes per ray
 #define RTK_STACK_SMEM 16
 #define RTK_RAY_BATCH 32
 #ifndef RTK_TRACE_MINB
 #define RTK_TRACE_MINB 4                 // resident CTAs per SM the register allocation must allow
 #endif
-#ifndef RTK_TRACE_BATCH
-#define RTK_TRACE_BATCH 0                // 1: a phase runs when >= 2 of the warp's 4 rays need it (or nothing else can run)
+#ifndef RTK_TRACE_LANES
+#define RTK_TRACE_LANES 2                // default lanes per ray (8, 4 or 2); RTK_B200_LANES overrides at run time
 #endif
-#ifndef RTK_TRACE_PREFETCH
-#define RTK_TRACE_PREFETCH 0             // 1: L1 prefetch of the next node / leaf as soon as it is known
-#endif
-
-RTK_DEV void rtk_prefetch_l1(const void *p)
-{
-#ifndef RTK_SIMT_EMU
-	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#endif
-}
 
 struct rtkd_hit16 { float t, u, v; uint32_t prim; };
 
@@ -62,16 +52,23 @@ struct rtkd_trace_args {
 	unsigned long long *stats;   // [6] when STATS
 };
 
-template <int CULL, bool STATS>
+// LANES = lanes per ray (8, 4 or 2): each lane owns 8/LANES children of the current node and
+// 8/LANES triangles of the current leaf.  Fewer lanes per ray put more rays in a warp (4, 8, 16),
+// which divides the per-ray serial work (setup, stack, control) by the same factor at the price of
+// more independent loads per instruction.
+template <int LANES, int CULL, bool STATS>
 __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtkd_trace_args p)
 {
+	constexpr int CPL = 8 / LANES;                       // children / triangles per lane
+	constexpr int GW = 32 / LANES;                       // rays (groups) per warp
+	constexpr int GROUPS = RTK_TRACE_WARPS * GW;         // rays per CTA
 	__shared__ float4 s_rays[RTK_TRACE_WARPS][2][RTK_RAY_BATCH * 2];
-	__shared__ uint2 s_stack[RTK_STACK_SMEM][RTK_GROUPS_PER_CTA];
+	__shared__ uint2 s_stack[RTK_STACK_SMEM][GROUPS];
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int c = lane & 7, g = lane >> 3;
-	const int gcta = warp * 4 + g;
-	const unsigned long long gglobal = (unsigned long long)blockIdx.x * RTK_GROUPS_PER_CTA + gcta;
+	const int c = lane & (LANES - 1), g = lane / LANES;
+	const int gcta = warp * GW + g;
+	const unsigned long long gglobal = (unsigned long long)blockIdx.x * GROUPS + gcta;
 	const uint32_t FULL = 0xffffffffu;
 	const float4 *__restrict__ nodes = p.sc.nodes;
 
@@ -105,7 +102,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 		__syncwarp();
 	}
 
-	// ---- per-ray state (identical in the 8 lanes of a group) -------------------------------
+	// ---- per-ray state (identical in the lanes of a group) ---------------------------------
 	rtk_ray_ctx rc;
 	bool has_ray = false;
 	uint32_t ray_index = 0;
@@ -134,19 +131,6 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 		} \
 	} while (0)
 
-#if RTK_TRACE_PREFETCH
-#define RTK_PREFETCH_CUR() do { \
-		if (cur_ref != RTK_REF_EMPTY) { \
-			if (rtk_ref_is_leaf(cur_ref)) { \
-				uint32_t _f = rtk_leaf_first(cur_ref) + (uint32_t)c; \
-				if ((uint32_t)c < rtk_leaf_count(cur_ref)) { rtk_prefetch_l1(&p.sc.tv0[_f]); rtk_prefetch_l1(&p.sc.tv1[_f]); rtk_prefetch_l1(&p.sc.tv2[_f]); } \
-			} else { rtk_prefetch_l1(nodes + 16ull * cur_ref + c); rtk_prefetch_l1(nodes + 16ull * cur_ref + 8 + c); } \
-		} \
-	} while (0)
-#else
-#define RTK_PREFETCH_CUR() do { } while (0)
-#endif
-
 	for (;;) {
 		// ---- (1) hand rays to idle groups --------------------------------------------------
 		uint32_t need_mask = __ballot_sync(FULL, !has_ray && c == 0);
@@ -172,7 +156,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 				}
 				continue;
 			}
-			uint32_t rank = __popc(need_mask & ((1u << (g * 8)) - 1u));
+			uint32_t rank = __popc(need_mask & ((1u << (g * LANES)) - 1u));
 			if (!has_ray && rank < avail) {
 				uint32_t slot = cur_pos + rank;
 				float4 r0 = s_rays[warp][cur_buf][slot * 2], r1 = s_rays[warp][cur_buf][slot * 2 + 1];
@@ -189,107 +173,111 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 		}
 		if (!__any_sync(FULL, has_ray)) break;
 
-		// ---- (2) leaf: 8 lanes test up to 8 triangles (rtk.c:181-388) ------------------------
+		// ---- (2) leaf: the group tests up to 8 triangles (rtk.c:181-388) ---------------------
 		const bool is_leaf = has_ray && cur_ref != RTK_REF_EMPTY && rtk_ref_is_leaf(cur_ref);
-#if RTK_TRACE_BATCH
-		// Both phases cost a full warp instruction stream however many of the four rays take part,
-		// so a ray whose next entry is a leaf waits (idle lanes, no extra issue slots) until a
-		// second ray reaches a leaf too, unless no ray has node work left; likewise for nodes.
-		const uint32_t leaf_groups = __ballot_sync(FULL, is_leaf && c == 0);
-		const uint32_t node_groups = __ballot_sync(FULL, has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref) && c == 0);
-		const int n_leaf = __popc(leaf_groups), n_node0 = __popc(node_groups);
-		const bool run_tri = n_leaf >= 2 || (n_leaf == 1 && n_node0 <= 1);
-		if (run_tri) {
-#else
-		const bool run_tri = true;
 		if (__any_sync(FULL, is_leaf)) {
-#endif
 			float t = INFINITY, u = 0.0f, v = 0.0f;
 			uint32_t prim = RTK_MISS;
 			if (is_leaf) {
-				uint32_t first = rtk_leaf_first(cur_ref), cnt = rtk_leaf_count(cur_ref);
-				if ((uint32_t)c < cnt) {
-					float4 p0 = __ldg(&p.sc.tv0[first + c]);
-					float4 p1 = __ldg(&p.sc.tv1[first + c]);
-					float4 p2 = __ldg(&p.sc.tv2[first + c]);
-					uint32_t id = __float_as_uint(p0.w);
-					float tt, uu, vv;
-					if (rtk_tri_test(rc, p0, p1, p2, best_t, tt, uu, vv)) {
-						// strict '<' against the running best (rtk.c:354, 371); an exact tie is
-						// taken only from a lower triangle number than the recorded hit
-						if (tt < best_t || (best_prim != RTK_MISS && id < best_prim)) { t = tt; u = uu; v = vv; prim = id; }
+				const uint32_t first = rtk_leaf_first(cur_ref), cnt = rtk_leaf_count(cur_ref);
+				// running best of this lane: starts at the ray's best so that each later triangle
+				// only has to beat what an earlier one of the same lane found
+				float lt = best_t;
+				uint32_t lp = best_prim;
+#pragma unroll
+				for (int j = 0; j < CPL; j++) {
+					const uint32_t k = (uint32_t)(c * CPL + j);
+					if (k < cnt) {
+						float4 p0 = __ldg(&p.sc.tv0[first + k]);
+						float4 p1 = __ldg(&p.sc.tv1[first + k]);
+						float4 p2 = __ldg(&p.sc.tv2[first + k]);
+						uint32_t id = __float_as_uint(p0.w);
+						float tt, uu, vv;
+						if (rtk_tri_test(rc, p0, p1, p2, lt, tt, uu, vv)) {
+							// strict '<' against the running best (rtk.c:354, 371); an exact tie is
+							// taken only from a lower triangle number than the recorded hit
+							if (tt < lt || (lp != RTK_MISS && id < lp)) { lt = tt; lp = id; t = tt; u = uu; v = vv; prim = id; }
+						}
 					}
 				}
 				if (STATS) { st_leaves++; st_tris += cnt; }
 			}
 			float tmin = t;
-			tmin = rtk_fmin(tmin, __shfl_xor_sync(FULL, tmin, 1));
-			tmin = rtk_fmin(tmin, __shfl_xor_sync(FULL, tmin, 2));
-			tmin = rtk_fmin(tmin, __shfl_xor_sync(FULL, tmin, 4));
+#pragma unroll
+			for (int o = 1; o < LANES; o <<= 1) tmin = rtk_fmin(tmin, __shfl_xor_sync(FULL, tmin, o));
 			uint32_t pmin = (t == tmin) ? prim : RTK_MISS;
-			pmin = rtk_umin(pmin, __shfl_xor_sync(FULL, pmin, 1));
-			pmin = rtk_umin(pmin, __shfl_xor_sync(FULL, pmin, 2));
-			pmin = rtk_umin(pmin, __shfl_xor_sync(FULL, pmin, 4));
+#pragma unroll
+			for (int o = 1; o < LANES; o <<= 1) pmin = rtk_umin(pmin, __shfl_xor_sync(FULL, pmin, o));
 			const bool winner = prim != RTK_MISS && t == tmin && prim == pmin;
-			uint32_t wm = (__ballot_sync(FULL, winner) >> (g * 8)) & 0xffu;
+			uint32_t wm = (__ballot_sync(FULL, winner) >> (g * LANES)) & ((1u << LANES) - 1u);
 			int src = wm ? __ffs(wm) - 1 : 0;
-			float wu = __shfl_sync(FULL, u, src, 8), wv = __shfl_sync(FULL, v, src, 8);
+			float wu = __shfl_sync(FULL, u, src, LANES), wv = __shfl_sync(FULL, v, src, LANES);
 			if (is_leaf) {
 				if (wm) { best_t = tmin; best_prim = pmin; best_u = wu; best_v = wv; }
 				RTK_STACK_POP();
-				RTK_PREFETCH_CUR();
 			}
 			__syncwarp();
 		}
 
-		// ---- (3) node: 8 lanes test the 8 children (rtk.c:457-473) ---------------------------
+		// ---- (3) node: the group tests the 8 children (rtk.c:457-473) ------------------------
 		const bool is_node = has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref);
-#if RTK_TRACE_BATCH
-		const uint32_t node_groups2 = __ballot_sync(FULL, is_node && c == 0);
-		const uint32_t leaf_groups2 = __ballot_sync(FULL, has_ray && cur_ref != RTK_REF_EMPTY && rtk_ref_is_leaf(cur_ref) && c == 0);
-		const int n_node = __popc(node_groups2);
-		// progress: if the leaf phase did not run this iteration, a lone node must
-		if (n_node >= 2 || (n_node == 1 && (leaf_groups2 == 0 || !run_tri))) {
-#else
 		if (__any_sync(FULL, is_node)) {
-#endif
-			bool hit = false;
-			float key = 0.0f, tn = 0.0f;
-			uint32_t ref = RTK_REF_EMPTY;
+			uint32_t hitbits = 0;                 // bit (child index) for the children of this lane
+			uint32_t ok = 0xffffffffu;            // best ordering key of this lane
+			float key[CPL];
+			uint32_t ref[CPL];
+#pragma unroll
+			for (int j = 0; j < CPL; j++) { key[j] = 0.0f; ref[j] = RTK_REF_EMPTY; }
 			if (is_node) {
 				const float4 *np = nodes + 16ull * cur_ref;
-				float4 lo = __ldg(np + c), hi = __ldg(np + 8 + c);
-				ref = __float_as_uint(lo.w);
 				const bool nx = rc.sgn & 1u, ny = rc.sgn & 2u, nz = rc.sgn & 4u;
-				float tnx = fmaf(nx ? hi.x : lo.x, rc.idx, rc.cnx), tfx = fmaf(nx ? lo.x : hi.x, rc.idx, rc.cfx);
-				float tny = fmaf(ny ? hi.y : lo.y, rc.idy, rc.cny), tfy = fmaf(ny ? lo.y : hi.y, rc.idy, rc.cfy);
-				float tnz = fmaf(nz ? hi.z : lo.z, rc.idz, rc.cnz), tfz = fmaf(nz ? lo.z : hi.z, rc.idz, rc.cfz);
-				tn = rtk_fmax(rtk_fmax(tnx, tny), tnz);
-				float tf = rtk_fmin(rtk_fmin(tfx, tfy), tfz);
-				float kn, kf;
-				if (CULL == 1) {
-					kn = rc.kz == 0 ? tnx : (rc.kz == 1 ? tny : tnz);
-					kf = rc.kz == 0 ? tfx : (rc.kz == 1 ? tfy : tfz);
-				} else { kn = tn; kf = tf; }
-				hit = ref != RTK_REF_EMPTY && tn <= tf && kn <= best_t && kf >= rc.min_t;
-				key = kn;
+#pragma unroll
+				for (int j = 0; j < CPL; j++) {
+					const int k = c * CPL + j;
+					float4 lo = __ldg(np + k), hi = __ldg(np + 8 + k);
+					ref[j] = __float_as_uint(lo.w);
+					float tnx = fmaf(nx ? hi.x : lo.x, rc.idx, rc.cnx), tfx = fmaf(nx ? lo.x : hi.x, rc.idx, rc.cfx);
+					float tny = fmaf(ny ? hi.y : lo.y, rc.idy, rc.cny), tfy = fmaf(ny ? lo.y : hi.y, rc.idy, rc.cfy);
+					float tnz = fmaf(nz ? hi.z : lo.z, rc.idz, rc.cnz), tfz = fmaf(nz ? lo.z : hi.z, rc.idz, rc.cfz);
+					float tn = rtk_fmax(rtk_fmax(tnx, tny), tnz);
+					float tf = rtk_fmin(rtk_fmin(tfx, tfy), tfz);
+					float kn, kf;
+					if (CULL == 1) {
+						kn = rc.kz == 0 ? tnx : (rc.kz == 1 ? tny : tnz);
+						kf = rc.kz == 0 ? tfx : (rc.kz == 1 ? tfy : tfz);
+					} else { kn = tn; kf = tf; }
+					const bool hit = ref[j] != RTK_REF_EMPTY && tn <= tf && kn <= best_t && kf >= rc.min_t;
+					key[j] = kn;
+					if (hit) {
+						hitbits |= 1u << k;
+						// nearest hit child: entry distance with the child number in the low 3 bits
+						// (the reference tags 2 bits the same way, rtk.c:496)
+						ok = rtk_umin(ok, (__float_as_uint(rtk_fmax(tn, 0.0f)) & ~7u) | (uint32_t)k);
+					}
+				}
 				if (STATS) st_nodes++;
 			}
-			// nearest hit child: order-preserving key with the lane number in the low 3 bits
-			// (the reference tags 2 bits the same way, rtk.c:496)
-			uint32_t ok = hit ? ((__float_as_uint(rtk_fmax(tn, 0.0f)) & ~7u) | (uint32_t)c) : 0xffffffffu;
-			uint32_t om = ok;
-			om = rtk_umin(om, __shfl_xor_sync(FULL, om, 1));
-			om = rtk_umin(om, __shfl_xor_sync(FULL, om, 2));
-			om = rtk_umin(om, __shfl_xor_sync(FULL, om, 4));
-			const uint32_t gm = (__ballot_sync(FULL, hit) >> (g * 8)) & 0xffu;
+			uint32_t om = ok, gm = hitbits;
+#pragma unroll
+			for (int o = 1; o < LANES; o <<= 1) {
+				om = rtk_umin(om, __shfl_xor_sync(FULL, om, o));
+				if (CPL > 1) gm |= __shfl_xor_sync(FULL, gm, o);
+			}
+			if (CPL == 1) gm = (__ballot_sync(FULL, hitbits != 0) >> (g * LANES)) & 0xffu;
 			const int cmin = (int)(om & 7u);
-			const uint32_t nref = __shfl_sync(FULL, ref, cmin, 8);
+			uint32_t myref = ref[0];
+#pragma unroll
+			for (int j = 1; j < CPL; j++) if ((cmin & (CPL - 1)) == j) myref = ref[j];
+			const uint32_t nref = __shfl_sync(FULL, myref, cmin / CPL, LANES);
 			if (is_node) {
 				const uint32_t others = gm & ~(1u << cmin);
-				if (hit && c != cmin) {
-					int pos = sp + __popc(others & ((1u << c) - 1u));
-					RTK_STACK_WRITE(pos, make_uint2(__float_as_uint(key), ref));
+#pragma unroll
+				for (int j = 0; j < CPL; j++) {
+					const int k = c * CPL + j;
+					if ((others >> k) & 1u) {
+						int pos = sp + __popc(others & ((1u << k) - 1u));
+						RTK_STACK_WRITE(pos, make_uint2(__float_as_uint(key[j]), ref[j]));
+					}
 				}
 				sp += __popc(others);
 				if (STATS) st_stack = rtk_umax(st_stack, (uint32_t)sp);
@@ -298,7 +286,6 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 			if (is_node) {
 				if (gm) cur_ref = nref;
 				else RTK_STACK_POP();
-				RTK_PREFETCH_CUR();
 			}
 			__syncwarp();
 		}
@@ -324,7 +311,6 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 	}
 #undef RTK_STACK_WRITE
 #undef RTK_STACK_POP
-#undef RTK_PREFETCH_CUR
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@
 
 static __thread char g_err[512];
 static int g_device = -1;
-static int g_sm_count = 0, g_trace_ctas = 0;
+static int g_sm_count = 0, g_trace_ctas = 0, g_trace_lanes = RTK_TRACE_LANES;
 static size_t g_l2_bytes = 0;
 static uint64_t g_next_id = 1;
 
@@ -55,8 +55,14 @@ extern "C" int rtkd_init(int device)
 	CK(cudaGetDeviceProperties(&prop, device));
 	g_sm_count = prop.multiProcessorCount;
 	g_l2_bytes = (size_t)prop.l2CacheSize;
+	{
+		const char *e = getenv("RTK_B200_LANES");          // experiment knob: lanes per ray
+		if (e && (atoi(e) == 8 || atoi(e) == 4 || atoi(e) == 2)) g_trace_lanes = atoi(e);
+	}
 	int ctas = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<1, false>, RTK_TRACE_THREADS, 0));
+	if (g_trace_lanes == 8) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<8, 1, false>, RTK_TRACE_THREADS, 0));
+	else if (g_trace_lanes == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<4, 1, false>, RTK_TRACE_THREADS, 0));
+	else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<2, 1, false>, RTK_TRACE_THREADS, 0));
 	g_trace_ctas = ctas > 0 ? ctas : 1;
 #ifndef RTK_SIMT_EMU
 	{
@@ -450,7 +456,7 @@ static int ensure_scratch(rtkd_scene *s)
 		CK(cudaMalloc((unsigned char**)&s->scratch, 256));
 		CK(cudaMemset(s->scratch, 0, 256));
 	}
-	size_t groups = (size_t)g_sm_count * g_trace_ctas * RTK_GROUPS_PER_CTA;
+	size_t groups = (size_t)g_sm_count * g_trace_ctas * RTK_TRACE_WARPS * (32 / g_trace_lanes);
 	size_t need = (size_t)7 * s->depth + 8;
 	size_t entries = need > RTK_STACK_SMEM ? need - RTK_STACK_SMEM : 0;
 	if (entries < 8) entries = 8;
@@ -484,13 +490,18 @@ extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size
 	size_t ctas = (size_t)g_sm_count * g_trace_ctas;
 	size_t want = (batches + RTK_TRACE_WARPS - 1) / RTK_TRACE_WARPS;
 	unsigned grid = (unsigned)(want < ctas ? want : ctas);
-	if (stats) {
-		if (cull_mode) { RTK_LAUNCH((k_trace<1, true>), grid, RTK_TRACE_THREADS, st, p); }
-		else { RTK_LAUNCH((k_trace<0, true>), grid, RTK_TRACE_THREADS, st, p); }
-	} else {
-		if (cull_mode) { RTK_LAUNCH((k_trace<1, false>), grid, RTK_TRACE_THREADS, st, p); }
-		else { RTK_LAUNCH((k_trace<0, false>), grid, RTK_TRACE_THREADS, st, p); }
-	}
+#define RTKD_TRACE_LAUNCH(L) do { \
+		if (stats) { \
+			if (cull_mode) { RTK_LAUNCH((k_trace<L, 1, true>), grid, RTK_TRACE_THREADS, st, p); } \
+			else { RTK_LAUNCH((k_trace<L, 0, true>), grid, RTK_TRACE_THREADS, st, p); } \
+		} else { \
+			if (cull_mode) { RTK_LAUNCH((k_trace<L, 1, false>), grid, RTK_TRACE_THREADS, st, p); } \
+			else { RTK_LAUNCH((k_trace<L, 0, false>), grid, RTK_TRACE_THREADS, st, p); } \
+		} } while (0)
+	if (g_trace_lanes == 8) RTKD_TRACE_LAUNCH(8);
+	else if (g_trace_lanes == 4) RTKD_TRACE_LAUNCH(4);
+	else RTKD_TRACE_LAUNCH(2);
+#undef RTKD_TRACE_LAUNCH
 	CK_LAUNCH();
 	if (stats) {
 		unsigned long long h[8];

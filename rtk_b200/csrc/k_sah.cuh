@@ -134,7 +134,7 @@ RTK_DEV rtk_sah_choice rtk_sah_sweep_warp(const uint32_t *bins, float4 plo, floa
 			float rx = r[3] - r[0], ry = r[4] - r[1], rz = r[5] - r[2];
 			float area_l = 2.0f * (lx * ly + ly * lz + lz * lx);                // rtk.c:729-733
 			float area_r = 2.0f * (rx * ry + ry * rz + rz * rx);
-			float cost_l = (float)((nl + 7u) / 8u), cost_r = (float)((nr + 7u) / 8u);  // rtk.c:934-935, 8-wide
+			float cost_l = (float)((nl + RTK_LEAF_MAX - 1u) / RTK_LEAF_MAX), cost_r = (float)((nr + RTK_LEAF_MAX - 1u) / RTK_LEAF_MAX);  // rtk.c:934-935
 			float cost = 1.0f + (area_l * cost_l + area_r * cost_r) * rcp_parent;     // rtk.c:936, split cost 1
 			if (cost < best_cost) {
 				best_cost = cost; best_axis = axis; best_nl = nl;

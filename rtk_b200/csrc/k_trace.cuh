@@ -29,7 +29,9 @@
 #define RTK_TRACE_WARPS 8
 #define RTK_TRACE_THREADS (RTK_TRACE_WARPS * 32)
 #define RTK_GROUPS_PER_CTA_MAX (RTK_TRACE_WARPS * 16)   // 2 lanes per ray
+#ifndef RTK_STACK_SMEM
 #define RTK_STACK_SMEM 16
+#endif
 #define RTK_RAY_BATCH 32
 #ifndef RTK_TRACE_MINB
 #define RTK_TRACE_MINB 4                 // resident CTAs per SM the register allocation must allow

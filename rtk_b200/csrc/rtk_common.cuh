@@ -40,7 +40,9 @@
 // ---------------------------------------------------------------------------------------------
 
 #define RTK_WIDE 8                       // children per node == lanes per ray
-#define RTK_LEAF_MAX 8                   // triangles per leaf (one per lane)
+#ifndef RTK_LEAF_MAX
+#define RTK_LEAF_MAX 8                   // triangles per leaf (<= 8: the leaf reference keeps count-1 in 3 bits)
+#endif
 #define RTK_REF_EMPTY 0xffffffffu
 #define RTK_REF_LEAF 0x80000000u
 

@@ -233,26 +233,43 @@ def main():
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
     d_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1, 32)).cuda()
-    d_h16 = torch.zeros((n, 16), dtype=torch.uint8, device="cuda")
+    # compact hits are double buffered so that, for N > 1, the NCCL gather of step k runs on the
+    # communication stream while step k+1 traces into the other buffer
+    d_h16s = [torch.zeros((n, 16), dtype=torch.uint8, device="cuda") for _ in range(2 if world > 1 else 1)]
+    d_h16 = d_h16s[0]
     d_hits = torch.zeros((n, 68), dtype=torch.uint8, device="cuda")
     d_mask = torch.zeros((n,), dtype=torch.uint8, device="cuda")
-    gather_list = None
-    if world > 1:
-        gather_list = [torch.empty_like(d_h16) for _ in range(world)] if rank == 0 else None
+    gather_lists = [None, None]
+    if world > 1 and rank == 0:
+        gather_lists = [[torch.empty_like(d_h16) for _ in range(world)] for _ in range(2)]
+    pending = [None, None]
+    counter = [0]
 
     def step(ev=None, exchange=True):
+        i = counter[0] & 1 if (world > 1 and exchange) else 0
+        if pending[i] is not None:
+            pending[i].wait()                # the buffer's previous gather must have drained
+            pending[i] = None
+        h16 = d_h16s[i]
         if ev:
             ev[0].record(stream)
-        rc = lib.rtk_trace_rays_compact_device(sc.ptr, d_rays.data_ptr(), d_h16.data_ptr(), n, sh)
+        rc = lib.rtk_trace_rays_compact_device(sc.ptr, d_rays.data_ptr(), h16.data_ptr(), n, sh)
         if ev:
             ev[1].record(stream)
-        rc |= lib.rtk_resolve_hits_device(sc.ptr, d_h16.data_ptr(), d_hits.data_ptr(), d_mask.data_ptr(), n, sh)
+        rc |= lib.rtk_resolve_hits_device(sc.ptr, h16.data_ptr(), d_hits.data_ptr(), d_mask.data_ptr(), n, sh)
         if ev:
             ev[2].record(stream)
         if rc:
             raise RuntimeError(lib.last_error())
         if world > 1 and exchange:
-            dist.gather(d_h16, gather_list, dst=0)
+            pending[i] = dist.gather(h16, gather_lists[i], dst=0, async_op=True)
+            counter[0] += 1
+
+    def drain():
+        for i in range(2):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     # ---- parity self-check against the CPU oracle (outside the timed region) -------------------
     parity = None
@@ -292,6 +309,7 @@ def main():
     sampler.start()
     for _ in range(args.warmup):
         step()
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -302,6 +320,7 @@ def main():
     e_start.record(stream)
     for i in range(args.steps):
         step(evs[i])
+    drain()                                  # the last gathers are inside the timed region
     e_end.record(stream)
     torch.cuda.synchronize()
     if world > 1:

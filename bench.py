@@ -43,7 +43,22 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def gen_rays(scene, n, rank=0):
+WORKLOADS = {
+    # name: (scene config, default rays per GPU, description)
+    "C3": ("C3", FULL_RAYS, "C3: 1M-triangle procedural terrain (1001x501 value-noise heightfield), "
+                            "16777216 incoherent diffuse-bounce rays per GPU"),
+    "C2": ("C2", 2_073_600, "C2: 1M-triangle random soup, 1920x1080 coherent primary rays per GPU"),
+    "C4": ("C4", 67_108_864, "C4: 10M-triangle procedural terrain in 2 meshes (2501x2001 vertices), 67108864 mixed rays "
+                             "per GPU (thirds of coherent primary / diffuse bounce / short segments, 64Ki blocks)"),
+}
+
+
+def gen_rays(scene, n, rank=0, workload="C3"):
+    if workload == "C2":
+        r = scenes.soup_primary_rays()
+        return np.ascontiguousarray(np.resize(r, n))
+    if workload == "C4":
+        return scenes.mixed_rays(scene, n, seed=0xD4 + 0x1000 * rank)
     out = np.empty(n, dtype=scenes.RAY_DTYPE)
     step = 1 << 21
     for lo in range(0, n, step):
@@ -163,7 +178,8 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=int, default=FULL_RAYS)
+    ap.add_argument("--rays", type=int, default=0, help="rays per GPU (default: the workload's own count)")
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS), help="BASELINE.json config; C3 is the headline")
     ap.add_argument("--scale", type=float, default=1.0, help="triangle-count scale of the terrain (1.0 = 1M)")
     ap.add_argument("--ref-sample", type=int, default=1 << 22)
     ap.add_argument("--cpu-sample", type=int, default=1 << 22)
@@ -180,20 +196,22 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
-    workload = {"workload": "C3: 1M-triangle procedural terrain (1001x501 value-noise heightfield), "
-                            "16777216 incoherent diffuse-bounce rays per GPU",
+    cfg_name, default_rays, cfg_text = WORKLOADS[args.workload]
+    if args.rays <= 0:
+        args.rays = default_rays
+    workload = {"workload": cfg_text,
                 "triangles": None, "rays_per_gpu": args.rays, "ray_bytes": 32, "hit_bytes": 68,
-                "l2_policy": "ray and hit buffers (0.5 GB in, 1.4 GB out per step) are far larger than the "
+                "l2_policy": "ray and hit buffers (%.2f GB in, %.2f GB out per step) are far larger than the "
                              "126 MB L2 and stream through it every step; the scene (BVH + triangles) is the "
-                             "reused working set",
+                             "reused working set" % (32 * args.rays / 1e9, 85 * args.rays / 1e9),
                 "parallelism": f"rays sharded over {world} GPU(s), scene replicated"}
 
     if args.impl == "reference":
         if rank != 0:
             return 0
-        scene = scenes.config_scene("C3", args.scale)
+        scene = scenes.config_scene(cfg_name, args.scale)
         workload["triangles"] = int(len(scene["tris"]))
-        rays = gen_rays(scene, min(args.rays, args.ref_sample))
+        rays = gen_rays(scene, min(args.rays, args.ref_sample), 0, args.workload)
         workload["rays_per_gpu"] = args.rays
         run_reference(args, workload, scene, rays)
         return 0
@@ -212,11 +230,11 @@ def main():
     lib.rtk_cuda_set_cull_mode(args.cull)
     lib.rtk_cuda_set_build_mode(api.RTK_CUDA_BUILD_SAH if args.build_mode == "sah" else api.RTK_CUDA_BUILD_LBVH)
 
-    scene = scenes.config_scene("C3", args.scale)
+    scene = scenes.config_scene(cfg_name, args.scale)
     ntris = int(len(scene["tris"]))
     workload["triangles"] = ntris
     n = args.rays
-    rays_np = gen_rays(scene, n, rank)
+    rays_np = gen_rays(scene, n, rank, args.workload)
 
     # ---- build: end to end from host buffers, then device-only rebuilds ------------------------
     t0 = time.perf_counter()
@@ -381,15 +399,16 @@ def main():
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one k_trace launch on this very
                      # workload (profiles/r1_k_trace_raw.csv); unknown for any other workload
-                     "traffic": 1.877e9 if (n == FULL_RAYS and args.scale == 1.0 and args.build_mode == "sah") else None,
+                     "traffic": 1.877e9 if (args.workload == "C3" and n == FULL_RAYS and args.scale == 1.0 and args.build_mode == "sah") else None,
                      "traffic_unit": "bytes per launch (ncu, profiles/r1_k_trace_raw.csv)",
                      "peak_source": peak_src,
                      "bytes_per_ray": bytes_per_ray,
                      "per_ray": {"wide_node_visits": nodes_per_ray, "leaf_visits": leaves_per_ray,
                                  "triangle_tests": tris_per_ray, "hit_fraction": hit_frac},
                      "note": "algorithmic bytes = 32 (ray) + 16 (compact hit) + 256 per wide-node visit + 48 per "
-                             "triangle tested, counted by the instrumented kernel on the first 2^20 rays; the 1M-"
-                             "triangle scene (about 107 MB) is L2-resident, so DRAM traffic is far below this"},
+                             "triangle tested, counted by the instrumented kernel on the first 2^20 rays; the scene "
+                             "is %.0f MB against a 126 MB L2, so DRAM traffic is %s this"
+                             % (info.device_bytes / 1e6, "far below" if info.device_bytes < 120e6 else "a fraction of")},
         "build": {"metric": "BVH build Mtris/s", "value": ntris / (build_dev_ms * 1e-3) / 1e6, "unit": "Mtris/s",
                   "device_ms": build_dev_ms, "mode": args.build_mode,
                   "e2e": {"value": ntris / build_e2e_s / 1e6, "unit": "Mtris/s", "ms": build_e2e_s * 1e3,

@@ -36,6 +36,12 @@
 #ifndef RTK_TRACE_MINB
 #define RTK_TRACE_MINB 4                 // resident CTAs per SM the register allocation must allow
 #endif
+#ifndef RTK_TRI_PERIOD
+#define RTK_TRI_PERIOD 3                 // the leaf phase runs every RTK_TRI_PERIOD-th iteration (or when no ray has node work)
+#endif
+#ifndef RTK_ASSIGN_MIN
+#define RTK_ASSIGN_MIN 3                 // idle rays of a warp wait for new work until this many are idle
+#endif
 #ifndef RTK_TRACE_LANES
 #define RTK_TRACE_LANES 2                // default lanes per ray (8, 4 or 2); RTK_B200_LANES overrides at run time
 #endif
@@ -114,6 +120,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 	uint32_t cur_ref = RTK_REF_EMPTY;
 	int sp = 0;
 	uint32_t st_nodes = 0, st_leaves = 0, st_tris = 0, st_stack = 0;
+	int tri_tick = 0;
 
 #define RTK_STACK_WRITE(pos, val) do { \
 		int _p = (pos); \
@@ -136,6 +143,11 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 	for (;;) {
 		// ---- (1) hand rays to idle groups --------------------------------------------------
 		uint32_t need_mask = __ballot_sync(FULL, !has_ray && c == 0);
+#if RTK_ASSIGN_MIN > 1
+		// ray setup is serial per ray but costs a warp-wide instruction stream: let finished rays
+		// wait until a few of the warp's rays are idle, then set them up together
+		if (__popc(need_mask) < RTK_ASSIGN_MIN && __popc(need_mask) < GW) need_mask = 0;
+#endif
 		while (need_mask) {
 			uint32_t avail = cur_cnt - cur_pos;
 			if (avail == 0) {
@@ -177,7 +189,19 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 
 		// ---- (2) leaf: the group tests up to 8 triangles (rtk.c:181-388) ---------------------
 		const bool is_leaf = has_ray && cur_ref != RTK_REF_EMPTY && rtk_ref_is_leaf(cur_ref);
+#if RTK_TRI_PERIOD > 1
+		// Both phases cost a full warp instruction stream however few of the warp's rays take part.
+		// With 16 rays per warp about 1 in 5 is at a leaf at any time, so the leaf phase is run only
+		// every RTK_TRI_PERIOD-th iteration: rays that reach a leaf wait (idle lanes, no issue slots,
+		// no speculative traversal) and are then tested together.  It still runs at once when no
+		// ray of the warp has node work.
+		const bool any_leaf = __any_sync(FULL, is_leaf);
+		const bool any_node0 = __any_sync(FULL, has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref));
+		if (any_leaf && (!any_node0 || ++tri_tick >= RTK_TRI_PERIOD)) {
+			tri_tick = 0;
+#else
 		if (__any_sync(FULL, is_leaf)) {
+#endif
 			float t = INFINITY, u = 0.0f, v = 0.0f;
 			uint32_t prim = RTK_MISS;
 			if (is_leaf) {

@@ -21,6 +21,7 @@ def build(force=False, verbose=False):
     dev_o, host_o = os.path.join(bdir, "rtk_device_emu.o"), os.path.join(bdir, "rtk_host_emu.o")
     cmds = [
         ["g++", "-x", "c++", "-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-mfma", "-w",
+         *os.environ.get("RTK_EMU_DEFINES", "").split(),
          "-DRTK_SIMT_EMU=1", "-DSIMT_IMPL=1", "-include", os.path.join(HERE, "simt.h"),
          "-c", os.path.join(CSRC, "rtk_device.cu"), "-o", dev_o],
         ["gcc", "-O2", "-g", "-fPIC", "-std=gnu11", "-c", os.path.join(CSRC, "rtk_host.c"), "-o", host_o],

@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-rays", type=int, default=1024)
     ap.add_argument("--cull", type=int, default=1, help="1 provable dominant-axis culling (default), 0 full-box culling")
+    ap.add_argument("--presort", action="store_true", help="experiment: order the rays by origin cell + direction octant on the host first")
     ap.add_argument("--lib", default=None, help="experiment: alternative build of librtk_b200 (same ABI)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -235,6 +236,21 @@ def main():
     workload["triangles"] = ntris
     n = args.rays
     rays_np = gen_rays(scene, n, rank, args.workload)
+    if args.presort:
+        lo = scene["tris"].reshape(-1, 3).min(0)
+        ext = scene["tris"].reshape(-1, 3).max(0) - lo
+        q = np.clip(((rays_np["o"] - lo) / ext * 1023).astype(np.int64), 0, 1023)
+
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            v = (v | (v << 2)) & 0x09249249
+            return v
+        key = (spread(q[:, 0]) << 2) | (spread(q[:, 1]) << 1) | spread(q[:, 2])
+        octant = ((rays_np["d"][:, 0] < 0).astype(np.int64) | ((rays_np["d"][:, 1] < 0).astype(np.int64) << 1) |
+                  ((rays_np["d"][:, 2] < 0).astype(np.int64) << 2))
+        rays_np = np.ascontiguousarray(rays_np[np.argsort((key << 3) | octant, kind="stable")])
 
     # ---- build: end to end from host buffers, then device-only rebuilds ------------------------
     t0 = time.perf_counter()

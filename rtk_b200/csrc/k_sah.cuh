@@ -85,6 +85,42 @@ RTK_DEV void rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, f
 	}
 }
 
+// Warp-cooperative variant (all 32 lanes call it; `valid` masks lanes without a triangle).  In
+// the upper levels a warp's 32 Morton-neighbours almost always fall into the same bin on every
+// axis: then the warp reduces its boxes with shuffles and one lane issues the 21 atomics instead
+// of 32 lanes fighting over the same 21 addresses.
+RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
+{
+	const uint32_t FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	int b0 = rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x), b1 = rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y), b2 = rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z);
+	uint32_t code = valid ? (uint32_t)(b0 | (b1 << 8) | (b2 << 16)) : 0xffffffffu;
+	uint32_t vm = __ballot_sync(FULL, valid);
+	if (vm == 0) return;
+	uint32_t first_code = __shfl_sync(FULL, code, __ffs(vm) - 1);
+	bool uniform = __all_sync(FULL, !valid || code == first_code);
+	if (!uniform) {
+		if (valid) rtk_sah_bin_add(bins, lo, hi, nlo, nhi);
+		return;
+	}
+	float v[6] = { valid ? lo.x : +RTK_INF_F, valid ? lo.y : +RTK_INF_F, valid ? lo.z : +RTK_INF_F,
+	               valid ? hi.x : -RTK_INF_F, valid ? hi.y : -RTK_INF_F, valid ? hi.z : -RTK_INF_F };
+	for (int o = 16; o > 0; o >>= 1) {
+		for (int k = 0; k < 3; k++) v[k] = rtk_fmin(v[k], __shfl_xor_sync(FULL, v[k], o));
+		for (int k = 3; k < 6; k++) v[k] = rtk_fmax(v[k], __shfl_xor_sync(FULL, v[k], o));
+	}
+	if (lane == 0) {
+		int b[3] = { (int)(first_code & 255u), (int)((first_code >> 8) & 255u), (int)((first_code >> 16) & 255u) };
+		uint32_t cnt = (uint32_t)__popc(vm);
+		for (int a = 0; a < 3; a++) {
+			uint32_t *p = bins + (a * RTK_SAH_BINS + b[a]) * RTK_SAH_BINWORDS;
+			atomicMin(p + 0, rtk_f2ord(v[0])); atomicMin(p + 1, rtk_f2ord(v[1])); atomicMin(p + 2, rtk_f2ord(v[2]));
+			atomicMax(p + 3, rtk_f2ord(v[3])); atomicMax(p + 4, rtk_f2ord(v[4])); atomicMax(p + 5, rtk_f2ord(v[5]));
+			atomicAdd(p + 6, cnt);
+		}
+	}
+}
+
 struct rtk_sah_choice {
 	int axis, bin;               // axis < 0: no valid split
 	uint32_t n_left;
@@ -271,9 +307,13 @@ __global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, uint32_t n_ac
 	const uint32_t end = rtk_umin(begin + RTK_SAH_CHUNK, last + 1);
 	const float4 nlo = s.blo[node], nhi = s.bhi[node];
 	const uint32_t *idx = src_buf ? s.idx1 : s.idx0;
-	for (uint32_t p = begin + threadIdx.x; p < end; p += 256) {
-		uint32_t j = idx[p];
-		rtk_sah_bin_add(s_bins, s.pb[2ull * j], s.pb[2ull * j + 1], nlo, nhi);
+	for (uint32_t base = begin; base < end; base += 256) {           // warp-uniform trip count
+		uint32_t p = base + threadIdx.x;
+		bool valid = p < end;
+		uint32_t j = valid ? idx[p] : 0;
+		float4 lo = make_float4(0, 0, 0, 0), hi = make_float4(0, 0, 0, 0);
+		if (valid) { lo = s.pb[2ull * j]; hi = s.pb[2ull * j + 1]; }
+		rtk_sah_bin_add_warp(s_bins, lo, hi, nlo, nhi, valid);
 	}
 	__syncthreads();
 	uint32_t *g = s.bins + (size_t)a * RTK_SAH_NODEBINS;
@@ -392,19 +432,105 @@ __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, uint32_
 // ---------------------------------------------------------------------------------------------
 
 #define RTK_SAH_SMALL_THREADS 128
+#define RTK_SAH_SMALL_WARPS (RTK_SAH_SMALL_THREADS / 32)
+#define RTK_SAH_WARP_MAX 64           // subtrees of at most this many triangles are finished by one warp
 
 struct rtk_sah_task { uint32_t node, begin, count, depth; float lo[3], hi[3]; };
 
+// split one node whose permutation range lives in shared memory; `nthreads` threads with ids
+// `tid` cooperate (a whole CTA with __syncthreads, or one warp with __syncwarp), `wl/wr` are
+// nthreads/32 words of scratch.  Returns the two child tasks through a and b (valid in every thread).
+template <bool WARP>
+RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *bins, const float4 *s_lo, const float4 *s_hi,
+                                  unsigned short *perm0, unsigned short *perm1, rtk_sah_choice *s_choice, uint32_t *s_child,
+                                  uint32_t *wl, uint32_t *wr, int tid, int nthreads, rtk_sah_task &a, rtk_sah_task &b)
+{
+#define RTK_SYNC() do { if (WARP) __syncwarp(); else __syncthreads(); } while (0)
+	const int lane = tid & 31, warp = tid >> 5;
+	const float4 nlo = make_float4(t.lo[0], t.lo[1], t.lo[2], 0.0f), nhi = make_float4(t.hi[0], t.hi[1], t.hi[2], 0.0f);
+	rtk_sah_bins_clear(bins, tid, nthreads);
+	RTK_SYNC();
+	for (uint32_t i = tid; i < t.count; i += nthreads) {
+		uint32_t k = perm0[t.begin + i];
+		rtk_sah_bin_add(bins, s_lo[k], s_hi[k], nlo, nhi);
+	}
+	RTK_SYNC();
+	if (warp == 0) {
+		rtk_sah_choice c = rtk_sah_sweep_warp(bins, nlo, nhi, t.count);
+		if (rtk_sah_must_halve(t.count, t.depth) && c.axis >= 0) {
+			c.axis = -1; c.n_left = t.count / 2;
+			for (int k = 0; k < 3; k++) { c.llo[k] = c.rlo[k] = t.lo[k]; c.lhi[k] = c.rhi[k] = t.hi[k]; }
+		}
+		if (lane == 0) {
+			uint32_t ch;
+			rtk_sah_emit_children(s, t.node, c, t.depth, -1, ch);
+			*s_choice = c; *s_child = ch;
+		}
+	}
+	RTK_SYNC();
+	const rtk_sah_choice c = *s_choice;
+	const uint32_t child = *s_child;
+	// stable partition of perm0[begin, begin+count) into perm1, then copy back
+	const float amin = c.axis <= 0 ? nlo.x : (c.axis == 1 ? nlo.y : nlo.z);
+	const float amax = c.axis <= 0 ? nhi.x : (c.axis == 1 ? nhi.y : nhi.z);
+	uint32_t run_l = 0, run_r = 0;
+	for (uint32_t base = 0; base < t.count; base += nthreads) {
+		uint32_t i = base + tid;
+		bool valid = i < t.count;
+		unsigned short k = valid ? perm0[t.begin + i] : (unsigned short)0;
+		bool goes_left = false;
+		if (valid) {
+			if (c.axis < 0) goes_left = i < c.n_left;
+			else {
+				float l = c.axis == 0 ? s_lo[k].x : (c.axis == 1 ? s_lo[k].y : s_lo[k].z);
+				float h = c.axis == 0 ? s_hi[k].x : (c.axis == 1 ? s_hi[k].y : s_hi[k].z);
+				goes_left = rtk_sah_bin(l, h, amin, amax) <= c.bin;
+			}
+		}
+		uint32_t ml = __ballot_sync(0xffffffffu, valid && goes_left);
+		uint32_t mr = __ballot_sync(0xffffffffu, valid && !goes_left);
+		uint32_t offl = run_l, offr = run_r, totl, totr;
+		if (WARP) { totl = __popc(ml); totr = __popc(mr); }
+		else {
+			if (lane == 0) { wl[warp] = __popc(ml); wr[warp] = __popc(mr); }
+			__syncthreads();
+			totl = 0; totr = 0;
+			for (int w = 0; w < nthreads / 32; w++) {
+				if (w < warp) { offl += wl[w]; offr += wr[w]; }
+				totl += wl[w]; totr += wr[w];
+			}
+		}
+		if (valid) {
+			uint32_t lt = (1u << lane) - 1u;
+			uint32_t pos = goes_left ? offl + __popc(ml & lt) : c.n_left + offr + __popc(mr & lt);
+			perm1[t.begin + pos] = k;
+		}
+		run_l += totl; run_r += totr;
+		RTK_SYNC();
+	}
+	for (uint32_t i = tid; i < t.count; i += nthreads) perm0[t.begin + i] = perm1[t.begin + i];
+	a.node = child; a.begin = t.begin; a.count = c.n_left; a.depth = t.depth + 1;
+	b.node = child + 1; b.begin = t.begin + c.n_left; b.count = t.count - c.n_left; b.depth = t.depth + 1;
+	for (int k = 0; k < 3; k++) { a.lo[k] = c.llo[k]; a.hi[k] = c.lhi[k]; b.lo[k] = c.rlo[k]; b.hi[k] = c.rhi[k]; }
+	RTK_SYNC();
+#undef RTK_SYNC
+}
+
+// One CTA per small subtree.  Phase 1: the whole CTA splits nodes above RTK_SAH_WARP_MAX
+// triangles; phase 2: the warps take the remaining subtrees from a shared queue and finish them
+// independently with warp-level synchronisation only.
 __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s, uint32_t n_small)
 {
 	__shared__ float4 s_lo[RTK_SAH_SMALL], s_hi[RTK_SAH_SMALL];
 	__shared__ uint32_t s_gid[RTK_SAH_SMALL];
 	__shared__ unsigned short s_perm[2][RTK_SAH_SMALL];
-	__shared__ uint32_t s_bins[RTK_SAH_NODEBINS];
-	__shared__ rtk_sah_task s_stack[24];
-	__shared__ int s_sp;
-	__shared__ rtk_sah_choice s_choice;
-	__shared__ uint32_t s_child, s_wl[4], s_wr[4];
+	__shared__ uint32_t s_bins[1 + RTK_SAH_SMALL_WARPS][RTK_SAH_NODEBINS];
+	__shared__ rtk_sah_task s_stack[16];
+	__shared__ rtk_sah_task s_wq[64];
+	__shared__ rtk_sah_task s_wstack[RTK_SAH_SMALL_WARPS][12];
+	__shared__ int s_sp, s_nwq, s_wq_next;
+	__shared__ rtk_sah_choice s_choice[1 + RTK_SAH_SMALL_WARPS];
+	__shared__ uint32_t s_child[1 + RTK_SAH_SMALL_WARPS], s_wl[RTK_SAH_SMALL_WARPS], s_wr[RTK_SAH_SMALL_WARPS];
 
 	if (blockIdx.x >= n_small) return;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -425,78 +551,26 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 		t.node = root; t.begin = 0; t.count = total; t.depth = s.ndepth[root];
 		t.lo[0] = lo.x; t.lo[1] = lo.y; t.lo[2] = lo.z; t.hi[0] = hi.x; t.hi[1] = hi.y; t.hi[2] = hi.z;
 		s_stack[0] = t;
-		s_sp = 1;
+		s_sp = 1; s_nwq = 0; s_wq_next = 0;
 	}
 	__syncthreads();
 
+	// ---- phase 1: whole CTA ----------------------------------------------------------------
 	while (s_sp > 0) {
 		const rtk_sah_task t = s_stack[s_sp - 1];
 		__syncthreads();
 		if (tid == 0) s_sp--;
-		if (t.count <= RTK_LEAF_MAX) { __syncthreads(); continue; }         // a leaf: nothing to do
-		const float4 nlo = make_float4(t.lo[0], t.lo[1], t.lo[2], 0.0f), nhi = make_float4(t.hi[0], t.hi[1], t.hi[2], 0.0f);
-		rtk_sah_bins_clear(s_bins, tid, RTK_SAH_SMALL_THREADS);
-		__syncthreads();
-		for (uint32_t i = tid; i < t.count; i += RTK_SAH_SMALL_THREADS) {
-			uint32_t k = s_perm[0][t.begin + i];
-			rtk_sah_bin_add(s_bins, s_lo[k], s_hi[k], nlo, nhi);
-		}
-		__syncthreads();
-		if (warp == 0) {
-			rtk_sah_choice c = rtk_sah_sweep_warp(s_bins, nlo, nhi, t.count);
-			if (rtk_sah_must_halve(t.count, t.depth) && c.axis >= 0) {
-				c.axis = -1; c.n_left = t.count / 2;
-				for (int k = 0; k < 3; k++) { c.llo[k] = c.rlo[k] = t.lo[k]; c.lhi[k] = c.rhi[k] = t.hi[k]; }
-			}
-			if (lane == 0) {
-				uint32_t ch;
-				rtk_sah_emit_children(s, t.node, c, t.depth, -1, ch);
-				s_choice = c; s_child = ch;
-			}
-		}
-		__syncthreads();
-		const rtk_sah_choice c = s_choice;
-		// stable partition of s_perm[0][begin, begin+count) into s_perm[1], then copy back
-		const float amin = c.axis <= 0 ? nlo.x : (c.axis == 1 ? nlo.y : nlo.z);
-		const float amax = c.axis <= 0 ? nhi.x : (c.axis == 1 ? nhi.y : nhi.z);
-		uint32_t run_l = 0, run_r = 0;
-		for (uint32_t base = 0; base < t.count; base += RTK_SAH_SMALL_THREADS) {
-			uint32_t i = base + tid;
-			bool valid = i < t.count;
-			unsigned short k = valid ? s_perm[0][t.begin + i] : (unsigned short)0;
-			bool goes_left = false;
-			if (valid) {
-				if (c.axis < 0) goes_left = i < c.n_left;
-				else {
-					float l = c.axis == 0 ? s_lo[k].x : (c.axis == 1 ? s_lo[k].y : s_lo[k].z);
-					float h = c.axis == 0 ? s_hi[k].x : (c.axis == 1 ? s_hi[k].y : s_hi[k].z);
-					goes_left = rtk_sah_bin(l, h, amin, amax) <= c.bin;
-				}
-			}
-			uint32_t ml = __ballot_sync(0xffffffffu, valid && goes_left);
-			uint32_t mr = __ballot_sync(0xffffffffu, valid && !goes_left);
-			if (lane == 0) { s_wl[warp] = __popc(ml); s_wr[warp] = __popc(mr); }
+		if (t.count <= RTK_LEAF_MAX) { __syncthreads(); continue; }          // a leaf: nothing to do
+		if (t.count <= RTK_SAH_WARP_MAX) {                                    // left to one warp
+			if (tid == 0) s_wq[s_nwq++] = t;
 			__syncthreads();
-			uint32_t offl = run_l, offr = run_r, totl = 0, totr = 0;
-			for (int w = 0; w < RTK_SAH_SMALL_THREADS / 32; w++) {
-				if (w < warp) { offl += s_wl[w]; offr += s_wr[w]; }
-				totl += s_wl[w]; totr += s_wr[w];
-			}
-			if (valid) {
-				uint32_t lt = (1u << lane) - 1u;
-				uint32_t pos = goes_left ? offl + __popc(ml & lt) : c.n_left + offr + __popc(mr & lt);
-				s_perm[1][t.begin + pos] = k;
-			}
-			run_l += totl; run_r += totr;
-			__syncthreads();
+			continue;
 		}
-		for (uint32_t i = tid; i < t.count; i += RTK_SAH_SMALL_THREADS) s_perm[0][t.begin + i] = s_perm[1][t.begin + i];
+		rtk_sah_task a, b;
+		rtk_sah_split_shared<false>(s, t, s_bins[0], s_lo, s_hi, s_perm[0], s_perm[1], &s_choice[0], &s_child[0],
+		                            s_wl, s_wr, tid, RTK_SAH_SMALL_THREADS, a, b);
 		if (tid == 0) {
-			// push the larger child first so that the stack stays logarithmic
-			rtk_sah_task a, b;
-			a.node = s_child; a.begin = t.begin; a.count = c.n_left; a.depth = t.depth + 1;
-			b.node = s_child + 1; b.begin = t.begin + c.n_left; b.count = t.count - c.n_left; b.depth = t.depth + 1;
-			for (int k = 0; k < 3; k++) { a.lo[k] = c.llo[k]; a.hi[k] = c.lhi[k]; b.lo[k] = c.rlo[k]; b.hi[k] = c.rhi[k]; }
+			// the larger child is pushed first so that the stack stays logarithmic
 			int sp = s_sp;
 			if (a.count >= b.count) { s_stack[sp] = a; s_stack[sp + 1] = b; }
 			else { s_stack[sp] = b; s_stack[sp + 1] = a; }
@@ -504,6 +578,36 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 		}
 		__syncthreads();
 	}
+	__syncthreads();
+
+	// ---- phase 2: one warp per remaining subtree --------------------------------------------
+	const int nwq = s_nwq;
+	for (;;) {
+		int q = 0;
+		if (lane == 0) q = atomicAdd(&s_wq_next, 1);
+		q = __shfl_sync(0xffffffffu, q, 0);
+		if (q >= nwq) break;
+		rtk_sah_task *st = s_wstack[warp];
+		int sp = 1;
+		if (lane == 0) st[0] = s_wq[q];
+		__syncwarp();
+		while (sp > 0) {
+			const rtk_sah_task t = st[sp - 1];
+			__syncwarp();
+			sp--;
+			if (t.count <= RTK_LEAF_MAX) continue;
+			rtk_sah_task a, b;
+			rtk_sah_split_shared<true>(s, t, s_bins[1 + warp], s_lo, s_hi, s_perm[0], s_perm[1], &s_choice[1 + warp], &s_child[1 + warp],
+			                           NULL, NULL, lane, 32, a, b);
+			if (lane == 0) {
+				if (a.count >= b.count) { st[sp] = a; st[sp + 1] = b; }
+				else { st[sp] = b; st[sp + 1] = a; }
+			}
+			sp += 2;
+			__syncwarp();
+		}
+	}
+	__syncthreads();
 	for (uint32_t i = tid; i < total; i += RTK_SAH_SMALL_THREADS) s.idx_final[gfirst + i] = s_gid[s_perm[0][i]];
 }
 

@@ -607,9 +607,23 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 		d_count = (unsigned long long*)((unsigned char*)s->scratch + 128);
 		if (cudaMemset(d_count, 0, sizeof(unsigned long long)) != cudaSuccess) rc = RTKD_ERR_CUDA;
 	}
-	// The traversal scratch (ray cursor, overflow slab) belongs to the scene, so the kernels of
-	// consecutive chunks are serialised on purpose: chunk k+1's kernels wait for chunk k's, while
-	// its H2D copy and chunk k's D2H copy run beside them (pinned caller buffers overlap fully).
+	// Pinned (page-locked) caller buffers are visible to the device under UVA: the expansion kernel
+	// then writes rtk_hit rows and mask bytes straight into the caller's arrays.  Only the rows of
+	// rays that hit cross PCIe and rows of misses stay untouched, as in the reference.  Pageable
+	// buffers go through device staging and a full copy (rows of misses arrive zero-filled).
+	uint32_t *direct_hits = NULL;
+	unsigned char *direct_mask = NULL;
+	{
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, hits) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+			direct_hits = (uint32_t*)at.devicePointer;
+		if (mask && cudaPointerGetAttributes(&at, mask) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+			direct_mask = (unsigned char*)at.devicePointer;
+		cudaGetLastError();                     // a pageable pointer may leave a sticky-free error code
+	}
+	// The traversal scratch (ray cursor, overflow slab) belongs to the scene, so the TRAVERSALS of
+	// consecutive chunks are serialised on purpose; the H2D copy of chunk k+1, the hit expansion and
+	// the D2H traffic of chunk k run beside them on the other stream.
 	const size_t chunk = G.chunk;
 	const size_t nchunks = (n + chunk - 1) / chunk;
 	for (size_t ci = 0; ci < nchunks && rc == RTKD_OK; ci++) {
@@ -617,20 +631,21 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 		size_t off = ci * chunk, cnt = n - off < chunk ? n - off : chunk;
 		cudaStream_t q = G.st[k];
 		if (cudaMemcpyAsync(G.d_rays[k], (const char*)rays + 32 * off, 32 * cnt, cudaMemcpyHostToDevice, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
-		// rows of rays that miss come back zero-filled (see rtk_cuda.h)
-		if (cudaMemsetAsync(G.d_hits[k], 0, 68 * cnt, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
+		if (!direct_hits && cudaMemsetAsync(G.d_hits[k], 0, 68 * cnt, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
 		if (ci > 0) cudaStreamWaitEvent(q, G.done[k ^ 1], 0);
 		rc = rtkd_trace(s, G.d_rays[k], G.d_h16[k], cnt, 1, NULL, q);
 		if (rc) break;
+		cudaEventRecord(G.done[k], q);
 		{
 			rtkd_arrays a;
 			fill_arrays(s, a);
+			uint32_t *oh = direct_hits ? direct_hits + 17 * off : G.d_hits[k];
+			unsigned char *om = mask ? (direct_mask ? direct_mask + off : G.d_mask[k]) : G.d_mask[k];
 			RTK_LAUNCH(k_resolve, (unsigned)((cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, q,
-			           a, (const float4*)G.d_h16[k], G.d_hits[k], G.d_mask[k], (uint32_t)cnt, d_count);
+			           a, (const float4*)G.d_h16[k], oh, om, (uint32_t)cnt, d_count);
 		}
-		cudaEventRecord(G.done[k], q);
-		if (cudaMemcpyAsync((char*)hits + 68 * off, G.d_hits[k], 68 * cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
-		if (mask && cudaMemcpyAsync(mask + off, G.d_mask[k], cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
+		if (!direct_hits && cudaMemcpyAsync((char*)hits + 68 * off, G.d_hits[k], 68 * cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
+		if (mask && !direct_mask && cudaMemcpyAsync(mask + off, G.d_mask[k], cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
 	}
 	if (G.ready) {
 		for (int k = 0; k < 2; k++) {

@@ -311,10 +311,10 @@ template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerM
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
 #define cudaFuncAttributePreferredSharedMemoryCarveout 9
-struct cudaPointerAttributes { int type; };
+struct cudaPointerAttributes { int type; void *devicePointer; void *hostPointer; };
 #define cudaMemoryTypeHost 1
 #define cudaMemoryTypeDevice 2
-static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = 0; return cudaSuccess; }
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = 0; a->devicePointer = 0; a->hostPointer = 0; return cudaSuccess; }
 
 // kernel launch: RTK_LAUNCH(kernel, grid, block, stream, args...)
 #define RTK_LAUNCH(kernel, grid, block, stream, ...) \

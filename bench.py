@@ -371,6 +371,21 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
 
+    # ---- occlusion (any-hit) query on the same rays: SURVEY 8(f) N3, reported beside the headline --
+    occ = None
+    if world == 1:
+        d_occ = torch.zeros((n,), dtype=torch.uint8, device="cuda")
+        eo = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for i in range(7):
+            if i == 2:
+                eo[0].record(stream)
+            assert lib.rtk_occluded_rays_device(sc.ptr, d_rays.data_ptr(), d_occ.data_ptr(), n, sh) == 0, lib.last_error()
+        eo[1].record(stream)
+        torch.cuda.synchronize()
+        occ_ms = eo[0].elapsed_time(eo[1]) / 5
+        occ = {"value": n / (occ_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": occ_ms,
+               "agrees_with_closest_hit_mask": bool(torch.equal(d_occ != 0, d_mask != 0))}
+
     # ---- end to end through the host API (pinned host buffers, H2D + D2H inside) ---------------
     e2e = None
     h_rays = torch.from_numpy(rays_np.view(np.uint8).reshape(-1, 32)).pin_memory()
@@ -431,7 +446,7 @@ def main():
                           "api": "rtk_build_scene (host mesh buffers in, first call, includes CUDA context warm-up)"},
                   "wide_nodes": int(info.num_wide_nodes), "leaves": int(info.num_leaves), "depth": int(info.wide_depth),
                   "sah_cost": info.sah_cost, "scene_bytes": int(info.device_bytes)},
-        "parity": parity, "clocks": clocks,
+        "occlusion": occ, "parity": parity, "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
         try:

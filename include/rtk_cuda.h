@@ -105,6 +105,12 @@ int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hi
 int rtk_trace_rays_compact_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream);
 int rtk_resolve_hits_device(const rtk_scene *scene, const void *d_hit16, void *d_hits, void *d_hit_mask, size_t n, void *stream);
 
+/* Occlusion (shadow-ray) query: d_occluded[i] = 1 iff some triangle is hit in
+ * (min_t, max_t), i.e. exactly where the closest-hit query reports a hit; the
+ * traversal stops at the first accepted triangle.  The any-hit half of what
+ * rtk_trace_ray_filter (rtk.h:130, a stub upstream) is for. */
+int rtk_occluded_rays_device(const rtk_scene *scene, const void *d_rays, void *d_occluded, size_t n, void *stream);
+
 /* Exhaustive ray x triangle kernel with the same arithmetic: the GPU-side
  * check used by the parity tests and by the bench's self-check. */
 int rtk_trace_rays_bruteforce_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream);

@@ -125,6 +125,7 @@ SYMBOLS = {
     "rtk_trace_rays_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     "rtk_trace_rays_compact_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_resolve_hits_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
+    "rtk_occluded_rays_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_trace_rays_bruteforce_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_trace_stats_device": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(rtk_cuda_trace_stats), _P]),
     "rtk_cuda_build_scene": (_P, [C.POINTER(rtk_cuda_mesh), C.c_size_t, _P]),

@@ -64,7 +64,9 @@ struct rtkd_trace_args {
 // 8/LANES triangles of the current leaf.  Fewer lanes per ray put more rays in a warp (4, 8, 16),
 // which divides the per-ray serial work (setup, stack, control) by the same factor at the price of
 // more independent loads per instruction.
-template <int LANES, int CULL, bool STATS>
+// ANY = true turns the kernel into the occlusion (shadow-ray) query: a ray ends at the first
+// triangle accepted in (min_t, max_t) and one byte per ray is written instead of a hit record.
+template <int LANES, int CULL, bool STATS, bool ANY = false>
 __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtkd_trace_args p)
 {
 	constexpr int CPL = 8 / LANES;                       // children / triangles per lane
@@ -240,7 +242,8 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 			float wu = __shfl_sync(FULL, u, src, LANES), wv = __shfl_sync(FULL, v, src, LANES);
 			if (is_leaf) {
 				if (wm) { best_t = tmin; best_prim = pmin; best_u = wu; best_v = wv; }
-				RTK_STACK_POP();
+				if (ANY && wm) { sp = 0; cur_ref = RTK_REF_EMPTY; }       // occluded: nothing else matters
+				else RTK_STACK_POP();
 			}
 			__syncwarp();
 		}
@@ -320,9 +323,12 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 		if (has_ray && cur_ref == RTK_REF_EMPTY) {
 			if (c == 0) {
 				const bool got = best_t < ray_max_t;                    // rtk.c:571
-				float4 o = got ? make_float4(best_t, best_u, best_v, __uint_as_float(best_prim))
-				               : make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RTK_MISS));
-				p.out[ray_index] = o;
+				if (ANY) ((unsigned char*)p.out)[ray_index] = got ? 1 : 0;
+				else {
+					float4 o = got ? make_float4(best_t, best_u, best_v, __uint_as_float(best_prim))
+					               : make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RTK_MISS));
+					p.out[ray_index] = o;
+				}
 				if (STATS) {
 					atomicAdd(&p.stats[1], (unsigned long long)(got ? 1 : 0));
 					atomicAdd(&p.stats[2], (unsigned long long)st_nodes);

@@ -474,7 +474,8 @@ extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size
 {
 	if (!n) { if (stats) memset(stats, 0, sizeof(*stats)); return RTKD_OK; }
 	if (n > 0xfffffff0ull) { rtkd_set_error("batch too large (%zu rays); split it", n); return RTKD_ERR_ARGUMENT; }
-	if (((uintptr_t)d_rays & 15) || ((uintptr_t)d_hit16 & 15)) { rtkd_set_error("device ray / hit buffers must be 16-byte aligned"); return RTKD_ERR_ARGUMENT; }
+	if (((uintptr_t)d_rays & 15) || (!(cull_mode & 2) && ((uintptr_t)d_hit16 & 15))) { rtkd_set_error("device ray / hit buffers must be 16-byte aligned"); return RTKD_ERR_ARGUMENT; }
+	if ((cull_mode & 2) && stats) { rtkd_set_error("no statistics variant of the occlusion query"); return RTKD_ERR_ARGUMENT; }
 	int r = ensure_scratch(s);
 	if (r) return r;
 	cudaStream_t st = (cudaStream_t)stream;
@@ -492,13 +493,20 @@ extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size
 	unsigned grid = (unsigned)(want < ctas ? want : ctas);
 #define RTKD_TRACE_LAUNCH(L) do { \
 		if (stats) { \
-			if (cull_mode) { RTK_LAUNCH((k_trace<L, 1, true>), grid, RTK_TRACE_THREADS, st, p); } \
+			if (cull_mode & 1) { RTK_LAUNCH((k_trace<L, 1, true>), grid, RTK_TRACE_THREADS, st, p); } \
 			else { RTK_LAUNCH((k_trace<L, 0, true>), grid, RTK_TRACE_THREADS, st, p); } \
 		} else { \
-			if (cull_mode) { RTK_LAUNCH((k_trace<L, 1, false>), grid, RTK_TRACE_THREADS, st, p); } \
+			if (cull_mode & 1) { RTK_LAUNCH((k_trace<L, 1, false>), grid, RTK_TRACE_THREADS, st, p); } \
 			else { RTK_LAUNCH((k_trace<L, 0, false>), grid, RTK_TRACE_THREADS, st, p); } \
 		} } while (0)
-	if (g_trace_lanes == 8) RTKD_TRACE_LAUNCH(8);
+	if (cull_mode & 2) {
+		// occlusion query (any hit): d_hit16 is a byte per ray
+		const bool c1 = (cull_mode & 1) != 0;
+		if (g_trace_lanes == 8) { if (c1) { RTK_LAUNCH((k_trace<8, 1, false, true>), grid, RTK_TRACE_THREADS, st, p); } else { RTK_LAUNCH((k_trace<8, 0, false, true>), grid, RTK_TRACE_THREADS, st, p); } }
+		else if (g_trace_lanes == 4) { if (c1) { RTK_LAUNCH((k_trace<4, 1, false, true>), grid, RTK_TRACE_THREADS, st, p); } else { RTK_LAUNCH((k_trace<4, 0, false, true>), grid, RTK_TRACE_THREADS, st, p); } }
+		else { if (c1) { RTK_LAUNCH((k_trace<2, 1, false, true>), grid, RTK_TRACE_THREADS, st, p); } else { RTK_LAUNCH((k_trace<2, 0, false, true>), grid, RTK_TRACE_THREADS, st, p); } }
+	}
+	else if (g_trace_lanes == 8) RTKD_TRACE_LAUNCH(8);
 	else if (g_trace_lanes == 4) RTKD_TRACE_LAUNCH(4);
 	else RTKD_TRACE_LAUNCH(2);
 #undef RTKD_TRACE_LAUNCH

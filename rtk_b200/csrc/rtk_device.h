@@ -58,7 +58,8 @@ int rtkd_decode_mesh(rtkd_scene *s, uint32_t first_prim, uint32_t ntris,
 /* build the BVH from the decoded triangles; synchronous with respect to `stream` on return */
 int rtkd_build(rtkd_scene *s, int mode, void *stream);
 
-/* queries: device pointers, asynchronous on stream */
+/* queries: device pointers, asynchronous on stream.  cull_mode bit 0: provable culling,
+ * bit 1: occlusion query (d_hit16 is then one byte per ray) */
 int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, int cull_mode,
                rtkd_trace_stats *stats, void *stream);
 int rtkd_trace_brute(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, void *stream);

@@ -582,6 +582,13 @@ int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hi
 	return rtkd_resolve(dev, h16, d_hits, d_hit_mask, n, stream);
 }
 
+int rtk_occluded_rays_device(const rtk_scene *scene, const void *d_rays, void *d_occluded, size_t n, void *stream)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return RTK_CUDA_ERR_SCENE;
+	return rtkd_trace(dev, d_rays, d_occluded, n, g_cull_mode | 2, NULL, stream);
+}
+
 int rtk_trace_rays_bruteforce_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream)
 {
 	rtkd_scene *dev = scene_device(scene);

@@ -386,3 +386,19 @@ def case_api_semantics(lib, orc):
     hits, mask, _ = sc.trace_rays(rays)
     assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want, "finish_build")
     sc.free()
+
+
+def case_occlusion(lib, orc, alloc):
+    """any-hit query == hit mask of the closest-hit query (device buffers via `alloc`, which maps a
+    numpy array to a device pointer holder and back)"""
+    s = scenes.config_scene("C3", 0.004)
+    rays = scenes.bounce_rays(s, 3000)
+    rays["max_t"][::3] = 0.05                      # short shadow-style segments too
+    want = orc.trace_brute(s["tris"], rays)["prim"] != api.RTK_CUDA_MISS
+    sc = lib.build_scene(s["meshes"])
+    d_rays, d_occ, fetch = alloc(rays, len(rays))
+    assert lib.rtk_occluded_rays_device(sc.ptr, d_rays, d_occ, len(rays), None) == 0, lib.last_error()
+    got = fetch().astype(bool)
+    assert np.array_equal(got, want), int((got != want).sum())
+    assert 0 < want.sum() < len(want)
+    sc.free()

@@ -37,3 +37,13 @@ def test_mesh_formats(emu_lib, orc):
 
 def test_api_semantics(emu_lib, orc):
     pc.case_api_semantics(emu_lib, orc)
+
+
+def test_occlusion_query(emu_lib, orc):
+    import numpy as np
+
+    def alloc(rays, n):                                 # emulated device memory is host memory
+        r = np.ascontiguousarray(rays)
+        out = np.full(n, 7, dtype=np.uint8)
+        return r.ctypes.data, out.ctypes.data, lambda keep=(r, out): keep[1]
+    pc.case_occlusion(emu_lib, orc, alloc)

@@ -155,3 +155,17 @@ def test_host_batch_pinned_vs_pageable(gpu_lib, orc):
     assert (t_hits.numpy()[~m] == 0).all() and (hits_p.view(np.uint8).reshape(-1, 68)[~m] == 0).all()
     pc.assert_same(api.hits_to_hit16(hits_d, mask_d, s["mesh_first"])[:1500], orc.trace_brute(s["tris"], rays[:1500]), "pinned path vs oracle")
     sc.free()
+
+
+def test_occlusion_query(gpu_lib, orc):
+    import torch
+
+    def alloc(rays, n):
+        r = torch.from_numpy(np.ascontiguousarray(rays).view(np.uint8).reshape(-1, 32)).cuda()
+        out = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+
+        def fetch(keep=(r, out)):
+            torch.cuda.synchronize()
+            return keep[1].cpu().numpy()
+        return r.data_ptr(), out.data_ptr(), fetch
+    pc.case_occlusion(gpu_lib, orc, alloc)

@@ -34,39 +34,43 @@ typedef float rtk_real;
 
 /* 12 bytes, align 4.  Components are reachable by name or by index
  * (reference rtk.h:15-22). */
-typedef struct rtk_vec3 {
+struct rtk_vec3 {
 	union {
-		struct { rtk_real x, y, z; };
-		rtk_real v[3];
+		rtk_real v[3];                       /* by index ...            */
+		struct { rtk_real x; rtk_real y; rtk_real z; };   /* ... or by name, same storage */
 	};
-} rtk_vec3;
+};
+typedef struct rtk_vec3 rtk_vec3;
 
 /* 16 bytes: a position plus the index the vertex had in its mesh's position
  * buffer (reference rtk.h:24-27). */
-typedef struct rtk_vertex {
-	rtk_vec3 position;
-	uint32_t index;
-} rtk_vertex;
+struct rtk_vertex {
+	rtk_vec3 position;                       /* @0  */
+	uint32_t index;                          /* @12 */
+};
+typedef struct rtk_vertex rtk_vertex;
 
 /* 32 bytes.  The direction need not be normalised: hit distances are in units
  * of |direction| (reference rtk.h:29-34). */
-typedef struct rtk_ray {
+struct rtk_ray {
 	rtk_vec3 origin;      /* @0  */
 	rtk_vec3 direction;   /* @12 */
 	rtk_real min_t;       /* @24  hits need t >  min_t */
 	rtk_real max_t;       /* @28  hits need t <  max_t, max_t <= RTK_INF */
-} rtk_ray;
+};
+typedef struct rtk_ray rtk_ray;
 
 /* 68 bytes.  u is the barycentric weight of vertex[0], v of vertex[1],
  * vertex[2] carries 1-u-v (reference rtk.h:36-43). */
-typedef struct rtk_hit {
+struct rtk_hit {
 	rtk_real   t;               /* @0  */
 	rtk_real   u;               /* @4  */
 	rtk_real   v;               /* @8  */
 	rtk_vertex vertex[3];       /* @12 */
 	uint32_t   mesh_index;      /* @60 position of the mesh in rtk_scene_desc::meshes */
 	uint32_t   triangle_index;  /* @64 index of the triangle inside that mesh */
-} rtk_hit;
+};
+typedef struct rtk_hit rtk_hit;
 
 /* Element types of mesh buffers; the enumerator order is ABI
  * (reference rtk.h:45-52). */
@@ -80,11 +84,12 @@ typedef enum rtk_type {
 } rtk_type;
 
 /* A strided view; stride 0 means tightly packed (reference rtk.h:54-58). */
-typedef struct rtk_buffer {
-	const void *data;
-	size_t      stride;
-	rtk_type    type;
-} rtk_buffer;
+struct rtk_buffer {
+	const void *data;       /* @0  first element */
+	size_t      stride;     /* @8  bytes between vertices / index triples, 0 = packed */
+	rtk_type    type;       /* @16 */
+};
+typedef struct rtk_buffer rtk_buffer;
 
 typedef struct rtk_mesh rtk_mesh;
 
@@ -92,8 +97,10 @@ typedef struct rtk_mesh rtk_mesh;
  * 3*count vertex indices and must write 3*count positions; index_cb must write
  * the 3*count indices of triangles [offset, offset+count).  They are invoked on
  * the calling thread in chunks of at most 128 triangles. */
-typedef void rtk_position_callback_fn(void *user, const rtk_mesh *mesh, rtk_vec3 *dst, const uint32_t *indices, size_t count);
-typedef void rtk_index_callback_fn(void *user, const rtk_mesh *mesh, uint32_t *dst, size_t offset, size_t count);
+typedef void rtk_position_callback_fn(void *user, const rtk_mesh *mesh, rtk_vec3 *positions_out,
+                                      const uint32_t *vertex_indices, size_t num_triangles);
+typedef void rtk_index_callback_fn(void *user, const rtk_mesh *mesh, uint32_t *indices_out,
+                                   size_t first_triangle, size_t num_triangles);
 
 /* 96 bytes (reference rtk.h:64-76). */
 struct rtk_mesh {
@@ -131,18 +138,19 @@ typedef struct rtk_task     rtk_task;
 typedef struct rtk_task_ctx rtk_task_ctx;
 
 /* Progress messages (reference rtk.h:95). */
-typedef void rtk_log_fn(void *user, rtk_build *build, const char *str);
+typedef void rtk_log_fn(void *user, rtk_build *build, const char *message);
 
 /* 32 bytes (reference rtk.h:97-105). */
-typedef struct rtk_scene_desc {
-	const rtk_mesh *meshes;
-	size_t          num_meshes;
-	rtk_log_fn     *log_fn;
-	void           *log_user;
-} rtk_scene_desc;
+struct rtk_scene_desc {
+	const rtk_mesh *meshes;       /* @0  */
+	size_t          num_meshes;   /* @8  */
+	rtk_log_fn     *log_fn;       /* @16 may be NULL */
+	void           *log_user;     /* @24 */
+};
+typedef struct rtk_scene_desc rtk_scene_desc;
 
 /* User-pumped build tasks, 40 bytes each (reference rtk.h:108-115). */
-typedef void rtk_task_fn(const rtk_task *task, rtk_task_ctx *ctx);
+typedef void rtk_task_fn(const rtk_task *task, rtk_task_ctx *context);
 struct rtk_task {
 	rtk_build   *build;
 	rtk_task_fn *fn;
@@ -151,32 +159,33 @@ struct rtk_task {
 	uintptr_t    arg;
 };
 
-typedef bool rtk_filter_fn(void *user, const rtk_ray *ray, const rtk_hit *hit);
+typedef bool rtk_filter_fn(void *user, const rtk_ray *ray, const rtk_hit *candidate);
 
 /* Split-phase build (reference rtk.h:119-124).  rtk_start_build ingests the
  * meshes; running *first_task performs the whole GPU build synchronously and
  * queues nothing, so a task pump written for the reference terminates after
  * one call.  rtk_finish_build_to returns NULL (and keeps the build alive) when
  * the buffer is too small. */
-rtk_build *rtk_start_build(const rtk_scene_desc *desc, rtk_task *first_task);
-size_t     rtk_run_task(const rtk_task *task, rtk_task *queue, size_t queue_size);
-size_t     rtk_get_build_size(const rtk_build *build);
-rtk_scene *rtk_finish_build_to(rtk_build *build, void *buffer, size_t size);
-rtk_scene *rtk_finish_build(rtk_build *build);
+rtk_build *rtk_start_build(const rtk_scene_desc *description, rtk_task *out_first_task);
+size_t     rtk_run_task(const rtk_task *task_to_run, rtk_task *new_tasks, size_t new_tasks_capacity);
+size_t     rtk_get_build_size(const rtk_build *finished_build);
+rtk_scene *rtk_finish_build_to(rtk_build *finished_build, void *blob_memory, size_t blob_capacity);
+rtk_scene *rtk_finish_build(rtk_build *finished_build);
 
 /* One-shot build and release (reference rtk.h:126-127). */
-rtk_scene *rtk_build_scene(const rtk_scene_desc *desc);
-void       rtk_free_scene(rtk_scene *scene);
+rtk_scene *rtk_build_scene(const rtk_scene_desc *description);
+void       rtk_free_scene(rtk_scene *scene_or_null);
 
 /* Closest hit of one ray (reference rtk.h:129).  *hit is written only when the
  * function returns true.  Implemented as a one-ray batch on the GPU: correct,
  * but latency-bound -- use rtk_trace_rays (rtk_cuda.h) for throughput. */
-bool rtk_trace_ray(const rtk_scene *scene, const rtk_ray *ray, rtk_hit *hit);
+bool rtk_trace_ray(const rtk_scene *scene, const rtk_ray *ray, rtk_hit *hit_out);
 
 /* Reference rtk.h:130.  The reference ships a stub that returns true and
  * ignores its arguments (rtk.c:579-582); here: closest hit, then the filter is
  * consulted once on the host; a rejected hit reports a miss. */
-bool rtk_trace_ray_filter(const rtk_scene *scene, const rtk_ray *ray, rtk_hit *hit, rtk_filter_fn *filter, void *filter_user);
+bool rtk_trace_ray_filter(const rtk_scene *scene, const rtk_ray *ray, rtk_hit *hit_out,
+                          rtk_filter_fn *accept, void *accept_user);
 
 #ifdef __cplusplus
 }

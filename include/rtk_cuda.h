@@ -118,6 +118,34 @@ int rtk_trace_rays_bruteforce_device(const rtk_scene *scene, const void *d_rays,
 /* Counter-instrumented traversal (slow; for the algorithmic-bytes figure). */
 int rtk_trace_stats_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, rtk_cuda_trace_stats *stats, void *stream);
 
+/* ---- wavefront ray generation on the device ------------ */
+
+/* Pinhole camera: right/up need not be unit length; rays are
+ * forward + sx*right + sy*up with sx,sy in [-tan, tan] (x scaled by the aspect). */
+typedef struct rtk_cuda_camera {
+	float eye[3], forward[3], right[3], up[3];
+	float tan_half_fov;           /* vertical */
+	uint32_t width, height;
+} rtk_cuda_camera;
+
+/* Jittered primary rays of pixels [first_pixel, first_pixel+count), row-major,
+ * sample number `sample` (< 64); counter-based jitter from `seed`. */
+int rtk_cuda_generate_primary_rays(const rtk_cuda_camera *camera, uint64_t seed, uint32_t sample,
+                                   size_t first_pixel, size_t count, void *d_rays, void *stream);
+
+/* Next-bounce rays from the compact hits of the previous bounce: origin = hit
+ * point pushed off the surface along the geometric normal (turned towards the
+ * incoming ray), direction = cosine-weighted hemisphere sample.  A path that
+ * missed gets a dead ray (max_t = 0) and d_alive[i] = 0, or -- with
+ * RTK_CUDA_BOUNCE_RELAUNCH in flags -- restarts on a uniformly chosen triangle
+ * (d_alive[i] = 2), which keeps the ray count of a wavefront fixed.  Paths that
+ * hit have d_alive[i] = 1; d_alive may be NULL.  first_ray numbers the rays for
+ * the random-number counter; bounce < 16. */
+#define RTK_CUDA_BOUNCE_RELAUNCH 1u
+int rtk_cuda_generate_bounce_rays(const rtk_scene *scene, const void *d_rays_in, const void *d_hit16, void *d_rays_out,
+                                  void *d_alive, size_t n, uint64_t seed, uint32_t bounce, uint64_t first_ray,
+                                  uint32_t flags, void *stream);
+
 /* ---- build with inputs already resident in HBM ------------------------ */
 
 /* A mesh whose buffers live on the device: float xyz positions (tightly

@@ -82,6 +82,11 @@ class rtk_cuda_mesh(C.Structure):
                 ("num_vertices", C.c_size_t), ("num_triangles", C.c_size_t)]
 
 
+class rtk_cuda_camera(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("forward", C.c_float * 3), ("right", C.c_float * 3), ("up", C.c_float * 3),
+                ("tan_half_fov", C.c_float), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
 class rtk_cuda_scene_info(C.Structure):
     _fields_ = [("num_triangles", C.c_uint64), ("num_meshes", C.c_uint64), ("num_wide_nodes", C.c_uint64),
                 ("num_leaves", C.c_uint64), ("wide_depth", C.c_uint32), ("build_mode", C.c_uint32),
@@ -93,6 +98,8 @@ class rtk_cuda_trace_stats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("hits", C.c_uint64), ("node_visits", C.c_uint64),
                 ("leaf_visits", C.c_uint64), ("tri_tests", C.c_uint64), ("stack_max", C.c_uint64)]
 
+
+RTK_CUDA_BOUNCE_RELAUNCH = 1
 
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("d", "<f4", 3), ("min_t", "<f4"), ("max_t", "<f4")])
 VERTEX_DTYPE = np.dtype([("position", "<f4", 3), ("index", "<u4")])
@@ -128,6 +135,8 @@ SYMBOLS = {
     "rtk_occluded_rays_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_trace_rays_bruteforce_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_trace_stats_device": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(rtk_cuda_trace_stats), _P]),
+    "rtk_cuda_generate_primary_rays": (C.c_int, [C.POINTER(rtk_cuda_camera), C.c_uint64, C.c_uint32, C.c_size_t, C.c_size_t, _P, _P]),
+    "rtk_cuda_generate_bounce_rays": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, _P]),
     "rtk_cuda_build_scene": (_P, [C.POINTER(rtk_cuda_mesh), C.c_size_t, _P]),
     "rtk_cuda_rebuild_scene": (C.c_int, [_P, _P]),
     "rtk_cuda_get_scene_info": (C.c_int, [_P, C.POINTER(rtk_cuda_scene_info)]),

@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librtk_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SOURCES = ["k_sah.cuh", "rtk_device.cu", "rtk_host.c", "rtk_common.cuh", "rtk_math.cuh", "k_build.cuh", "k_trace.cuh", "rtk_device.h"]
+SOURCES = ["k_sah.cuh", "rtk_device.cu", "rtk_host.c", "rtk_common.cuh", "rtk_math.cuh", "k_build.cuh", "k_trace.cuh", "k_wavefront.cuh", "rtk_device.h"]
 
 
 def _newer(target, deps):

@@ -7,6 +7,7 @@
 #include "k_build.cuh"
 #include "k_sah.cuh"
 #include "k_trace.cuh"
+#include "k_wavefront.cuh"
 #include <stdarg.h>
 #include <pthread.h>
 
@@ -545,6 +546,41 @@ extern "C" int rtkd_resolve(rtkd_scene *s, const void *d_hit16, void *d_hits, vo
 	CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), (cudaStream_t)stream));
 	RTK_LAUNCH(k_resolve, (unsigned)((n + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, stream,
 	           a, (const float4*)d_hit16, (uint32_t*)d_hits, (unsigned char*)d_mask, (uint32_t)n, cnt);
+	CK_LAUNCH();
+	return RTKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// wavefront ray generation (k_wavefront.cuh)
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int rtkd_gen_primary(const float *cam20, uint32_t width, uint32_t height, unsigned long long seed, uint32_t sample,
+                                unsigned long long first_pixel, size_t count, void *d_rays, void *stream)
+{
+	if (!count) return RTKD_OK;
+	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
+	if (!width || !height || first_pixel + count > (unsigned long long)width * height || count > 0xfffffff0ull) {
+		rtkd_set_error("pixel range outside the frame"); return RTKD_ERR_ARGUMENT;
+	}
+	rtkd_camera cam;
+	memcpy(cam.eye, cam20, 12); memcpy(cam.forward, cam20 + 3, 12); memcpy(cam.right, cam20 + 6, 12); memcpy(cam.up, cam20 + 9, 12);
+	cam.tan_half_fov = cam20[12]; cam.width = width; cam.height = height;
+	RTK_LAUNCH(k_gen_primary, (unsigned)((count + 255) / 256), 256, stream, cam, seed, sample, first_pixel, (uint32_t)count, (float4*)d_rays);
+	CK_LAUNCH();
+	return RTKD_OK;
+}
+
+extern "C" int rtkd_gen_bounce(rtkd_scene *s, const void *d_rays_in, const void *d_hit16, void *d_rays_out, void *d_alive,
+                               size_t n, unsigned long long seed, uint32_t bounce, unsigned long long first_ray, uint32_t flags, void *stream)
+{
+	if (!n) return RTKD_OK;
+	if (n > 0xfffffff0ull) { rtkd_set_error("batch too large"); return RTKD_ERR_ARGUMENT; }
+	rtkd_arrays a;
+	fill_arrays(s, a);
+	// push the new origin off the surface by 2^-13 of the scene's largest coordinate
+	float push = s->abs_max * 1.220703125e-4f;
+	RTK_LAUNCH(k_gen_bounce, (unsigned)((n + 255) / 256), 256, stream, a, (const float4*)d_rays_in, (const float4*)d_hit16,
+	           (float4*)d_rays_out, (unsigned char*)d_alive, (uint32_t)n, seed, bounce, first_ray, push, flags);
 	CK_LAUNCH();
 	return RTKD_OK;
 }

@@ -66,6 +66,12 @@ int rtkd_trace_brute(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n,
 int rtkd_resolve(rtkd_scene *s, const void *d_hit16, void *d_hits, void *d_mask, size_t n, void *stream);
 void *rtkd_scene_hit16(rtkd_scene *s, size_t n);   /* scene-owned compact hit buffer of >= n records */
 
+/* wavefront ray generation: cam20 = eye, forward, right, up (3 floats each), tan(half vertical fov) */
+int rtkd_gen_primary(const float *cam20, uint32_t width, uint32_t height, unsigned long long seed, uint32_t sample,
+                     unsigned long long first_pixel, size_t count, void *d_rays, void *stream);
+int rtkd_gen_bounce(rtkd_scene *s, const void *d_rays_in, const void *d_hit16, void *d_rays_out, void *d_alive,
+                    size_t n, unsigned long long seed, uint32_t bounce, unsigned long long first_ray, uint32_t flags, void *stream);
+
 /* host-buffer batch: H2D, trace, resolve, D2H; returns hits or -1 */
 long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n);
 

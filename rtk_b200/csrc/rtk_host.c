@@ -589,6 +589,27 @@ int rtk_occluded_rays_device(const rtk_scene *scene, const void *d_rays, void *d
 	return rtkd_trace(dev, d_rays, d_occluded, n, g_cull_mode | 2, NULL, stream);
 }
 
+int rtk_cuda_generate_primary_rays(const rtk_cuda_camera *camera, uint64_t seed, uint32_t sample,
+                                   size_t first_pixel, size_t count, void *d_rays, void *stream)
+{
+	if (!camera || (count && !d_rays)) { rtkd_set_error("bad camera / ray buffer"); return RTK_CUDA_ERR_ARGUMENT; }
+	if (sample >= 64) { rtkd_set_error("sample number must be below 64"); return RTK_CUDA_ERR_ARGUMENT; }
+	float cam[13];
+	memcpy(cam, camera->eye, 12); memcpy(cam + 3, camera->forward, 12);
+	memcpy(cam + 6, camera->right, 12); memcpy(cam + 9, camera->up, 12);
+	cam[12] = camera->tan_half_fov;
+	return rtkd_gen_primary(cam, camera->width, camera->height, seed, sample, first_pixel, count, d_rays, stream);
+}
+
+int rtk_cuda_generate_bounce_rays(const rtk_scene *scene, const void *d_rays_in, const void *d_hit16, void *d_rays_out,
+                                  void *d_alive, size_t n, uint64_t seed, uint32_t bounce, uint64_t first_ray, uint32_t flags, void *stream)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return RTK_CUDA_ERR_SCENE;
+	if (bounce >= 16) { rtkd_set_error("bounce number must be below 16"); return RTK_CUDA_ERR_ARGUMENT; }
+	return rtkd_gen_bounce(dev, d_rays_in, d_hit16, d_rays_out, d_alive, n, seed, bounce, first_ray, flags, stream);
+}
+
 int rtk_trace_rays_bruteforce_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream)
 {
 	rtkd_scene *dev = scene_device(scene);

@@ -402,3 +402,84 @@ def case_occlusion(lib, orc, alloc):
     assert np.array_equal(got, want), int((got != want).sum())
     assert 0 < want.sum() < len(want)
     sc.free()
+
+
+class HostDevice:
+    """'Device memory' of the emulated tier is host memory.  put/empty return (handle, pointer);
+    get copies a handle back as a numpy array of `dtype`."""
+    stream = None
+
+    def put(self, arr):
+        a = np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()
+        return a, a.ctypes.data
+
+    def empty(self, nbytes, fill=0):
+        a = np.full(max(nbytes, 16), fill, dtype=np.uint8)
+        return a, a.ctypes.data
+
+    def get(self, handle, dtype, count):
+        return handle[:count * np.dtype(dtype).itemsize].copy().view(dtype)
+
+
+def case_wavefront(lib, orc, dev):
+    """primary rays and bounce rays generated on the device, traced without leaving
+    it.  Generators against the numpy restatement (oracle/wavefront_ref.py): primary rays bit for
+    bit, bounce rays within 1e-5; every traced bounce against the brute-force oracle on the very
+    rays the device produced (bit-exact)."""
+    from oracle import wavefront_ref as wf
+    s = scenes.config_scene("C1")
+    sc = lib.build_scene(s["meshes"])
+    info = sc.info()
+    W, H = 48, 40
+    cam = api.rtk_cuda_camera()
+    eye, fwd, right, up, tan = (278.0, 273.0, -800.0), (0.0, 0.0, 1.0), (1.0, 0.0, 0.0), (0.0, 1.0, 0.0), 0.36
+    cam.eye[:], cam.forward[:], cam.right[:], cam.up[:] = eye, fwd, right, up
+    cam.tan_half_fov, cam.width, cam.height = tan, W, H
+    seed, n = 0xD5, W * H - 7
+    first_pixel = 5
+    h_rays, d_rays = dev.empty(32 * n)
+    h_next, d_next = dev.empty(32 * n)
+    h_hit, d_hit = dev.empty(16 * n)
+    h_alive, d_alive = dev.empty(n, fill=9)
+    assert lib.rtk_cuda_generate_primary_rays(C.byref(cam), seed, 3, first_pixel, n, d_rays, dev.stream) == 0, lib.last_error()
+    rays = dev.get(h_rays, api.RAY_DTYPE, n)
+    want = wf.primary_rays(eye, fwd, right, up, tan, W, H, seed, 3, first_pixel, n)
+    assert rays.tobytes() == want.tobytes(), "primary rays differ from the restatement"
+    # argument checks: pixel range outside the frame
+    assert lib.rtk_cuda_generate_primary_rays(C.byref(cam), seed, 3, W * H - 3, 8, d_rays, dev.stream) != 0
+    assert lib.rtk_cuda_generate_primary_rays(C.byref(cam), seed, 64, 0, 8, d_rays, dev.stream) != 0
+
+    amax = np.float32(max(np.abs(np.array(info.bounds_min[:])).max(), np.abs(np.array(info.bounds_max[:])).max()))
+    push = np.float32(amax * np.float32(2.0 ** -13))
+    tris = s["tris"]
+    total_hits = 0
+    for bounce in range(4):
+        flags = api.RTK_CUDA_BOUNCE_RELAUNCH if bounce % 2 else 0
+        assert lib.rtk_trace_rays_compact_device(sc.ptr, d_rays, d_hit, n, dev.stream) == 0, lib.last_error()
+        rays = dev.get(h_rays, api.RAY_DTYPE, n)
+        hit = dev.get(h_hit, api.HIT16_DTYPE, n)
+        assert_same(hit, orc.trace_brute(tris, rays), f"bounce {bounce}")
+        total_hits += int((hit["prim"] != api.RTK_CUDA_MISS).sum())
+        assert lib.rtk_cuda_generate_bounce_rays(sc.ptr, d_rays, d_hit, d_next, d_alive, n, seed, bounce, 1000, flags, dev.stream) == 0, lib.last_error()
+        got = dev.get(h_next, api.RAY_DTYPE, n)
+        alive = dev.get(h_alive, np.uint8, n)
+        ref, state = wf.bounce_rays(tris, rays, hit, seed, bounce, 1000, push, flags)
+        assert np.array_equal(alive, state)
+        if flags:
+            assert (alive != 0).all()
+        else:
+            dead = alive == 0
+            assert np.array_equal(dead, hit["prim"] == api.RTK_CUDA_MISS)
+            assert (got["max_t"][dead] == 0).all() and got[dead].tobytes() == ref[dead].tobytes()
+        live = alive != 0
+        scale = float(amax)
+        assert np.allclose(got["o"][live], ref["o"][live], rtol=1e-5, atol=1e-5 * scale)
+        assert np.allclose(got["d"][live], ref["d"][live], rtol=1e-5, atol=2e-5)
+        assert (got["max_t"][live] == api.RTK_INF).all() and (got["min_t"] == 0).all()
+        # directions are unit length and leave the surface on the side the path arrived from
+        assert np.allclose(np.linalg.norm(got["d"][live].astype(np.float64), axis=1), 1.0, atol=1e-4)
+        d_rays, d_next = d_next, d_rays
+        h_rays, h_next = h_next, h_rays
+    assert total_hits > n          # the Cornell box is closed on five sides: most paths keep hitting
+    assert lib.rtk_cuda_generate_bounce_rays(sc.ptr, d_rays, d_hit, d_next, d_alive, n, seed, 16, 0, 0, dev.stream) != 0
+    sc.free()

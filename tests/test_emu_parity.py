@@ -47,3 +47,7 @@ def test_occlusion_query(emu_lib, orc):
         out = np.full(n, 7, dtype=np.uint8)
         return r.ctypes.data, out.ctypes.data, lambda keep=(r, out): keep[1]
     pc.case_occlusion(emu_lib, orc, alloc)
+
+
+def test_wavefront_generators(emu_lib, orc):
+    pc.case_wavefront(emu_lib, orc, pc.HostDevice())

@@ -169,3 +169,28 @@ def test_occlusion_query(gpu_lib, orc):
             return keep[1].cpu().numpy()
         return r.data_ptr(), out.data_ptr(), fetch
     pc.case_occlusion(gpu_lib, orc, alloc)
+
+
+class TorchDevice:
+    """device buffers for the shared cases: torch owns the memory, the library sees raw pointers"""
+    stream = None
+
+    def put(self, arr):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).cuda()
+        return t, t.data_ptr()
+
+    def empty(self, nbytes, fill=0):
+        import torch
+        t = torch.full((max(nbytes, 16),), fill, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        return t, t.data_ptr()
+
+    def get(self, handle, dtype, count):
+        import torch
+        torch.cuda.synchronize()
+        return handle[:count * np.dtype(dtype).itemsize].cpu().numpy().view(dtype)
+
+
+def test_wavefront_generators(gpu_lib, orc):
+    pc.case_wavefront(gpu_lib, orc, TorchDevice())

@@ -37,10 +37,16 @@
 #define RTK_TRACE_MINB 4                 // resident CTAs per SM the register allocation must allow
 #endif
 #ifndef RTK_TRI_PERIOD
-#define RTK_TRI_PERIOD 3                 // the leaf phase runs every RTK_TRI_PERIOD-th iteration (or when no ray has node work)
+#define RTK_TRI_PERIOD 5                 // the leaf phase runs every RTK_TRI_PERIOD-th iteration (or when no ray has node work)
 #endif
 #ifndef RTK_ASSIGN_MIN
 #define RTK_ASSIGN_MIN 3                 // idle rays of a warp wait for new work until this many are idle
+#endif
+#ifndef RTK_PD_MIN
+#define RTK_PD_MIN 4                     // PD leaf phase: run as soon as this many rays of the warp wait at a leaf
+#endif
+#ifndef RTK_PD_FULL_ROUNDS
+#define RTK_PD_FULL_ROUNDS 1
 #endif
 #ifndef RTK_TRACE_LANES
 #define RTK_TRACE_LANES 2                // default lanes per ray (8, 4 or 2); RTK_B200_LANES overrides at run time
@@ -66,14 +72,33 @@ struct rtkd_trace_args {
 // more independent loads per instruction.
 // ANY = true turns the kernel into the occlusion (shadow-ray) query: a ray ends at the first
 // triangle accepted in (min_t, max_t) and one byte per ray is written instead of a hit record.
-template <int LANES, int CULL, bool STATS, bool ANY = false>
+//
+// PD = true ("pair distributed" leaf phase): the (ray, triangle) pairs of all the warp's rays that
+// wait at a leaf are dealt out to the 32 lanes -- four leaves of up to 8 triangles per round, each
+// lane testing ONE triangle for some ray of the warp -- instead of every ray's own lanes walking
+// their leaf while the lanes of the other rays idle (ncu, round 1: the leaf phase was 42 % of the
+// instructions at 6 of 32 threads active).  The per-ray constants of the triangle test live in
+// shared memory (written once at ray setup), candidates are min-reduced per ray with a 64-bit
+// shared-memory atomicMin on (ordered t, triangle number) -- which is exactly the tie rule --
+// and the winner deposits (t, u, v).  A lane's 8 triangles are 128 contiguous bytes per array, so
+// a round is 3 x 4 full-line requests.
+template <int LANES, int CULL, bool STATS, bool ANY = false, bool PD = false>
 __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtkd_trace_args p)
 {
 	constexpr int CPL = 8 / LANES;                       // children / triangles per lane
 	constexpr int GW = 32 / LANES;                       // rays (groups) per warp
 	constexpr int GROUPS = RTK_TRACE_WARPS * GW;         // rays per CTA
-	__shared__ float4 s_rays[RTK_TRACE_WARPS][2][RTK_RAY_BATCH * 2];
+	// !PD: two raw batches (double buffer).  PD: buffer 0 receives the raw batch in flight, s_prep
+	// holds the current batch after the warp-wide preparation pass (rtk_ray_prepare)
+	__shared__ float4 s_rays[RTK_TRACE_WARPS][PD ? 1 : 2][RTK_RAY_BATCH * 2];
+	__shared__ float4 s_prep[PD ? RTK_TRACE_WARPS : 1][PD ? RTK_RAY_BATCH * 3 : 1];
 	__shared__ uint2 s_stack[RTK_STACK_SMEM][GROUPS];
+	// PD: per-ray record for the distributed triangle test
+	__shared__ float4 s_recA[PD ? GROUPS : 1];                // origin, min_t            (q0 of rtk_ray_prepare)
+	__shared__ float4 s_recB[PD ? GROUPS : 1];                // shear sx, sy, sz, kz|sgn (q1)
+	__shared__ unsigned long long s_key[PD ? GROUPS : 1];     // (ordered best t) << 32 | best triangle
+	__shared__ uint32_t s_ref[PD ? GROUPS : 1];               // leaf the ray waits at
+	__shared__ float4 s_hit[PD ? GROUPS : 1];                 // t, u, v of the best hit
 
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int c = lane & (LANES - 1), g = lane / LANES;
@@ -85,7 +110,19 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 	// ---- warp-level ray batches ------------------------------------------------------------
 	uint32_t cur_base = 0, cur_cnt = 0, cur_pos = 0, next_base = 0, next_cnt = 0;
 	int cur_buf = 0;
-	{
+	if (PD) {
+		// first batch into the raw buffer; the first pass of the assignment loop prepares it
+		uint32_t b = 0;
+		if (lane == 0) b = atomicAdd(p.counter, (uint32_t)RTK_RAY_BATCH);
+		b = __shfl_sync(FULL, b, 0);
+		next_base = b;
+		next_cnt = b < p.nrays ? rtk_umin(RTK_RAY_BATCH, p.nrays - b) : 0u;
+		if ((uint32_t)lane < next_cnt) {
+			rtk_cp_async16(&s_rays[warp][0][lane * 2], p.rays + 2ull * (b + lane));
+			rtk_cp_async16(&s_rays[warp][0][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
+		}
+		rtk_cp_async_commit();
+	} else {
 		// first batch into buffer 0, second into buffer 1
 		uint32_t b = 0;
 		if (lane == 0) b = atomicAdd(p.counter, (uint32_t)RTK_RAY_BATCH);
@@ -103,8 +140,8 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 			next_base = b;
 			next_cnt = b < p.nrays ? rtk_umin(RTK_RAY_BATCH, p.nrays - b) : 0u;
 			if ((uint32_t)lane < next_cnt) {
-				rtk_cp_async16(&s_rays[warp][1][lane * 2], p.rays + 2ull * (b + lane));
-				rtk_cp_async16(&s_rays[warp][1][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
+				rtk_cp_async16(&s_rays[warp][PD ? 0 : 1][lane * 2], p.rays + 2ull * (b + lane));
+				rtk_cp_async16(&s_rays[warp][PD ? 0 : 1][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
 			}
 			rtk_cp_async_commit();
 		}
@@ -156,6 +193,30 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 				if (next_cnt == 0) break;                     // input exhausted
 				rtk_cp_async_wait_all();
 				__syncwarp();
+				if (PD) {
+					// the staged batch becomes current: every lane prepares one of its rays
+					cur_base = next_base; cur_cnt = next_cnt; cur_pos = 0;
+					next_cnt = 0;
+					if ((uint32_t)lane < cur_cnt) {
+						float4 q0, q1, q2;
+						rtk_ray_prepare(s_rays[warp][0][lane * 2], s_rays[warp][0][lane * 2 + 1], q0, q1, q2);
+						s_prep[warp][lane * 3] = q0; s_prep[warp][lane * 3 + 1] = q1; s_prep[warp][lane * 3 + 2] = q2;
+					}
+					__syncwarp();
+					if (cur_cnt == RTK_RAY_BATCH) {
+						uint32_t b = 0;
+						if (lane == 0) b = atomicAdd(p.counter, (uint32_t)RTK_RAY_BATCH);
+						b = __shfl_sync(FULL, b, 0);
+						next_base = b;
+						next_cnt = b < p.nrays ? rtk_umin(RTK_RAY_BATCH, p.nrays - b) : 0u;
+						if ((uint32_t)lane < next_cnt) {
+							rtk_cp_async16(&s_rays[warp][0][lane * 2], p.rays + 2ull * (b + lane));
+							rtk_cp_async16(&s_rays[warp][0][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
+						}
+						rtk_cp_async_commit();
+					}
+					continue;
+				}
 				cur_buf ^= 1; cur_base = next_base; cur_cnt = next_cnt; cur_pos = 0;
 				next_cnt = 0;
 				if (cur_cnt == RTK_RAY_BATCH) {
@@ -165,8 +226,8 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 					next_base = b;
 					next_cnt = b < p.nrays ? rtk_umin(RTK_RAY_BATCH, p.nrays - b) : 0u;
 					if ((uint32_t)lane < next_cnt) {
-						rtk_cp_async16(&s_rays[warp][cur_buf ^ 1][lane * 2], p.rays + 2ull * (b + lane));
-						rtk_cp_async16(&s_rays[warp][cur_buf ^ 1][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
+						rtk_cp_async16(&s_rays[warp][PD ? 0 : (cur_buf ^ 1)][lane * 2], p.rays + 2ull * (b + lane));
+						rtk_cp_async16(&s_rays[warp][PD ? 0 : (cur_buf ^ 1)][lane * 2 + 1], p.rays + 2ull * (b + lane) + 1);
 					}
 					rtk_cp_async_commit();
 				}
@@ -175,11 +236,18 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 			uint32_t rank = __popc(need_mask & ((1u << (g * LANES)) - 1u));
 			if (!has_ray && rank < avail) {
 				uint32_t slot = cur_pos + rank;
-				float4 r0 = s_rays[warp][cur_buf][slot * 2], r1 = s_rays[warp][cur_buf][slot * 2 + 1];
-				rtk_ray_setup(rc, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, p.sc.abs_max);
+				if (PD) {
+					const float4 q0 = s_prep[warp][slot * 3], q1 = s_prep[warp][slot * 3 + 1], q2 = s_prep[warp][slot * 3 + 2];
+					rtk_ray_node_ctx(rc, q0, q1, q2, p.sc.abs_max);
+					ray_max_t = q2.w;
+					if (c == 0) { s_recA[gcta] = q0; s_recB[gcta] = q1; }
+				} else {
+					float4 r0 = s_rays[warp][PD ? 0 : cur_buf][slot * 2], r1 = s_rays[warp][PD ? 0 : cur_buf][slot * 2 + 1];
+					rtk_ray_setup(rc, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, p.sc.abs_max);
+					ray_max_t = r1.w;
+				}
 				ray_index = cur_base + slot;
-				ray_max_t = r1.w;
-				best_t = r1.w; best_u = 0.0f; best_v = 0.0f; best_prim = RTK_MISS;   // rtk.c:548
+				best_t = ray_max_t; best_u = 0.0f; best_v = 0.0f; best_prim = RTK_MISS;   // rtk.c:548
 				sp = 0;
 				cur_ref = p.sc.num_nodes ? 0u : RTK_REF_EMPTY;                        // root = node 0
 				has_ray = true;
@@ -191,6 +259,80 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 
 		// ---- (2) leaf: the group tests up to 8 triangles (rtk.c:181-388) ---------------------
 		const bool is_leaf = has_ray && cur_ref != RTK_REF_EMPTY && rtk_ref_is_leaf(cur_ref);
+		if (PD) {
+			uint32_t lm = __ballot_sync(FULL, is_leaf && c == 0);
+			const int nl = __popc(lm);
+			const bool any_node0 = __any_sync(FULL, has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref));
+			// a round serves four leaves: run when a full round is waiting, or when waiting longer
+			// would only idle lanes (no node work) or has lasted RTK_TRI_PERIOD iterations
+			const bool force = !any_node0 || (nl && ++tri_tick >= RTK_TRI_PERIOD);
+			if (nl >= RTK_PD_MIN || (nl && force)) {
+				tri_tick = 0;
+				if (!force && RTK_PD_FULL_ROUNDS) {
+					// full rounds only: the last (nl mod 4) rays keep waiting
+					for (int r = nl & 3; r > 0; r--) lm &= ~(0x80000000u >> __clz((int)lm));
+				}
+				const bool mine = is_leaf && ((lm >> (g * LANES)) & 1u);
+				if (mine && c == 0) {
+					s_key[gcta] = ((unsigned long long)rtk_f2ord(best_t) << 32) | best_prim;
+					s_ref[gcta] = cur_ref;
+				}
+				__syncwarp();
+				const int q = lane >> 3, k = lane & 7;
+				while (lm) {
+					// lanes 8q..8q+7 take the q-th waiting ray
+					uint32_t m = lm;
+					int b = -1;
+#pragma unroll
+					for (int j = 0; j < 4; j++) {
+						if (q == j && m) b = __ffs((int)m) - 1;
+						m &= m - 1u;
+					}
+					lm = m;
+					bool acc = false;
+					unsigned long long mykey = 0;
+					float tt = 0.0f, uu = 0.0f, vv = 0.0f;
+					int slot = 0;
+					if (b >= 0) {
+						slot = warp * GW + b / LANES;
+						const uint32_t ref = s_ref[slot];
+						const uint32_t first = rtk_leaf_first(ref), cnt = rtk_leaf_count(ref);
+						if ((uint32_t)k < cnt) {
+							const unsigned long long key0 = s_key[slot];
+							const float bt = rtk_ord2f((uint32_t)(key0 >> 32));
+							const uint32_t bp = (uint32_t)key0;
+							const float4 A = s_recA[slot], B = s_recB[slot];
+							rtk_ray_ctx tc;
+							rtk_ray_tri_ctx(tc, A, B);
+							float4 p0 = __ldg(&p.sc.tv0[first + k]);
+							float4 p1 = __ldg(&p.sc.tv1[first + k]);
+							float4 p2 = __ldg(&p.sc.tv2[first + k]);
+							const uint32_t id = __float_as_uint(p0.w);
+							// strict '<' against the recorded best (rtk.c:354, 371); an exact tie is taken
+							// only from a lower triangle number than the recorded hit
+							if (rtk_tri_test(tc, p0, p1, p2, bt, tt, uu, vv) && (tt < bt || (bp != RTK_MISS && id < bp))) {
+								acc = true;
+								// + 0.0f: -0.0 and +0.0 are the same distance
+								mykey = ((unsigned long long)rtk_f2ord(__fadd_rn(tt, 0.0f)) << 32) | id;
+								atomicMin(&s_key[slot], mykey);
+							}
+						}
+					}
+					__syncwarp();
+					if (acc && s_key[slot] == mykey) s_hit[slot] = make_float4(tt, uu, vv, 0.0f);
+				}
+				__syncwarp();
+				if (mine) {
+					const unsigned long long key = s_key[gcta];
+					best_t = rtk_ord2f((uint32_t)(key >> 32));
+					best_prim = (uint32_t)key;
+					if (STATS) { st_leaves++; st_tris += rtk_leaf_count(cur_ref); }
+					if (ANY && best_prim != RTK_MISS) { sp = 0; cur_ref = RTK_REF_EMPTY; }   // occluded: nothing else matters
+					else RTK_STACK_POP();
+				}
+				__syncwarp();
+			}
+		} else {
 #if RTK_TRI_PERIOD > 1
 		// Both phases cost a full warp instruction stream however few of the warp's rays take part.
 		// With 16 rays per warp about 1 in 5 is at a leaf at any time, so the leaf phase is run only
@@ -247,6 +389,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 			}
 			__syncwarp();
 		}
+		}   // !PD
 
 		// ---- (3) node: the group tests the 8 children (rtk.c:457-473) ------------------------
 		const bool is_node = has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref);
@@ -325,8 +468,11 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 				const bool got = best_t < ray_max_t;                    // rtk.c:571
 				if (ANY) ((unsigned char*)p.out)[ray_index] = got ? 1 : 0;
 				else {
-					float4 o = got ? make_float4(best_t, best_u, best_v, __uint_as_float(best_prim))
-					               : make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RTK_MISS));
+					float4 o = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RTK_MISS));
+					if (got) {
+						if (PD) { o = s_hit[gcta]; o.w = __uint_as_float(best_prim); }
+						else o = make_float4(best_t, best_u, best_v, __uint_as_float(best_prim));
+					}
 					p.out[ray_index] = o;
 				}
 				if (STATS) {

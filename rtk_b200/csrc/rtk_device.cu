@@ -21,7 +21,7 @@
 
 static __thread char g_err[512];
 static int g_device = -1;
-static int g_sm_count = 0, g_trace_ctas = 0, g_trace_lanes = RTK_TRACE_LANES;
+static int g_sm_count = 0, g_trace_ctas = 0, g_trace_lanes = RTK_TRACE_LANES, g_trace_pd = 1;
 static size_t g_l2_bytes = 0;
 static uint64_t g_next_id = 1;
 
@@ -60,9 +60,16 @@ extern "C" int rtkd_init(int device)
 		const char *e = getenv("RTK_B200_LANES");          // experiment knob: lanes per ray
 		if (e && (atoi(e) == 8 || atoi(e) == 4 || atoi(e) == 2)) g_trace_lanes = atoi(e);
 	}
+	{
+		const char *e = getenv("RTK_B200_PD");             // experiment knob: 0 = every ray's own lanes walk its leaf
+		if (e) g_trace_pd = atoi(e) != 0;
+		if (g_trace_lanes == 8) g_trace_pd = 0;
+	}
 	int ctas = 0;
 	if (g_trace_lanes == 8) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<8, 1, false>, RTK_TRACE_THREADS, 0));
+	else if (g_trace_lanes == 4 && g_trace_pd) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<4, 1, false, false, true>, RTK_TRACE_THREADS, 0));
 	else if (g_trace_lanes == 4) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<4, 1, false>, RTK_TRACE_THREADS, 0));
+	else if (g_trace_pd) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<2, 1, false, false, true>, RTK_TRACE_THREADS, 0));
 	else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<2, 1, false>, RTK_TRACE_THREADS, 0));
 	g_trace_ctas = ctas > 0 ? ctas : 1;
 #ifndef RTK_SIMT_EMU
@@ -470,6 +477,30 @@ static int ensure_scratch(rtkd_scene *s)
 	return RTKD_OK;
 }
 
+// one instantiation per (lanes per ray, cull mode, statistics, any-hit, leaf-phase variant)
+template <int L, bool PD>
+static void launch_trace_l(int cull_mode, bool stats, unsigned grid, cudaStream_t st, const rtkd_trace_args &p)
+{
+	const bool c1 = (cull_mode & 1) != 0;
+	if (cull_mode & 2) {
+		// occlusion query (any hit): the output is a byte per ray
+		if (c1) { RTK_LAUNCH((k_trace<L, 1, false, true, PD>), grid, RTK_TRACE_THREADS, st, p); }
+		else { RTK_LAUNCH((k_trace<L, 0, false, true, PD>), grid, RTK_TRACE_THREADS, st, p); }
+	} else if (stats) {
+		if (c1) { RTK_LAUNCH((k_trace<L, 1, true, false, PD>), grid, RTK_TRACE_THREADS, st, p); }
+		else { RTK_LAUNCH((k_trace<L, 0, true, false, PD>), grid, RTK_TRACE_THREADS, st, p); }
+	} else {
+		if (c1) { RTK_LAUNCH((k_trace<L, 1, false, false, PD>), grid, RTK_TRACE_THREADS, st, p); }
+		else { RTK_LAUNCH((k_trace<L, 0, false, false, PD>), grid, RTK_TRACE_THREADS, st, p); }
+	}
+}
+static void launch_trace(int lanes, int cull_mode, bool stats, bool pd, unsigned grid, cudaStream_t st, const rtkd_trace_args &p)
+{
+	if (lanes == 8) launch_trace_l<8, false>(cull_mode, stats, grid, st, p);
+	else if (lanes == 4) { if (pd) launch_trace_l<4, true>(cull_mode, stats, grid, st, p); else launch_trace_l<4, false>(cull_mode, stats, grid, st, p); }
+	else { if (pd) launch_trace_l<2, true>(cull_mode, stats, grid, st, p); else launch_trace_l<2, false>(cull_mode, stats, grid, st, p); }
+}
+
 extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, int cull_mode,
                           rtkd_trace_stats *stats, void *stream)
 {
@@ -492,25 +523,7 @@ extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size
 	size_t ctas = (size_t)g_sm_count * g_trace_ctas;
 	size_t want = (batches + RTK_TRACE_WARPS - 1) / RTK_TRACE_WARPS;
 	unsigned grid = (unsigned)(want < ctas ? want : ctas);
-#define RTKD_TRACE_LAUNCH(L) do { \
-		if (stats) { \
-			if (cull_mode & 1) { RTK_LAUNCH((k_trace<L, 1, true>), grid, RTK_TRACE_THREADS, st, p); } \
-			else { RTK_LAUNCH((k_trace<L, 0, true>), grid, RTK_TRACE_THREADS, st, p); } \
-		} else { \
-			if (cull_mode & 1) { RTK_LAUNCH((k_trace<L, 1, false>), grid, RTK_TRACE_THREADS, st, p); } \
-			else { RTK_LAUNCH((k_trace<L, 0, false>), grid, RTK_TRACE_THREADS, st, p); } \
-		} } while (0)
-	if (cull_mode & 2) {
-		// occlusion query (any hit): d_hit16 is a byte per ray
-		const bool c1 = (cull_mode & 1) != 0;
-		if (g_trace_lanes == 8) { if (c1) { RTK_LAUNCH((k_trace<8, 1, false, true>), grid, RTK_TRACE_THREADS, st, p); } else { RTK_LAUNCH((k_trace<8, 0, false, true>), grid, RTK_TRACE_THREADS, st, p); } }
-		else if (g_trace_lanes == 4) { if (c1) { RTK_LAUNCH((k_trace<4, 1, false, true>), grid, RTK_TRACE_THREADS, st, p); } else { RTK_LAUNCH((k_trace<4, 0, false, true>), grid, RTK_TRACE_THREADS, st, p); } }
-		else { if (c1) { RTK_LAUNCH((k_trace<2, 1, false, true>), grid, RTK_TRACE_THREADS, st, p); } else { RTK_LAUNCH((k_trace<2, 0, false, true>), grid, RTK_TRACE_THREADS, st, p); } }
-	}
-	else if (g_trace_lanes == 8) RTKD_TRACE_LAUNCH(8);
-	else if (g_trace_lanes == 4) RTKD_TRACE_LAUNCH(4);
-	else RTKD_TRACE_LAUNCH(2);
-#undef RTKD_TRACE_LAUNCH
+	launch_trace(g_trace_lanes, cull_mode, stats != NULL, g_trace_pd != 0, grid, st, p);
 	CK_LAUNCH();
 	if (stats) {
 		unsigned long long h[8];

@@ -72,6 +72,63 @@ RTK_DEV void rtk_ray_setup(rtk_ray_ctx &r, float ox, float oy, float oz, float d
 	r.sgn = (__float_as_uint(dx) >> 31) | ((__float_as_uint(dy) >> 31) << 1) | ((__float_as_uint(dz) >> 31) << 2);
 }
 
+// The same setup in two halves, for the traversal kernel's distributed ray preparation: the 32 lanes
+// of a warp each prepare ONE ray of a staged batch (the divides, full lane utilisation) into three
+// float4, and the lanes that later own the ray finish the cheap rest.
+//   q0 = (o.x, o.y, o.z, min_t)   q1 = (sx, sy, sz, bits: kz | sgn << 2)   q2 = (1/d.x, 1/d.y, 1/d.z, max_t)
+RTK_DEV void rtk_ray_prepare(float4 r0, float4 r1, float4 &q0, float4 &q1, float4 &q2)
+{
+	const float ox = r0.x, oy = r0.y, oz = r0.z, dx = r0.w, dy = r1.x, dz = r1.y;
+	float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+	float mx = ax > ay ? ax : ay;
+	mx = mx > az ? mx : az;
+	int kz = (ax == mx) ? 0 : ((ay == mx) ? 1 : 2);            // rtk.c:550-555
+	int kx = kz == 2 ? 0 : kz + 1;
+	int ky = kx == 2 ? 0 : kx + 1;
+	float dkx = rtk_sel3(dx, dy, dz, kx), dky = rtk_sel3(dx, dy, dz, ky), dkz = rtk_sel3(dx, dy, dz, kz);
+	float thr = mx * 5.9604645e-08f;
+	float ddx = copysignf(fmaxf(ax, thr), dx);
+	float ddy = copysignf(fmaxf(ay, thr), dy);
+	float ddz = copysignf(fmaxf(az, thr), dz);
+	uint32_t sgn = (__float_as_uint(dx) >> 31) | ((__float_as_uint(dy) >> 31) << 1) | ((__float_as_uint(dz) >> 31) << 2);
+	q0 = make_float4(ox, oy, oz, r1.z);
+	q1 = make_float4(__fdiv_rn(-dkx, dkz), __fdiv_rn(-dky, dkz), __fdiv_rn(1.0f, dkz), __uint_as_float((uint32_t)kz | (sgn << 2)));
+	q2 = make_float4(rtk_fast_rcp(ddx), rtk_fast_rcp(ddy), rtk_fast_rcp(ddz), r1.w);
+}
+
+// node-test half of the context from a prepared ray (the triangle-test half stays in shared memory)
+RTK_DEV void rtk_ray_node_ctx(rtk_ray_ctx &r, float4 q0, float4 q1, float4 q2, float scene_abs_max)
+{
+	const uint32_t bits = __float_as_uint(q1.w);
+	r.kz = (int)(bits & 3u);
+	r.sgn = bits >> 2;
+	r.min_t = q0.w;
+	r.idx = q2.x; r.idy = q2.y; r.idz = q2.z;
+	float S = fmaxf(fmaxf(fabsf(q0.x), fabsf(q0.y)), fmaxf(fabsf(q0.z), scene_abs_max));
+	float pad = S * 3.8146973e-06f;                        // 64 * 2^-24
+	float px = (r.sgn & 1u) ? -pad : pad, py = (r.sgn & 2u) ? -pad : pad, pz = (r.sgn & 4u) ? -pad : pad;
+	r.cnx = -((q0.x + px) * r.idx);
+	r.cny = -((q0.y + py) * r.idy);
+	r.cnz = -((q0.z + pz) * r.idz);
+	r.cfx = -((q0.x - px) * r.idx);
+	r.cfy = -((q0.y - py) * r.idy);
+	r.cfz = -((q0.z - pz) * r.idz);
+}
+
+// triangle-test half from the shared-memory record (q0, q1 as above)
+RTK_DEV void rtk_ray_tri_ctx(rtk_ray_ctx &r, float4 q0, float4 q1)
+{
+	const int kz = (int)(__float_as_uint(q1.w) & 3u);
+	const int kx = kz == 2 ? 0 : kz + 1;
+	const int ky = kx == 2 ? 0 : kx + 1;
+	r.kz = kz;
+	r.ox = rtk_sel3(q0.x, q0.y, q0.z, kx);                  // rtk.c:564-566
+	r.oy = rtk_sel3(q0.x, q0.y, q0.z, ky);
+	r.oz = rtk_sel3(q0.x, q0.y, q0.z, kz);
+	r.sx = q1.x; r.sy = q1.y; r.sz = q1.z;
+	r.min_t = q0.w;
+}
+
 // One triangle, reference rtk.c:256-354 for a single lane with the own-lane fp64 rule
 // (SURVEY 8(c)): returns true and t,u,v when min_t < t <= max_t_incl.  The upper bound is
 // inclusive so that the caller can resolve exact ties towards the lowest triangle number; the

@@ -50,6 +50,9 @@ WORKLOADS = {
     "C2": ("C2", 2_073_600, "C2: 1M-triangle random soup, 1920x1080 coherent primary rays per GPU"),
     "C4": ("C4", 67_108_864, "C4: 10M-triangle procedural terrain in 2 meshes (2501x2001 vertices), 67108864 mixed rays "
                              "per GPU (thirds of coherent primary / diffuse bounce / short segments, 64Ki blocks)"),
+    # wavefront path tracing: rays are generated on the device and never leave it (run_wavefront)
+    "C5": ("C4", 66_355_200, "C5: 4K frame (3840x2160) x 16 spp x 4 bounces on the 10M-triangle terrain, pixel rows "
+                             "split in 8 bands; one band (3840x270 pixels, 66355200 rays per step) per GPU"),
 }
 
 
@@ -160,6 +163,140 @@ def run_reference(args, workload, scene, rays):
     emit(line)
 
 
+
+# ------------------------------------------------------------------------------------------------
+# C5: wavefront path tracing, rays generated on the device
+# ------------------------------------------------------------------------------------------------
+
+def terrain_camera(api, scene, width, height):
+    """the camera of scenes.terrain_primary_rays as an rtk_cuda_camera"""
+    tris = scene["tris"].reshape(-1, 3)
+    lo, hi = tris.min(0), tris.max(0)
+    c = (lo + hi) / 2
+    eye = np.array([c[0], hi[1] + 0.8 * (hi[2] - lo[2]), lo[2] - 0.6 * (hi[2] - lo[2])], dtype=np.float32)
+    fwd = c - eye
+    fwd = fwd / np.linalg.norm(fwd)
+    right = np.cross([0.0, 1.0, 0.0], fwd)
+    right /= np.linalg.norm(right)
+    upv = np.cross(fwd, right)
+    cam = api.rtk_cuda_camera()
+    cam.eye[:], cam.forward[:], cam.right[:], cam.up[:] = [float(x) for x in eye], [float(x) for x in fwd], \
+        [float(x) for x in right], [float(x) for x in upv]
+    cam.tan_half_fov, cam.width, cam.height = float(np.tan(np.radians(50.0) / 2)), width, height
+    return cam
+
+
+def run_wavefront(args, workload, lib, api, scene, rank, world, local_rank):
+    """A step = one band of the 4K frame: 16 jittered primary rays per pixel generated on the device,
+    then 4 x (k_trace, k_gen_bounce with relaunch of the paths that left the scene).  Rays and hits
+    never leave HBM; for N > 1 the last bounce's compact hit records are gathered on rank 0."""
+    import torch
+    import torch.distributed as dist
+    W, H, SPP, BOUNCES, BANDS = 3840, 2160, 16, 4, 8
+    band = (rank % BANDS) if world > 1 else 0
+    rows = H // BANDS
+    npx = W * rows
+    n = npx * SPP
+    sc = lib.build_scene(scene["meshes"])
+    info = sc.info()
+    cam = terrain_camera(api, scene, W, H)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    bufs = [torch.empty((n, 32), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    d_h16 = torch.empty((n, 16), dtype=torch.uint8, device="cuda")
+    d_alive = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    gather_list = [torch.empty_like(d_h16) for _ in range(world)] if (world > 1 and rank == 0) else None
+    seed = 0xD5
+    counts = {}
+
+    def step(ev=None):
+        if ev:
+            ev[0].record(stream)
+        for s_ in range(SPP):
+            rc = lib.rtk_cuda_generate_primary_rays(C.byref(cam), seed, s_, band * npx, npx,
+                                                    bufs[0].data_ptr() + 32 * npx * s_, sh)
+            if rc:
+                raise RuntimeError(lib.last_error())
+        cur = 0
+        for b in range(BOUNCES):
+            rc = lib.rtk_trace_rays_compact_device(sc.ptr, bufs[cur].data_ptr(), d_h16.data_ptr(), n, sh)
+            if b + 1 < BOUNCES:
+                rc |= lib.rtk_cuda_generate_bounce_rays(sc.ptr, bufs[cur].data_ptr(), d_h16.data_ptr(), bufs[cur ^ 1].data_ptr(),
+                                                        d_alive.data_ptr(), n, seed, b, band * n, api.RTK_CUDA_BOUNCE_RELAUNCH, sh)
+                cur ^= 1
+            if rc:
+                raise RuntimeError(lib.last_error())
+        if ev:
+            ev[1].record(stream)
+        if world > 1:
+            dist.gather(d_h16, gather_list, dst=0)
+    step()
+    torch.cuda.synchronize()
+    counts["last_bounce_hit_fraction"] = float((d_h16.view(torch.int32)[:, 3] != -1).float().mean().item())
+    counts["relaunched_fraction_bounce3"] = float((d_alive == 2).float().mean().item())
+
+    # parity: the last bounce's rays (as the device generated them) against the exhaustive GPU kernel
+    # and, for a few, against the CPU oracle
+    parity = None
+    if rank == 0 and args.parity_rays > 0:
+        from oracle import orc
+        last = bufs[(BOUNCES - 1) & 1]
+        kb = min(n, 65536)
+        d_b = torch.zeros((kb, 16), dtype=torch.uint8, device="cuda")
+        assert lib.rtk_trace_rays_bruteforce_device(sc.ptr, last.data_ptr(), d_b.data_ptr(), kb, sh) == 0
+        torch.cuda.synchronize()
+        a = d_h16[:kb].cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)
+        bb = d_b.cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)
+        k = min(args.parity_rays, 512)
+        rays_np = last[:k].cpu().numpy().view(api.RAY_DTYPE).reshape(-1)
+        want = orc.trace_brute(scene["tris"], rays_np)
+        parity = {"rays_checked": k, "index_mismatches": int((a[:k]["prim"] != want["prim"]).sum()),
+                  "bit_exact": bool(a[:k].tobytes() == want.tobytes()), "against": "oracle (CPU brute force) on device-generated bounce-3 rays",
+                  "gpu_bruteforce_rays": kb, "gpu_bruteforce_bit_exact": bool(a.tobytes() == bb.tobytes())}
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.mark()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record(stream)
+    for i in range(args.steps):
+        step(evs[i])
+    e_end.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = e_start.elapsed_time(e_end)
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    rays_per_step = n * BOUNCES
+    if rank != 0:
+        return
+    workload = dict(workload)
+    workload.update({"triangles": int(len(scene["tris"])), "rays_per_gpu": rays_per_step,
+                     "l2_policy": "ray, hit and alive buffers (%.1f GB per bounce) stream through the 126 MB L2; the 10M-triangle "
+                                  "scene (%.2f GB) does not fit it" % (n * 81 / 1e9, info.device_bytes / 1e9)})
+    line = {"metric": "closest-hit Mrays/s (wavefront, device-generated rays)", "value": world * rays_per_step / (ms_per_step * 1e-3) / 1e6,
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload, "gpu_launches": (SPP + 2 * BOUNCES - 1) * args.steps,
+            "e2e": None, "wavefront": counts, "parity": parity, "clocks": clocks,
+            "build": {"metric": "BVH build Mtris/s", "value": len(scene["tris"]) / (info.build_device_ms * 1e-3) / 1e6,
+                      "unit": "Mtris/s", "device_ms": info.build_device_ms}}
+    emit(line)
+    sc.free()
+
 # ------------------------------------------------------------------------------------------------
 
 def emit(line):
@@ -234,6 +371,11 @@ def main():
     scene = scenes.config_scene(cfg_name, args.scale)
     ntris = int(len(scene["tris"]))
     workload["triangles"] = ntris
+    if args.workload == "C5":
+        run_wavefront(args, workload, lib, api, scene, rank, world, local_rank)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     n = args.rays
     rays_np = gen_rays(scene, n, rank, args.workload)
     if args.presort:
@@ -409,9 +551,16 @@ def main():
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": world * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 69 * n,
+    # what crosses PCIe per step: rays up; per ray one mask byte, per 128 rays a 4-byte block base,
+    # and the 68-byte rows of the rays that hit (rows of misses stay untouched, rtk.c:571-576)
+    d2h = 68 * int(nh) + n + 4 * ((n + 127) // 128) + 16 * ((n + (1 << 20) - 1) >> 20)
+    k = min(n, 1 << 21)
+    hm = h_mask[:k].numpy().astype(bool)
+    same_rows = bool(np.array_equal(h_hits[:k].numpy()[hm], d_hits[:k].cpu().numpy()[hm]) and
+                     np.array_equal(hm, d_mask[:k].cpu().numpy().astype(bool)))
+    e2e = {"value": world * n / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3, "api": "rtk_trace_rays (host rtk_ray[] in, rtk_hit[] + mask out, pinned)",
-           "hits_per_step": int(nh)}
+           "hits_per_step": int(nh), "rows_equal_device_path": same_rows, "rows_compared": k}
 
     if rank != 0:
         if world > 1:

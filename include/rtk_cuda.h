@@ -88,11 +88,13 @@ int  rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *trace_ctas_per_s
 
 /* ---- batched closest hit (replaces a user loop over rtk_trace_ray) ----- */
 
-/* Host buffers.  rays[n] in, hits[n] / hit_mask[n] out.  hits[i] is meaningful
- * only where hit_mask[i] != 0; rows of rays that missed come back zero-filled
- * (the device variant below leaves them untouched, the miss rule of
- * rtk.c:571-576).  hit_mask may be NULL.  Pinned (page-locked) buffers let the
- * H2D copy, the kernels and the D2H copy of consecutive 2M-ray chunks overlap.
+/* Host buffers.  rays[n] in, hits[n] / hit_mask[n] out.  hits[i] is written
+ * only where hit_mask[i] != 0; rows of rays that missed are left untouched,
+ * the miss rule of rtk.c:571-576.  hit_mask may be NULL.  The batch runs as a
+ * pipeline over 1M-ray chunks: rays go up, only the rows of rays that hit
+ * (plus one mask byte per ray) come back, and a few library threads
+ * (RTK_B200_HOST_THREADS, default 8) copy each row to hits[i].  Pinned
+ * (page-locked) caller buffers let the uploads overlap the kernels.
  * Returns the number of hits, or (size_t)-1 on error. */
 size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits, uint8_t *hit_mask, size_t n);
 

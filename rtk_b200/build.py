@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librtk_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-SOURCES = ["k_sah.cuh", "rtk_device.cu", "rtk_host.c", "rtk_common.cuh", "rtk_math.cuh", "k_build.cuh", "k_trace.cuh", "k_wavefront.cuh", "rtk_device.h"]
+SOURCES = ["k_sah.cuh", "rtk_device.cu", "rtk_host.c", "rtk_place.c", "rtk_common.cuh", "rtk_math.cuh", "k_build.cuh", "k_trace.cuh", "k_wavefront.cuh", "rtk_device.h"]
 
 
 def _newer(target, deps):
@@ -41,11 +41,13 @@ def _build(force, verbose, defines):
     tag = os.path.basename(OUT).replace(".so", "")
     dev_o = os.path.join(bdir, tag + "_device.o")
     host_o = os.path.join(bdir, tag + "_host.o")
+    place_o = os.path.join(bdir, tag + "_place.o")
     cmds = [
         [NVCC, *ARCH, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v", *defines,
          "-c", os.path.join(CSRC, "rtk_device.cu"), "-o", dev_o],
         ["gcc", "-O2", "-fPIC", "-Wall", "-std=gnu11", "-c", os.path.join(CSRC, "rtk_host.c"), "-o", host_o],
-        [NVCC, *ARCH, "-shared", "-o", OUT, dev_o, host_o, "-lpthread"],
+        ["gcc", "-O2", "-fPIC", "-Wall", "-std=gnu11", "-c", os.path.join(CSRC, "rtk_place.c"), "-o", place_o],
+        [NVCC, *ARCH, "-shared", "-o", OUT, dev_o, host_o, place_o, "-lpthread"],
     ]
     for c in cmds:
         r = subprocess.run(c, capture_output=True, text=True)

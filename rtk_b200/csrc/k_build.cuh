@@ -415,8 +415,8 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 	uint32_t leaves = 0;
 	for (int k = 0; k < RTK_WIDE; k++) {
 		if (k >= ns) {
-			node[k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, __uint_as_float(RTK_REF_EMPTY));
-			node[8 + k] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
+			node[2 * k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, __uint_as_float(RTK_REF_EMPTY));
+			node[2 * k + 1] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
 			continue;
 		}
 		int c = slot[k];
@@ -436,7 +436,7 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 		}
 		cost += (double)rtk_half_area(lo, hi);       // node step or one 8-lane triangle round: cost 1
 		lo.w = __uint_as_float(ref); hi.w = 0.0f;
-		node[k] = lo; node[8 + k] = hi;
+		node[2 * k] = lo; node[2 * k + 1] = hi;
 	}
 #undef RTK_OPENABLE
 #undef RTK_BIDX
@@ -451,12 +451,12 @@ __global__ void k_single_root(const float4 *tri_orig, const uint32_t *vals, floa
 	uint32_t prim = vals[0];
 	float4 a = tri_orig[3ull * prim], b = tri_orig[3ull * prim + 1], c = tri_orig[3ull * prim + 2];
 	for (int k = 0; k < RTK_WIDE; k++) {
-		nodes[k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, __uint_as_float(RTK_REF_EMPTY));
-		nodes[8 + k] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
+		nodes[2 * k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, __uint_as_float(RTK_REF_EMPTY));
+		nodes[2 * k + 1] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
 	}
 	nodes[0] = make_float4(rtk_fmin(rtk_fmin(a.x, b.x), c.x), rtk_fmin(rtk_fmin(a.y, b.y), c.y), rtk_fmin(rtk_fmin(a.z, b.z), c.z),
 	                       __uint_as_float(rtk_leaf_ref(0, 1)));
-	nodes[8] = make_float4(rtk_fmax(rtk_fmax(a.x, b.x), c.x), rtk_fmax(rtk_fmax(a.y, b.y), c.y), rtk_fmax(rtk_fmax(a.z, b.z), c.z), 0.0f);
+	nodes[1] = make_float4(rtk_fmax(rtk_fmax(a.x, b.x), c.x), rtk_fmax(rtk_fmax(a.y, b.y), c.y), rtk_fmax(rtk_fmax(a.z, b.z), c.z), 0.0f);
 }
 
 // leaf-ordered SoA triangles: tv0[i].w = global triangle number

@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 	rtk_ray_ctx rc;
 	bool has_ray = false;
 	uint32_t ray_index = 0;
-	float ray_max_t = 0.0f;
 	float best_t = 0.0f, best_u = 0.0f, best_v = 0.0f;
 	uint32_t best_prim = RTK_MISS;
 	uint32_t cur_ref = RTK_REF_EMPTY;
@@ -239,15 +238,15 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 				if (PD) {
 					const float4 q0 = s_prep[warp][slot * 3], q1 = s_prep[warp][slot * 3 + 1], q2 = s_prep[warp][slot * 3 + 2];
 					rtk_ray_node_ctx(rc, q0, q1, q2, p.sc.abs_max);
-					ray_max_t = q2.w;
+					best_t = q2.w;                                                       // max_t, rtk.c:548
 					if (c == 0) { s_recA[gcta] = q0; s_recB[gcta] = q1; }
 				} else {
 					float4 r0 = s_rays[warp][PD ? 0 : cur_buf][slot * 2], r1 = s_rays[warp][PD ? 0 : cur_buf][slot * 2 + 1];
 					rtk_ray_setup(rc, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, p.sc.abs_max);
-					ray_max_t = r1.w;
+					best_t = r1.w;
 				}
 				ray_index = cur_base + slot;
-				best_t = ray_max_t; best_u = 0.0f; best_v = 0.0f; best_prim = RTK_MISS;   // rtk.c:548
+				best_u = 0.0f; best_v = 0.0f; best_prim = RTK_MISS;
 				sp = 0;
 				cur_ref = p.sc.num_nodes ? 0u : RTK_REF_EMPTY;                        // root = node 0
 				has_ray = true;
@@ -395,7 +394,8 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 		const bool is_node = has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref);
 		if (__any_sync(FULL, is_node)) {
 			uint32_t hitbits = 0;                 // bit (child index) for the children of this lane
-			uint32_t ok = 0xffffffffu;            // best ordering key of this lane
+			uint32_t ok = 0xffffffffu;            // best ordering key of this lane ...
+			uint32_t okref = RTK_REF_EMPTY;       // ... and the child it belongs to
 			float key[CPL];
 			uint32_t ref[CPL];
 #pragma unroll
@@ -405,8 +405,9 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 				const bool nx = rc.sgn & 1u, ny = rc.sgn & 2u, nz = rc.sgn & 4u;
 #pragma unroll
 				for (int j = 0; j < CPL; j++) {
-					const int k = c * CPL + j;
-					float4 lo = __ldg(np + k), hi = __ldg(np + 8 + k);
+					const int k = j * LANES + c;             // child slot: the lanes of a ray read adjacent slots
+					float4 lo, hi;
+					rtk_ldg256(np + 2 * k, lo, hi);
 					ref[j] = __float_as_uint(lo.w);
 					float tnx = fmaf(nx ? hi.x : lo.x, rc.idx, rc.cnx), tfx = fmaf(nx ? lo.x : hi.x, rc.idx, rc.cfx);
 					float tny = fmaf(ny ? hi.y : lo.y, rc.idy, rc.cny), tfy = fmaf(ny ? lo.y : hi.y, rc.idy, rc.cfy);
@@ -424,7 +425,8 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 						hitbits |= 1u << k;
 						// nearest hit child: entry distance with the child number in the low 3 bits
 						// (the reference tags 2 bits the same way, rtk.c:496)
-						ok = rtk_umin(ok, (__float_as_uint(rtk_fmax(tn, 0.0f)) & ~7u) | (uint32_t)k);
+						const uint32_t kk = (__float_as_uint(rtk_fmax(tn, 0.0f)) & ~7u) | (uint32_t)k;
+						if (kk < ok) { ok = kk; okref = ref[j]; }
 					}
 				}
 				if (STATS) st_nodes++;
@@ -437,15 +439,12 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 			}
 			if (CPL == 1) gm = (__ballot_sync(FULL, hitbits != 0) >> (g * LANES)) & 0xffu;
 			const int cmin = (int)(om & 7u);
-			uint32_t myref = ref[0];
-#pragma unroll
-			for (int j = 1; j < CPL; j++) if ((cmin & (CPL - 1)) == j) myref = ref[j];
-			const uint32_t nref = __shfl_sync(FULL, myref, cmin / CPL, LANES);
+			const uint32_t nref = __shfl_sync(FULL, okref, cmin & (LANES - 1), LANES);
 			if (is_node) {
 				const uint32_t others = gm & ~(1u << cmin);
 #pragma unroll
 				for (int j = 0; j < CPL; j++) {
-					const int k = c * CPL + j;
+					const int k = j * LANES + c;
 					if ((others >> k) & 1u) {
 						int pos = sp + __popc(others & ((1u << k) - 1u));
 						RTK_STACK_WRITE(pos, make_uint2(__float_as_uint(key[j]), ref[j]));
@@ -465,7 +464,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 		// ---- (4) finished rays --------------------------------------------------------------
 		if (has_ray && cur_ref == RTK_REF_EMPTY) {
 			if (c == 0) {
-				const bool got = best_t < ray_max_t;                    // rtk.c:571
+				const bool got = best_prim != RTK_MISS;                 // a hit is only ever recorded below max_t (rtk.c:571)
 				if (ANY) ((unsigned char*)p.out)[ray_index] = got ? 1 : 0;
 				else {
 					float4 o = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RTK_MISS));
@@ -546,48 +545,73 @@ __global__ void __launch_bounds__(128) k_trace_brute(rtkd_arrays sc, const float
 
 #define RTK_RESOLVE_THREADS 128
 
+// DENSE: the rows of the rays that hit are packed instead -- block b's rows are contiguous from
+// row block_base[b] of `hits`, blocks in the order they reserved their range from *hit_count --
+// which is what the host-buffer path sends over PCIe (rtk_place.c puts them back in place).
+template <bool DENSE>
 __global__ void __launch_bounds__(RTK_RESOLVE_THREADS) k_resolve(rtkd_arrays sc, const float4 *hit16, uint32_t *hits,
                                                                  unsigned char *mask, uint32_t nrays,
-                                                                 unsigned long long *hit_count)
+                                                                 unsigned long long *hit_count, uint32_t *block_base)
 {
 	__shared__ uint32_t s_row[RTK_RESOLVE_THREADS][17];
 	__shared__ unsigned char s_hit[RTK_RESOLVE_THREADS];
+	__shared__ uint32_t s_warp[RTK_RESOLVE_THREADS / 32 + 1];
 	const uint32_t base = blockIdx.x * RTK_RESOLVE_THREADS;
 	const uint32_t i = base + threadIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	bool got = false;
+	float4 h = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	if (i < nrays) {
-		float4 h = hit16[i];
-		uint32_t prim = __float_as_uint(h.w);
-		got = prim != RTK_MISS;
-		if (got) {
-			// mesh of the triangle: mesh_first is a short sorted table
-			uint32_t lo = 0, hi = sc.num_meshes;
-			while (hi - lo > 1) {
-				uint32_t mid = (lo + hi) >> 1;
-				if (sc.mesh_first[mid] <= prim) lo = mid; else hi = mid;
-			}
-			const float4 *tv = sc.tri_orig + 3ull * prim;
-			float4 a = __ldg(tv), b = __ldg(tv + 1), cc = __ldg(tv + 2);
-			uint32_t *r = s_row[threadIdx.x];
-			r[0] = __float_as_uint(h.x); r[1] = __float_as_uint(h.y); r[2] = __float_as_uint(h.z);
-			r[3] = __float_as_uint(a.x); r[4] = __float_as_uint(a.y); r[5] = __float_as_uint(a.z); r[6] = __float_as_uint(a.w);
-			r[7] = __float_as_uint(b.x); r[8] = __float_as_uint(b.y); r[9] = __float_as_uint(b.z); r[10] = __float_as_uint(b.w);
-			r[11] = __float_as_uint(cc.x); r[12] = __float_as_uint(cc.y); r[13] = __float_as_uint(cc.z); r[14] = __float_as_uint(cc.w);
-			r[15] = lo;
-			r[16] = prim - sc.mesh_first[lo];
-		}
+		h = hit16[i];
+		got = __float_as_uint(h.w) != RTK_MISS;
 		if (mask) mask[i] = got ? 1 : 0;
 	}
-	s_hit[threadIdx.x] = got ? 1 : 0;
-	{
-		uint32_t m = __ballot_sync(0xffffffffu, got);
-		if (hit_count && (threadIdx.x & 31) == 0 && m) atomicAdd(hit_count, (unsigned long long)__popc(m));
+	const uint32_t m = __ballot_sync(0xffffffffu, got);
+	uint32_t slot = threadIdx.x;                 // row of the staging buffer this thread fills
+	if (DENSE) {
+		if (lane == 0) s_warp[warp] = (uint32_t)__popc(m);
+		__syncthreads();
+		uint32_t before = 0, total = 0;
+		for (int w = 0; w < RTK_RESOLVE_THREADS / 32; w++) { uint32_t c = s_warp[w]; if (w < warp) before += c; total += c; }
+		slot = before + (uint32_t)__popc(m & ((1u << lane) - 1u));
+		if (threadIdx.x == 0) {
+			uint32_t b = total ? (uint32_t)atomicAdd(hit_count, (unsigned long long)total) : 0u;
+			s_warp[RTK_RESOLVE_THREADS / 32] = b;
+			block_base[blockIdx.x] = b;
+		}
+	} else if (hit_count && lane == 0 && m) atomicAdd(hit_count, (unsigned long long)__popc(m));
+	if (got) {
+		const uint32_t prim = __float_as_uint(h.w);
+		// mesh of the triangle: mesh_first is a short sorted table
+		uint32_t lo = 0, hi = sc.num_meshes;
+		while (hi - lo > 1) {
+			uint32_t mid = (lo + hi) >> 1;
+			if (sc.mesh_first[mid] <= prim) lo = mid; else hi = mid;
+		}
+		const float4 *tv = sc.tri_orig + 3ull * prim;
+		float4 a = __ldg(tv), b = __ldg(tv + 1), cc = __ldg(tv + 2);
+		uint32_t *r = s_row[slot];
+		r[0] = __float_as_uint(h.x); r[1] = __float_as_uint(h.y); r[2] = __float_as_uint(h.z);
+		r[3] = __float_as_uint(a.x); r[4] = __float_as_uint(a.y); r[5] = __float_as_uint(a.z); r[6] = __float_as_uint(a.w);
+		r[7] = __float_as_uint(b.x); r[8] = __float_as_uint(b.y); r[9] = __float_as_uint(b.z); r[10] = __float_as_uint(b.w);
+		r[11] = __float_as_uint(cc.x); r[12] = __float_as_uint(cc.y); r[13] = __float_as_uint(cc.z); r[14] = __float_as_uint(cc.w);
+		r[15] = lo;
+		r[16] = prim - sc.mesh_first[lo];
 	}
+	s_hit[threadIdx.x] = got ? 1 : 0;
 	__syncthreads();
-	uint32_t rows = rtk_umin(RTK_RESOLVE_THREADS, nrays > base ? nrays - base : 0u);
-	uint32_t *dst = hits + 17ull * base;
-	for (uint32_t w = threadIdx.x; w < rows * 17u; w += RTK_RESOLVE_THREADS) {
-		uint32_t row = w / 17u;
-		if (s_hit[row]) dst[w] = s_row[row][w - row * 17u];
+	if (DENSE) {
+		uint32_t total = 0;
+		for (int w = 0; w < RTK_RESOLVE_THREADS / 32; w++) total += s_warp[w];
+		uint32_t *dst = hits + 17ull * s_warp[RTK_RESOLVE_THREADS / 32];
+		const uint32_t *src = &s_row[0][0];
+		for (uint32_t w = threadIdx.x; w < total * 17u; w += RTK_RESOLVE_THREADS) dst[w] = src[w];
+	} else {
+		uint32_t rows = rtk_umin(RTK_RESOLVE_THREADS, nrays > base ? nrays - base : 0u);
+		uint32_t *dst = hits + 17ull * base;
+		for (uint32_t w = threadIdx.x; w < rows * 17u; w += RTK_RESOLVE_THREADS) {
+			uint32_t row = w / 17u;
+			if (s_hit[row]) dst[w] = s_row[row][w - row * 17u];
+		}
 	}
 }

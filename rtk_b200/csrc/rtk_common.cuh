@@ -29,13 +29,13 @@
 //                            BVH leaf order; tv0[i].w carries the global triangle number.  A leaf
 //                            is a contiguous run of <= 8 entries, so the 8 lanes of a ray group
 //                            fetch 3 x 128 contiguous bytes.
-//   nodes      [16*M] float4 8-wide nodes, 256 bytes each, two 128-byte lines:
-//                              line 0: child c -> (lo.x, lo.y, lo.z, ref)
-//                              line 1: child c -> (hi.x, hi.y, hi.z, unused)
+//   nodes      [16*M] float4 8-wide nodes, 256 bytes each: child slot k is 32 bytes,
+//                              (lo.x, lo.y, lo.z, ref) (hi.x, hi.y, hi.z, unused)
 //                            ref: 0xffffffff empty | bit31 set: leaf, bits[30:3] first triangle
 //                            (leaf order), bits[2:0] count-1 | else index of an 8-wide node.
-//                            Lane c of a ray group loads float4 c of each line: one coalesced
-//                            128-byte request per line per ray.
+//                            A lane fetches a child with ONE 256-bit load (LDG.E.256, new on
+//                            sm_100); with L lanes per ray, lane c owns slots c, c+L, ... so the
+//                            j-th load of a ray's lanes covers L*32 contiguous bytes.
 //   mesh_first [num_meshes+1] first global triangle number of each mesh.
 // ---------------------------------------------------------------------------------------------
 
@@ -76,6 +76,17 @@ RTK_DEV uint32_t rtk_f2ord(float f)
 RTK_DEV float rtk_ord2f(uint32_t u)
 {
 	return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// 32-byte read-only global load: one LDG.E.256 on sm_100a
+RTK_DEV void rtk_ldg256(const float4 *p, float4 &a, float4 &b)
+{
+#ifdef RTK_SIMT_EMU
+	a = p[0]; b = p[1];
+#else
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+#endif
 }
 
 // asynchronous 16-byte global->shared copy (LDGSTS); the emulator copies synchronously

@@ -557,8 +557,8 @@ extern "C" int rtkd_resolve(rtkd_scene *s, const void *d_hit16, void *d_hits, vo
 	fill_arrays(s, a);
 	unsigned long long *cnt = (unsigned long long*)((unsigned char*)s->scratch + 128);
 	CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), (cudaStream_t)stream));
-	RTK_LAUNCH(k_resolve, (unsigned)((n + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, stream,
-	           a, (const float4*)d_hit16, (uint32_t*)d_hits, (unsigned char*)d_mask, (uint32_t)n, cnt);
+	RTK_LAUNCH(k_resolve<false>, (unsigned)((n + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, stream,
+	           a, (const float4*)d_hit16, (uint32_t*)d_hits, (unsigned char*)d_mask, (uint32_t)n, cnt, (uint32_t*)NULL);
 	CK_LAUNCH();
 	return RTKD_OK;
 }
@@ -610,44 +610,107 @@ extern "C" void *rtkd_scene_hit16(rtkd_scene *s, size_t n)
 	return s->hit16;
 }
 
-// Host-buffer batch.  Rays go up and hits come back in chunks on two streams so that the
-// H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap.  The
-// device staging buffers and streams are created once per process and reused.
+// Host-buffer batch: a three-stage pipeline over chunks of RTKD_HOST_CHUNK rays, RTKD_HOST_BUFS chunks
+// in flight on their own streams.
+//   stage A (enqueue)  H2D rays -> k_trace -> k_resolve<dense> -> D2H of the chunk's mask bytes,
+//                      block bases and hit count into pinned staging
+//   stage B            once the count is known: D2H of exactly the rows of the rays that hit
+//   stage C            the host worker pool (rtk_place.c) copies each row to hits[i]
+// Only hit rows cross PCIe (68 bytes per HIT plus 1 byte per ray instead of 69 bytes per ray), and
+// rows of rays that missed are left untouched in the caller's array, the reference's miss rule
+// (rtk.c:571-576).  The traversal scratch (ray cursor, overflow slab) belongs to the scene, so the
+// TRAVERSALS of consecutive chunks are serialised with an event; everything else overlaps.
+#define RTKD_HOST_CHUNK ((size_t)1 << 20)
+#define RTKD_HOST_BUFS 4
+
+struct host_buf {
+	cudaStream_t st;
+	cudaEvent_t traced, meta_done, rows_done;
+	float4 *d_rays, *d_h16;
+	uint32_t *d_rows, *d_base;          // d_base: [blocks] block bases, then the 64-bit hit count
+	unsigned char *d_mask;
+	unsigned char *h_meta;              // pinned: mask bytes | block bases | hit count
+	unsigned char *h_rows;              // pinned: dense rows
+	size_t off, cnt, hits;              // the chunk this buffer currently carries
+	int ticket, state;                  // state: 0 free, 1 stage A queued, 2 stage B queued, 3 placing
+};
 struct host_stage {
-	size_t chunk;
-	cudaStream_t st[2];
-	cudaEvent_t done[2];
-	float4 *d_rays[2], *d_h16[2];
-	uint32_t *d_hits[2];
-	unsigned char *d_mask[2];
+	size_t chunk, blocks, meta_bytes;
+	host_buf b[RTKD_HOST_BUFS];
 	bool ready;
 };
 static host_stage g_stage;
 static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;
 
+static void stage_release(void)
+{
+	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
+		host_buf &B = g_stage.b[k];
+		cudaFree(B.d_rays); cudaFree(B.d_h16); cudaFree(B.d_rows); cudaFree(B.d_base); cudaFree(B.d_mask);
+		cudaFreeHost(B.h_meta); cudaFreeHost(B.h_rows);
+		B.d_rays = B.d_h16 = NULL; B.d_rows = B.d_base = NULL; B.d_mask = NULL; B.h_meta = B.h_rows = NULL;
+	}
+}
+
 static int stage_prepare(size_t want)
 {
-	const size_t CH = (size_t)1 << 21;            // 2 Mi rays = 64 MiB up, 136 MiB down per chunk
-	size_t chunk = want < CH ? want : CH;
+	size_t chunk = want < RTKD_HOST_CHUNK ? want : RTKD_HOST_CHUNK;
 	if (chunk < 4096) chunk = 4096;
 	if (g_stage.ready && g_stage.chunk >= chunk) return RTKD_OK;
-	if (g_stage.ready) {
-		for (int k = 0; k < 2; k++) { cudaFree(g_stage.d_rays[k]); cudaFree(g_stage.d_h16[k]); cudaFree(g_stage.d_hits[k]); cudaFree(g_stage.d_mask[k]); }
-	} else {
-		for (int k = 0; k < 2; k++) {
-			CK(cudaStreamCreateWithFlags(&g_stage.st[k], cudaStreamNonBlocking));
-			CK(cudaEventCreate(&g_stage.done[k]));
+	if (g_stage.ready) stage_release();
+	else {
+		for (int k = 0; k < RTKD_HOST_BUFS; k++) {
+			host_buf &B = g_stage.b[k];
+			CK(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&B.traced, cudaEventDisableTiming));
+			CK(cudaEventCreateWithFlags(&B.meta_done, cudaEventDisableTiming));
+			CK(cudaEventCreateWithFlags(&B.rows_done, cudaEventDisableTiming));
 		}
 	}
 	g_stage.ready = false;
-	for (int k = 0; k < 2; k++) {
-		CK(cudaMalloc(&g_stage.d_rays[k], 32 * chunk));
-		CK(cudaMalloc(&g_stage.d_h16[k], 16 * chunk));
-		CK(cudaMalloc(&g_stage.d_hits[k], 68 * chunk));
-		CK(cudaMalloc(&g_stage.d_mask[k], chunk));
-	}
 	g_stage.chunk = chunk;
+	g_stage.blocks = ((chunk + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS + 3) & ~(size_t)3;   // the 64-bit count follows: keep it aligned
+	g_stage.meta_bytes = ((chunk + 15) & ~(size_t)15) + 4 * g_stage.blocks + 16;
+	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
+		host_buf &B = g_stage.b[k];
+		CK(cudaMalloc(&B.d_rays, 32 * chunk));
+		CK(cudaMalloc(&B.d_h16, 16 * chunk));
+		CK(cudaMalloc(&B.d_rows, 68 * chunk));
+		CK(cudaMalloc(&B.d_base, 4 * g_stage.blocks + 16));
+		CK(cudaMalloc(&B.d_mask, (chunk + 15) & ~(size_t)15));
+		CK(cudaMallocHost(&B.h_meta, g_stage.meta_bytes));
+		CK(cudaMallocHost(&B.h_rows, 68 * chunk));
+		B.state = 0; B.ticket = -1;
+	}
 	g_stage.ready = true;
+	return RTKD_OK;
+}
+
+// stage B of one buffer: wait for the chunk's count, then fetch exactly its rows
+static int host_stage_b(host_buf &B)
+{
+	CK(cudaEventSynchronize(B.meta_done));
+	const size_t mask_bytes = (g_stage.chunk + 15) & ~(size_t)15;
+	unsigned long long hc = 0;
+	memcpy(&hc, B.h_meta + mask_bytes + 4 * g_stage.blocks, sizeof(hc));
+	B.hits = (size_t)hc;
+	if (B.hits) CK(cudaMemcpyAsync(B.h_rows, B.d_rows, 68 * B.hits, cudaMemcpyDeviceToHost, B.st));
+	CK(cudaEventRecord(B.rows_done, B.st));
+	B.state = 2;
+	return RTKD_OK;
+}
+
+// stage C: hand the rows to the placement workers
+static int host_stage_c(host_buf &B, void *hits, unsigned char *mask)
+{
+	CK(cudaEventSynchronize(B.rows_done));
+	const size_t mask_bytes = (g_stage.chunk + 15) & ~(size_t)15;
+	rtkd_place_desc d;
+	d.hits = hits; d.mask_out = mask;
+	d.rows = B.h_rows; d.mask = B.h_meta; d.block_base = (const uint32_t*)(B.h_meta + mask_bytes);
+	d.first_ray = B.off; d.nrays = B.cnt;
+	B.ticket = rtkd_place_submit(&d);
+	B.state = 3;
 	return RTKD_OK;
 }
 
@@ -655,59 +718,55 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 {
 	if (!n) return 0;
 	pthread_mutex_lock(&g_stage_lock);
-	long long total = -1;
+	long long total = 0;
 	int rc = stage_prepare(n);
 	if (rc == RTKD_OK) rc = ensure_scratch(s);
 	host_stage &G = g_stage;
-	unsigned long long *d_count = NULL;
-	if (rc == RTKD_OK) {
-		d_count = (unsigned long long*)((unsigned char*)s->scratch + 128);
-		if (cudaMemset(d_count, 0, sizeof(unsigned long long)) != cudaSuccess) rc = RTKD_ERR_CUDA;
-	}
-	// Hit rows always travel through device staging and one bulk D2H copy per chunk.  (Writing the
-	// rows of rays that hit straight into pinned caller memory from k_resolve was measured: 522 vs
-	// 627 Mrays/s end to end on C3 -- 68-byte rows with holes make poor PCIe writes.)
-	uint32_t *direct_hits = NULL;
-	unsigned char *direct_mask = NULL;
-	// The traversal scratch (ray cursor, overflow slab) belongs to the scene, so the TRAVERSALS of
-	// consecutive chunks are serialised on purpose; the H2D copy of chunk k+1, the hit expansion and
-	// the D2H traffic of chunk k run beside them on the other stream.
 	const size_t chunk = G.chunk;
 	const size_t nchunks = (n + chunk - 1) / chunk;
-	for (size_t ci = 0; ci < nchunks && rc == RTKD_OK; ci++) {
-		int k = (int)(ci & 1);
-		size_t off = ci * chunk, cnt = n - off < chunk ? n - off : chunk;
-		cudaStream_t q = G.st[k];
-		if (cudaMemcpyAsync(G.d_rays[k], (const char*)rays + 32 * off, 32 * cnt, cudaMemcpyHostToDevice, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
-		if (!direct_hits && cudaMemsetAsync(G.d_hits[k], 0, 68 * cnt, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
-		if (ci > 0) cudaStreamWaitEvent(q, G.done[k ^ 1], 0);
-		rc = rtkd_trace(s, G.d_rays[k], G.d_h16[k], cnt, 1, NULL, q);
-		if (rc) break;
-		cudaEventRecord(G.done[k], q);
-		{
-			rtkd_arrays a;
-			fill_arrays(s, a);
-			uint32_t *oh = direct_hits ? direct_hits + 17 * off : G.d_hits[k];
-			unsigned char *om = mask ? (direct_mask ? direct_mask + off : G.d_mask[k]) : G.d_mask[k];
-			RTK_LAUNCH(k_resolve, (unsigned)((cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, q,
-			           a, (const float4*)G.d_h16[k], oh, om, (uint32_t)cnt, d_count);
+	const size_t mask_bytes = (chunk + 15) & ~(size_t)15;
+	rtkd_arrays a;
+	fill_arrays(s, a);
+	cudaEvent_t prev_traced = NULL;
+	// chunk ci enters stage A in iteration ci, stage B in iteration ci+1, stage C in iteration ci+2
+	// and its buffer is reused in iteration ci + RTKD_HOST_BUFS
+	for (size_t it = 0; it < nchunks + 2 && rc == RTKD_OK; it++) {
+		if (it < nchunks) {
+			host_buf &B = G.b[it % RTKD_HOST_BUFS];
+			if (B.state == 3) { rtkd_place_wait(B.ticket); total += (long long)B.hits; B.state = 0; }
+			B.off = it * chunk; B.cnt = n - B.off < chunk ? n - B.off : chunk;
+			unsigned long long *d_count = (unsigned long long*)((unsigned char*)B.d_base + 4 * G.blocks);
+			cudaError_t e = cudaMemcpyAsync(B.d_rays, (const char*)rays + 32 * B.off, 32 * B.cnt, cudaMemcpyHostToDevice, B.st);
+			if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, 16, B.st);
+			if (e == cudaSuccess && prev_traced) e = cudaStreamWaitEvent(B.st, prev_traced, 0);
+			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
+			rc = rtkd_trace(s, B.d_rays, B.d_h16, B.cnt, 1, NULL, B.st);
+			if (rc) break;
+			cudaEventRecord(B.traced, B.st);
+			prev_traced = B.traced;
+			const unsigned blocks = (unsigned)((B.cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS);
+			RTK_LAUNCH(k_resolve<true>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)B.cnt, d_count, B.d_base);
+			e = cudaGetLastError();
+			// mask bytes and bases+count land in one pinned block: [mask | bases | count]
+			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_meta, B.d_mask, B.cnt, cudaMemcpyDeviceToHost, B.st);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_meta + mask_bytes, B.d_base, 4 * G.blocks + 16, cudaMemcpyDeviceToHost, B.st);
+			if (e == cudaSuccess) e = cudaEventRecord(B.meta_done, B.st);
+			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
+			B.state = 1;
 		}
-		if (!direct_hits && cudaMemcpyAsync((char*)hits + 68 * off, G.d_hits[k], 68 * cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
-		if (mask && !direct_mask && cudaMemcpyAsync(mask + off, G.d_mask[k], cnt, cudaMemcpyDeviceToHost, q) != cudaSuccess) { rc = RTKD_ERR_CUDA; break; }
+		if (it >= 1 && it - 1 < nchunks) rc = host_stage_b(G.b[(it - 1) % RTKD_HOST_BUFS]);
+		if (rc == RTKD_OK && it >= 2 && it - 2 < nchunks) rc = host_stage_c(G.b[(it - 2) % RTKD_HOST_BUFS], hits, mask);
 	}
-	if (G.ready) {
-		for (int k = 0; k < 2; k++) {
-			if (cudaStreamSynchronize(G.st[k]) != cudaSuccess && rc == RTKD_OK) {
-				rtkd_set_error("batch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = RTKD_ERR_CUDA;
-			}
-		}
+	// drain: placements still running, and -- after an error -- whatever is still queued
+	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
+		host_buf &B = G.b[k];
+		if (B.state == 3) { rtkd_place_wait(B.ticket); total += (long long)B.hits; }
+		else if (B.state) cudaStreamSynchronize(B.st);
+		B.state = 0; B.ticket = -1;
 	}
 	if (rc == RTKD_OK) {
-		unsigned long long hc = 0;
 		uint32_t herr = 0;
-		if (cudaMemcpy(&hc, d_count, sizeof(hc), cudaMemcpyDeviceToHost) != cudaSuccess) rc = RTKD_ERR_CUDA;
 		if (cudaMemcpy(&herr, (unsigned char*)s->scratch + 192, sizeof(herr), cudaMemcpyDeviceToHost) != cudaSuccess) rc = RTKD_ERR_CUDA;
-		total = (long long)hc;
 		if (herr & 2u) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
 	}
 	if (rc == RTKD_ERR_CUDA && !g_err[0]) rtkd_set_error("CUDA failure in rtk_trace_rays");
@@ -720,7 +779,7 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 // ---------------------------------------------------------------------------------------------
 
 struct rtkd_blob_sub {          // 128 bytes, first thing in the payload
-	uint64_t magic2;            // "B200RTK1"
+	uint64_t magic2;            // "B200RTK2"
 	uint64_t id;
 	uint32_t num_tris, num_meshes, num_nodes, num_leaves, depth, build_mode;
 	float bounds_min[3], bounds_max[3], abs_max;
@@ -753,7 +812,7 @@ extern "C" int rtkd_blob_write(const rtkd_scene *s, void *payload)
 {
 	rtkd_blob_sub b;
 	memset(&b, 0, sizeof(b));
-	memcpy(&b.magic2, "B200RTK1", 8);
+	memcpy(&b.magic2, "B200RTK2", 8);
 	b.id = s->id;
 	b.num_tris = s->num_tris; b.num_meshes = s->num_meshes; b.num_nodes = s->num_nodes;
 	b.num_leaves = s->num_leaves; b.depth = s->depth; b.build_mode = s->build_mode;
@@ -781,7 +840,7 @@ extern "C" rtkd_scene *rtkd_blob_read(const void *payload, size_t payload_size)
 	rtkd_blob_sub b;
 	if (payload_size < sizeof(b)) { rtkd_set_error("scene blob truncated"); return NULL; }
 	memcpy(&b, payload, sizeof(b));
-	if (memcmp(&b.magic2, "B200RTK1", 8) != 0) { rtkd_set_error("blob was not written by rtk_b200 (device-layout magic missing)"); return NULL; }
+	if (memcmp(&b.magic2, "B200RTK2", 8) != 0) { rtkd_set_error("blob was not written by rtk_b200 (device-layout magic missing)"); return NULL; }
 	if (b.off_mesh + 4 * ((size_t)b.num_meshes + 1) > payload_size) { rtkd_set_error("scene blob truncated"); return NULL; }
 	const char *p = (const char*)payload;
 	rtkd_scene *s = rtkd_scene_new(b.num_tris, b.num_meshes, (const uint32_t*)(p + b.off_mesh));

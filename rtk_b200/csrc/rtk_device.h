@@ -75,6 +75,21 @@ int rtkd_gen_bounce(rtkd_scene *s, const void *d_rays_in, const void *d_hit16, v
 /* host-buffer batch: H2D, trace, resolve, D2H; returns hits or -1 */
 long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n);
 
+/* host placement of dense hit rows (rtk_place.c): for every ray i of the chunk with mask[i] != 0
+ * the next 68-byte row of its 128-ray block -- block b's rows start at rows[block_base[b]] --
+ * is copied to hits[first_ray + i]; mask_out (may be NULL) receives the mask bytes. */
+typedef struct rtkd_place_desc {
+	void *hits;                       /* caller's rtk_hit array (whole batch) */
+	unsigned char *mask_out;          /* caller's mask array (whole batch) or NULL */
+	const void *rows;                 /* dense rows of this chunk */
+	const unsigned char *mask;        /* mask bytes of this chunk */
+	const uint32_t *block_base;       /* first row of each 128-ray block */
+	size_t first_ray, nrays;          /* the chunk's position in the batch */
+} rtkd_place_desc;
+int  rtkd_place_submit(const rtkd_place_desc *d);   /* returns a ticket (or -1: done synchronously) */
+void rtkd_place_wait(int ticket);
+int  rtkd_place_threads(void);
+
 /* serialisation of the device layout into a relocatable blob (payload after the 128-byte
  * header block that rtk_host.c writes) */
 size_t      rtkd_blob_payload_size(const rtkd_scene *s);

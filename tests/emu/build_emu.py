@@ -19,13 +19,15 @@ def build(force=False, verbose=False):
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
     dev_o, host_o = os.path.join(bdir, "rtk_device_emu.o"), os.path.join(bdir, "rtk_host_emu.o")
+    place_o = os.path.join(bdir, "rtk_place_emu.o")
     cmds = [
         ["g++", "-x", "c++", "-std=c++17", "-O2", "-g", "-fPIC", "-ffp-contract=off", "-mfma", "-w",
          *os.environ.get("RTK_EMU_DEFINES", "").split(),
          "-DRTK_SIMT_EMU=1", "-DSIMT_IMPL=1", "-include", os.path.join(HERE, "simt.h"),
          "-c", os.path.join(CSRC, "rtk_device.cu"), "-o", dev_o],
         ["gcc", "-O2", "-g", "-fPIC", "-std=gnu11", "-c", os.path.join(CSRC, "rtk_host.c"), "-o", host_o],
-        ["g++", "-shared", "-o", OUT, dev_o, host_o, "-lpthread", "-lm"],
+        ["gcc", "-O2", "-g", "-fPIC", "-std=gnu11", "-c", os.path.join(CSRC, "rtk_place.c"), "-o", place_o],
+        ["g++", "-shared", "-o", OUT, dev_o, host_o, place_o, "-lpthread", "-lm"],
     ]
     for c in cmds:
         r = subprocess.run(c, capture_output=True, text=True)

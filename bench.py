@@ -198,6 +198,7 @@ def run_wavefront(args, workload, lib, api, scene, rank, world, local_rank):
     npx = W * rows
     n = npx * SPP
     sc = lib.build_scene(scene["meshes"])
+    assert lib.rtk_cuda_rebuild_scene(sc.ptr, None) == 0, lib.last_error()     # device time of a warm build
     info = sc.info()
     cam = terrain_camera(api, scene, W, H)
     stream = torch.cuda.current_stream()

@@ -377,7 +377,8 @@ struct rtkd_collapse_args {
 	const uint2 *work_in; const uint32_t *n_in;    // the level's item count lives on the device
 	uint2 *work_out; uint32_t *n_out;
 	uint32_t *node_alloc; uint32_t node_cap;
-	uint32_t *leaf_count;
+	uint32_t *leaf_count;        // also the leaf slot allocator
+	uint2 *leaf_list;            // [slot] = (first sorted position, count): filled here, read by k_emit_leaves
 	double *sah_cost;            // accumulates area-weighted cost (divide by root area on host)
 	float4 *nodes;
 	int n;                       // triangles
@@ -412,7 +413,6 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 	}
 	float4 *node = a.nodes + 16ull * dst;
 	double cost = 0.0;
-	uint32_t leaves = 0;
 	for (int k = 0; k < RTK_WIDE; k++) {
 		if (k >= ns) {
 			node[2 * k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, __uint_as_float(RTK_REF_EMPTY));
@@ -431,8 +431,11 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 		} else {
 			uint32_t first = c >= 0 ? (uint32_t)t.first[c] : (uint32_t)~c;
 			uint32_t count = c >= 0 ? (uint32_t)(t.last[c] - t.first[c] + 1) : 1u;
-			ref = rtk_leaf_ref(first, count);
-			leaves++;
+			// every leaf owns an 8-triangle slot of the traversal arrays: 128 aligned bytes per array
+			uint32_t slot = atomicAdd(a.leaf_count, 1u);
+			if (slot >= RTK_MAX_LEAVES) { atomicOr(a.err, 2u); slot = 0; }
+			a.leaf_list[slot] = make_uint2(first, count);
+			ref = rtk_leaf_ref(slot * RTK_LEAF_MAX, count);
 		}
 		cost += (double)rtk_half_area(lo, hi);       // node step or one 8-lane triangle round: cost 1
 		lo.w = __uint_as_float(ref); hi.w = 0.0f;
@@ -441,7 +444,6 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 #undef RTK_OPENABLE
 #undef RTK_BIDX
 	atomicAdd(a.sah_cost, cost);
-	if (leaves) atomicAdd(a.leaf_count, leaves);
 }
 
 // scene with a single triangle: a root node with one leaf child
@@ -459,14 +461,23 @@ __global__ void k_single_root(const float4 *tri_orig, const uint32_t *vals, floa
 	nodes[1] = make_float4(rtk_fmax(rtk_fmax(a.x, b.x), c.x), rtk_fmax(rtk_fmax(a.y, b.y), c.y), rtk_fmax(rtk_fmax(a.z, b.z), c.z), 0.0f);
 }
 
-// leaf-ordered SoA triangles: tv0[i].w = global triangle number
-__global__ void k_emit_tris(const float4 *tri_orig, const uint32_t *vals, uint32_t n,
-                            float4 *tv0, float4 *tv1, float4 *tv2)
+// traversal triangles, SoA, one 8-entry slot per leaf (tv0[i].w = global triangle number): the
+// triangles of a leaf are 128 contiguous, 128-byte aligned bytes in each of the three arrays, so
+// the 8 lanes that test a leaf touch exactly one line per array.  Unused entries of a slot are
+// never read by the traversal (the leaf reference carries the count); they are zero-filled with
+// id RTK_MISS.
+__global__ void k_emit_leaves(const float4 *tri_orig, const uint32_t *vals, const uint2 *leaf_list, uint32_t num_leaves,
+                              float4 *tv0, float4 *tv1, float4 *tv2)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	uint32_t prim = vals[i];
-	float4 a = tri_orig[3ull * prim], b = tri_orig[3ull * prim + 1], c = tri_orig[3ull * prim + 2];
-	a.w = __uint_as_float(prim);
+	if (i >= num_leaves * RTK_LEAF_MAX) return;
+	const uint2 lf = leaf_list[i / RTK_LEAF_MAX];
+	const uint32_t j = i % RTK_LEAF_MAX;
+	float4 a = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(RTK_MISS)), b = make_float4(0.0f, 0.0f, 0.0f, 0.0f), c = b;
+	if (j < lf.y) {
+		const uint32_t prim = vals[lf.x + j];
+		a = tri_orig[3ull * prim]; b = tri_orig[3ull * prim + 1]; c = tri_orig[3ull * prim + 2];
+		a.w = __uint_as_float(prim);
+	}
 	tv0[i] = a; tv1[i] = b; tv2[i] = c;
 }

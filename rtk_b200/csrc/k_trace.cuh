@@ -168,7 +168,14 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 	} while (0)
 #define RTK_STACK_POP() do { \
 		cur_ref = RTK_REF_EMPTY; \
-		while (sp > 0) { \
+		if (sp <= RTK_STACK_SMEM) { \
+			/* common case: everything the ray has pushed lives in shared memory */ \
+			while (sp > 0) { \
+				--sp; \
+				const uint2 _e = s_stack[sp][gcta]; \
+				if (__uint_as_float(_e.x) <= best_t) { cur_ref = _e.y; break; } \
+			} \
+		} else while (sp > 0) { \
 			--sp; \
 			uint2 _e; \
 			if (sp < RTK_STACK_SMEM) _e = s_stack[sp][gcta]; \
@@ -442,15 +449,25 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 			const uint32_t nref = __shfl_sync(FULL, okref, cmin & (LANES - 1), LANES);
 			if (is_node) {
 				const uint32_t others = gm & ~(1u << cmin);
+				const int npush = __popc(others);
+				if (sp + npush <= RTK_STACK_SMEM) {
+					// common case: the pushes fit in shared memory, no bounds checks
 #pragma unroll
-				for (int j = 0; j < CPL; j++) {
-					const int k = j * LANES + c;
-					if ((others >> k) & 1u) {
-						int pos = sp + __popc(others & ((1u << k) - 1u));
-						RTK_STACK_WRITE(pos, make_uint2(__float_as_uint(key[j]), ref[j]));
+					for (int j = 0; j < CPL; j++) {
+						const int k = j * LANES + c;
+						if ((others >> k) & 1u) s_stack[sp + __popc(others & ((1u << k) - 1u))][gcta] = make_uint2(__float_as_uint(key[j]), ref[j]);
+					}
+				} else {
+#pragma unroll
+					for (int j = 0; j < CPL; j++) {
+						const int k = j * LANES + c;
+						if ((others >> k) & 1u) {
+							int pos = sp + __popc(others & ((1u << k) - 1u));
+							RTK_STACK_WRITE(pos, make_uint2(__float_as_uint(key[j]), ref[j]));
+						}
 					}
 				}
-				sp += __popc(others);
+				sp += npush;
 				if (STATS) st_stack = rtk_umax(st_stack, (uint32_t)sp);
 			}
 			__syncwarp();
@@ -510,19 +527,19 @@ __global__ void __launch_bounds__(128) k_trace_brute(rtkd_arrays sc, const float
 		rtk_ray_setup(rc, r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, sc.abs_max);
 		best_t = max_t = r1.w;
 	}
-	for (uint32_t base = 0; base < sc.num_tris; base += RTK_BRUTE_TILE) {
+	for (uint32_t base = 0; base < sc.num_tv; base += RTK_BRUTE_TILE) {
 		uint32_t k = base + threadIdx.x;
 		__syncthreads();
-		if (threadIdx.x < RTK_BRUTE_TILE && k < sc.num_tris) {
+		if (threadIdx.x < RTK_BRUTE_TILE && k < sc.num_tv) {
 			s_v0[threadIdx.x] = sc.tv0[k]; s_v1[threadIdx.x] = sc.tv1[k]; s_v2[threadIdx.x] = sc.tv2[k];
 		}
 		__syncthreads();
-		uint32_t cnt = rtk_umin(RTK_BRUTE_TILE, sc.num_tris - base);
+		uint32_t cnt = rtk_umin(RTK_BRUTE_TILE, sc.num_tv - base);
 		if (live) {
 			for (uint32_t j = 0; j < cnt; j++) {
 				float t, u, v;
-				if (rtk_tri_test(rc, s_v0[j], s_v1[j], s_v2[j], best_t, t, u, v)) {
-					uint32_t id = __float_as_uint(s_v0[j].w);
+				const uint32_t id = __float_as_uint(s_v0[j].w);
+				if (id != RTK_MISS && rtk_tri_test(rc, s_v0[j], s_v1[j], s_v2[j], best_t, t, u, v)) {
 					if (t < best_t || (best_prim != RTK_MISS && id < best_prim)) {
 						best_t = t; best_u = u; best_v = v; best_prim = id;
 					}

@@ -25,10 +25,10 @@
 //   tri_orig   [3*N] float4  original-order triangles, one rtk_vertex (xyz + mesh vertex index)
 //                            per corner: exactly the 48 bytes rtk_hit::vertex[3] wants
 //                            (reference rtk.c:1162-1167, 376-378).  Read by the resolve kernel.
-//   tv0,tv1,tv2 [N] float4   leaf-ordered SoA copy for traversal: corner k of the i-th triangle in
-//                            BVH leaf order; tv0[i].w carries the global triangle number.  A leaf
-//                            is a contiguous run of <= 8 entries, so the 8 lanes of a ray group
-//                            fetch 3 x 128 contiguous bytes.
+//   tv0,tv1,tv2 [8*leaves] float4  SoA copy for traversal, one 8-entry slot per leaf: corner k of
+//                            the j-th triangle of leaf L is tvk[8L+j]; tv0[i].w carries the global
+//                            triangle number (RTK_MISS in the unused tail of a slot).  The 8 lanes
+//                            that test a leaf fetch one aligned 128-byte line per array.
 //   nodes      [16*M] float4 8-wide nodes, 256 bytes each: child slot k is 32 bytes,
 //                              (lo.x, lo.y, lo.z, ref) (hi.x, hi.y, hi.z, unused)
 //                            ref: 0xffffffff empty | bit31 set: leaf, bits[30:3] first triangle
@@ -43,6 +43,7 @@
 #ifndef RTK_LEAF_MAX
 #define RTK_LEAF_MAX 8                   // triangles per leaf (<= 8: the leaf reference keeps count-1 in 3 bits)
 #endif
+#define RTK_MAX_LEAVES (1u << 25)         // 8 * leaves must fit the 28-bit "first" field of a leaf reference
 #define RTK_REF_EMPTY 0xffffffffu
 #define RTK_REF_LEAF 0x80000000u
 
@@ -52,6 +53,7 @@ struct rtkd_arrays {
 	const float4 *nodes;
 	const uint32_t *mesh_first;
 	uint32_t num_tris, num_meshes, num_nodes;
+	uint32_t num_tv;                     // entries of tv0/tv1/tv2 = 8 * leaves
 	float abs_max;                       // largest |coordinate| of the scene bounds
 };
 

@@ -213,6 +213,7 @@ struct build_bufs {
 	float4 *wide;
 	uint2 *work[2];
 	uint32_t *ctr;
+	uint2 *leaf_list;
 	double *d_cost;
 	uint32_t cap, nblocks;
 	size_t act_cap, small_cap;
@@ -256,6 +257,7 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 	B.wide = A.take<float4>(16 * (size_t)B.cap);
 	B.work[0] = A.take<uint2>(B.cap); B.work[1] = A.take<uint2>(B.cap);
 	B.ctr = A.take<uint32_t>(8 + RTKD_COLLAPSE_LEVELS);
+	B.leaf_list = A.take<uint2>(n);
 	B.d_cost = A.take<double>(1);
 }
 
@@ -301,7 +303,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
 	CK(cudaEventRecord(e0, st));
 
-	s->num_nodes = 0; s->num_leaves = 0; s->depth = 0; s->sah_cost = 0.0;
+	s->num_nodes = 0; s->num_leaves = 0; s->num_tv = 0; s->depth = 0; s->sah_cost = 0.0;
 	for (int k = 0; k < 3; k++) { s->bounds_min[k] = 0.0f; s->bounds_max[k] = 0.0f; }
 	s->abs_max = 0.0f;
 	if (n == 0) {
@@ -310,13 +312,6 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		cudaEventDestroy(e0); cudaEventDestroy(e1);
 		return RTKD_OK;
 	}
-	// traversal triangle arrays depend on n only: allocated once, reused by rebuilds
-	if (!s->tv0) {
-		CK(cudaMalloc((float4**)&s->tv0, sizeof(float4) * (size_t)n));
-		CK(cudaMalloc((float4**)&s->tv1, sizeof(float4) * (size_t)n));
-		CK(cudaMalloc((float4**)&s->tv2, sizeof(float4) * (size_t)n));
-	}
-
 	const bool use_sah = mode == 1 && n > RTK_LEAF_MAX;
 	build_arena A = { NULL, 0, 0 };
 	build_bufs B;
@@ -359,13 +354,12 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		RTK_LAUNCH(k_hierarchy, (n - 1 + 255) / 256, 256, st, skeys, (int)n, t); CK_LAUNCH();
 		RTK_LAUNCH(k_refit, (n + 255) / 256, 256, st, tri, svals, (int)n, t); CK_LAUNCH();
 	}
-	// traversal triangles in leaf order
-	RTK_LAUNCH(k_emit_tris, (n + 255) / 256, 256, st, tri, svals, n, (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
-
 	uint32_t num_nodes = 0, num_leaves = 0, depth = 0;
 	double h_cost = 0.0;
 	if (n == 1) {
 		RTK_LAUNCH(k_single_root, 1, 32, st, tri, svals, B.wide); CK_LAUNCH();
+		const uint2 l0 = make_uint2(0u, 1u);
+		CK(cudaMemcpyAsync(B.leaf_list, &l0, sizeof(l0), cudaMemcpyHostToDevice, st));
 		num_nodes = 1; num_leaves = 1; depth = 1;
 	} else {
 		// ctr: [0] node_alloc [1] leaf_count [2] err [8 + L] items queued for level L
@@ -386,7 +380,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 				rtkd_collapse_args a;
 				a.work_in = B.work[level & 1]; a.n_in = B.ctr + 8 + level;
 				a.work_out = B.work[(level & 1) ^ 1]; a.n_out = B.ctr + 8 + level + 1;
-				a.node_alloc = B.ctr; a.node_cap = B.cap; a.leaf_count = B.ctr + 1; a.sah_cost = B.d_cost;
+				a.node_alloc = B.ctr; a.node_cap = B.cap; a.leaf_count = B.ctr + 1; a.leaf_list = B.leaf_list; a.sah_cost = B.d_cost;
 				a.nodes = B.wide; a.n = (int)n; a.err = B.ctr + 2;
 				uint32_t width = (uint32_t)(bound < B.cap ? bound : B.cap);
 				RTK_LAUNCH(k_collapse, (width + 127) / 128, 128, st, a, t); CK_LAUNCH();
@@ -399,7 +393,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		for (depth = 0; depth < RTKD_COLLAPSE_LEVELS && h_ctr[8 + depth]; depth++) { }
 		num_nodes = h_ctr[0]; num_leaves = h_ctr[1];
 		if (h_ctr[2] || h_ctr[8 + RTKD_COLLAPSE_LEVELS - 1]) {
-			rtkd_set_error("wide-node pool exhausted (cap %u) or tree deeper than %d", B.cap, RTKD_COLLAPSE_LEVELS);
+			rtkd_set_error("wide-node pool exhausted (cap %u), tree deeper than %d or more than %u leaves", B.cap, RTKD_COLLAPSE_LEVELS, RTK_MAX_LEAVES);
 			cudaFreeAsync(A.base, st);
 			return RTKD_ERR_MEMORY;
 		}
@@ -414,6 +408,20 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		s->nodes_cap = num_nodes;
 	}
 	CK(cudaMemcpyAsync(s->nodes, B.wide, sizeof(float4) * 16 * (size_t)num_nodes, cudaMemcpyDeviceToDevice, st));
+	// traversal triangles: one 8-entry slot per leaf, sized now that the leaves are counted
+	const uint32_t num_tv = num_leaves * RTK_LEAF_MAX;
+	if (!s->tv0 || s->tv_cap < num_tv) {
+		if (s->tv0) { cudaFree(s->tv0); cudaFree(s->tv1); cudaFree(s->tv2); }
+		s->tv0 = s->tv1 = s->tv2 = NULL;
+		const uint32_t cap = num_tv + num_tv / 16 + 64;        // rebuilds of a deforming mesh rarely need a new allocation
+		CK(cudaMalloc((float4**)&s->tv0, sizeof(float4) * (size_t)cap));
+		CK(cudaMalloc((float4**)&s->tv1, sizeof(float4) * (size_t)cap));
+		CK(cudaMalloc((float4**)&s->tv2, sizeof(float4) * (size_t)cap));
+		s->tv_cap = cap;
+	}
+	RTK_LAUNCH(k_emit_leaves, (num_tv + 255) / 256, 256, st, tri, svals, (const uint2*)B.leaf_list, num_leaves,
+	           (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
+	s->num_tv = num_tv;
 	cudaFreeAsync(A.base, st);
 
 	CK(cudaEventRecord(e1, st));
@@ -454,6 +462,7 @@ static void fill_arrays(const rtkd_scene *s, rtkd_arrays &a)
 	a.nodes = (const float4*)s->nodes;
 	a.mesh_first = (const uint32_t*)s->mesh_first;
 	a.num_tris = s->num_tris; a.num_meshes = s->num_meshes; a.num_nodes = s->num_nodes;
+	a.num_tv = s->num_tv;
 	a.abs_max = s->abs_max;
 }
 
@@ -654,7 +663,12 @@ static void stage_release(void)
 
 static int stage_prepare(size_t want)
 {
-	size_t chunk = want < RTKD_HOST_CHUNK ? want : RTKD_HOST_CHUNK;
+	size_t max_chunk = RTKD_HOST_CHUNK;
+	{
+		const char *e = getenv("RTK_B200_HOST_CHUNK_LOG2");       // experiment knob
+		if (e && atoi(e) >= 12 && atoi(e) <= 24) max_chunk = (size_t)1 << atoi(e);
+	}
+	size_t chunk = want < max_chunk ? want : max_chunk;
 	if (chunk < 4096) chunk = 4096;
 	if (g_stage.ready && g_stage.chunk >= chunk) return RTKD_OK;
 	if (g_stage.ready) stage_release();
@@ -779,11 +793,11 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 // ---------------------------------------------------------------------------------------------
 
 struct rtkd_blob_sub {          // 128 bytes, first thing in the payload
-	uint64_t magic2;            // "B200RTK2"
+	uint64_t magic2;            // "B200RTK3"
 	uint64_t id;
 	uint32_t num_tris, num_meshes, num_nodes, num_leaves, depth, build_mode;
 	float bounds_min[3], bounds_max[3], abs_max;
-	float pad0;
+	uint32_t num_tv;            // entries of each traversal triangle array (8 per leaf)
 	double sah_cost;
 	uint64_t off_nodes, off_tv0, off_tv1, off_tv2, off_orig, off_mesh;   // from payload start
 };
@@ -794,9 +808,9 @@ static void blob_layout(const rtkd_scene *s, rtkd_blob_sub *b)
 {
 	size_t o = a128(sizeof(rtkd_blob_sub));
 	b->off_nodes = o; o = a128(o + 256 * (size_t)s->num_nodes);
-	b->off_tv0 = o;   o = a128(o + 16 * (size_t)s->num_tris);
-	b->off_tv1 = o;   o = a128(o + 16 * (size_t)s->num_tris);
-	b->off_tv2 = o;   o = a128(o + 16 * (size_t)s->num_tris);
+	b->off_tv0 = o;   o = a128(o + 16 * (size_t)s->num_tv);
+	b->off_tv1 = o;   o = a128(o + 16 * (size_t)s->num_tv);
+	b->off_tv2 = o;   o = a128(o + 16 * (size_t)s->num_tv);
 	b->off_orig = o;  o = a128(o + 48 * (size_t)s->num_tris);
 	b->off_mesh = o;
 }
@@ -812,12 +826,12 @@ extern "C" int rtkd_blob_write(const rtkd_scene *s, void *payload)
 {
 	rtkd_blob_sub b;
 	memset(&b, 0, sizeof(b));
-	memcpy(&b.magic2, "B200RTK2", 8);
+	memcpy(&b.magic2, "B200RTK3", 8);
 	b.id = s->id;
 	b.num_tris = s->num_tris; b.num_meshes = s->num_meshes; b.num_nodes = s->num_nodes;
 	b.num_leaves = s->num_leaves; b.depth = s->depth; b.build_mode = s->build_mode;
 	memcpy(b.bounds_min, s->bounds_min, 12); memcpy(b.bounds_max, s->bounds_max, 12);
-	b.abs_max = s->abs_max; b.sah_cost = s->sah_cost;
+	b.abs_max = s->abs_max; b.sah_cost = s->sah_cost; b.num_tv = s->num_tv;
 	blob_layout(s, &b);
 	char *p = (char*)payload;
 	memset(p, 0, a128(sizeof(b)));
@@ -825,9 +839,9 @@ extern "C" int rtkd_blob_write(const rtkd_scene *s, void *payload)
 	CK(cudaDeviceSynchronize());
 	if (s->num_nodes) CK(cudaMemcpy(p + b.off_nodes, s->nodes, 256 * (size_t)s->num_nodes, cudaMemcpyDeviceToHost));
 	if (s->num_tris) {
-		CK(cudaMemcpy(p + b.off_tv0, s->tv0, 16 * (size_t)s->num_tris, cudaMemcpyDeviceToHost));
-		CK(cudaMemcpy(p + b.off_tv1, s->tv1, 16 * (size_t)s->num_tris, cudaMemcpyDeviceToHost));
-		CK(cudaMemcpy(p + b.off_tv2, s->tv2, 16 * (size_t)s->num_tris, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(p + b.off_tv0, s->tv0, 16 * (size_t)s->num_tv, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(p + b.off_tv1, s->tv1, 16 * (size_t)s->num_tv, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(p + b.off_tv2, s->tv2, 16 * (size_t)s->num_tv, cudaMemcpyDeviceToHost));
 		CK(cudaMemcpy(p + b.off_orig, s->tri_orig, 48 * (size_t)s->num_tris, cudaMemcpyDeviceToHost));
 	}
 	memcpy(p + b.off_mesh, s->h_mesh_first, 4 * ((size_t)s->num_meshes + 1));
@@ -840,7 +854,7 @@ extern "C" rtkd_scene *rtkd_blob_read(const void *payload, size_t payload_size)
 	rtkd_blob_sub b;
 	if (payload_size < sizeof(b)) { rtkd_set_error("scene blob truncated"); return NULL; }
 	memcpy(&b, payload, sizeof(b));
-	if (memcmp(&b.magic2, "B200RTK2", 8) != 0) { rtkd_set_error("blob was not written by rtk_b200 (device-layout magic missing)"); return NULL; }
+	if (memcmp(&b.magic2, "B200RTK3", 8) != 0) { rtkd_set_error("blob was not written by rtk_b200 (device-layout magic missing)"); return NULL; }
 	if (b.off_mesh + 4 * ((size_t)b.num_meshes + 1) > payload_size) { rtkd_set_error("scene blob truncated"); return NULL; }
 	const char *p = (const char*)payload;
 	rtkd_scene *s = rtkd_scene_new(b.num_tris, b.num_meshes, (const uint32_t*)(p + b.off_mesh));
@@ -848,16 +862,16 @@ extern "C" rtkd_scene *rtkd_blob_read(const void *payload, size_t payload_size)
 	s->id = b.id;
 	s->num_nodes = b.num_nodes; s->num_leaves = b.num_leaves; s->depth = b.depth; s->build_mode = b.build_mode;
 	memcpy(s->bounds_min, b.bounds_min, 12); memcpy(s->bounds_max, b.bounds_max, 12);
-	s->abs_max = b.abs_max; s->sah_cost = b.sah_cost;
+	s->abs_max = b.abs_max; s->sah_cost = b.sah_cost; s->num_tv = b.num_tv; s->tv_cap = b.num_tv;
 	cudaError_t e = cudaSuccess;
 	if (b.num_tris) {
 		e = cudaMemcpy(s->tri_orig, p + b.off_orig, 48 * (size_t)b.num_tris, cudaMemcpyHostToDevice);
-		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv0, 16 * (size_t)b.num_tris);
-		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv1, 16 * (size_t)b.num_tris);
-		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv2, 16 * (size_t)b.num_tris);
-		if (e == cudaSuccess) e = cudaMemcpy(s->tv0, p + b.off_tv0, 16 * (size_t)b.num_tris, cudaMemcpyHostToDevice);
-		if (e == cudaSuccess) e = cudaMemcpy(s->tv1, p + b.off_tv1, 16 * (size_t)b.num_tris, cudaMemcpyHostToDevice);
-		if (e == cudaSuccess) e = cudaMemcpy(s->tv2, p + b.off_tv2, 16 * (size_t)b.num_tris, cudaMemcpyHostToDevice);
+		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv0, 16 * (size_t)b.num_tv);
+		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv1, 16 * (size_t)b.num_tv);
+		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv2, 16 * (size_t)b.num_tv);
+		if (e == cudaSuccess) e = cudaMemcpy(s->tv0, p + b.off_tv0, 16 * (size_t)b.num_tv, cudaMemcpyHostToDevice);
+		if (e == cudaSuccess) e = cudaMemcpy(s->tv1, p + b.off_tv1, 16 * (size_t)b.num_tv, cudaMemcpyHostToDevice);
+		if (e == cudaSuccess) e = cudaMemcpy(s->tv2, p + b.off_tv2, 16 * (size_t)b.num_tv, cudaMemcpyHostToDevice);
 	}
 	if (e == cudaSuccess && b.num_nodes) {
 		e = cudaMalloc((float4**)&s->nodes, 256 * (size_t)b.num_nodes);

@@ -18,7 +18,8 @@ typedef struct rtkd_scene {
 	uint64_t id;                 /* unique per process, also stored in serialised blobs */
 	uint32_t num_tris, num_meshes, num_nodes, num_leaves, depth, build_mode;
 	void *tri_orig;              /* float4[3*num_tris] */
-	void *tv0, *tv1, *tv2;       /* float4[num_tris] each */
+	void *tv0, *tv1, *tv2;       /* float4[num_tv] each: one 8-entry slot per leaf */
+	uint32_t num_tv, tv_cap;
 	void *nodes;                 /* float4[16*num_nodes] */
 	uint32_t nodes_cap;
 	void *mesh_first;            /* uint32[num_meshes+1] */

@@ -536,7 +536,7 @@ int rtk_cuda_get_scene_info(const rtk_scene *scene, rtk_cuda_scene_info *info)
 	info->num_triangles = dev->num_tris; info->num_meshes = dev->num_meshes;
 	info->num_wide_nodes = dev->num_nodes; info->num_leaves = dev->num_leaves;
 	info->wide_depth = dev->depth; info->build_mode = dev->build_mode;
-	info->device_bytes = 256ull * dev->num_nodes + 96ull * dev->num_tris + 4ull * (dev->num_meshes + 1);
+	info->device_bytes = 256ull * dev->num_nodes + 48ull * dev->num_tris + 48ull * dev->num_tv + 4ull * (dev->num_meshes + 1);
 	info->build_device_ms = dev->build_device_ms; info->build_total_ms = dev->build_total_ms;
 	info->sah_cost = dev->sah_cost;
 	memcpy(info->bounds_min, dev->bounds_min, 12); memcpy(info->bounds_max, dev->bounds_max, 12);

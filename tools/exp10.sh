@@ -11,6 +11,8 @@ run
 RTK_B200_LANES=4 run
 run --lib rtk_b200/librtk_b200_st12.so
 run --lib rtk_b200/librtk_b200_st8.so
+run --lib rtk_b200/librtk_b200_fp.so
+run --presort
 RTK_B200_HOST_THREADS=4 run
 RTK_B200_HOST_THREADS=16 run
 run --workload C2 --rays 16588800

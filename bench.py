@@ -570,6 +570,11 @@ def main():
 
     peak, peak_src = measured_peaks()
     achieved = bytes_per_ray * n / (trace_ms * 1e-3) / 1e9
+    # the scene of the 1M-triangle workloads lives in L2: measure the L2 (and HBM) read bandwidth of
+    # this very GPU with the library's probe kernel
+    l2_gbs, hbm_read_gbs = C.c_double(0), C.c_double(0)
+    lib.rtk_cuda_measure_read_bandwidth(64 << 20, 40, C.byref(l2_gbs))
+    lib.rtk_cuda_measure_read_bandwidth(4 << 30, 3, C.byref(hbm_read_gbs))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -583,6 +588,11 @@ def main():
                      "traffic": 1.877e9 if (args.workload == "C3" and n == FULL_RAYS and args.scale == 1.0 and args.build_mode == "sah") else None,
                      "traffic_unit": "bytes per launch (ncu, profiles/r1_k_trace_raw.csv)",
                      "peak_source": peak_src,
+                     "l2": {"achieved": achieved, "peak": l2_gbs.value, "unit": "GB/s",
+                            "frac": achieved / l2_gbs.value if l2_gbs.value else None,
+                            "peak_source": "measured in this run: 16-byte loads over a 64 MiB buffer, 40 passes "
+                                           "(rtk_cuda_measure_read_bandwidth); the same probe over 4 GiB reads "
+                                           "%.0f GB/s from HBM" % hbm_read_gbs.value},
                      "bytes_per_ray": bytes_per_ray,
                      "per_ray": {"wide_node_visits": nodes_per_ray, "leaf_visits": leaves_per_ray,
                                  "triangle_tests": tris_per_ray, "hit_fraction": hit_frac},

@@ -86,6 +86,11 @@ int  rtk_cuda_set_cull_mode(int mode);
 /* SM count, L2 bytes, resident CTAs of the traversal kernel... for the bench. */
 int  rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *trace_ctas_per_sm, int *trace_threads_per_cta);
 
+/* Read-bandwidth probe for roofline denominators: streams a `bytes`-sized device buffer `passes`
+ * times with 16-byte loads.  A buffer well below the L2 size measures L2 read bandwidth, one well
+ * above it HBM read bandwidth. */
+int  rtk_cuda_measure_read_bandwidth(size_t bytes, int passes, double *gb_per_s);
+
 /* ---- batched closest hit (replaces a user loop over rtk_trace_ray) ----- */
 
 /* Host buffers.  rays[n] in, hits[n] / hit_mask[n] out.  hits[i] is written
@@ -93,7 +98,7 @@ int  rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *trace_ctas_per_s
  * the miss rule of rtk.c:571-576.  hit_mask may be NULL.  The batch runs as a
  * pipeline over 1M-ray chunks: rays go up, only the rows of rays that hit
  * (plus one mask byte per ray) come back, and a few library threads
- * (RTK_B200_HOST_THREADS, default 8) copy each row to hits[i].  Pinned
+ * (RTK_B200_HOST_THREADS, default 3/4 of the CPUs, at most 16) copy each row to hits[i].  Pinned
  * (page-locked) caller buffers let the uploads overlap the kernels.
  * Returns the number of hits, or (size_t)-1 on error. */
 size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits, uint8_t *hit_mask, size_t n);
@@ -167,6 +172,15 @@ rtk_scene *rtk_cuda_build_scene(const rtk_cuda_mesh *meshes, size_t num_meshes, 
 /* Re-run the device build of an existing scene from its resident decoded
  * triangles (bench loop for build Mtris/s; also refits after nothing moved). */
 int rtk_cuda_rebuild_scene(const rtk_scene *scene, void *stream);
+
+/* Animated meshes: new vertex positions for the scene's meshes, same triangle
+ * counts.  RTK_CUDA_UPDATE_REFIT keeps the tree and recomputes every box bottom-up (fast; the tree
+ * quality decays as the mesh deforms), RTK_CUDA_UPDATE_REBUILD builds a new tree.  Results after
+ * either are exactly those of a scene built from the new positions: the BVH is not part of the
+ * contract.  build_device_ms of rtk_cuda_get_scene_info reports the update's device time. */
+#define RTK_CUDA_UPDATE_REFIT 0
+#define RTK_CUDA_UPDATE_REBUILD 1
+int rtk_cuda_update_scene(const rtk_scene *scene, const rtk_cuda_mesh *meshes, size_t num_meshes, int mode, void *stream);
 
 int rtk_cuda_get_scene_info(const rtk_scene *scene, rtk_cuda_scene_info *info);
 

@@ -100,6 +100,7 @@ class rtk_cuda_trace_stats(C.Structure):
 
 
 RTK_CUDA_BOUNCE_RELAUNCH = 1
+RTK_CUDA_UPDATE_REFIT, RTK_CUDA_UPDATE_REBUILD = 0, 1
 
 RAY_DTYPE = np.dtype([("o", "<f4", 3), ("d", "<f4", 3), ("min_t", "<f4"), ("max_t", "<f4")])
 VERTEX_DTYPE = np.dtype([("position", "<f4", 3), ("index", "<u4")])
@@ -128,6 +129,7 @@ SYMBOLS = {
     "rtk_cuda_set_build_mode": (C.c_int, [C.c_int]),
     "rtk_cuda_set_cull_mode": (C.c_int, [C.c_int]),
     "rtk_cuda_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "rtk_cuda_measure_read_bandwidth": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "rtk_trace_rays": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),
     "rtk_trace_rays_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     "rtk_trace_rays_compact_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
@@ -139,6 +141,7 @@ SYMBOLS = {
     "rtk_cuda_generate_bounce_rays": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, _P]),
     "rtk_cuda_build_scene": (_P, [C.POINTER(rtk_cuda_mesh), C.c_size_t, _P]),
     "rtk_cuda_rebuild_scene": (C.c_int, [_P, _P]),
+    "rtk_cuda_update_scene": (C.c_int, [_P, C.POINTER(rtk_cuda_mesh), C.c_size_t, C.c_int, _P]),
     "rtk_cuda_get_scene_info": (C.c_int, [_P, C.POINTER(rtk_cuda_scene_info)]),
     "rtk_cuda_attach_scene": (C.c_int, [_P]),
     "rtk_cuda_detach_scene": (C.c_int, [_P]),

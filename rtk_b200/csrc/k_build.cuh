@@ -379,6 +379,8 @@ struct rtkd_collapse_args {
 	uint32_t *node_alloc; uint32_t node_cap;
 	uint32_t *leaf_count;        // also the leaf slot allocator
 	uint2 *leaf_list;            // [slot] = (first sorted position, count): filled here, read by k_emit_leaves
+	unsigned char *node_level;   // [wide node] = depth of the node (root 0): the refit walks levels bottom-up
+	uint32_t level;              // depth of the nodes this launch fills
 	double *sah_cost;            // accumulates area-weighted cost (divide by root area on host)
 	float4 *nodes;
 	int n;                       // triangles
@@ -427,6 +429,7 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 			if (idx >= a.node_cap) { atomicOr(a.err, 1u); idx = 0; }
 			uint32_t o = atomicAdd(a.n_out, 1u);
 			a.work_out[o] = make_uint2((uint32_t)c, idx);
+			a.node_level[idx] = (unsigned char)(a.level + 1u);
 			ref = idx;
 		} else {
 			uint32_t first = c >= 0 ? (uint32_t)t.first[c] : (uint32_t)~c;
@@ -480,4 +483,53 @@ __global__ void k_emit_leaves(const float4 *tri_orig, const uint32_t *vals, cons
 		a.w = __uint_as_float(prim);
 	}
 	tv0[i] = a; tv1[i] = b; tv2[i] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Refit: the vertices moved, the topology did not.  k_refit_tris reloads the
+// traversal triangles from the decoded corners; k_refit_level then recomputes the child boxes of
+// every wide node of one depth -- one thread per child slot -- from the leaf's triangles or from
+// the 8 (already refitted) child boxes of the node below.  Levels run deepest first.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void k_refit_tris(const float4 *tri_orig, uint32_t num_tv, float4 *tv0, float4 *tv1, float4 *tv2)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= num_tv) return;
+	const uint32_t prim = __float_as_uint(tv0[i].w);
+	if (prim == RTK_MISS) return;
+	float4 a = tri_orig[3ull * prim], b = tri_orig[3ull * prim + 1], c = tri_orig[3ull * prim + 2];
+	a.w = __uint_as_float(prim);
+	tv0[i] = a; tv1[i] = b; tv2[i] = c;
+}
+
+__global__ void k_refit_level(float4 *nodes, const unsigned char *node_level, uint32_t num_nodes, uint32_t level,
+                              const float4 *tv0, const float4 *tv1, const float4 *tv2)
+{
+	uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t node = t / RTK_WIDE, k = t % RTK_WIDE;
+	if (node >= num_nodes || node_level[node] != level) return;
+	float4 *slot = nodes + 16ull * node + 2 * k;
+	const uint32_t ref = __float_as_uint(slot[0].w);
+	if (ref == RTK_REF_EMPTY) return;
+	float lo[3] = { +RTK_INF_F, +RTK_INF_F, +RTK_INF_F }, hi[3] = { -RTK_INF_F, -RTK_INF_F, -RTK_INF_F };
+	if (rtk_ref_is_leaf(ref)) {
+		const uint32_t first = rtk_leaf_first(ref), cnt = rtk_leaf_count(ref);
+		for (uint32_t j = 0; j < cnt; j++) {
+			const float4 a = tv0[first + j], b = tv1[first + j], c = tv2[first + j];
+			lo[0] = rtk_fmin(lo[0], rtk_fmin(rtk_fmin(a.x, b.x), c.x)); hi[0] = rtk_fmax(hi[0], rtk_fmax(rtk_fmax(a.x, b.x), c.x));
+			lo[1] = rtk_fmin(lo[1], rtk_fmin(rtk_fmin(a.y, b.y), c.y)); hi[1] = rtk_fmax(hi[1], rtk_fmax(rtk_fmax(a.y, b.y), c.y));
+			lo[2] = rtk_fmin(lo[2], rtk_fmin(rtk_fmin(a.z, b.z), c.z)); hi[2] = rtk_fmax(hi[2], rtk_fmax(rtk_fmax(a.z, b.z), c.z));
+		}
+	} else {
+		const float4 *ch = nodes + 16ull * ref;
+		for (int j = 0; j < RTK_WIDE; j++) {
+			const float4 l = ch[2 * j], h = ch[2 * j + 1];
+			if (__float_as_uint(l.w) == RTK_REF_EMPTY) continue;
+			lo[0] = rtk_fmin(lo[0], l.x); lo[1] = rtk_fmin(lo[1], l.y); lo[2] = rtk_fmin(lo[2], l.z);
+			hi[0] = rtk_fmax(hi[0], h.x); hi[1] = rtk_fmax(hi[1], h.y); hi[2] = rtk_fmax(hi[2], h.z);
+		}
+	}
+	slot[0] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(ref));
+	slot[1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
 }

@@ -103,6 +103,53 @@ extern "C" int rtkd_device_info(int *sm_count, size_t *l2_bytes, int *ctas_per_s
 }
 
 // ---------------------------------------------------------------------------------------------
+// read-bandwidth probe: the denominator of the L2 roofline ("L2 peak must be measured
+// with a read microbenchmark on the same box").  A persistent grid streams a buffer `passes` times
+// with 16-byte loads; a buffer smaller than the L2 measures L2, a larger one HBM.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_read_probe(const float4 *buf, size_t n16, int passes, float *sink)
+{
+	float acc = 0.0f;
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (int p = 0; p < passes; p++) {
+		size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+		for (; i + 3 * stride < n16; i += 4 * stride) {
+			float4 a = __ldcg(buf + i), b = __ldcg(buf + i + stride), c = __ldcg(buf + i + 2 * stride), d = __ldcg(buf + i + 3 * stride);
+			acc += (a.x + b.y) + (c.z + d.w);
+		}
+		for (; i < n16; i += stride) acc += __ldcg(buf + i).x;
+	}
+	if (acc == 123.456f) *sink = acc;            // never true: keeps the loads alive
+}
+
+extern "C" int rtkd_read_bandwidth(size_t bytes, int passes, double *gbs)
+{
+	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
+	if (bytes < 4096 || passes < 1 || !gbs) { rtkd_set_error("bad probe arguments"); return RTKD_ERR_ARGUMENT; }
+	float4 *buf = NULL;
+	float *sink = NULL;
+	const size_t n16 = bytes / 16;
+	CK(cudaMalloc(&buf, n16 * 16));
+	CK(cudaMalloc(&sink, 4));
+	CK(cudaMemset(buf, 0, n16 * 16));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+	const unsigned grid = (unsigned)g_sm_count * 8;
+	RTK_LAUNCH(k_read_probe, grid, 256, 0, (const float4*)buf, n16, 2, sink);       // warm the cache
+	CK(cudaEventRecord(e0, 0));
+	RTK_LAUNCH(k_read_probe, grid, 256, 0, (const float4*)buf, n16, passes, sink);
+	CK(cudaEventRecord(e1, 0));
+	CK(cudaEventSynchronize(e1));
+	float ms = 0.0f;
+	CK(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	cudaFree(buf); cudaFree(sink);
+	*gbs = ms > 0.0f ? (double)n16 * 16.0 * passes / (ms * 1e-3) / 1e9 : 0.0;
+	return RTKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // scene lifetime
 // ---------------------------------------------------------------------------------------------
 
@@ -135,6 +182,7 @@ extern "C" void rtkd_scene_free(rtkd_scene *s)
 	if (s->tv1) cudaFree(s->tv1);
 	if (s->tv2) cudaFree(s->tv2);
 	if (s->nodes) cudaFree(s->nodes);
+	if (s->node_level) cudaFree(s->node_level);
 	if (s->mesh_first) cudaFree(s->mesh_first);
 	if (s->scratch) cudaFree(s->scratch);
 	if (s->overflow) cudaFree(s->overflow);
@@ -214,6 +262,7 @@ struct build_bufs {
 	uint2 *work[2];
 	uint32_t *ctr;
 	uint2 *leaf_list;
+	unsigned char *node_level;
 	double *d_cost;
 	uint32_t cap, nblocks;
 	size_t act_cap, small_cap;
@@ -258,6 +307,7 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 	B.work[0] = A.take<uint2>(B.cap); B.work[1] = A.take<uint2>(B.cap);
 	B.ctr = A.take<uint32_t>(8 + RTKD_COLLAPSE_LEVELS);
 	B.leaf_list = A.take<uint2>(n);
+	B.node_level = A.take<unsigned char>(B.cap);
 	B.d_cost = A.take<double>(1);
 }
 
@@ -356,6 +406,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	}
 	uint32_t num_nodes = 0, num_leaves = 0, depth = 0;
 	double h_cost = 0.0;
+	CK(cudaMemsetAsync(B.node_level, 0, B.cap, st));       // the root is at depth 0
 	if (n == 1) {
 		RTK_LAUNCH(k_single_root, 1, 32, st, tri, svals, B.wide); CK_LAUNCH();
 		const uint2 l0 = make_uint2(0u, 1u);
@@ -381,6 +432,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 				a.work_in = B.work[level & 1]; a.n_in = B.ctr + 8 + level;
 				a.work_out = B.work[(level & 1) ^ 1]; a.n_out = B.ctr + 8 + level + 1;
 				a.node_alloc = B.ctr; a.node_cap = B.cap; a.leaf_count = B.ctr + 1; a.leaf_list = B.leaf_list; a.sah_cost = B.d_cost;
+				a.node_level = B.node_level; a.level = (uint32_t)level;
 				a.nodes = B.wide; a.n = (int)n; a.err = B.ctr + 2;
 				uint32_t width = (uint32_t)(bound < B.cap ? bound : B.cap);
 				RTK_LAUNCH(k_collapse, (width + 127) / 128, 128, st, a, t); CK_LAUNCH();
@@ -405,8 +457,13 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		if (s->nodes) cudaFree(s->nodes);
 		s->nodes = NULL;
 		CK(cudaMalloc((float4**)&s->nodes, sizeof(float4) * 16 * (size_t)num_nodes));
+		if (s->node_level) cudaFree(s->node_level);
+		s->node_level = NULL;
+		CK(cudaMalloc((unsigned char**)&s->node_level, (size_t)num_nodes));
 		s->nodes_cap = num_nodes;
 	}
+	if (!s->node_level) CK(cudaMalloc((unsigned char**)&s->node_level, (size_t)s->nodes_cap));
+	CK(cudaMemcpyAsync(s->node_level, B.node_level, (size_t)num_nodes, cudaMemcpyDeviceToDevice, st));
 	CK(cudaMemcpyAsync(s->nodes, B.wide, sizeof(float4) * 16 * (size_t)num_nodes, cudaMemcpyDeviceToDevice, st));
 	// traversal triangles: one 8-entry slot per leaf, sized now that the leaves are counted
 	const uint32_t num_tv = num_leaves * RTK_LEAF_MAX;
@@ -448,6 +505,54 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		s->sah_cost = ra > 0.0 ? 1.0 + h_cost / ra : 0.0;
 	}
 	// the stack scratch depends on the depth: re-created on the next query if too small
+	return RTKD_OK;
+}
+
+// Refit: same tree, new boxes (k_refit_tris + one k_refit_level launch per depth, deepest first),
+// new scene bounds.  Valid after rtkd_decode_mesh rewrote the corners of a scene built here.
+extern "C" int rtkd_refit(rtkd_scene *s, void *stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	if (!s->num_tris || !s->num_nodes) return RTKD_OK;
+	if (!s->node_level) { rtkd_set_error("this scene carries no level table (loaded from a blob): rebuild it instead"); return RTKD_ERR_SCENE; }
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+	CK(cudaEventRecord(e0, st));
+	const float4 *tri = (const float4*)s->tri_orig;
+	uint32_t *d_bounds = NULL;
+	CK(cudaMallocAsync(&d_bounds, 8 * sizeof(uint32_t), st));
+	CK(cudaMemsetAsync(d_bounds, 0xff, 3 * sizeof(uint32_t), st));
+	CK(cudaMemsetAsync(d_bounds + 3, 0x00, 3 * sizeof(uint32_t), st));
+	RTK_LAUNCH(k_scene_bounds, (s->num_tris + 255) / 256, 256, st, tri, s->num_tris, d_bounds); CK_LAUNCH();
+	RTK_LAUNCH(k_refit_tris, (s->num_tv + 255) / 256, 256, st, tri, s->num_tv, (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
+	const unsigned blocks = (unsigned)(((size_t)s->num_nodes * RTK_WIDE + 255) / 256);
+	if (s->num_tris == 1) {
+		// the single-triangle scene is one root with one leaf child
+		RTK_LAUNCH(k_refit_level, blocks, 256, st, (float4*)s->nodes, (const unsigned char*)s->node_level, s->num_nodes, 0u,
+		           (const float4*)s->tv0, (const float4*)s->tv1, (const float4*)s->tv2); CK_LAUNCH();
+	} else for (int level = (int)s->depth - 1; level >= 0; level--) {
+		RTK_LAUNCH(k_refit_level, blocks, 256, st, (float4*)s->nodes, (const unsigned char*)s->node_level, s->num_nodes, (uint32_t)level,
+		           (const float4*)s->tv0, (const float4*)s->tv1, (const float4*)s->tv2); CK_LAUNCH();
+	}
+	uint32_t h_bounds[6];
+	CK(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, st));
+	cudaFreeAsync(d_bounds, st);
+	CK(cudaEventRecord(e1, st));
+	CK(cudaEventSynchronize(e1));
+	float ms = 0.0f;
+	CK(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	s->build_device_ms = ms;
+	float amax = 0.0f;
+	for (int k = 0; k < 3; k++) {
+		uint32_t u = h_bounds[k], v = h_bounds[3 + k];
+		u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+		v = (v & 0x80000000u) ? (v & 0x7fffffffu) : ~v;
+		memcpy(&s->bounds_min[k], &u, 4);
+		memcpy(&s->bounds_max[k], &v, 4);
+		amax = fmaxf(amax, fmaxf(fabsf(s->bounds_min[k]), fabsf(s->bounds_max[k])));
+	}
+	s->abs_max = amax;
 	return RTKD_OK;
 }
 

@@ -22,6 +22,7 @@ typedef struct rtkd_scene {
 	uint32_t num_tv, tv_cap;
 	void *nodes;                 /* float4[16*num_nodes] */
 	uint32_t nodes_cap;
+	unsigned char *node_level;   /* uint8[num_nodes]: depth of each wide node (NULL for a scene loaded from a blob) */
 	void *mesh_first;            /* uint32[num_meshes+1] */
 	uint32_t *h_mesh_first;      /* host copy */
 	float bounds_min[3], bounds_max[3], abs_max;
@@ -42,6 +43,8 @@ const char *rtkd_last_error(void);
 void        rtkd_set_error(const char *fmt, ...);
 int         rtkd_device_info(int *sm_count, size_t *l2_bytes, int *ctas_per_sm, int *threads_per_cta);
 
+int         rtkd_read_bandwidth(size_t bytes, int passes, double *gbs);   /* read probe: L2 (small buffer) or HBM */
+
 rtkd_scene *rtkd_scene_new(uint32_t num_tris, uint32_t num_meshes, const uint32_t *mesh_first);
 void        rtkd_scene_free(rtkd_scene *s);
 
@@ -58,6 +61,9 @@ int rtkd_decode_mesh(rtkd_scene *s, uint32_t first_prim, uint32_t ntris,
 
 /* build the BVH from the decoded triangles; synchronous with respect to `stream` on return */
 int rtkd_build(rtkd_scene *s, int mode, void *stream);
+
+/* the vertices of the decoded triangles moved, the topology did not: refit all boxes in place */
+int rtkd_refit(rtkd_scene *s, void *stream);
 
 /* queries: device pointers, asynchronous on stream.  cull_mode bit 0: provable culling,
  * bit 1: occlusion query (d_hit16 is then one byte per ray) */

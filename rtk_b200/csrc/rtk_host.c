@@ -75,6 +75,11 @@ int rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *ctas, int *thread
 	return rtkd_device_info(sm_count, l2_bytes, ctas, threads);
 }
 
+int rtk_cuda_measure_read_bandwidth(size_t bytes, int passes, double *gb_per_s)
+{
+	return rtkd_read_bandwidth(bytes, passes, gb_per_s);
+}
+
 /* ---------------------------------------------------------------------------------------- */
 /* scene table: blob address -> device scene                                                  */
 /* ---------------------------------------------------------------------------------------- */
@@ -526,6 +531,26 @@ int rtk_cuda_rebuild_scene(const rtk_scene *scene, void *stream)
 	rtkd_scene *dev = scene_device(scene);
 	if (!dev) return RTK_CUDA_ERR_SCENE;
 	return rtkd_build(dev, g_build_mode, stream);
+}
+
+int rtk_cuda_update_scene(const rtk_scene *scene, const rtk_cuda_mesh *meshes, size_t num_meshes, int mode, void *stream)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return RTK_CUDA_ERR_SCENE;
+	if (mode != RTK_CUDA_UPDATE_REFIT && mode != RTK_CUDA_UPDATE_REBUILD) { rtkd_set_error("unknown update mode %d", mode); return RTK_CUDA_ERR_ARGUMENT; }
+	if (num_meshes != dev->num_meshes || (num_meshes && !meshes)) { rtkd_set_error("update needs the scene's %u meshes", dev->num_meshes); return RTK_CUDA_ERR_ARGUMENT; }
+	for (size_t i = 0; i < num_meshes; i++) {
+		if (meshes[i].num_triangles != (size_t)(dev->h_mesh_first[i + 1] - dev->h_mesh_first[i])) {
+			rtkd_set_error("mesh %zu changed its triangle count: build a new scene", i);
+			return RTK_CUDA_ERR_ARGUMENT;
+		}
+	}
+	int r = RTK_CUDA_OK;
+	for (size_t i = 0; i < num_meshes && r == RTK_CUDA_OK; i++)
+		r = rtkd_decode_mesh(dev, dev->h_mesh_first[i], (uint32_t)meshes[i].num_triangles, meshes[i].d_positions, 12, 0,
+		                     meshes[i].d_indices, 12, 4, 0, stream);
+	if (r != RTK_CUDA_OK) return r;
+	return mode == RTK_CUDA_UPDATE_REFIT ? rtkd_refit(dev, stream) : rtkd_build(dev, g_build_mode, stream);
 }
 
 int rtk_cuda_get_scene_info(const rtk_scene *scene, rtk_cuda_scene_info *info)

@@ -92,7 +92,11 @@ static void pool_start(void)
 	if (e) want = atoi(e);
 	if (want <= 0) {
 		long n = sysconf(_SC_NPROCESSORS_ONLN);
-		want = n >= 16 ? 8 : (n >= 4 ? (int)(n / 2) : 1);
+		/* measured on a 16-vCPU host: 4 threads 31.6 ms, 8 threads 23.9 ms, 16 threads 22.1 ms per
+		 * 16.7M-ray batch (the copies are bound by host memory bandwidth, which the PCIe traffic
+		 * shares) -- three quarters of the CPUs, at most 16 */
+		want = n >= 4 ? (int)(n * 3 / 4) : 1;
+		if (want > 16) want = 16;
 	}
 	if (want > PLACE_MAX_THREADS) want = PLACE_MAX_THREADS;
 	for (int i = 0; i < want; i++) {

@@ -483,3 +483,47 @@ def case_wavefront(lib, orc, dev):
     assert total_hits > n          # the Cornell box is closed on five sides: most paths keep hitting
     assert lib.rtk_cuda_generate_bounce_rays(sc.ptr, d_rays, d_hit, d_next, d_alive, n, seed, 16, 0, 0, dev.stream) != 0
     sc.free()
+
+
+def case_refit(lib, orc, dev):
+    """deform the vertices of a built scene, refit (or rebuild) on the device, and get
+    exactly the hits of the oracle on the deformed triangles.  `dev` owns the device buffers."""
+    s = scenes.config_scene("C3", 0.006)
+    m = s["meshes"][0]
+    pos0, idx = m["positions"].astype(np.float32), m["indices"].astype(np.uint32)
+    rays = scenes.bounce_rays(s, 2500)
+    keep, meshes = [], (api.rtk_cuda_mesh * 1)()
+
+    def upload(pos):
+        hp, dp = dev.put(pos)
+        hi, di = dev.put(idx)
+        keep[:] = [hp, hi]
+        meshes[0].d_positions, meshes[0].d_indices = dp, di
+        meshes[0].num_vertices, meshes[0].num_triangles = len(pos), len(idx)
+    upload(pos0)
+    ptr = lib.rtk_cuda_build_scene(meshes, 1, dev.stream)
+    assert ptr, lib.last_error()
+    sc = api.Scene(lib, ptr)
+    h_rays, d_rays = dev.put(rays)
+    h_hit, d_hit = dev.empty(16 * len(rays))
+
+    def trace():
+        assert lib.rtk_trace_rays_compact_device(sc.ptr, d_rays, d_hit, len(rays), dev.stream) == 0, lib.last_error()
+        return dev.get(h_hit, api.HIT16_DTYPE, len(rays))
+    assert_same(trace(), orc.trace_brute(pos0[idx.astype(np.int64)], rays), "before the update")
+    rng = np.random.default_rng(17)
+    for step, mode in enumerate([api.RTK_CUDA_UPDATE_REFIT, api.RTK_CUDA_UPDATE_REFIT, api.RTK_CUDA_UPDATE_REBUILD, api.RTK_CUDA_UPDATE_REFIT]):
+        pos = pos0.copy()
+        pos[:, 1] += (0.02 * (step + 1) * np.sin(9.0 * pos0[:, 0] + step) * np.cos(7.0 * pos0[:, 2])).astype(np.float32)
+        pos += (rng.random(pos.shape).astype(np.float32) - 0.5) * np.float32(2e-3)
+        if step == 1:
+            pos *= np.float32(3.0)                      # the scene bounds change as well
+        upload(pos)
+        assert lib.rtk_cuda_update_scene(sc.ptr, meshes, 1, mode, dev.stream) == 0, lib.last_error()
+        want = orc.trace_brute(pos[idx.astype(np.int64)], rays)
+        assert_same(trace(), want, f"update {step} mode {mode}")
+        assert (want["prim"] != api.RTK_CUDA_MISS).any()
+    # a different triangle count is refused
+    meshes[0].num_triangles = len(idx) - 1
+    assert lib.rtk_cuda_update_scene(sc.ptr, meshes, 1, api.RTK_CUDA_UPDATE_REFIT, dev.stream) != 0
+    sc.free()

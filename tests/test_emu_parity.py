@@ -51,3 +51,7 @@ def test_occlusion_query(emu_lib, orc):
 
 def test_wavefront_generators(emu_lib, orc):
     pc.case_wavefront(emu_lib, orc, pc.HostDevice())
+
+
+def test_refit_and_rebuild_of_a_deformed_mesh(emu_lib, orc):
+    pc.case_refit(emu_lib, orc, pc.HostDevice())

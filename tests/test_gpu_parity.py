@@ -194,3 +194,7 @@ class TorchDevice:
 
 def test_wavefront_generators(gpu_lib, orc):
     pc.case_wavefront(gpu_lib, orc, TorchDevice())
+
+
+def test_refit_and_rebuild_of_a_deformed_mesh(gpu_lib, orc):
+    pc.case_refit(gpu_lib, orc, TorchDevice())

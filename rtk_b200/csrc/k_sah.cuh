@@ -307,13 +307,26 @@ __global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, uint32_t n_ac
 	const uint32_t end = rtk_umin(begin + RTK_SAH_CHUNK, last + 1);
 	const float4 nlo = s.blo[node], nhi = s.bhi[node];
 	const uint32_t *idx = src_buf ? s.idx1 : s.idx0;
-	for (uint32_t base = begin; base < end; base += 256) {           // warp-uniform trip count
-		uint32_t p = base + threadIdx.x;
-		bool valid = p < end;
-		uint32_t j = valid ? idx[p] : 0;
-		float4 lo = make_float4(0, 0, 0, 0), hi = make_float4(0, 0, 0, 0);
-		if (valid) { lo = s.pb[2ull * j]; hi = s.pb[2ull * j + 1]; }
-		rtk_sah_bin_add_warp(s_bins, lo, hi, nlo, nhi, valid);
+	// four 256-triangle rows at a time: the index loads, then the dependent box gathers, are all in
+	// flight together before the first bin is touched (the kernel was bound by that two-load latency
+	// chain, 8 times per chunk).  The trip count is warp-uniform.
+	for (uint32_t base = begin; base < end; base += 256 * 4) {
+		uint32_t j[4];
+		bool valid[4];
+		float4 lo[4], hi[4];
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const uint32_t p = base + u * 256 + threadIdx.x;
+			valid[u] = p < end;
+			j[u] = valid[u] ? idx[p] : 0u;
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			lo[u] = make_float4(0, 0, 0, 0); hi[u] = make_float4(0, 0, 0, 0);
+			if (valid[u]) { lo[u] = s.pb[2ull * j[u]]; hi[u] = s.pb[2ull * j[u] + 1]; }
+		}
+#pragma unroll
+		for (int u = 0; u < 4; u++) rtk_sah_bin_add_warp(s_bins, lo[u], hi[u], nlo, nhi, valid[u]);
 	}
 	__syncthreads();
 	uint32_t *g = s.bins + (size_t)a * RTK_SAH_NODEBINS;
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(128) k_sah_split_large(rtkd_sah s, uint32_t n_
 
 __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, uint32_t n_act, int src_buf)
 {
-	__shared__ uint32_t s_a, s_cntl[8], s_cntr[8], s_basel, s_baser;
+	__shared__ uint32_t s_a, s_cntl[8], s_basel, s_baser;
 	if (threadIdx.x == 0) s_a = rtk_sah_find_node(s.chunk_base, n_act, blockIdx.x);
 	__syncthreads();
 	const uint32_t a = s_a;
@@ -392,38 +405,66 @@ __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, uint32_
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const float amin = sp.x == 0 ? nlo.x : (sp.x == 1 ? nlo.y : nlo.z);
 	const float amax = sp.x == 0 ? nhi.x : (sp.x == 1 ? nhi.y : nhi.z);
-	for (uint32_t base = begin; base < end; base += 256) {
-		uint32_t p = base + threadIdx.x;
-		bool valid = p < end;
-		uint32_t j = valid ? src[p] : 0;
-		bool goes_left = false;
-		if (valid) {
-			if (sp.x < 0) goes_left = (p - first) < (uint32_t)sp.z;           // equal split by position
-			else {
-				float4 lo = s.pb[2ull * j], hi = s.pb[2ull * j + 1];
-				float l = sp.x == 0 ? lo.x : (sp.x == 1 ? lo.y : lo.z);
-				float h = sp.x == 0 ? hi.x : (sp.x == 1 ? hi.y : hi.z);
-				goes_left = rtk_sah_bin(l, h, amin, amax) <= sp.y;            // rtk.c:973-977
+	// The whole 2048-triangle chunk in one pass: every thread classifies its 8 triangles (all index
+	// loads, then all box gathers, in flight together), the block scans the per-thread counts and
+	// reserves its left / right ranges with ONE pair of atomics (it used to take a pair, and three
+	// barriers, per 256 triangles).  The order inside a side is irrelevant to the tree.
+	constexpr int PER = RTK_SAH_CHUNK / 256;
+	uint32_t j[PER];
+	uint32_t vmask = 0, lmask = 0;
+#pragma unroll
+	for (int u = 0; u < PER; u++) {
+		const uint32_t p = begin + u * 256 + threadIdx.x;
+		j[u] = 0;
+		if (p < end) { vmask |= 1u << u; j[u] = src[p]; }
+	}
+	if (sp.x < 0) {
+#pragma unroll
+		for (int u = 0; u < PER; u++) {
+			const uint32_t p = begin + u * 256 + threadIdx.x;
+			if (((vmask >> u) & 1u) && (p - first) < (uint32_t)sp.z) lmask |= 1u << u;      // equal split by position
+		}
+	} else {
+		float l[PER], h[PER];
+#pragma unroll
+		for (int u = 0; u < PER; u++) {
+			l[u] = 0.0f; h[u] = 0.0f;
+			if ((vmask >> u) & 1u) {
+				const float4 lo = s.pb[2ull * j[u]], hi = s.pb[2ull * j[u] + 1];
+				l[u] = sp.x == 0 ? lo.x : (sp.x == 1 ? lo.y : lo.z);
+				h[u] = sp.x == 0 ? hi.x : (sp.x == 1 ? hi.y : hi.z);
 			}
 		}
-		uint32_t ml = __ballot_sync(0xffffffffu, valid && goes_left);
-		uint32_t mr = __ballot_sync(0xffffffffu, valid && !goes_left);
-		if (lane == 0) { s_cntl[warp] = __popc(ml); s_cntr[warp] = __popc(mr); }
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			uint32_t tl = 0, tr = 0;
-			for (int w = 0; w < 8; w++) { uint32_t x = s_cntl[w]; s_cntl[w] = tl; tl += x; uint32_t y = s_cntr[w]; s_cntr[w] = tr; tr += y; }
-			s_basel = tl ? atomicAdd(&s.cursor[2 * a], tl) : 0;
-			s_baser = tr ? atomicAdd(&s.cursor[2 * a + 1], tr) : 0;
+#pragma unroll
+		for (int u = 0; u < PER; u++)
+			if (((vmask >> u) & 1u) && rtk_sah_bin(l[u], h[u], amin, amax) <= sp.y) lmask |= 1u << u;   // rtk.c:973-977
+	}
+	const uint32_t cl = (uint32_t)__popc(lmask), cr = (uint32_t)__popc(vmask & ~lmask);
+	// exclusive scan of (cl, cr) over the block: packed in one word (a chunk holds at most 2048)
+	uint32_t x = cl | (cr << 16);
+	uint32_t incl = x;
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) incl += y;
+	}
+	if (lane == 31) s_cntl[warp] = incl;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0;
+		for (int w = 0; w < 8; w++) { uint32_t v = s_cntl[w]; s_cntl[w] = t; t += v; }
+		const uint32_t tl = t & 0xffffu, tr = t >> 16;
+		s_basel = tl ? atomicAdd(&s.cursor[2 * a], tl) : 0;
+		s_baser = tr ? atomicAdd(&s.cursor[2 * a + 1], tr) : 0;
+	}
+	__syncthreads();
+	const uint32_t excl = s_cntl[warp] + incl - x;
+	uint32_t pl = first + s_basel + (excl & 0xffffu);
+	uint32_t pr = first + (uint32_t)sp.z + s_baser + (excl >> 16);
+#pragma unroll
+	for (int u = 0; u < PER; u++) {
+		if ((vmask >> u) & 1u) {
+			if ((lmask >> u) & 1u) dst[pl++] = j[u]; else dst[pr++] = j[u];
 		}
-		__syncthreads();
-		if (valid) {
-			uint32_t lt = (1u << lane) - 1u;
-			uint32_t pos = goes_left ? first + s_basel + s_cntl[warp] + __popc(ml & lt)
-			                         : first + (uint32_t)sp.z + s_baser + s_cntr[warp] + __popc(mr & lt);
-			dst[pos] = j;
-		}
-		__syncthreads();
 	}
 }
 

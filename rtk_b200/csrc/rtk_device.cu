@@ -377,9 +377,11 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	RTK_LAUNCH(k_scene_bounds, (n + 255) / 256, 256, st, tri, n, B.d_bounds); CK_LAUNCH();
 	RTK_LAUNCH(k_morton, (n + 255) / 256, 256, st, tri, n, (const uint32_t*)B.d_bounds, B.keys[0], B.vals[0]); CK_LAUNCH();
 
-	// LSD radix sort over the 63 code bits
+	// LSD radix sort: all 63 code bits for the radix tree of the LBVH mode (it needs them to tell
+	// neighbours apart); the SAH builder only wants spatial locality in its input order, for which
+	// the upper 31 bits (10 per axis) are plenty -- half the passes
 	int src = 0;
-	for (int shift = 0; shift < 64; shift += 8) {
+	for (int shift = use_sah ? 32 : 0; shift < 64; shift += 8) {
 		RTK_LAUNCH(k_radix_hist, B.nblocks, RTK_SORT_THREADS, st, (const unsigned long long*)B.keys[src], n, shift, B.counts, B.nblocks); CK_LAUNCH();
 		RTK_LAUNCH(k_radix_scan, 256, 256, st, B.counts, B.nblocks, B.totals); CK_LAUNCH();
 		RTK_LAUNCH(k_radix_scatter, B.nblocks, RTK_SORT_THREADS, st, (const unsigned long long*)B.keys[src], (const uint32_t*)B.vals[src],

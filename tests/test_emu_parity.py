@@ -55,3 +55,11 @@ def test_wavefront_generators(emu_lib, orc):
 
 def test_refit_and_rebuild_of_a_deformed_mesh(emu_lib, orc):
     pc.case_refit(emu_lib, orc, pc.HostDevice())
+
+
+def test_read_bandwidth_probe(emu_lib):
+    import ctypes as C
+    g = C.c_double(0)
+    assert emu_lib.rtk_cuda_measure_read_bandwidth(1 << 16, 2, C.byref(g)) == 0
+    assert g.value > 0
+    assert emu_lib.rtk_cuda_measure_read_bandwidth(16, 2, C.byref(g)) != 0          # too small: refused

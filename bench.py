@@ -584,9 +584,9 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one k_trace launch on this very
-                     # workload (profiles/r1_k_trace_raw.csv); unknown for any other workload
-                     "traffic": 1.877e9 if (args.workload == "C3" and n == FULL_RAYS and args.scale == 1.0 and args.build_mode == "sah") else None,
-                     "traffic_unit": "bytes per launch (ncu, profiles/r1_k_trace_raw.csv)",
+                     # workload (profiles/r1e_k_trace_raw.csv); unknown for any other workload
+                     "traffic": 1.728e9 if (args.workload == "C3" and n == FULL_RAYS and args.scale == 1.0 and args.build_mode == "sah") else None,
+                     "traffic_unit": "bytes per launch (ncu, profiles/r1e_k_trace_raw.csv)",
                      "peak_source": peak_src,
                      "l2": {"achieved": achieved, "peak": l2_gbs.value, "unit": "GB/s",
                             "frac": achieved / l2_gbs.value if l2_gbs.value else None,

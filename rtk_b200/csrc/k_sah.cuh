@@ -85,38 +85,42 @@ RTK_DEV void rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, f
 	}
 }
 
-// Warp-cooperative variant (all 32 lanes call it; `valid` masks lanes without a triangle).  In
-// the upper levels a warp's 32 Morton-neighbours almost always fall into the same bin on every
-// axis: then the warp reduces its boxes with shuffles and one lane issues the 21 atomics instead
-// of 32 lanes fighting over the same 21 addresses.
+// Warp-cooperative variant (all 32 lanes call it; `valid` masks lanes without a triangle).  A
+// warp's 32 neighbours fall into very few bins per axis -- one in the upper levels, two or three
+// near the small-subtree threshold -- so per axis the warp walks the distinct bins present: the
+// lanes of one bin reduce their boxes with the hardware warp reductions (REDUX on the order-
+// preserving integer image of the floats) and one lane issues the 7 atomics, instead of 32 lanes
+// fighting over the same addresses.
 RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
 {
 	const uint32_t FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
-	int b0 = rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x), b1 = rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y), b2 = rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z);
-	uint32_t code = valid ? (uint32_t)(b0 | (b1 << 8) | (b2 << 16)) : 0xffffffffu;
-	uint32_t vm = __ballot_sync(FULL, valid);
+	const uint32_t vm = __ballot_sync(FULL, valid);
 	if (vm == 0) return;
-	uint32_t first_code = __shfl_sync(FULL, code, __ffs(vm) - 1);
-	bool uniform = __all_sync(FULL, !valid || code == first_code);
-	if (!uniform) {
-		if (valid) rtk_sah_bin_add(bins, lo, hi, nlo, nhi);
-		return;
-	}
-	float v[6] = { valid ? lo.x : +RTK_INF_F, valid ? lo.y : +RTK_INF_F, valid ? lo.z : +RTK_INF_F,
-	               valid ? hi.x : -RTK_INF_F, valid ? hi.y : -RTK_INF_F, valid ? hi.z : -RTK_INF_F };
-	for (int o = 16; o > 0; o >>= 1) {
-		for (int k = 0; k < 3; k++) v[k] = rtk_fmin(v[k], __shfl_xor_sync(FULL, v[k], o));
-		for (int k = 3; k < 6; k++) v[k] = rtk_fmax(v[k], __shfl_xor_sync(FULL, v[k], o));
-	}
-	if (lane == 0) {
-		int b[3] = { (int)(first_code & 255u), (int)((first_code >> 8) & 255u), (int)((first_code >> 16) & 255u) };
-		uint32_t cnt = (uint32_t)__popc(vm);
-		for (int a = 0; a < 3; a++) {
-			uint32_t *p = bins + (a * RTK_SAH_BINS + b[a]) * RTK_SAH_BINWORDS;
-			atomicMin(p + 0, rtk_f2ord(v[0])); atomicMin(p + 1, rtk_f2ord(v[1])); atomicMin(p + 2, rtk_f2ord(v[2]));
-			atomicMax(p + 3, rtk_f2ord(v[3])); atomicMax(p + 4, rtk_f2ord(v[4])); atomicMax(p + 5, rtk_f2ord(v[5]));
-			atomicAdd(p + 6, cnt);
+	const int b[3] = { rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x), rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y), rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z) };
+	const uint32_t ol[3] = { rtk_f2ord(lo.x), rtk_f2ord(lo.y), rtk_f2ord(lo.z) };
+	const uint32_t oh[3] = { rtk_f2ord(hi.x), rtk_f2ord(hi.y), rtk_f2ord(hi.z) };
+#pragma unroll
+	for (int a = 0; a < 3; a++) {
+		uint32_t remaining = vm;                              // warp-uniform
+		while (remaining) {
+			const int leader = __ffs((int)remaining) - 1;
+			const int lb = __shfl_sync(FULL, b[a], leader);
+			const bool in = valid && b[a] == lb;
+			const uint32_t grp = __ballot_sync(FULL, in);
+			const uint32_t m0 = __reduce_min_sync(FULL, in ? ol[0] : 0xffffffffu);
+			const uint32_t m1 = __reduce_min_sync(FULL, in ? ol[1] : 0xffffffffu);
+			const uint32_t m2 = __reduce_min_sync(FULL, in ? ol[2] : 0xffffffffu);
+			const uint32_t x0 = __reduce_max_sync(FULL, in ? oh[0] : 0u);
+			const uint32_t x1 = __reduce_max_sync(FULL, in ? oh[1] : 0u);
+			const uint32_t x2 = __reduce_max_sync(FULL, in ? oh[2] : 0u);
+			if (lane == leader) {
+				uint32_t *p = bins + (a * RTK_SAH_BINS + lb) * RTK_SAH_BINWORDS;
+				atomicMin(p + 0, m0); atomicMin(p + 1, m1); atomicMin(p + 2, m2);
+				atomicMax(p + 3, x0); atomicMax(p + 4, x1); atomicMax(p + 5, x2);
+				atomicAdd(p + 6, (uint32_t)__popc(grp));
+			}
+			remaining &= ~grp;
 		}
 	}
 }
@@ -472,9 +476,16 @@ __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, uint32_
 // small subtrees: one CTA, everything in shared memory
 // ---------------------------------------------------------------------------------------------
 
+#ifndef RTK_SAH_SMALL_THREADS
 #define RTK_SAH_SMALL_THREADS 128
+#endif
 #define RTK_SAH_SMALL_WARPS (RTK_SAH_SMALL_THREADS / 32)
+#ifndef RTK_SAH_COOP_MIN
+#define RTK_SAH_COOP_MIN 192          // CTA-wide splits of at least this many triangles bin warp-cooperatively
+#endif
+#ifndef RTK_SAH_WARP_MAX
 #define RTK_SAH_WARP_MAX 64           // subtrees of at most this many triangles are finished by one warp
+#endif
 
 struct rtk_sah_task { uint32_t node, begin, count, depth; float lo[3], hi[3]; };
 
@@ -491,9 +502,19 @@ RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *
 	const float4 nlo = make_float4(t.lo[0], t.lo[1], t.lo[2], 0.0f), nhi = make_float4(t.hi[0], t.hi[1], t.hi[2], 0.0f);
 	rtk_sah_bins_clear(bins, tid, nthreads);
 	RTK_SYNC();
-	for (uint32_t i = tid; i < t.count; i += nthreads) {
-		uint32_t k = perm0[t.begin + i];
-		rtk_sah_bin_add(bins, s_lo[k], s_hi[k], nlo, nhi);
+	if (!WARP && t.count >= RTK_SAH_COOP_MIN) {
+		// many triangles per bin: neighbours share bins, reduce per warp first (warp-uniform loop)
+		for (uint32_t base = 0; base < t.count; base += nthreads) {
+			const uint32_t i = base + tid;
+			const bool valid = i < t.count;
+			const uint32_t k = valid ? perm0[t.begin + i] : 0u;
+			rtk_sah_bin_add_warp(bins, s_lo[k], s_hi[k], nlo, nhi, valid);
+		}
+	} else {
+		for (uint32_t i = tid; i < t.count; i += nthreads) {
+			uint32_t k = perm0[t.begin + i];
+			rtk_sah_bin_add(bins, s_lo[k], s_hi[k], nlo, nhi);
+		}
 	}
 	RTK_SYNC();
 	if (warp == 0) {

@@ -192,6 +192,22 @@ static inline unsigned __match_any_sync(unsigned mask, unsigned v)
 	simt::warp_barrier(mask);
 	return r;
 }
+static inline unsigned simt_reduce(unsigned mask, unsigned v, int op)
+{
+	simt::Warp *w = simt::cur->w;
+	w->slot[simt::cur->lane] = v;
+	simt::warp_barrier(mask);
+	unsigned r = op == 0 ? 0xffffffffu : 0u;
+	for (int i = 0; i < 32; i++) if ((mask & w->live_mask) >> i & 1) {
+		unsigned x = (unsigned)w->slot[i];
+		r = op == 0 ? (x < r ? x : r) : (op == 1 ? (x > r ? x : r) : r + x);
+	}
+	simt::warp_barrier(mask);
+	return r;
+}
+static inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return simt_reduce(mask, v, 0); }
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return simt_reduce(mask, v, 1); }
+static inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return simt_reduce(mask, v, 2); }
 static inline unsigned __activemask() { return simt::cur->w->live_mask; }
 
 // ------------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ from rtk_b200 import api, scenes  # noqa: E402
 
 workload = sys.argv[1] if len(sys.argv) > 1 else "C3"
 mode = api.RTK_CUDA_BUILD_SAH if (len(sys.argv) < 3 or sys.argv[2] == "sah") else api.RTK_CUDA_BUILD_LBVH
-lib = api.load()
+lib = api.load() if not os.environ.get("RTK_LIB") else api.Library(os.path.abspath(os.environ["RTK_LIB"]))
 assert lib.rtk_cuda_init(0) == 0, lib.last_error()
 lib.rtk_cuda_set_build_mode(mode)
 s = scenes.config_scene(workload)

@@ -25,6 +25,9 @@
 #include "k_build.cuh"
 
 #define RTK_SAH_BINS 32
+#ifndef RTK_SAH_BIN_HYBRID
+#define RTK_SAH_BIN_HYBRID 0
+#endif
 #define RTK_SAH_SMALL 512
 #define RTK_SAH_CHUNK 2048
 #define RTK_SAH_MAX_DEPTH 64          // RTK_BVH_MAX_DEPTH, rtk.c:5
@@ -85,45 +88,82 @@ RTK_DEV void rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, f
 	}
 }
 
-// Warp-cooperative variant (all 32 lanes call it; `valid` masks lanes without a triangle).  A
-// warp's 32 neighbours fall into very few bins per axis -- one in the upper levels, two or three
-// near the small-subtree threshold -- so per axis the warp walks the distinct bins present: the
-// lanes of one bin reduce their boxes with the hardware warp reductions (REDUX on the order-
-// preserving integer image of the floats) and one lane issues the 7 atomics, instead of 32 lanes
-// fighting over the same addresses.
+#if RTK_SAH_BIN_HYBRID
+// Experiment (measured next round): uniformity is decided per axis, and a uniform axis is reduced
+// with the hardware warp reductions (REDUX) instead of a shuffle tree.  A first version that walked
+// ALL distinct bins of an axis with REDUX was 2.7x faster on the top level (23 vs 61 us) but 3x
+// slower on the deep large levels, where a warp's 32 triangles spread over many bins.
 RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
 {
 	const uint32_t FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const uint32_t vm = __ballot_sync(FULL, valid);
 	if (vm == 0) return;
+	const int leader = __ffs((int)vm) - 1;
 	const int b[3] = { rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x), rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y), rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z) };
 	const uint32_t ol[3] = { rtk_f2ord(lo.x), rtk_f2ord(lo.y), rtk_f2ord(lo.z) };
 	const uint32_t oh[3] = { rtk_f2ord(hi.x), rtk_f2ord(hi.y), rtk_f2ord(hi.z) };
 #pragma unroll
 	for (int a = 0; a < 3; a++) {
-		uint32_t remaining = vm;                              // warp-uniform
-		while (remaining) {
-			const int leader = __ffs((int)remaining) - 1;
-			const int lb = __shfl_sync(FULL, b[a], leader);
-			const bool in = valid && b[a] == lb;
-			const uint32_t grp = __ballot_sync(FULL, in);
-			const uint32_t m0 = __reduce_min_sync(FULL, in ? ol[0] : 0xffffffffu);
-			const uint32_t m1 = __reduce_min_sync(FULL, in ? ol[1] : 0xffffffffu);
-			const uint32_t m2 = __reduce_min_sync(FULL, in ? ol[2] : 0xffffffffu);
-			const uint32_t x0 = __reduce_max_sync(FULL, in ? oh[0] : 0u);
-			const uint32_t x1 = __reduce_max_sync(FULL, in ? oh[1] : 0u);
-			const uint32_t x2 = __reduce_max_sync(FULL, in ? oh[2] : 0u);
+		const int lb = __shfl_sync(FULL, b[a], leader);
+		if (__all_sync(FULL, !valid || b[a] == lb)) {
+			const uint32_t m0 = __reduce_min_sync(FULL, valid ? ol[0] : 0xffffffffu);
+			const uint32_t m1 = __reduce_min_sync(FULL, valid ? ol[1] : 0xffffffffu);
+			const uint32_t m2 = __reduce_min_sync(FULL, valid ? ol[2] : 0xffffffffu);
+			const uint32_t x0 = __reduce_max_sync(FULL, valid ? oh[0] : 0u);
+			const uint32_t x1 = __reduce_max_sync(FULL, valid ? oh[1] : 0u);
+			const uint32_t x2 = __reduce_max_sync(FULL, valid ? oh[2] : 0u);
 			if (lane == leader) {
 				uint32_t *p = bins + (a * RTK_SAH_BINS + lb) * RTK_SAH_BINWORDS;
 				atomicMin(p + 0, m0); atomicMin(p + 1, m1); atomicMin(p + 2, m2);
 				atomicMax(p + 3, x0); atomicMax(p + 4, x1); atomicMax(p + 5, x2);
-				atomicAdd(p + 6, (uint32_t)__popc(grp));
+				atomicAdd(p + 6, (uint32_t)__popc(vm));
 			}
-			remaining &= ~grp;
+		} else if (valid) {
+			uint32_t *p = bins + (a * RTK_SAH_BINS + b[a]) * RTK_SAH_BINWORDS;
+			atomicMin(p + 0, ol[0]); atomicMin(p + 1, ol[1]); atomicMin(p + 2, ol[2]);
+			atomicMax(p + 3, oh[0]); atomicMax(p + 4, oh[1]); atomicMax(p + 5, oh[2]);
+			atomicAdd(p + 6, 1u);
 		}
 	}
 }
+#else
+// Warp-cooperative variant (all 32 lanes call it; `valid` masks lanes without a triangle).  In
+// the upper levels a warp's 32 Morton-neighbours almost always fall into the same bin on every
+// axis: then the warp reduces its boxes with shuffles and one lane issues the 21 atomics instead
+// of 32 lanes fighting over the same 21 addresses.
+RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
+{
+	const uint32_t FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	int b0 = rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x), b1 = rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y), b2 = rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z);
+	uint32_t code = valid ? (uint32_t)(b0 | (b1 << 8) | (b2 << 16)) : 0xffffffffu;
+	uint32_t vm = __ballot_sync(FULL, valid);
+	if (vm == 0) return;
+	uint32_t first_code = __shfl_sync(FULL, code, __ffs(vm) - 1);
+	bool uniform = __all_sync(FULL, !valid || code == first_code);
+	if (!uniform) {
+		if (valid) rtk_sah_bin_add(bins, lo, hi, nlo, nhi);
+		return;
+	}
+	float v[6] = { valid ? lo.x : +RTK_INF_F, valid ? lo.y : +RTK_INF_F, valid ? lo.z : +RTK_INF_F,
+	               valid ? hi.x : -RTK_INF_F, valid ? hi.y : -RTK_INF_F, valid ? hi.z : -RTK_INF_F };
+	for (int o = 16; o > 0; o >>= 1) {
+		for (int k = 0; k < 3; k++) v[k] = rtk_fmin(v[k], __shfl_xor_sync(FULL, v[k], o));
+		for (int k = 3; k < 6; k++) v[k] = rtk_fmax(v[k], __shfl_xor_sync(FULL, v[k], o));
+	}
+	if (lane == 0) {
+		int b[3] = { (int)(first_code & 255u), (int)((first_code >> 8) & 255u), (int)((first_code >> 16) & 255u) };
+		uint32_t cnt = (uint32_t)__popc(vm);
+		for (int a = 0; a < 3; a++) {
+			uint32_t *p = bins + (a * RTK_SAH_BINS + b[a]) * RTK_SAH_BINWORDS;
+			atomicMin(p + 0, rtk_f2ord(v[0])); atomicMin(p + 1, rtk_f2ord(v[1])); atomicMin(p + 2, rtk_f2ord(v[2]));
+			atomicMax(p + 3, rtk_f2ord(v[3])); atomicMax(p + 4, rtk_f2ord(v[4])); atomicMax(p + 5, rtk_f2ord(v[5]));
+			atomicAdd(p + 6, cnt);
+		}
+	}
+}
+#endif
 
 struct rtk_sah_choice {
 	int axis, bin;               // axis < 0: no valid split
@@ -481,7 +521,7 @@ __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, uint32_
 #endif
 #define RTK_SAH_SMALL_WARPS (RTK_SAH_SMALL_THREADS / 32)
 #ifndef RTK_SAH_COOP_MIN
-#define RTK_SAH_COOP_MIN 192          // CTA-wide splits of at least this many triangles bin warp-cooperatively
+#define RTK_SAH_COOP_MIN 100000          // CTA-wide small-subtree splits of at least this many triangles bin warp-cooperatively (measured: 192 is 3 % slower than never)
 #endif
 #ifndef RTK_SAH_WARP_MAX
 #define RTK_SAH_WARP_MAX 64           // subtrees of at most this many triangles are finished by one warp

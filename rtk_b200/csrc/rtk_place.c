@@ -97,6 +97,9 @@ static void pool_start(void)
 		 * shares) -- three quarters of the CPUs, at most 16 */
 		want = n >= 4 ? (int)(n * 3 / 4) : 1;
 		if (want > 16) want = 16;
+		/* one process per GPU: the ranks of a node share its CPUs (torchrun exports LOCAL_WORLD_SIZE) */
+		const char *lw = getenv("LOCAL_WORLD_SIZE");
+		if (lw && atoi(lw) > 1) want = want / atoi(lw) > 0 ? want / atoi(lw) : 1;
 	}
 	if (want > PLACE_MAX_THREADS) want = PLACE_MAX_THREADS;
 	for (int i = 0; i < want; i++) {

@@ -728,8 +728,12 @@ extern "C" void *rtkd_scene_hit16(rtkd_scene *s, size_t n)
 
 // Host-buffer batch: a three-stage pipeline over chunks of RTKD_HOST_CHUNK rays, RTKD_HOST_BUFS chunks
 // in flight on their own streams.
-//   stage A (enqueue)  H2D rays -> k_trace -> k_resolve<dense> -> D2H of the chunk's mask bytes,
-//                      block bases and hit count into pinned staging
+//   upload             the rays of the whole batch go to one device buffer, chunk by chunk on a
+//                      copy stream of their own that runs RTKD_HOST_AHEAD chunks ahead of the
+//                      kernels, so the H2D engine -- the bottleneck resource of the batch: 32 bytes
+//                      per ray up against ~26 down -- never waits for the host
+//   stage A (enqueue)  k_trace -> k_resolve<dense> -> D2H of the chunk's mask bytes, block bases
+//                      and hit count into pinned staging
 //   stage B            once the count is known: D2H of exactly the rows of the rays that hit
 //   stage C            the host worker pool (rtk_place.c) copies each row to hits[i]
 // Only hit rows cross PCIe (68 bytes per HIT plus 1 byte per ray instead of 69 bytes per ray), and
@@ -738,11 +742,13 @@ extern "C" void *rtkd_scene_hit16(rtkd_scene *s, size_t n)
 // TRAVERSALS of consecutive chunks are serialised with an event; everything else overlaps.
 #define RTKD_HOST_CHUNK ((size_t)1 << 20)
 #define RTKD_HOST_BUFS 4
+#define RTKD_HOST_AHEAD 4
+#define RTKD_HOST_RING 8             // upload events: more than RTKD_HOST_AHEAD + 1
 
 struct host_buf {
 	cudaStream_t st;
 	cudaEvent_t traced, meta_done, rows_done;
-	float4 *d_rays, *d_h16;
+	float4 *d_h16;
 	uint32_t *d_rows, *d_base;          // d_base: [blocks] block bases, then the 64-bit hit count
 	unsigned char *d_mask;
 	unsigned char *h_meta;              // pinned: mask bytes | block bases | hit count
@@ -753,6 +759,9 @@ struct host_buf {
 struct host_stage {
 	size_t chunk, blocks, meta_bytes;
 	host_buf b[RTKD_HOST_BUFS];
+	cudaStream_t up;                    // upload stream
+	cudaEvent_t uploaded[RTKD_HOST_RING];
+	float4 *d_rays; size_t rays_cap;    // the whole batch's rays (grow-only)
 	bool ready;
 };
 static host_stage g_stage;
@@ -762,9 +771,9 @@ static void stage_release(void)
 {
 	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
 		host_buf &B = g_stage.b[k];
-		cudaFree(B.d_rays); cudaFree(B.d_h16); cudaFree(B.d_rows); cudaFree(B.d_base); cudaFree(B.d_mask);
+		cudaFree(B.d_h16); cudaFree(B.d_rows); cudaFree(B.d_base); cudaFree(B.d_mask);
 		cudaFreeHost(B.h_meta); cudaFreeHost(B.h_rows);
-		B.d_rays = B.d_h16 = NULL; B.d_rows = B.d_base = NULL; B.d_mask = NULL; B.h_meta = B.h_rows = NULL;
+		B.d_h16 = NULL; B.d_rows = B.d_base = NULL; B.d_mask = NULL; B.h_meta = B.h_rows = NULL;
 	}
 }
 
@@ -787,6 +796,8 @@ static int stage_prepare(size_t want)
 			CK(cudaEventCreateWithFlags(&B.meta_done, cudaEventDisableTiming));
 			CK(cudaEventCreateWithFlags(&B.rows_done, cudaEventDisableTiming));
 		}
+		CK(cudaStreamCreateWithFlags(&g_stage.up, cudaStreamNonBlocking));
+		for (int k = 0; k < RTKD_HOST_RING; k++) CK(cudaEventCreateWithFlags(&g_stage.uploaded[k], cudaEventDisableTiming));
 	}
 	g_stage.ready = false;
 	g_stage.chunk = chunk;
@@ -794,7 +805,6 @@ static int stage_prepare(size_t want)
 	g_stage.meta_bytes = ((chunk + 15) & ~(size_t)15) + 4 * g_stage.blocks + 16;
 	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
 		host_buf &B = g_stage.b[k];
-		CK(cudaMalloc(&B.d_rays, 32 * chunk));
 		CK(cudaMalloc(&B.d_h16, 16 * chunk));
 		CK(cudaMalloc(&B.d_rows, 68 * chunk));
 		CK(cudaMalloc(&B.d_base, 4 * g_stage.blocks + 16));
@@ -843,25 +853,40 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 	int rc = stage_prepare(n);
 	if (rc == RTKD_OK) rc = ensure_scratch(s);
 	host_stage &G = g_stage;
+	if (rc == RTKD_OK && G.rays_cap < n) {
+		if (G.d_rays) cudaFree(G.d_rays);
+		G.d_rays = NULL; G.rays_cap = 0;
+		if (cudaMalloc(&G.d_rays, 32 * n) != cudaSuccess) { rtkd_set_error("out of device memory for %zu rays", n); rc = RTKD_ERR_MEMORY; }
+		else G.rays_cap = n;
+	}
 	const size_t chunk = G.chunk;
 	const size_t nchunks = (n + chunk - 1) / chunk;
 	const size_t mask_bytes = (chunk + 15) & ~(size_t)15;
 	rtkd_arrays a;
 	fill_arrays(s, a);
 	cudaEvent_t prev_traced = NULL;
+	size_t uploads = 0;                 // chunks whose upload has been enqueued
 	// chunk ci enters stage A in iteration ci, stage B in iteration ci+1, stage C in iteration ci+2
 	// and its buffer is reused in iteration ci + RTKD_HOST_BUFS
 	for (size_t it = 0; it < nchunks + 2 && rc == RTKD_OK; it++) {
+		// keep the upload stream RTKD_HOST_AHEAD chunks ahead of the kernels
+		for (; uploads < nchunks && uploads <= it + RTKD_HOST_AHEAD; uploads++) {
+			const size_t off = uploads * chunk, cnt = n - off < chunk ? n - off : chunk;
+			cudaError_t e = cudaMemcpyAsync(G.d_rays + 2 * off, (const char*)rays + 32 * off, 32 * cnt, cudaMemcpyHostToDevice, G.up);
+			if (e == cudaSuccess) e = cudaEventRecord(G.uploaded[uploads % RTKD_HOST_RING], G.up);
+			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
+		}
+		if (rc != RTKD_OK) break;
 		if (it < nchunks) {
 			host_buf &B = G.b[it % RTKD_HOST_BUFS];
 			if (B.state == 3) { rtkd_place_wait(B.ticket); total += (long long)B.hits; B.state = 0; }
 			B.off = it * chunk; B.cnt = n - B.off < chunk ? n - B.off : chunk;
 			unsigned long long *d_count = (unsigned long long*)((unsigned char*)B.d_base + 4 * G.blocks);
-			cudaError_t e = cudaMemcpyAsync(B.d_rays, (const char*)rays + 32 * B.off, 32 * B.cnt, cudaMemcpyHostToDevice, B.st);
+			cudaError_t e = cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0);
 			if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, 16, B.st);
 			if (e == cudaSuccess && prev_traced) e = cudaStreamWaitEvent(B.st, prev_traced, 0);
 			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
-			rc = rtkd_trace(s, B.d_rays, B.d_h16, B.cnt, 1, NULL, B.st);
+			rc = rtkd_trace(s, G.d_rays + 2 * B.off, B.d_h16, B.cnt, 1, NULL, B.st);
 			if (rc) break;
 			cudaEventRecord(B.traced, B.st);
 			prev_traced = B.traced;
@@ -885,6 +910,7 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 		else if (B.state) cudaStreamSynchronize(B.st);
 		B.state = 0; B.ticket = -1;
 	}
+	if (rc != RTKD_OK) cudaStreamSynchronize(G.up);
 	if (rc == RTKD_OK) {
 		uint32_t herr = 0;
 		if (cudaMemcpy(&herr, (unsigned char*)s->scratch + 192, sizeof(herr), cudaMemcpyDeviceToHost) != cudaSuccess) rc = RTKD_ERR_CUDA;

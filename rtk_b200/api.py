@@ -128,6 +128,7 @@ SYMBOLS = {
     "rtk_cuda_last_error": (C.c_char_p, []),
     "rtk_cuda_set_build_mode": (C.c_int, [C.c_int]),
     "rtk_cuda_set_cull_mode": (C.c_int, [C.c_int]),
+    "rtk_cuda_reserve_sms": (C.c_int, [C.c_int]),
     "rtk_cuda_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rtk_cuda_measure_read_bandwidth": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "rtk_trace_rays": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),

@@ -22,6 +22,7 @@
 static __thread char g_err[512];
 static int g_device = -1;
 static int g_sm_count = 0, g_trace_ctas = 0, g_trace_lanes = RTK_TRACE_LANES, g_trace_pd = 1;
+static int g_reserved_sms = 0;      // SMs the persistent traversal grid leaves free (for concurrent NCCL kernels)
 static size_t g_l2_bytes = 0;
 static uint64_t g_next_id = 1;
 
@@ -90,6 +91,15 @@ extern "C" int rtkd_init(int device)
 static int ensure_init(void) { return g_sm_count ? RTKD_OK : rtkd_init(0); }
 
 extern "C" void rtkd_shutdown(void) { g_device = -1; g_sm_count = 0; }
+
+extern "C" int rtkd_reserve_sms(int sms)
+{
+	int r = ensure_init();
+	if (r) return r;
+	if (sms < 0 || sms >= g_sm_count) { rtkd_set_error("cannot reserve %d of %d SMs", sms, g_sm_count); return RTKD_ERR_ARGUMENT; }
+	g_reserved_sms = sms;
+	return RTKD_OK;
+}
 
 extern "C" int rtkd_device_info(int *sm_count, size_t *l2_bytes, int *ctas_per_sm, int *threads_per_cta)
 {
@@ -636,7 +646,7 @@ extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size
 	p.overflow = (uint2*)s->overflow; p.ovf_entries = (uint32_t)s->overflow_entries;
 	// persistent grid: one wave of resident CTAs, never more CTAs than ray batches
 	size_t batches = (n + RTK_RAY_BATCH - 1) / RTK_RAY_BATCH;
-	size_t ctas = (size_t)g_sm_count * g_trace_ctas;
+	size_t ctas = (size_t)(g_sm_count - g_reserved_sms) * g_trace_ctas;
 	size_t want = (batches + RTK_TRACE_WARPS - 1) / RTK_TRACE_WARPS;
 	unsigned grid = (unsigned)(want < ctas ? want : ctas);
 	launch_trace(g_trace_lanes, cull_mode, stats != NULL, g_trace_pd != 0, grid, st, p);

@@ -41,6 +41,7 @@ int         rtkd_init(int device);           /* 0 or negative rtk_cuda_status */
 void        rtkd_shutdown(void);
 const char *rtkd_last_error(void);
 void        rtkd_set_error(const char *fmt, ...);
+int         rtkd_reserve_sms(int sms);       /* the traversal grid leaves this many SMs free */
 int         rtkd_device_info(int *sm_count, size_t *l2_bytes, int *ctas_per_sm, int *threads_per_cta);
 
 int         rtkd_read_bandwidth(size_t bytes, int passes, double *gbs);   /* read probe: L2 (small buffer) or HBM */

@@ -75,6 +75,8 @@ int rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *ctas, int *thread
 	return rtkd_device_info(sm_count, l2_bytes, ctas, threads);
 }
 
+int rtk_cuda_reserve_sms(int sms) { return rtkd_reserve_sms(sms); }
+
 int rtk_cuda_measure_read_bandwidth(size_t bytes, int passes, double *gb_per_s)
 {
 	return rtkd_read_bandwidth(bytes, passes, gb_per_s);

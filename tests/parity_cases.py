@@ -527,3 +527,36 @@ def case_refit(lib, orc, dev):
     meshes[0].num_triangles = len(idx) - 1
     assert lib.rtk_cuda_update_scene(sc.ptr, meshes, 1, api.RTK_CUDA_UPDATE_REFIT, dev.stream) != 0
     sc.free()
+
+
+def case_deep_stack(lib, orc, dev=None):
+    """Thousands of coincident triangles: the builder cannot separate them (forced halving,
+    rtk.c:1429-1443), every box overlaps every other, so a ray has to visit all of them: the
+    traversal stack outgrows its shared-memory part and spills to the global slab.  All hits tie
+    exactly and the lowest triangle number must win."""
+    base = np.array([[(0, 0, 1), (1, 0, 1), (0, 1, 1)]], dtype=np.float32)
+    tris = np.repeat(base, 21500, axis=0)
+    tris[20000:] += np.float32(0.25)                   # a second coincident cluster, further away
+    rays = np.zeros(64, dtype=api.RAY_DTYPE)
+    rng = np.random.default_rng(23)
+    rays["o"] = np.concatenate([rng.random((64, 2)) * 0.6, np.zeros((64, 1))], axis=1).astype(np.float32)
+    rays["d"] = (0, 0, 1)
+    rays["max_t"] = api.RTK_INF
+    got, _, _ = trace_hit16(lib, soup_mesh(tris), rays)
+    want = orc.trace_brute(tris, rays)
+    assert_same(got, want, "coincident triangles")
+    hit = want["prim"] != api.RTK_CUDA_MISS
+    assert hit.any() and np.isin(want["prim"][hit], (0, 20000)).all() and (want["prim"] == 0).any()
+    # the statistics variant reports how deep the stack went
+    sc = lib.build_scene(soup_mesh(tris))
+    info = sc.info()
+    assert info.num_wide_nodes > 8
+    if dev is not None:
+        h_rays, d_rays = dev.put(rays)
+        h_hit, d_hit = dev.empty(16 * len(rays))
+        st = api.rtk_cuda_trace_stats()
+        assert lib.rtk_trace_stats_device(sc.ptr, d_rays, d_hit, len(rays), C.byref(st), dev.stream) == 0, lib.last_error()
+        assert_same(dev.get(h_hit, api.HIT16_DTYPE, len(rays)), want, "statistics kernel")
+        assert st.stack_max > 16, st.stack_max                 # beyond the shared-memory part (RTK_STACK_SMEM)
+        assert st.tri_tests >= 1500 * int(hit.sum())
+    sc.free()

@@ -63,3 +63,7 @@ def test_read_bandwidth_probe(emu_lib):
     assert emu_lib.rtk_cuda_measure_read_bandwidth(1 << 16, 2, C.byref(g)) == 0
     assert g.value > 0
     assert emu_lib.rtk_cuda_measure_read_bandwidth(16, 2, C.byref(g)) != 0          # too small: refused
+
+
+def test_deep_stack_spills(emu_lib, orc):
+    pc.case_deep_stack(emu_lib, orc, pc.HostDevice())

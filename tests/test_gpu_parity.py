@@ -198,3 +198,7 @@ def test_wavefront_generators(gpu_lib, orc):
 
 def test_refit_and_rebuild_of_a_deformed_mesh(gpu_lib, orc):
     pc.case_refit(gpu_lib, orc, TorchDevice())
+
+
+def test_deep_stack_spills(gpu_lib, orc):
+    pc.case_deep_stack(gpu_lib, orc, TorchDevice())

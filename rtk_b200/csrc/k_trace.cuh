@@ -2,12 +2,14 @@
 //
 // k_trace replaces the reference's per-ray rtk_trace_ray (rtk.c:543-577) with a persistent,
 // warp-cooperative kernel:
-//   * one ray per group of 8 lanes, four rays per warp.  Lane c of a group owns child c of the
-//     current 8-wide node and triangle c of the current leaf, so a node visit is two coalesced
-//     128-byte requests and a leaf visit three, instead of 8 scattered fetches per thread;
+//   * one ray per group of LANES lanes (2 by default: 16 rays per warp).  Lane c of a group owns
+//     the child slots c, c+LANES, ... of the current 8-wide node -- one 256-bit load per child, the
+//     lanes of a ray reading adjacent slots -- instead of 8 scattered fetches per thread;
 //   * persistent CTAs pull batches of 32 rays per warp from a global counter and stage them in
-//     shared memory with asynchronous copies, double buffered (the next batch is in flight
-//     while the current one is traced);
+//     shared memory with asynchronous copies (the next batch is in flight while the current one
+//     is traced); the warp prepares a whole batch at once, one ray per lane (PD, see below);
+//   * rays that reach a leaf wait until the warp tests the leaves of up to four rays together,
+//     ONE triangle per lane (PD);
 //   * the traversal stack (distance key + reference, 8 bytes) lives in shared memory,
 //     interleaved across groups, and spills to a per-group slab in global memory when a ray
 //     needs more than RTK_STACK_SMEM entries;

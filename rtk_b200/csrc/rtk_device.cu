@@ -790,13 +790,15 @@ static void stage_release(void)
 static int stage_prepare(size_t want)
 {
 	size_t max_chunk = RTKD_HOST_CHUNK;
+	bool forced = false;
 	{
-		const char *e = getenv("RTK_B200_HOST_CHUNK_LOG2");       // experiment knob
-		if (e && atoi(e) >= 12 && atoi(e) <= 24) max_chunk = (size_t)1 << atoi(e);
+		// experiment / test knob: chunk size 2^k rays (the tests use it to run many small chunks)
+		const char *e = getenv("RTK_B200_HOST_CHUNK_LOG2");
+		if (e && atoi(e) >= 12 && atoi(e) <= 24) { max_chunk = (size_t)1 << atoi(e); forced = true; }
 	}
 	size_t chunk = want < max_chunk ? want : max_chunk;
 	if (chunk < 4096) chunk = 4096;
-	if (g_stage.ready && g_stage.chunk >= chunk) return RTKD_OK;
+	if (g_stage.ready && (forced ? g_stage.chunk == chunk : g_stage.chunk >= chunk)) return RTKD_OK;
 	if (g_stage.ready) stage_release();
 	else {
 		for (int k = 0; k < RTKD_HOST_BUFS; k++) {

@@ -560,3 +560,37 @@ def case_deep_stack(lib, orc, dev=None):
         assert st.stack_max > 16, st.stack_max                 # beyond the shared-memory part (RTK_STACK_SMEM)
         assert st.tri_tests >= 1500 * int(hit.sum())
     sc.free()
+
+
+def case_host_batch_chunks(lib, orc, nrays=30000, chunk_log2=12):
+    """rtk_trace_rays over many chunks: the pipeline's buffer rotation (4 chunks in flight, upload
+    stream ahead of the kernels, dense rows put back in place by the host threads) must give the
+    rows of a one-chunk run, leave the rows of misses untouched, and agree with the oracle."""
+    s = scenes.config_scene("C3", 0.004)
+    rays = scenes.bounce_rays(s, nrays)
+    sc = lib.build_scene(s["meshes"])
+    old = os.environ.pop("RTK_B200_HOST_CHUNK_LOG2", None)
+    try:
+        hits1 = np.zeros(nrays, dtype=api.HIT_DTYPE)
+        hits1.view(np.uint8)[:] = 0x5A
+        _, mask1, n1 = sc.trace_rays(rays, hits=hits1)
+        os.environ["RTK_B200_HOST_CHUNK_LOG2"] = str(chunk_log2)
+        hits2 = np.zeros(nrays, dtype=api.HIT_DTYPE)
+        hits2.view(np.uint8)[:] = 0x5A
+        _, mask2, n2 = sc.trace_rays(rays, hits=hits2)
+        # no mask requested: rows still land where they belong
+        hits3 = np.zeros(nrays, dtype=api.HIT_DTYPE)
+        r = lib.rtk_trace_rays(sc.ptr, rays.ctypes.data, hits3.ctypes.data, None, nrays)
+    finally:
+        os.environ.pop("RTK_B200_HOST_CHUNK_LOG2", None)
+        if old is not None:
+            os.environ["RTK_B200_HOST_CHUNK_LOG2"] = old
+    assert n1 == n2 == r and 0 < n1 < nrays
+    assert np.array_equal(mask1, mask2)
+    assert hits1.tobytes() == hits2.tobytes()
+    m = mask1.astype(bool)
+    assert (hits2.view(np.uint8).reshape(-1, 68)[~m] == 0x5A).all()          # misses untouched (rtk.c:571-576)
+    assert hits3[m].tobytes() == hits2[m].tobytes()
+    k = min(nrays, 1500)
+    assert_same(api.hits_to_hit16(hits2, mask2, s["mesh_first"])[:k], orc.trace_brute(s["tris"], rays[:k]), "chunked host batch")
+    sc.free()

@@ -67,3 +67,7 @@ def test_read_bandwidth_probe(emu_lib):
 
 def test_deep_stack_spills(emu_lib, orc):
     pc.case_deep_stack(emu_lib, orc, pc.HostDevice())
+
+
+def test_host_batch_many_chunks(emu_lib, orc):
+    pc.case_host_batch_chunks(emu_lib, orc, nrays=30000, chunk_log2=12)

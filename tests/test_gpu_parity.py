@@ -202,3 +202,7 @@ def test_refit_and_rebuild_of_a_deformed_mesh(gpu_lib, orc):
 
 def test_deep_stack_spills(gpu_lib, orc):
     pc.case_deep_stack(gpu_lib, orc, TorchDevice())
+
+
+def test_host_batch_many_chunks(gpu_lib, orc):
+    pc.case_host_batch_chunks(gpu_lib, orc, nrays=300000, chunk_log2=14)

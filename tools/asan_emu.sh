@@ -8,7 +8,8 @@ mkdir -p /tmp/rtk_asan
 g++ -x c++ -std=c++17 -O1 -g -fPIC -fsanitize=address -fno-omit-frame-pointer -ffp-contract=off -mfma -w \
     -DRTK_SIMT_EMU=1 -DSIMT_IMPL=1 -include tests/emu/simt.h -c rtk_b200/csrc/rtk_device.cu -o /tmp/rtk_asan/dev.o
 gcc -O1 -g -fPIC -fsanitize=address -std=gnu11 -c rtk_b200/csrc/rtk_host.c -o /tmp/rtk_asan/host.o
-g++ -shared -fsanitize=address -o /tmp/rtk_asan/librtk_emu_asan.so /tmp/rtk_asan/dev.o /tmp/rtk_asan/host.o -lpthread -lm
+gcc -O1 -g -fPIC -fsanitize=address -std=gnu11 -c rtk_b200/csrc/rtk_place.c -o /tmp/rtk_asan/place.o
+g++ -shared -fsanitize=address -o /tmp/rtk_asan/librtk_emu_asan.so /tmp/rtk_asan/dev.o /tmp/rtk_asan/host.o /tmp/rtk_asan/place.o -lpthread -lm
 cat > /tmp/rtk_asan/run.py <<'PY'
 import sys
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
@@ -24,6 +25,11 @@ for mode in (0, 1):
 pc.case_config(lib, orc, "C4", 0.0005, 500, mode=1)
 pc.case_mesh_formats(lib, orc)
 pc.case_api_semantics(lib, orc)
+pc.case_ties(lib, orc)
+pc.case_wavefront(lib, orc, pc.HostDevice())
+pc.case_refit(lib, orc, pc.HostDevice())
+pc.case_deep_stack(lib, orc, pc.HostDevice())
+pc.case_host_batch_chunks(lib, orc, nrays=20000, chunk_log2=12)
 print("asan run clean")
 PY
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \

@@ -123,6 +123,21 @@ int rtk_resolve_hits_device(const rtk_scene *scene, const void *d_hit16, void *d
  * rtk_trace_ray_filter (rtk.h:130, a stub upstream) is for. */
 int rtk_occluded_rays_device(const rtk_scene *scene, const void *d_rays, void *d_occluded, size_t n, void *stream);
 
+/* Device-side triangle predicate (the filtered half of what
+ * rtk_trace_ray_filter, rtk.h:117,130, is for): a bitset over the scene's GLOBAL
+ * triangle numbers (mesh_first[mesh_index] + triangle_index, meshes in
+ * rtk_scene_desc order, rtk.c:1131-1170).  Bit (i & 31) of word (i >> 5) set =
+ * triangle i takes part; a cleared bit removes the triangle from EVERY later
+ * query on this scene (closest hit, occlusion, host and device entry points)
+ * exactly as if it had not been in the mesh, while triangle numbering stays as
+ * it was.  num_words >= ceil(num_triangles / 32); bits == NULL removes the
+ * filter.  The predicate is baked into the leaf slots by one pass over them
+ * (16 + 16 bytes per triangle), so traversal costs the same with or without a
+ * filter; it survives rtk_cuda_update_scene / rtk_cuda_rebuild_scene.  Not
+ * stored in blobs.  Must not run concurrently with a query on the scene. */
+int rtk_cuda_set_triangle_filter(const rtk_scene *scene, const uint32_t *bits, size_t num_words);
+int rtk_cuda_set_triangle_filter_device(const rtk_scene *scene, const void *d_bits, size_t num_words, void *stream);
+
 /* Exhaustive ray x triangle kernel with the same arithmetic: the GPU-side
  * check used by the parity tests and by the bench's self-check. */
 int rtk_trace_rays_bruteforce_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream);

@@ -136,6 +136,8 @@ SYMBOLS = {
     "rtk_trace_rays_compact_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_resolve_hits_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     "rtk_occluded_rays_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
+    "rtk_cuda_set_triangle_filter": (C.c_int, [_P, _P, C.c_size_t]),
+    "rtk_cuda_set_triangle_filter_device": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "rtk_trace_rays_bruteforce_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_trace_stats_device": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(rtk_cuda_trace_stats), _P]),
     "rtk_cuda_generate_primary_rays": (C.c_int, [C.POINTER(rtk_cuda_camera), C.c_uint64, C.c_uint32, C.c_size_t, C.c_size_t, _P, _P]),
@@ -293,6 +295,17 @@ class Scene:
             raise RtkError("rtk_trace_rays failed: " + self.lib.last_error())
         return hits, mask, int(r)
 
+    def set_triangle_filter(self, keep):
+        """rtk_cuda_set_triangle_filter: `keep` is a boolean array over the scene's global triangle
+        numbers (True = the triangle takes part in queries) or None to remove the filter."""
+        if keep is None:
+            r = self.lib.rtk_cuda_set_triangle_filter(self.ptr, None, 0)
+        else:
+            bits = pack_triangle_filter(keep)
+            r = self.lib.rtk_cuda_set_triangle_filter(self.ptr, bits.ctypes.data, len(bits))
+        if r:
+            raise RtkError("rtk_cuda_set_triangle_filter: " + self.lib.last_error())
+
     def free(self):
         if self.ptr:
             self.lib.rtk_free_scene(self.ptr)
@@ -314,6 +327,16 @@ def load():
     if _lib is None:
         _lib = Library(LIB_PATH)
     return _lib
+
+
+def pack_triangle_filter(keep):
+    """Boolean array over global triangle numbers -> the uint32 bitset of rtk_cuda_set_triangle_filter
+    (bit i & 31 of word i >> 5)."""
+    keep = np.asarray(keep, dtype=bool)
+    words = (len(keep) + 31) // 32
+    padded = np.zeros(words * 32, dtype=np.uint8)
+    padded[:len(keep)] = keep
+    return np.ascontiguousarray(np.packbits(padded, bitorder="little").view("<u4"))
 
 
 def hits_to_hit16(hits, mask, mesh_first):

@@ -533,3 +533,28 @@ __global__ void k_refit_level(float4 *nodes, const unsigned char *node_level, ui
 	slot[0] = make_float4(lo[0], lo[1], lo[2], __uint_as_float(ref));
 	slot[1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Triangle filter: a device-side predicate as a bitset over global triangle
+// numbers.  The predicate is baked into the leaf slots instead of being evaluated per ray: corner 0
+// of a triangle that is switched off becomes NaN, which the watertight test can never accept
+// (v, w, det and t are NaN; rtk_tri_test's `t > min_t` is false), so the traversal kernels need no
+// extra load, register or branch.  Corner 0 of every other triangle is restored from the decoded
+// corners, which makes the pass idempotent and lets bits == NULL remove the filter.  Boxes are not
+// touched (they stay conservative); a refit rewrites the slots first and re-applies the filter last.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void k_apply_filter(const float4 *tri_orig, const uint32_t *bits, uint32_t num_tv, float4 *tv0)
+{
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= num_tv) return;
+	const uint32_t prim = __float_as_uint(tv0[i].w);
+	if (prim == RTK_MISS) return;
+	float4 a = tri_orig[3ull * prim];
+	if (bits && !((bits[prim >> 5] >> (prim & 31u)) & 1u)) {
+		const float qnan = __uint_as_float(0x7fc00000u);
+		a.x = qnan; a.y = qnan; a.z = qnan;
+	}
+	a.w = __uint_as_float(prim);
+	tv0[i] = a;
+}

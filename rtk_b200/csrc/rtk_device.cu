@@ -197,6 +197,7 @@ extern "C" void rtkd_scene_free(rtkd_scene *s)
 	if (s->scratch) cudaFree(s->scratch);
 	if (s->overflow) cudaFree(s->overflow);
 	if (s->hit16) cudaFree(s->hit16);
+	if (s->filter_bits) cudaFree(s->filter_bits);
 	free(s->h_mesh_first);
 	free(s);
 }
@@ -354,6 +355,40 @@ static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, 
 	return RTKD_OK;
 }
 
+// (re)writes corner 0 of every leaf-slot triangle according to the scene's filter bitset
+static int apply_filter(rtkd_scene *s, cudaStream_t st)
+{
+	if (!s->num_tv) return RTKD_OK;
+	RTK_LAUNCH(k_apply_filter, (s->num_tv + 255) / 256, 256, st, (const float4*)s->tri_orig, (const uint32_t*)s->filter_bits,
+	           s->num_tv, (float4*)s->tv0);
+	CK_LAUNCH();
+	return RTKD_OK;
+}
+
+extern "C" int rtkd_set_filter(rtkd_scene *s, const void *bits, size_t num_words, int on_device, void *stream)
+{
+	cudaStream_t st = (cudaStream_t)stream;
+	const size_t words = ((size_t)s->num_tris + 31) / 32;
+	if (!bits) {
+		if (!s->filter_bits) return RTKD_OK;
+		// the slots go back to the decoded corners; the bitset is released once that pass has run
+		void *old = s->filter_bits;
+		s->filter_bits = NULL;
+		int r = apply_filter(s, st);
+		CK(cudaStreamSynchronize(st));
+		cudaFree(old);
+		return r;
+	}
+	if (num_words < words) { rtkd_set_error("triangle filter needs %zu words for %u triangles, got %zu", words, s->num_tris, num_words); return RTKD_ERR_ARGUMENT; }
+	if (!words) return RTKD_OK;
+	if (!s->filter_bits) CK(cudaMalloc((uint32_t**)&s->filter_bits, sizeof(uint32_t) * words));
+	CK(cudaMemcpyAsync(s->filter_bits, bits, sizeof(uint32_t) * words, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+	int r = apply_filter(s, st);
+	// filters change rarely: return with the pass done, whatever stream the next query uses
+	CK(cudaStreamSynchronize(st));
+	return r;
+}
+
 extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 {
 	cudaStream_t st = (cudaStream_t)stream;
@@ -492,6 +527,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	           (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
 	s->num_tv = num_tv;
 	cudaFreeAsync(A.base, st);
+	if (s->filter_bits) { int fr = apply_filter(s, st); if (fr) return fr; }
 
 	CK(cudaEventRecord(e1, st));
 	CK(cudaEventSynchronize(e1));
@@ -546,6 +582,7 @@ extern "C" int rtkd_refit(rtkd_scene *s, void *stream)
 		RTK_LAUNCH(k_refit_level, blocks, 256, st, (float4*)s->nodes, (const unsigned char*)s->node_level, s->num_nodes, (uint32_t)level,
 		           (const float4*)s->tv0, (const float4*)s->tv1, (const float4*)s->tv2); CK_LAUNCH();
 	}
+	if (s->filter_bits) { int fr = apply_filter(s, st); if (fr) return fr; }
 	uint32_t h_bounds[6];
 	CK(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, st));
 	cudaFreeAsync(d_bounds, st);

@@ -31,6 +31,7 @@ typedef struct rtkd_scene {
 	void *scratch;               /* counter, err, stats */
 	void *overflow; size_t overflow_entries, overflow_groups;
 	void *hit16; size_t hit16_cap;   /* compact hits of rtk_trace_rays_device */
+	void *filter_bits;           /* uint32[(num_tris+31)/32] or NULL: triangle filter baked into the leaf slots */
 } rtkd_scene;
 
 typedef struct rtkd_trace_stats {
@@ -65,6 +66,11 @@ int rtkd_build(rtkd_scene *s, int mode, void *stream);
 
 /* the vertices of the decoded triangles moved, the topology did not: refit all boxes in place */
 int rtkd_refit(rtkd_scene *s, void *stream);
+
+/* triangle filter: bit i of the bitset = triangle i takes part in every query on
+ * this scene.  bits == NULL removes it.  on_device: bits is a device pointer.  Survives refits
+ * and rebuilds of the scene. */
+int rtkd_set_filter(rtkd_scene *s, const void *bits, size_t num_words, int on_device, void *stream);
 
 /* queries: device pointers, asynchronous on stream.  cull_mode bit 0: provable culling,
  * bit 1: occlusion query (d_hit16 is then one byte per ray) */

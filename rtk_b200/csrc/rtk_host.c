@@ -616,6 +616,20 @@ int rtk_occluded_rays_device(const rtk_scene *scene, const void *d_rays, void *d
 	return rtkd_trace(dev, d_rays, d_occluded, n, g_cull_mode | 2, NULL, stream);
 }
 
+int rtk_cuda_set_triangle_filter(const rtk_scene *scene, const uint32_t *bits, size_t num_words)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return RTK_CUDA_ERR_SCENE;
+	return rtkd_set_filter(dev, bits, num_words, 0, NULL);
+}
+
+int rtk_cuda_set_triangle_filter_device(const rtk_scene *scene, const void *d_bits, size_t num_words, void *stream)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return RTK_CUDA_ERR_SCENE;
+	return rtkd_set_filter(dev, d_bits, num_words, 1, stream);
+}
+
 int rtk_cuda_generate_primary_rays(const rtk_cuda_camera *camera, uint64_t seed, uint32_t sample,
                                    size_t first_pixel, size_t count, void *d_rays, void *stream)
 {

@@ -529,6 +529,125 @@ def case_refit(lib, orc, dev):
     sc.free()
 
 
+def filtered_oracle(orc, tris, rays, keep):
+    """the oracle on the scene WITHOUT the triangles that are switched off, numbered as before"""
+    kept = np.flatnonzero(keep).astype(np.uint32)
+    want = orc.trace_brute(np.ascontiguousarray(tris[kept]), rays) if len(kept) else None
+    if want is None:
+        want = np.zeros(len(rays), dtype=api.HIT16_DTYPE)
+        want["prim"] = api.RTK_CUDA_MISS
+        return want
+    hit = want["prim"] != api.RTK_CUDA_MISS
+    want["prim"][hit] = kept[want["prim"][hit]]
+    return want
+
+
+def case_triangle_filter(lib, orc, dev):
+    """the device-side triangle predicate (bitset over global triangle numbers).
+    With a filter every entry point must answer exactly as the oracle does on the scene without the
+    switched-off triangles (numbering unchanged): compact device trace, exhaustive kernel, occlusion
+    query, host batch; the filter survives refits and rebuilds; removing it restores the scene."""
+    s = scenes.config_scene("C4", 0.0012)                       # two meshes: global numbering matters
+    tris, first = s["tris"], s["mesh_first"]
+    n = len(tris)
+    rays = scenes.mixed_rays(s, 2400, block=256)
+    sc = lib.build_scene(s["meshes"])
+    h_rays, d_rays = dev.put(rays)
+    h_hit, d_hit = dev.empty(16 * len(rays))
+    h_occ, d_occ = dev.empty(len(rays), fill=7)
+
+    def trace(brute=False):
+        fn = lib.rtk_trace_rays_bruteforce_device if brute else lib.rtk_trace_rays_compact_device
+        assert fn(sc.ptr, d_rays, d_hit, len(rays), dev.stream) == 0, lib.last_error()
+        return dev.get(h_hit, api.HIT16_DTYPE, len(rays))
+
+    def check(keep, what):
+        want = filtered_oracle(orc, tris, rays, keep)
+        assert_same(trace(), want, what + ": traversal")
+        assert_same(trace(brute=True), want, what + ": exhaustive kernel")
+        assert lib.rtk_occluded_rays_device(sc.ptr, d_rays, d_occ, len(rays), dev.stream) == 0, lib.last_error()
+        occ = dev.get(h_occ, np.uint8, len(rays)).astype(bool)
+        assert np.array_equal(occ, want["prim"] != api.RTK_CUDA_MISS), what + ": occlusion query"
+        hits, mask, nh = sc.trace_rays(rays)
+        assert_same(api.hits_to_hit16(hits, mask, first), want, what + ": host batch")
+        m = mask.astype(bool)
+        if m.any():                                              # expanded rows still carry per-mesh numbering
+            g = want["prim"][m].astype(np.int64)
+            mi = np.searchsorted(np.asarray(first), g, side="right") - 1
+            assert np.array_equal(hits["mesh_index"][m], mi) and np.array_equal(hits["triangle_index"][m], g - np.asarray(first)[mi])
+        return want
+
+    everything = np.ones(n, dtype=bool)
+    base = check(everything, "no filter")
+    assert 0 < (base["prim"] != api.RTK_CUDA_MISS).sum() < len(rays)
+    rng = np.random.default_rng(41)
+    half = rng.random(n) < 0.5
+    sc.set_triangle_filter(half)
+    w = check(half, "random half")
+    assert (w["prim"] != base["prim"]).any()
+    # depth peeling: switch off exactly the triangles the rays hit first and look behind them
+    peel = everything.copy()
+    peel[base["prim"][base["prim"] != api.RTK_CUDA_MISS]] = False
+    h_bits, d_bits = dev.put(api.pack_triangle_filter(peel))
+    assert lib.rtk_cuda_set_triangle_filter_device(sc.ptr, d_bits, (n + 31) // 32, dev.stream) == 0, lib.last_error()
+    w = check(peel, "peeled (device bitset)")
+    hit = (w["prim"] != api.RTK_CUDA_MISS) & (base["prim"] != api.RTK_CUDA_MISS)
+    assert hit.any() and (w["t"][hit] >= base["t"][hit]).all()
+    # one whole mesh off, then everything off
+    only1 = everything.copy()
+    only1[:first[1]] = False
+    sc.set_triangle_filter(only1)
+    w = check(only1, "mesh 0 off")
+    assert (w["prim"][w["prim"] != api.RTK_CUDA_MISS] >= first[1]).all()
+    sc.set_triangle_filter(~everything)
+    check(~everything, "all off")
+    # a bitset that is too short is refused and changes nothing
+    short = np.zeros(1, dtype=np.uint32)
+    assert lib.rtk_cuda_set_triangle_filter(sc.ptr, short.ctypes.data, (n + 31) // 32 - 1) != 0
+    check(~everything, "after the refused call")
+    # the filter outlives a rebuild; removing it gives the unfiltered scene back
+    sc.set_triangle_filter(half)
+    assert lib.rtk_cuda_rebuild_scene(sc.ptr, dev.stream) == 0, lib.last_error()
+    check(half, "after a rebuild")
+    sc.set_triangle_filter(None)
+    assert_same(trace(), base, "filter removed")
+    sc.set_triangle_filter(None)                                 # removing twice is fine
+    sc.free()
+
+    # ... and a refit: deformed device mesh, filter in place
+    s = scenes.config_scene("C3", 0.005)
+    m = s["meshes"][0]
+    pos0, idx = m["positions"].astype(np.float32), m["indices"].astype(np.uint32)
+    rays = scenes.bounce_rays(s, 1500)
+    meshes = (api.rtk_cuda_mesh * 1)()
+    hp, dp = dev.put(pos0)
+    hi, di = dev.put(idx)
+    meshes[0].d_positions, meshes[0].d_indices = dp, di
+    meshes[0].num_vertices, meshes[0].num_triangles = len(pos0), len(idx)
+    ptr = lib.rtk_cuda_build_scene(meshes, 1, dev.stream)
+    assert ptr, lib.last_error()
+    sc = api.Scene(lib, ptr)
+    keep = np.random.default_rng(43).random(len(idx)) < 0.7
+    sc.set_triangle_filter(keep)
+    h_rays, d_rays = dev.put(rays)
+    h_hit, d_hit = dev.empty(16 * len(rays))
+    for step, mode in enumerate([api.RTK_CUDA_UPDATE_REFIT, api.RTK_CUDA_UPDATE_REBUILD, api.RTK_CUDA_UPDATE_REFIT]):
+        pos = pos0.copy()
+        pos[:, 1] += (0.03 * (step + 1) * np.sin(8.0 * pos0[:, 0] + step) * np.cos(6.0 * pos0[:, 2])).astype(np.float32)
+        hp2, dp2 = dev.put(pos)
+        meshes[0].d_positions = dp2
+        assert lib.rtk_cuda_update_scene(sc.ptr, meshes, 1, mode, dev.stream) == 0, lib.last_error()
+        assert lib.rtk_trace_rays_compact_device(sc.ptr, d_rays, d_hit, len(rays), dev.stream) == 0, lib.last_error()
+        got = dev.get(h_hit, api.HIT16_DTYPE, len(rays))
+        want = filtered_oracle(orc, pos[idx.astype(np.int64)], rays, keep)
+        assert_same(got, want, f"filtered, update {step} mode {mode}")
+        assert (want["prim"] != api.RTK_CUDA_MISS).any()
+    sc.set_triangle_filter(None)
+    assert lib.rtk_trace_rays_compact_device(sc.ptr, d_rays, d_hit, len(rays), dev.stream) == 0, lib.last_error()
+    assert_same(dev.get(h_hit, api.HIT16_DTYPE, len(rays)), orc.trace_brute(pos[idx.astype(np.int64)], rays), "filter removed after refits")
+    sc.free()
+
+
 def case_deep_stack(lib, orc, dev=None):
     """Thousands of coincident triangles: the builder cannot separate them (forced halving,
     rtk.c:1429-1443), every box overlaps every other, so a ray has to visit all of them: the

@@ -57,6 +57,10 @@ def test_refit_and_rebuild_of_a_deformed_mesh(emu_lib, orc):
     pc.case_refit(emu_lib, orc, pc.HostDevice())
 
 
+def test_triangle_filter(emu_lib, orc):
+    pc.case_triangle_filter(emu_lib, orc, pc.HostDevice())
+
+
 def test_read_bandwidth_probe(emu_lib):
     import ctypes as C
     g = C.c_double(0)

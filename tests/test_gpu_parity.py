@@ -206,3 +206,7 @@ def test_deep_stack_spills(gpu_lib, orc):
 
 def test_host_batch_many_chunks(gpu_lib, orc):
     pc.case_host_batch_chunks(gpu_lib, orc, nrays=300000, chunk_log2=14)
+
+
+def test_triangle_filter(gpu_lib, orc):
+    pc.case_triangle_filter(gpu_lib, orc, TorchDevice())

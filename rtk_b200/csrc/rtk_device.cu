@@ -43,7 +43,7 @@ extern "C" void rtkd_set_error(const char *fmt, ...)
 
 extern "C" int rtkd_init(int device)
 {
-	if (g_device == device && g_sm_count) return RTKD_OK;
+	if (g_device == device && g_sm_count) { CK(cudaSetDevice(device)); return RTKD_OK; }   // another host thread binding itself
 	int count = 0;
 	cudaError_t e = cudaGetDeviceCount(&count);
 	if (e != cudaSuccess || count <= 0) {
@@ -88,7 +88,18 @@ extern "C" int rtkd_init(int device)
 	return RTKD_OK;
 }
 
-static int ensure_init(void) { return g_sm_count ? RTKD_OK : rtkd_init(0); }
+// Every entry point passes through here (directly or via rtkd_bind_thread): the library is bound to
+// ONE device per process, but CUDA's current device is per host thread and starts at 0 -- a worker
+// thread of the caller that traces against a scene on device 3 must be switched to device 3 first
+// (the reference's rtk_trace_ray is called from many user threads, rtk.h:129).
+static int ensure_init(void)
+{
+	if (!g_sm_count) return rtkd_init(0);
+	int cur = -1;
+	if (cudaGetDevice(&cur) != cudaSuccess || cur != g_device) CK(cudaSetDevice(g_device));
+	return RTKD_OK;
+}
+extern "C" int rtkd_bind_thread(void) { return ensure_init(); }
 
 extern "C" void rtkd_shutdown(void) { g_device = -1; g_sm_count = 0; }
 
@@ -186,6 +197,7 @@ extern "C" rtkd_scene *rtkd_scene_new(uint32_t num_tris, uint32_t num_meshes, co
 extern "C" void rtkd_scene_free(rtkd_scene *s)
 {
 	if (!s) return;
+	if (g_sm_count) ensure_init();           // the freeing thread may not be the one that built the scene
 	cudaDeviceSynchronize();
 	if (s->tri_orig) cudaFree(s->tri_orig);
 	if (s->tv0) cudaFree(s->tv0);

@@ -39,6 +39,7 @@ typedef struct rtkd_trace_stats {
 } rtkd_trace_stats;
 
 int         rtkd_init(int device);           /* 0 or negative rtk_cuda_status */
+int         rtkd_bind_thread(void);          /* make the library's device current on the calling thread (initialises device 0 if needed) */
 void        rtkd_shutdown(void);
 const char *rtkd_last_error(void);
 void        rtkd_set_error(const char *fmt, ...);

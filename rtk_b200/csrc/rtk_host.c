@@ -137,6 +137,7 @@ static int header_valid(const rtk_scene *sc)
 static rtkd_scene *scene_device(const rtk_scene *scene)
 {
 	if (!scene) { rtkd_set_error("scene is NULL"); return NULL; }
+	if (rtkd_bind_thread() != RTK_CUDA_OK) { warn_once(); return NULL; }     /* callers' worker threads start on device 0 */
 	pthread_mutex_lock(&g_lock);
 	scene_entry *e = table_find(scene);
 	if (e && e->dev->id == EXT_OF(scene)->scene_id) {

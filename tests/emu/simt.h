@@ -24,6 +24,7 @@
 #include <string.h>
 #include <time.h>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------
@@ -398,8 +399,14 @@ static void prepare(Fiber *f)
 	f->at_block_barrier = false;
 }
 
+// One kernel at a time: the scheduler state, the fiber pool and the `static` shared memory of the
+// kernels are process-wide.  Host threads that launch concurrently (tests of the thread-safe entry
+// points) are serialised here, which is a legal schedule for independent streams.
+static std::mutex g_launch_lock;
+
 void launch(dim3 grid, dim3 block, const std::function<void()> &body)
 {
+	std::lock_guard<std::mutex> guard(g_launch_lock);
 	std::function<void()> b = body;
 	std::function<void()> *saved_body = g_body;
 	g_body = &b;

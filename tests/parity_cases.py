@@ -388,6 +388,61 @@ def case_api_semantics(lib, orc):
     sc.free()
 
 
+def case_threads(lib, orc, nthreads=4):
+    """rtk_trace_ray is re-entrant and read-only on the scene in the reference (rtk.h:129, called from
+    the user's own worker threads): several host threads query ONE scene at once -- single rays and
+    batches -- and every answer must be the oracle's; one thread builds and frees other scenes
+    meanwhile."""
+    import threading
+    s = scenes.config_scene("C1")
+    rays = scenes.config_rays("C1", s)[::211]
+    want = orc.trace_brute(s["tris"], rays)
+    sc = lib.build_scene(s["meshes"])
+    errors = []
+
+    def single(tid):
+        try:
+            for i in range(tid, len(rays), nthreads):
+                h = sc.trace_ray(rays[i])
+                if want["prim"][i] == api.RTK_CUDA_MISS:
+                    assert h is None, f"ray {i}: hit instead of a miss"
+                else:
+                    assert h is not None and h["t"] == want["t"][i] and h["u"] == want["u"][i] and h["triangle_index"] == want["prim"][i], f"ray {i}"
+        except Exception as ex:                                   # noqa: BLE001 -- reported by the main thread
+            errors.append(ex)
+
+    def batch(tid):
+        try:
+            for rep in range(3):
+                sub = np.ascontiguousarray(rays[tid::2])
+                hits, mask, _ = sc.trace_rays(sub)
+                assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want[tid::2], f"batch thread {tid} rep {rep}")
+        except Exception as ex:                                   # noqa: BLE001
+            errors.append(ex)
+
+    def builder():
+        try:
+            s2 = scenes.config_scene("C3", 0.002)
+            r2 = scenes.bounce_rays(s2, 300)
+            w2 = orc.trace_brute(s2["tris"], r2)
+            for rep in range(2):
+                got, _, _ = trace_hit16(lib, s2, r2)
+                assert_same(got, w2, f"builder thread rep {rep}")
+        except Exception as ex:                                   # noqa: BLE001
+            errors.append(ex)
+
+    threads = [threading.Thread(target=single, args=(t,)) for t in range(nthreads)]
+    threads += [threading.Thread(target=batch, args=(t,)) for t in range(2)]
+    threads.append(threading.Thread(target=builder))
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    sc.free()
+    if errors:
+        raise errors[0]
+
+
 def case_occlusion(lib, orc, alloc):
     """any-hit query == hit mask of the closest-hit query (device buffers via `alloc`, which maps a
     numpy array to a device pointer holder and back)"""

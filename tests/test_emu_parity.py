@@ -57,6 +57,10 @@ def test_refit_and_rebuild_of_a_deformed_mesh(emu_lib, orc):
     pc.case_refit(emu_lib, orc, pc.HostDevice())
 
 
+def test_concurrent_host_threads(emu_lib, orc):
+    pc.case_threads(emu_lib, orc)
+
+
 def test_triangle_filter(emu_lib, orc):
     pc.case_triangle_filter(emu_lib, orc, pc.HostDevice())
 

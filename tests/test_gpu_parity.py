@@ -210,3 +210,7 @@ def test_host_batch_many_chunks(gpu_lib, orc):
 
 def test_triangle_filter(gpu_lib, orc):
     pc.case_triangle_filter(gpu_lib, orc, TorchDevice())
+
+
+def test_concurrent_host_threads(gpu_lib, orc):
+    pc.case_threads(gpu_lib, orc, nthreads=6)

@@ -8,7 +8,8 @@ A step is one pass of the hot path over one batch of synthetic rays: the travers
 N=1 workload: BASELINE.json configs[2] -- 1M-triangle procedural terrain, 16 777 216 incoherent
 diffuse-bounce rays (the configuration the headline "incoherent Mrays/s" metric is quoted on).
 N>1 (torchrun): scene replicated per GPU, every rank traces its own 16 777 216 rays (weak
-scaling), compact hit records are gathered on rank 0 with NCCL inside the timed region.
+scaling), compact hit records are gathered on rank 0 inside the timed region -- with NCCL
+(default) or, with --gather p2p, by copy-engine pushes into a peer-memory window on rank 0.
 
 `--impl reference` times the reference's own CPU path instead: the patched rtk.c traversal
 (oracle/_ref, built from /root/reference/rtk.c) over a reference-format blob packed by the
@@ -329,6 +330,10 @@ def main():
     ap.add_argument("--presort", action="store_true", help="experiment: order the rays by origin cell + direction octant on the host first")
     ap.add_argument("--reserve-sms", type=int, default=0, help="experiment: SMs kept out of the traversal grid for the NCCL kernels of "
                                                                "the overlapped gather (measured at 2 GPUs: 0 -> 3131, 4 -> 3066, 8 -> 3003 Mrays/s)")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"],
+                    help="N > 1: how the compact hit records reach rank 0.  nccl (default, measured): torch.distributed gather, "
+                         "overlapped with the next step.  p2p: copy-engine pushes into a peer-memory window on rank 0 "
+                         "(rtk_cuda_peer_*, CUDA IPC over NVLink; no NCCL kernels beside the persistent traversal grid)")
     ap.add_argument("--lib", default=None, help="experiment: alternative build of librtk_b200 (same ABI)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -423,7 +428,21 @@ def main():
     d_hits = torch.zeros((n, 68), dtype=torch.uint8, device="cuda")
     d_mask = torch.zeros((n,), dtype=torch.uint8, device="cuda")
     gather_lists = [None, None]
-    if world > 1 and rank == 0:
+    p2p = world > 1 and args.gather == "p2p"
+    workload["gather"] = (args.gather if world > 1 else None)
+    peer, copy_stream = None, None
+    if p2p:
+        from rtk_b200 import shard
+
+        def exchange(handle):
+            box = [handle]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        peer = shard.PeerGather(lib, rank, world, 16 * n, 2, exchange)
+        copy_stream = torch.cuda.Stream()
+        traced_ev = [torch.cuda.Event() for _ in range(2)]
+        pushed_ev = [None, None]
+    elif world > 1 and rank == 0:
         gather_lists = [[torch.empty_like(d_h16) for _ in range(world)] for _ in range(2)]
     pending = [None, None]
     counter = [0]
@@ -433,19 +452,32 @@ def main():
         if pending[i] is not None:
             pending[i].wait()                # the buffer's previous gather must have drained
             pending[i] = None
-        h16 = d_h16s[i]
+        h16_ptr = d_h16s[i].data_ptr()
+        if p2p and exchange:
+            if rank == 0:
+                h16_ptr = peer.slot(i)       # the gathering rank traces straight into its slot of the window
+            elif pushed_ev[i] is not None:
+                stream.wait_event(pushed_ev[i])      # the push of step k-2 read this buffer
         if ev:
             ev[0].record(stream)
-        rc = lib.rtk_trace_rays_compact_device(sc.ptr, d_rays.data_ptr(), h16.data_ptr(), n, sh)
+        rc = lib.rtk_trace_rays_compact_device(sc.ptr, d_rays.data_ptr(), h16_ptr, n, sh)
         if ev:
             ev[1].record(stream)
-        rc |= lib.rtk_resolve_hits_device(sc.ptr, h16.data_ptr(), d_hits.data_ptr(), d_mask.data_ptr(), n, sh)
+        if p2p and exchange and rank != 0:
+            # the records cross NVLink on the copy engines while k_resolve and the next k_trace run
+            traced_ev[i].record(stream)
+            copy_stream.wait_event(traced_ev[i])
+            peer.push(i, h16_ptr, 16 * n, copy_stream.cuda_stream)
+            pushed_ev[i] = torch.cuda.Event()
+            pushed_ev[i].record(copy_stream)
+        rc |= lib.rtk_resolve_hits_device(sc.ptr, h16_ptr, d_hits.data_ptr(), d_mask.data_ptr(), n, sh)
         if ev:
             ev[2].record(stream)
         if rc:
             raise RuntimeError(lib.last_error())
         if world > 1 and exchange:
-            pending[i] = dist.gather(h16, gather_lists[i], dst=0, async_op=True)
+            if not p2p:
+                pending[i] = dist.gather(d_h16s[i], gather_lists[i], dst=0, async_op=True)
             counter[0] += 1
 
     def drain():
@@ -453,6 +485,8 @@ def main():
             if pending[i] is not None:
                 pending[i].wait()
                 pending[i] = None
+        if copy_stream is not None:
+            copy_stream.synchronize()        # this rank's pushes have landed in rank 0's HBM
 
     # ---- parity self-check against the CPU oracle (outside the timed region) -------------------
     parity = None
@@ -519,6 +553,30 @@ def main():
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
+
+    # ---- what rank 0 gathered from the LAST rank in the last step is what that rank's rays give here
+    # (outside the timed region; the scene is replicated, so rank 0 can trace them itself) ----------
+    gather_check = None
+    if world > 1 and args.workload in ("C3", "C2") and not args.presort:
+        kv = min(n, 1 << 20)
+        last = (counter[0] - 1) & 1
+        if rank == 0:
+            theirs = gen_rays(scene, kv, 0, args.workload) if args.workload == "C2" else \
+                scenes.bounce_rays(scene, kv, seed=0xD3, first=(world - 1) * n)
+            d_r = torch.from_numpy(theirs.view(np.uint8).reshape(-1, 32)).cuda()
+            d_o = torch.zeros((kv, 16), dtype=torch.uint8, device="cuda")
+            assert lib.rtk_trace_rays_compact_device(sc.ptr, d_r.data_ptr(), d_o.data_ptr(), kv, sh) == 0, lib.last_error()
+            torch.cuda.synchronize()
+            if p2p:
+                got = torch.empty((kv, 16), dtype=torch.uint8, device="cuda")
+                assert lib.rtk_cuda_peer_push(got.data_ptr(), peer.slot(last, world - 1), 16 * kv, sh) == 0, lib.last_error()
+                torch.cuda.synchronize()
+            else:
+                got = gather_lists[last][world - 1][:kv]
+            gather_check = {"records_compared": kv, "from_rank": world - 1, "equal": bool(torch.equal(got, d_o))}
+    if peer is not None:
+        dist.barrier()                       # nobody unmaps the window while rank 0 still reads it
+        peer.close()
 
     # ---- occlusion (any-hit) query on the same rays: SURVEY 8(f) N3, reported beside the headline --
     occ = None
@@ -614,6 +672,8 @@ def main():
                   "sah_cost": info.sah_cost, "scene_bytes": int(info.device_bytes)},
         "occlusion": occ, "parity": parity, "clocks": clocks,
     }
+    if gather_check is not None:
+        line["gather_check"] = gather_check
     if world == 1 and not args.no_cpu_baseline:
         try:
             cb = cpu_reference_run(scene, rays_np, min(n, args.cpu_sample), 1, 0)

@@ -145,6 +145,27 @@ int rtk_trace_rays_bruteforce_device(const rtk_scene *scene, const void *d_rays,
 /* Counter-instrumented traversal (slow; for the algorithmic-bytes figure). */
 int rtk_trace_stats_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, rtk_cuda_trace_stats *stats, void *stream);
 
+/* ---- multi-GPU hit gather over NVLink peer memory ---------- */
+
+/* The sharded path (one process per GPU, scene replicated, rays partitioned)
+ * has ONE exchange step: the compact hit records end up on the gathering rank.
+ * Besides NCCL (torch.distributed in the bench) the library offers the gather
+ * as plain peer-memory pushes: the gathering process creates a window in its
+ * HBM and hands the 64-byte handle (a CUDA IPC handle) to the other processes
+ * of the box by whatever channel it has; they open it once and then push their
+ * records into their slice with the copy engines -- no send/receive kernels
+ * competing with the persistent traversal grid for SMs.  Ordering is the
+ * caller's: a push is asynchronous on `stream` of the pushing process; the
+ * gathering process may read a slice once the pusher has synchronised that
+ * stream and told it so (a barrier).  The reference has no counterpart
+ * (single-ray, single-process API). */
+typedef struct rtk_cuda_peer_handle { unsigned char bytes[64]; } rtk_cuda_peer_handle;
+int rtk_cuda_peer_window_create(size_t bytes, void **d_window, rtk_cuda_peer_handle *handle);
+int rtk_cuda_peer_window_open(const rtk_cuda_peer_handle *handle, void **d_window);   /* in ANOTHER process */
+int rtk_cuda_peer_window_close(void *d_window);                                        /* what _open returned */
+int rtk_cuda_peer_window_destroy(void *d_window);                                      /* what _create returned */
+int rtk_cuda_peer_push(void *d_dst, const void *d_src, size_t bytes, void *stream);
+
 /* ---- wavefront ray generation on the device ------------ */
 
 /* Pinhole camera: right/up need not be unit length; rays are

@@ -136,6 +136,11 @@ SYMBOLS = {
     "rtk_trace_rays_compact_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_resolve_hits_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     "rtk_occluded_rays_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
+    "rtk_cuda_peer_window_create": (C.c_int, [C.c_size_t, C.POINTER(_P), _P]),
+    "rtk_cuda_peer_window_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "rtk_cuda_peer_window_close": (C.c_int, [_P]),
+    "rtk_cuda_peer_window_destroy": (C.c_int, [_P]),
+    "rtk_cuda_peer_push": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "rtk_cuda_set_triangle_filter": (C.c_int, [_P, _P, C.c_size_t]),
     "rtk_cuda_set_triangle_filter_device": (C.c_int, [_P, _P, C.c_size_t, _P]),
     "rtk_trace_rays_bruteforce_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),

@@ -739,6 +739,71 @@ extern "C" int rtkd_resolve(rtkd_scene *s, const void *d_hit16, void *d_hits, vo
 }
 
 // ---------------------------------------------------------------------------------------------
+// hit gather over peer memory: the one exchange step of the sharded path.  The
+// gathering process owns a window in its HBM and exports it with CUDA IPC; every other process of
+// the box maps it (NVLink peer access is enabled on first use) and pushes its compact hit records
+// into its own slice with cudaMemcpyAsync, i.e. with the COPY ENGINES: no send/receive kernel has to
+// find room beside the persistent traversal grid, which owns every SM's registers.
+// ---------------------------------------------------------------------------------------------
+
+extern "C" int rtkd_peer_create(size_t bytes, void **d_window, unsigned char *handle64)
+{
+	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
+	if (!bytes || !d_window || !handle64) { rtkd_set_error("bad peer window arguments"); return RTKD_ERR_ARGUMENT; }
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+	unsigned char *p = NULL;
+	// plain cudaMalloc: stream-ordered pool memory cannot be exported with the legacy IPC calls
+	CK(cudaMalloc(&p, bytes));
+	cudaIpcMemHandle_t h;
+	cudaError_t e = cudaIpcGetMemHandle(&h, p);
+	if (e != cudaSuccess) { rtkd_set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); cudaFree(p); return RTKD_ERR_CUDA; }
+	memcpy(handle64, &h, 64);
+	*d_window = p;
+	return RTKD_OK;
+}
+
+extern "C" int rtkd_peer_open(const unsigned char *handle64, void **d_window)
+{
+	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
+	if (!handle64 || !d_window) { rtkd_set_error("bad peer window arguments"); return RTKD_ERR_ARGUMENT; }
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle64, 64);
+	void *p = NULL;
+	cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+	if (e != cudaSuccess) {
+		rtkd_set_error("cudaIpcOpenMemHandle failed: %s (a window cannot be opened by the process that created it, "
+		               "and both GPUs must be peers on one box)", cudaGetErrorString(e));
+		return RTKD_ERR_CUDA;
+	}
+	*d_window = p;
+	return RTKD_OK;
+}
+
+extern "C" int rtkd_peer_close(void *d_window)
+{
+	if (!d_window) return RTKD_OK;
+	CK(cudaIpcCloseMemHandle(d_window));
+	return RTKD_OK;
+}
+
+extern "C" int rtkd_peer_destroy(void *d_window)
+{
+	if (!d_window) return RTKD_OK;
+	CK(cudaDeviceSynchronize());
+	CK(cudaFree(d_window));
+	return RTKD_OK;
+}
+
+extern "C" int rtkd_peer_push(void *d_dst, const void *d_src, size_t bytes, void *stream)
+{
+	if (!bytes) return RTKD_OK;
+	if (!d_dst || !d_src) { rtkd_set_error("bad peer push arguments"); return RTKD_ERR_ARGUMENT; }
+	// unified addressing resolves the owning devices; across GPUs this is an NVLink copy-engine transfer
+	CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+	return RTKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // wavefront ray generation (k_wavefront.cuh)
 // ---------------------------------------------------------------------------------------------
 

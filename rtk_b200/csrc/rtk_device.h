@@ -81,6 +81,14 @@ int rtkd_trace_brute(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n,
 int rtkd_resolve(rtkd_scene *s, const void *d_hit16, void *d_hits, void *d_mask, size_t n, void *stream);
 void *rtkd_scene_hit16(rtkd_scene *s, size_t n);   /* scene-owned compact hit buffer of >= n records */
 
+/* hit gather over NVLink peer memory (CUDA IPC): a window owned by the gathering process, opened
+ * by the others, filled with copy-engine pushes.  handle64 is a cudaIpcMemHandle_t. */
+int rtkd_peer_create(size_t bytes, void **d_window, unsigned char *handle64);
+int rtkd_peer_open(const unsigned char *handle64, void **d_window);
+int rtkd_peer_close(void *d_window);
+int rtkd_peer_destroy(void *d_window);
+int rtkd_peer_push(void *d_dst, const void *d_src, size_t bytes, void *stream);
+
 /* wavefront ray generation: cam20 = eye, forward, right, up (3 floats each), tan(half vertical fov) */
 int rtkd_gen_primary(const float *cam20, uint32_t width, uint32_t height, unsigned long long seed, uint32_t sample,
                      unsigned long long first_pixel, size_t count, void *d_rays, void *stream);

@@ -617,6 +617,18 @@ int rtk_occluded_rays_device(const rtk_scene *scene, const void *d_rays, void *d
 	return rtkd_trace(dev, d_rays, d_occluded, n, g_cull_mode | 2, NULL, stream);
 }
 
+int rtk_cuda_peer_window_create(size_t bytes, void **d_window, rtk_cuda_peer_handle *handle)
+{
+	return rtkd_peer_create(bytes, d_window, handle ? handle->bytes : NULL);
+}
+int rtk_cuda_peer_window_open(const rtk_cuda_peer_handle *handle, void **d_window)
+{
+	return rtkd_peer_open(handle ? handle->bytes : NULL, d_window);
+}
+int rtk_cuda_peer_window_close(void *d_window) { return rtkd_peer_close(d_window); }
+int rtk_cuda_peer_window_destroy(void *d_window) { return rtkd_peer_destroy(d_window); }
+int rtk_cuda_peer_push(void *d_dst, const void *d_src, size_t bytes, void *stream) { return rtkd_peer_push(d_dst, d_src, bytes, stream); }
+
 int rtk_cuda_set_triangle_filter(const rtk_scene *scene, const uint32_t *bits, size_t num_words)
 {
 	rtkd_scene *dev = scene_device(scene);

@@ -335,6 +335,13 @@ struct cudaPointerAttributes { int type; void *devicePointer; void *hostPointer;
 #define cudaMemoryTypeDevice 2
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = 0; a->devicePointer = 0; a->hostPointer = 0; return cudaSuccess; }
 
+// CUDA IPC: the emulated "other process" is this process, a handle is the pointer itself
+struct cudaIpcMemHandle_t { char reserved[64]; };
+#define cudaIpcMemLazyEnablePeerAccess 1
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+
 // kernel launch: RTK_LAUNCH(kernel, grid, block, stream, args...)
 #define RTK_LAUNCH(kernel, grid, block, stream, ...) \
 	simt::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); })

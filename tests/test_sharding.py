@@ -61,3 +61,47 @@ def test_two_ranks_gloo(tmp_path):
     res = open(out).read()
     assert res.startswith("ok"), res
     assert int(res.split()[1]) > 100
+
+
+def test_peer_gather_window_emulated(emu_lib, orc):
+    """The copy-engine gather (shard.PeerGather over rtk_cuda_peer_*): three 'ranks' played by one
+    process on the emulator (whose IPC handles are plain pointers).  Rank 0 traces straight into its
+    slot of the window, the others push theirs; the window then holds exactly the records of the
+    unsharded trace, in both buffers of the double-buffered scheme."""
+    import ctypes as C
+    from rtk_b200 import api, scenes, shard
+    lib = emu_lib
+    s = scenes.config_scene("C3", 0.004)
+    world, per = 3, 400
+    rays = scenes.bounce_rays(s, world * per)
+    sc = lib.build_scene(s["meshes"])
+    want = orc.trace_brute(s["tris"], rays)
+    box = {}
+
+    def exchange(h):
+        if h is not None:
+            box["h"] = h
+        return box["h"]
+    gathers = [shard.PeerGather(lib, r, world, 16 * per, 2, exchange) for r in range(world)]
+    assert gathers[0].owner and not gathers[1].owner
+    for buf in (0, 1):
+        for r in range(world):
+            lo, hi = shard.ray_range(r, world, len(rays))
+            sub = np.ascontiguousarray(rays[lo:hi])
+            if r == 0:
+                dst = gathers[0].slot(buf)                     # the gathering rank needs no copy at all
+                assert lib.rtk_trace_rays_compact_device(sc.ptr, sub.ctypes.data, dst, len(sub), None) == 0, lib.last_error()
+            else:
+                local = np.zeros(len(sub), dtype=api.HIT16_DTYPE)
+                assert lib.rtk_trace_rays_compact_device(sc.ptr, sub.ctypes.data, local.ctypes.data, len(sub), None) == 0, lib.last_error()
+                gathers[r].push(buf, local.ctypes.data, local.nbytes, None)
+        got = np.ctypeslib.as_array(C.cast(gathers[0].slot(buf, 0), C.POINTER(C.c_ubyte)), shape=(world * per * 16,)).copy().view(api.HIT16_DTYPE)
+        assert got.tobytes() == want.tobytes(), f"buffer {buf}"
+    # a push that does not fit its slot is a caller bug
+    import pytest
+    with pytest.raises(AssertionError):
+        gathers[1].push(0, 0, 16 * per + 16, None)
+    for g in reversed(gathers):
+        g.close()
+    assert lib.rtk_cuda_peer_push(None, None, 16, None) != 0
+    sc.free()

@@ -561,19 +561,24 @@ def main():
         kv = min(n, 1 << 20)
         last = (counter[0] - 1) & 1
         if rank == 0:
-            theirs = gen_rays(scene, kv, 0, args.workload) if args.workload == "C2" else \
-                scenes.bounce_rays(scene, kv, seed=0xD3, first=(world - 1) * n)
-            d_r = torch.from_numpy(theirs.view(np.uint8).reshape(-1, 32)).cuda()
-            d_o = torch.zeros((kv, 16), dtype=torch.uint8, device="cuda")
-            assert lib.rtk_trace_rays_compact_device(sc.ptr, d_r.data_ptr(), d_o.data_ptr(), kv, sh) == 0, lib.last_error()
-            torch.cuda.synchronize()
-            if p2p:
-                got = torch.empty((kv, 16), dtype=torch.uint8, device="cuda")
-                assert lib.rtk_cuda_peer_push(got.data_ptr(), peer.slot(last, world - 1), 16 * kv, sh) == 0, lib.last_error()
+            try:
+                theirs = gen_rays(scene, kv, 0, args.workload) if args.workload == "C2" else \
+                    scenes.bounce_rays(scene, kv, seed=0xD3, first=(world - 1) * n)
+                d_r = torch.from_numpy(theirs.view(np.uint8).reshape(-1, 32)).cuda()
+                d_o = torch.zeros((kv, 16), dtype=torch.uint8, device="cuda")
+                if lib.rtk_trace_rays_compact_device(sc.ptr, d_r.data_ptr(), d_o.data_ptr(), kv, sh) != 0:
+                    raise RuntimeError(lib.last_error())
                 torch.cuda.synchronize()
-            else:
-                got = gather_lists[last][world - 1][:kv]
-            gather_check = {"records_compared": kv, "from_rank": world - 1, "equal": bool(torch.equal(got, d_o))}
+                if p2p:
+                    got = torch.empty((kv, 16), dtype=torch.uint8, device="cuda")
+                    if lib.rtk_cuda_peer_push(got.data_ptr(), peer.slot(last, world - 1), 16 * kv, sh) != 0:
+                        raise RuntimeError(lib.last_error())
+                    torch.cuda.synchronize()
+                else:
+                    got = gather_lists[last][world - 1][:kv]
+                gather_check = {"records_compared": kv, "from_rank": world - 1, "equal": bool(torch.equal(got, d_o))}
+            except Exception as ex:          # a failed self-check must not cost the measurement
+                gather_check = {"error": str(ex)}
     if peer is not None:
         dist.barrier()                       # nobody unmaps the window while rank 0 still reads it
         peer.close()

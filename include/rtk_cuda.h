@@ -223,6 +223,24 @@ int rtk_cuda_rebuild_scene(const rtk_scene *scene, void *stream);
 #define RTK_CUDA_UPDATE_REBUILD 1
 int rtk_cuda_update_scene(const rtk_scene *scene, const rtk_cuda_mesh *meshes, size_t num_meshes, int mode, void *stream);
 
+/* Multi-mesh instancing (the other half of SURVEY 8(f) N4), BAKED: every instance is its mesh pushed
+ * through a 3x4 transform (row-major, world = M * (x, y, z, 1), each product and sum rounded on
+ * its own in fp32) into the scene's own triangle storage, and ONE tree is built over all of them --
+ * traversal stays single-level and as fast as for any other scene, at 112 bytes of HBM per
+ * instanced triangle (180 GB per GPU is the budget this trades against; up to 2^28 - 1 triangles per scene).
+ * In a hit, mesh_index is the INSTANCE number, triangle_index the triangle within its mesh and the
+ * vertices are in world space.  rtk_cuda_update_instanced_scene moves the instances (same
+ * instance -> mesh assignment, same triangle counts) and refits or rebuilds as
+ * rtk_cuda_update_scene does. */
+typedef struct rtk_cuda_instance {
+	uint32_t mesh;                /* index into the mesh array */
+	float    transform[12];       /* row-major 3x4 */
+} rtk_cuda_instance;
+rtk_scene *rtk_cuda_build_instanced_scene(const rtk_cuda_mesh *meshes, size_t num_meshes,
+                                          const rtk_cuda_instance *instances, size_t num_instances, void *stream);
+int rtk_cuda_update_instanced_scene(const rtk_scene *scene, const rtk_cuda_mesh *meshes, size_t num_meshes,
+                                    const rtk_cuda_instance *instances, size_t num_instances, int mode, void *stream);
+
 int rtk_cuda_get_scene_info(const rtk_scene *scene, rtk_cuda_scene_info *info);
 
 /* Upload a relocated / reloaded blob (written by rtk_finish_build_to) so that

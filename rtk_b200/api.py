@@ -82,6 +82,10 @@ class rtk_cuda_mesh(C.Structure):
                 ("num_vertices", C.c_size_t), ("num_triangles", C.c_size_t)]
 
 
+class rtk_cuda_instance(C.Structure):
+    _fields_ = [("mesh", C.c_uint32), ("transform", C.c_float * 12)]
+
+
 class rtk_cuda_camera(C.Structure):
     _fields_ = [("eye", C.c_float * 3), ("forward", C.c_float * 3), ("right", C.c_float * 3), ("up", C.c_float * 3),
                 ("tan_half_fov", C.c_float), ("width", C.c_uint32), ("height", C.c_uint32)]
@@ -150,6 +154,8 @@ SYMBOLS = {
     "rtk_cuda_build_scene": (_P, [C.POINTER(rtk_cuda_mesh), C.c_size_t, _P]),
     "rtk_cuda_rebuild_scene": (C.c_int, [_P, _P]),
     "rtk_cuda_update_scene": (C.c_int, [_P, C.POINTER(rtk_cuda_mesh), C.c_size_t, C.c_int, _P]),
+    "rtk_cuda_build_instanced_scene": (_P, [C.POINTER(rtk_cuda_mesh), C.c_size_t, C.POINTER(rtk_cuda_instance), C.c_size_t, _P]),
+    "rtk_cuda_update_instanced_scene": (C.c_int, [_P, C.POINTER(rtk_cuda_mesh), C.c_size_t, C.POINTER(rtk_cuda_instance), C.c_size_t, C.c_int, _P]),
     "rtk_cuda_get_scene_info": (C.c_int, [_P, C.POINTER(rtk_cuda_scene_info)]),
     "rtk_cuda_attach_scene": (C.c_int, [_P]),
     "rtk_cuda_detach_scene": (C.c_int, [_P]),

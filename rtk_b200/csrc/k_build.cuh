@@ -29,6 +29,8 @@ struct rtkd_decode_args {
 	int idx_bytes;                // 0 implicit, 2 uint16, 4 uint32
 	int pregathered;              // positions are stored per corner (3 per triangle, in order)
 	uint32_t ntris, first_prim;
+	int has_xf;                   // instance transform: world = xf * (x, y, z, 1), row-major 3x4
+	float xf[12];
 };
 
 RTK_DEV float4 rtk_fetch_corner(const rtkd_decode_args &a, unsigned long long slot, uint32_t index)
@@ -43,6 +45,14 @@ RTK_DEV float4 rtk_fetch_corner(const rtkd_decode_args &a, unsigned long long sl
 	} else {
 		const float *f = (const float*)p;
 		x = f[0]; y = f[1]; z = f[2];
+	}
+	if (a.has_xf) {
+		// baked instance: ((m0*x + m1*y) + m2*z) + m3 per row, every operation rounded on its own (no
+		// FMA contraction) so that a host restatement in plain fp32 reproduces the corners bit for bit
+		const float wx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.xf[0], x), __fmul_rn(a.xf[1], y)), __fmul_rn(a.xf[2], z)), a.xf[3]);
+		const float wy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.xf[4], x), __fmul_rn(a.xf[5], y)), __fmul_rn(a.xf[6], z)), a.xf[7]);
+		const float wz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a.xf[8], x), __fmul_rn(a.xf[9], y)), __fmul_rn(a.xf[10], z)), a.xf[11]);
+		x = wx; y = wy; z = wz;
 	}
 	return make_float4(x, y, z, __uint_as_float(index));
 }

@@ -244,6 +244,14 @@ extern "C" int rtkd_decode_mesh(rtkd_scene *s, uint32_t first_prim, uint32_t ntr
                                 const void *d_pos, size_t pos_stride, int pos_f64,
                                 const void *d_idx, size_t idx_stride, int idx_bytes, int pregathered, void *stream)
 {
+	return rtkd_decode_mesh_xf(s, first_prim, ntris, d_pos, pos_stride, pos_f64, d_idx, idx_stride, idx_bytes, pregathered, NULL, stream);
+}
+
+extern "C" int rtkd_decode_mesh_xf(rtkd_scene *s, uint32_t first_prim, uint32_t ntris,
+                                   const void *d_pos, size_t pos_stride, int pos_f64,
+                                   const void *d_idx, size_t idx_stride, int idx_bytes, int pregathered,
+                                   const float *xf12, void *stream)
+{
 	if (!ntris) return RTKD_OK;
 	if ((size_t)first_prim + ntris > s->num_tris) { rtkd_set_error("decode range outside the scene"); return RTKD_ERR_ARGUMENT; }
 	rtkd_decode_args a;
@@ -251,6 +259,8 @@ extern "C" int rtkd_decode_mesh(rtkd_scene *s, uint32_t first_prim, uint32_t ntr
 	a.pos_stride = pos_stride; a.idx_stride = idx_stride;
 	a.pos_f64 = pos_f64; a.idx_bytes = d_idx ? idx_bytes : 0; a.pregathered = pregathered;
 	a.ntris = ntris; a.first_prim = first_prim;
+	a.has_xf = xf12 != NULL;
+	for (int k = 0; k < 12; k++) a.xf[k] = xf12 ? xf12[k] : 0.0f;
 	RTK_LAUNCH(k_decode_mesh, (ntris + 255) / 256, 256, stream, a, (float4*)s->tri_orig);
 	CK_LAUNCH();
 	return RTKD_OK;

@@ -62,6 +62,12 @@ int rtkd_decode_mesh(rtkd_scene *s, uint32_t first_prim, uint32_t ntris,
                      const void *d_pos, size_t pos_stride, int pos_f64,
                      const void *d_idx, size_t idx_stride, int idx_bytes, int pregathered, void *stream);
 
+/* the same with an instance transform baked in: xf12 is a row-major 3x4 matrix (NULL = none) */
+int rtkd_decode_mesh_xf(rtkd_scene *s, uint32_t first_prim, uint32_t ntris,
+                        const void *d_pos, size_t pos_stride, int pos_f64,
+                        const void *d_idx, size_t idx_stride, int idx_bytes, int pregathered,
+                        const float *xf12, void *stream);
+
 /* build the BVH from the decoded triangles; synchronous with respect to `stream` on return */
 int rtkd_build(rtkd_scene *s, int mode, void *stream);
 

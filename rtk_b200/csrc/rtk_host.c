@@ -12,6 +12,7 @@
 #include "../../include/rtk_cuda.h"
 #include "rtk_device.h"
 
+#include <math.h>
 #include <pthread.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -552,6 +553,71 @@ int rtk_cuda_update_scene(const rtk_scene *scene, const rtk_cuda_mesh *meshes, s
 	for (size_t i = 0; i < num_meshes && r == RTK_CUDA_OK; i++)
 		r = rtkd_decode_mesh(dev, dev->h_mesh_first[i], (uint32_t)meshes[i].num_triangles, meshes[i].d_positions, 12, 0,
 		                     meshes[i].d_indices, 12, 4, 0, stream);
+	if (r != RTK_CUDA_OK) return r;
+	return mode == RTK_CUDA_UPDATE_REFIT ? rtkd_refit(dev, stream) : rtkd_build(dev, g_build_mode, stream);
+}
+
+/* baked instancing: instance i = mesh instances[i].mesh pushed through instances[i].transform */
+static int instances_valid(const rtk_cuda_mesh *meshes, size_t num_meshes, const rtk_cuda_instance *inst, size_t n)
+{
+	if ((num_meshes && !meshes) || (n && !inst)) { rtkd_set_error("bad mesh / instance array"); return 0; }
+	for (size_t i = 0; i < n; i++) {
+		if (inst[i].mesh >= num_meshes) { rtkd_set_error("instance %zu names mesh %u of %zu", i, inst[i].mesh, num_meshes); return 0; }
+		for (int k = 0; k < 12; k++) if (!isfinite(inst[i].transform[k])) { rtkd_set_error("instance %zu has a non-finite transform", i); return 0; }
+	}
+	return 1;
+}
+
+static int decode_instances(rtkd_scene *dev, const uint32_t *first, const rtk_cuda_mesh *meshes,
+                            const rtk_cuda_instance *inst, size_t n, void *stream)
+{
+	int r = RTK_CUDA_OK;
+	for (size_t i = 0; i < n && r == RTK_CUDA_OK; i++) {
+		const rtk_cuda_mesh *m = &meshes[inst[i].mesh];
+		r = rtkd_decode_mesh_xf(dev, first[i], (uint32_t)m->num_triangles, m->d_positions, 12, 0, m->d_indices, 12, 4, 0,
+		                        inst[i].transform, stream);
+	}
+	return r;
+}
+
+rtk_scene *rtk_cuda_build_instanced_scene(const rtk_cuda_mesh *meshes, size_t num_meshes,
+                                          const rtk_cuda_instance *instances, size_t num_instances, void *stream)
+{
+	if (!instances_valid(meshes, num_meshes, instances, num_instances)) return NULL;
+	uint32_t *first = (uint32_t*)malloc(sizeof(uint32_t) * (num_instances + 1));
+	if (!first) return NULL;
+	size_t total = 0;
+	for (size_t i = 0; i < num_instances; i++) {
+		first[i] = (uint32_t)total;
+		total += meshes[instances[i].mesh].num_triangles;
+		if (total > 0x0fffffffu) { free(first); rtkd_set_error("too many instanced triangles (baked instancing holds at most 2^28 - 1)"); return NULL; }
+	}
+	first[num_instances] = (uint32_t)total;
+	double t0 = now_ms();
+	rtkd_scene *dev = rtkd_scene_new((uint32_t)total, (uint32_t)num_instances, first);
+	int r = dev ? decode_instances(dev, first, meshes, instances, num_instances, stream) : RTK_CUDA_ERR_CUDA;
+	if (r == RTK_CUDA_OK) r = rtkd_build(dev, g_build_mode, stream);
+	free(first);
+	if (r != RTK_CUDA_OK) { warn_once(); if (dev) rtkd_scene_free(dev); return NULL; }
+	dev->build_total_ms = now_ms() - t0;
+	return make_handle(dev);
+}
+
+int rtk_cuda_update_instanced_scene(const rtk_scene *scene, const rtk_cuda_mesh *meshes, size_t num_meshes,
+                                    const rtk_cuda_instance *instances, size_t num_instances, int mode, void *stream)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return RTK_CUDA_ERR_SCENE;
+	if (mode != RTK_CUDA_UPDATE_REFIT && mode != RTK_CUDA_UPDATE_REBUILD) { rtkd_set_error("unknown update mode %d", mode); return RTK_CUDA_ERR_ARGUMENT; }
+	if (!instances_valid(meshes, num_meshes, instances, num_instances)) return RTK_CUDA_ERR_ARGUMENT;
+	if (num_instances != dev->num_meshes) { rtkd_set_error("update needs the scene's %u instances", dev->num_meshes); return RTK_CUDA_ERR_ARGUMENT; }
+	for (size_t i = 0; i < num_instances; i++) {
+		if (meshes[instances[i].mesh].num_triangles != (size_t)(dev->h_mesh_first[i + 1] - dev->h_mesh_first[i])) {
+			rtkd_set_error("instance %zu changed its triangle count: build a new scene", i);
+			return RTK_CUDA_ERR_ARGUMENT;
+		}
+	}
+	int r = decode_instances(dev, dev->h_mesh_first, meshes, instances, num_instances, stream);
 	if (r != RTK_CUDA_OK) return r;
 	return mode == RTK_CUDA_UPDATE_REFIT ? rtkd_refit(dev, stream) : rtkd_build(dev, g_build_mode, stream);
 }

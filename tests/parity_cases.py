@@ -703,6 +703,107 @@ def case_triangle_filter(lib, orc, dev):
     sc.free()
 
 
+def bake_instance(pos, xf):
+    """the library's instance transform restated in plain fp32: ((m0*x + m1*y) + m2*z) + m3 per row"""
+    pos = np.asarray(pos, dtype=np.float32)
+    m = np.asarray(xf, dtype=np.float32).reshape(3, 4)
+    x, y, z = pos[:, 0], pos[:, 1], pos[:, 2]
+    return np.stack([((m[r, 0] * x + m[r, 1] * y) + m[r, 2] * z) + m[r, 3] for r in range(3)], axis=1).astype(np.float32)
+
+
+def case_instancing(lib, orc, dev):
+    """SURVEY 8(f) N4, instancing (baked): instances of two meshes under rigid, scaled and mirrored
+    transforms; hits must be the oracle's on the transformed triangles, mesh_index the instance
+    number, triangle_index the triangle within its mesh, vertices in world space; instances then
+    move (refit and rebuild)."""
+    a = scenes.config_scene("C3", 0.002)["meshes"][0]                       # a terrain patch
+    b = scenes.config_scene("C1")["meshes"][0]                               # the Cornell box
+    src = []
+    for m in (a, b):
+        pos = m["positions"].astype(np.float32)
+        pos = (pos - pos.min(0)) / np.float32((pos.max(0) - pos.min(0)).max())     # unit-sized
+        src.append((np.ascontiguousarray(pos), m["indices"].astype(np.uint32)))
+    meshes, keep = (api.rtk_cuda_mesh * 2)(), []
+    for i, (pos, idx) in enumerate(src):
+        hp, dp = dev.put(pos)
+        hi, di = dev.put(idx)
+        keep += [hp, hi]
+        meshes[i].d_positions, meshes[i].d_indices = dp, di
+        meshes[i].num_vertices, meshes[i].num_triangles = len(pos), len(idx)
+
+    def rot_y(t):
+        c, s_ = np.cos(t), np.sin(t)
+        return np.array([[c, 0, s_], [0, 1, 0], [-s_, 0, c]])
+
+    def layout(phase):
+        out = []
+        for i in range(7):
+            lin = rot_y(0.7 * i + phase) * (0.6 + 0.15 * i)
+            if i == 3:
+                lin = lin @ np.diag([1.0, -1.0, 1.0])                       # mirrored
+            if i == 5:
+                lin = lin @ np.diag([2.0, 0.5, 1.0])                        # non-uniform scale
+            t = np.array([1.7 * (i % 3) + 0.3 * phase, 0.4 * (i // 3), 1.9 * (i // 3) - 0.2 * phase])
+            out.append((i % 2, np.concatenate([lin, t[:, None]], axis=1).astype(np.float32)))
+        return out
+
+    def pack(lay):
+        inst = (api.rtk_cuda_instance * len(lay))()
+        for i, (mi, xf) in enumerate(lay):
+            inst[i].mesh = mi
+            inst[i].transform[:] = [float(v) for v in xf.reshape(-1)]
+        return inst
+
+    def world(lay):
+        tris, first = [], [0]
+        for mi, xf in lay:
+            pos, idx = src[mi]
+            tris.append(bake_instance(pos, xf)[idx.astype(np.int64)])
+            first.append(first[-1] + len(idx))
+        return np.ascontiguousarray(np.concatenate(tris)), np.array(first)
+
+    lay = layout(0.0)
+    ptr = lib.rtk_cuda_build_instanced_scene(meshes, 2, pack(lay), len(lay), dev.stream)
+    assert ptr, lib.last_error()
+    sc = api.Scene(lib, ptr)
+    info = sc.info()
+    tris, first = world(lay)
+    assert info.num_triangles == len(tris) and info.num_meshes == len(lay)
+    rays = scenes.bounce_rays({"tris": tris}, 2500)
+    rays["o"][::2] += np.float32(0.5) * rays["d"][::2]                       # some start further out
+    rays["d"][1::2] *= np.float32(-1.0)
+    for step, mode in enumerate([None, api.RTK_CUDA_UPDATE_REFIT, api.RTK_CUDA_UPDATE_REBUILD]):
+        if mode is not None:
+            lay = layout(0.35 * step)
+            assert lib.rtk_cuda_update_instanced_scene(sc.ptr, meshes, 2, pack(lay), len(lay), mode, dev.stream) == 0, lib.last_error()
+            tris, first = world(lay)
+        want = orc.trace_brute(tris, rays)
+        hits, mask, nh = sc.trace_rays(rays)
+        assert_same(api.hits_to_hit16(hits, mask, first), want, f"instanced scene, step {step}")
+        m = mask.astype(bool)
+        assert 50 < nh < len(rays)
+        g = want["prim"][m].astype(np.int64)
+        ii = np.searchsorted(first, g, side="right") - 1
+        assert np.array_equal(hits["mesh_index"][m], ii), "mesh_index is the instance number"
+        assert np.array_equal(hits["triangle_index"][m], g - first[ii])
+        assert len(np.unique(ii)) >= 4
+        assert hits["vertex"]["position"][m].tobytes() == tris[g].tobytes(), "vertices are in world space"
+        local_idx = np.concatenate([src[mi][1] for mi, _ in lay])[g]
+        assert np.array_equal(hits["vertex"]["index"][m], local_idx), "original vertex indices of the mesh"
+    # refused: unknown mesh, wrong instance count, non-finite transform
+    bad = pack(lay)
+    bad[2].mesh = 9
+    assert not lib.rtk_cuda_build_instanced_scene(meshes, 2, bad, len(lay), dev.stream)
+    assert lib.rtk_cuda_update_instanced_scene(sc.ptr, meshes, 2, pack(lay), len(lay) - 1, api.RTK_CUDA_UPDATE_REFIT, dev.stream) != 0
+    bad = pack(lay)
+    bad[0].transform[5] = float("nan")
+    assert lib.rtk_cuda_update_instanced_scene(sc.ptr, meshes, 2, bad, len(lay), api.RTK_CUDA_UPDATE_REFIT, dev.stream) != 0
+    swapped = pack(lay)
+    swapped[0].mesh, swapped[1].mesh = 1, 0                                  # different triangle counts
+    assert lib.rtk_cuda_update_instanced_scene(sc.ptr, meshes, 2, swapped, len(lay), api.RTK_CUDA_UPDATE_REFIT, dev.stream) != 0
+    sc.free()
+
+
 def case_deep_stack(lib, orc, dev=None):
     """Thousands of coincident triangles: the builder cannot separate them (forced halving,
     rtk.c:1429-1443), every box overlaps every other, so a ray has to visit all of them: the

@@ -61,6 +61,10 @@ def test_concurrent_host_threads(emu_lib, orc):
     pc.case_threads(emu_lib, orc)
 
 
+def test_baked_instancing(emu_lib, orc):
+    pc.case_instancing(emu_lib, orc, pc.HostDevice())
+
+
 def test_triangle_filter(emu_lib, orc):
     pc.case_triangle_filter(emu_lib, orc, pc.HostDevice())
 

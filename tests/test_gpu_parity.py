@@ -214,3 +214,7 @@ def test_triangle_filter(gpu_lib, orc):
 
 def test_concurrent_host_threads(gpu_lib, orc):
     pc.case_threads(gpu_lib, orc, nthreads=6)
+
+
+def test_baked_instancing(gpu_lib, orc):
+    pc.case_instancing(gpu_lib, orc, TorchDevice())

@@ -31,6 +31,8 @@ pc.case_refit(lib, orc, pc.HostDevice())
 pc.case_deep_stack(lib, orc, pc.HostDevice())
 pc.case_host_batch_chunks(lib, orc, nrays=20000, chunk_log2=12)
 pc.case_triangle_filter(lib, orc, pc.HostDevice())
+pc.case_instancing(lib, orc, pc.HostDevice())
+pc.case_threads(lib, orc)
 print("asan run clean")
 PY
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \

@@ -179,7 +179,7 @@ extern "C" rtkd_scene *rtkd_scene_new(uint32_t num_tris, uint32_t num_meshes, co
 	if (ensure_init()) return NULL;
 	rtkd_scene *s = (rtkd_scene*)calloc(1, sizeof(rtkd_scene));
 	if (!s) { rtkd_set_error("out of host memory"); return NULL; }
-	s->id = ((uint64_t)time(NULL) << 20) ^ (g_next_id++ * 0x9E3779B97F4A7C15ull);
+	s->id = ((uint64_t)time(NULL) << 20) ^ (__atomic_fetch_add(&g_next_id, 1, __ATOMIC_RELAXED) * 0x9E3779B97F4A7C15ull);   // scenes may be built from several host threads
 	s->num_tris = num_tris; s->num_meshes = num_meshes;
 	s->h_mesh_first = (uint32_t*)malloc(sizeof(uint32_t) * (num_meshes + 1));
 	memcpy(s->h_mesh_first, mesh_first, sizeof(uint32_t) * (num_meshes + 1));

@@ -41,6 +41,17 @@ extern "C" void rtkd_set_error(const char *fmt, ...)
 	rtkd_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); return NULL; } } while (0)
 #define CK_LAUNCH() CK(cudaGetLastError())
 
+// CK() returns from the middle of a function: these release what the function holds on every path
+struct event_pair {
+	cudaEvent_t e0 = NULL, e1 = NULL;
+	~event_pair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+struct async_free {
+	void *&ptr; cudaStream_t st;
+	async_free(void *&p, cudaStream_t s) : ptr(p), st(s) {}
+	~async_free() { if (ptr) cudaFreeAsync(ptr, st); }
+};
+
 extern "C" int rtkd_init(int device)
 {
 	if (g_device == device && g_sm_count) { CK(cudaSetDevice(device)); return RTKD_OK; }   // another host thread binding itself
@@ -151,11 +162,15 @@ extern "C" int rtkd_read_bandwidth(size_t bytes, int passes, double *gbs)
 	float4 *buf = NULL;
 	float *sink = NULL;
 	const size_t n16 = bytes / 16;
+	struct dev_free { void *p = NULL; ~dev_free() { if (p) cudaFree(p); } } buf_guard, sink_guard;
 	CK(cudaMalloc(&buf, n16 * 16));
+	buf_guard.p = buf;
 	CK(cudaMalloc(&sink, 4));
+	sink_guard.p = sink;
 	CK(cudaMemset(buf, 0, n16 * 16));
-	cudaEvent_t e0, e1;
-	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+	event_pair ev;
+	CK(cudaEventCreate(&ev.e0)); CK(cudaEventCreate(&ev.e1));
+	cudaEvent_t e0 = ev.e0, e1 = ev.e1;
 	const unsigned grid = (unsigned)g_sm_count * 8;
 	RTK_LAUNCH(k_read_probe, grid, 256, 0, (const float4*)buf, n16, 2, sink);       // warm the cache
 	CK(cudaEventRecord(e0, 0));
@@ -164,8 +179,6 @@ extern "C" int rtkd_read_bandwidth(size_t bytes, int passes, double *gbs)
 	CK(cudaEventSynchronize(e1));
 	float ms = 0.0f;
 	CK(cudaEventElapsedTime(&ms, e0, e1));
-	cudaEventDestroy(e0); cudaEventDestroy(e1);
-	cudaFree(buf); cudaFree(sink);
 	*gbs = ms > 0.0f ? (double)n16 * 16.0 * passes / (ms * 1e-3) / 1e9 : 0.0;
 	return RTKD_OK;
 }
@@ -416,8 +429,9 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	cudaStream_t st = (cudaStream_t)stream;
 	const uint32_t n = s->num_tris;
 	s->build_mode = (uint32_t)mode;
-	cudaEvent_t e0, e1;
-	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+	event_pair ev;
+	CK(cudaEventCreate(&ev.e0)); CK(cudaEventCreate(&ev.e1));
+	cudaEvent_t e0 = ev.e0, e1 = ev.e1;
 	CK(cudaEventRecord(e0, st));
 
 	s->num_nodes = 0; s->num_leaves = 0; s->num_tv = 0; s->depth = 0; s->sah_cost = 0.0;
@@ -426,7 +440,6 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	if (n == 0) {
 		CK(cudaEventRecord(e1, st)); CK(cudaEventSynchronize(e1));
 		s->build_device_ms = 0.0;
-		cudaEventDestroy(e0); cudaEventDestroy(e1);
 		return RTKD_OK;
 	}
 	const bool use_sah = mode == 1 && n > RTK_LEAF_MAX;
@@ -435,6 +448,8 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	carve(A, B, n, use_sah);                               // sizing pass
 	A.size = A.used; A.used = 0;
 	CK(cudaMallocAsync(&A.base, A.size, st));
+	void *arena_mem = A.base;
+	async_free arena_guard(arena_mem, st);                 // the temporaries go back to the pool on every path
 	carve(A, B, n, use_sah);
 
 	const float4 *tri = (const float4*)s->tri_orig;
@@ -465,7 +480,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	rtkd_bvh2 t = B.t;
 	if (use_sah) {
 		int r = build_sah(st, tri, svals, B, n);
-		if (r) { cudaFreeAsync(A.base, st); return r; }
+		if (r) return r;
 		t.left = B.h.left; t.right = B.h.right; t.first = B.h.first; t.last = B.h.last; t.blo = B.h.blo; t.bhi = B.h.bhi;
 		svals = B.order;
 	} else if (n > 1) {
@@ -515,7 +530,6 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		num_nodes = h_ctr[0]; num_leaves = h_ctr[1];
 		if (h_ctr[2] || h_ctr[8 + RTKD_COLLAPSE_LEVELS - 1]) {
 			rtkd_set_error("wide-node pool exhausted (cap %u), tree deeper than %d or more than %u leaves", B.cap, RTKD_COLLAPSE_LEVELS, RTK_MAX_LEAVES);
-			cudaFreeAsync(A.base, st);
 			return RTKD_ERR_MEMORY;
 		}
 		CK(cudaMemcpyAsync(&h_cost, B.d_cost, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -548,14 +562,12 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	RTK_LAUNCH(k_emit_leaves, (num_tv + 255) / 256, 256, st, tri, svals, (const uint2*)B.leaf_list, num_leaves,
 	           (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
 	s->num_tv = num_tv;
-	cudaFreeAsync(A.base, st);
 	if (s->filter_bits) { int fr = apply_filter(s, st); if (fr) return fr; }
 
 	CK(cudaEventRecord(e1, st));
 	CK(cudaEventSynchronize(e1));
 	float ms = 0.0f;
 	CK(cudaEventElapsedTime(&ms, e0, e1));
-	cudaEventDestroy(e0); cudaEventDestroy(e1);
 
 	s->num_nodes = num_nodes; s->num_leaves = num_leaves; s->depth = depth;
 	s->build_device_ms = ms;
@@ -585,12 +597,15 @@ extern "C" int rtkd_refit(rtkd_scene *s, void *stream)
 	cudaStream_t st = (cudaStream_t)stream;
 	if (!s->num_tris || !s->num_nodes) return RTKD_OK;
 	if (!s->node_level) { rtkd_set_error("this scene carries no level table (loaded from a blob): rebuild it instead"); return RTKD_ERR_SCENE; }
-	cudaEvent_t e0, e1;
-	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+	event_pair ev;
+	CK(cudaEventCreate(&ev.e0)); CK(cudaEventCreate(&ev.e1));
+	cudaEvent_t e0 = ev.e0, e1 = ev.e1;
 	CK(cudaEventRecord(e0, st));
 	const float4 *tri = (const float4*)s->tri_orig;
 	uint32_t *d_bounds = NULL;
 	CK(cudaMallocAsync(&d_bounds, 8 * sizeof(uint32_t), st));
+	void *bounds_mem = d_bounds;
+	async_free bounds_guard(bounds_mem, st);
 	CK(cudaMemsetAsync(d_bounds, 0xff, 3 * sizeof(uint32_t), st));
 	CK(cudaMemsetAsync(d_bounds + 3, 0x00, 3 * sizeof(uint32_t), st));
 	RTK_LAUNCH(k_scene_bounds, (s->num_tris + 255) / 256, 256, st, tri, s->num_tris, d_bounds); CK_LAUNCH();
@@ -607,12 +622,10 @@ extern "C" int rtkd_refit(rtkd_scene *s, void *stream)
 	if (s->filter_bits) { int fr = apply_filter(s, st); if (fr) return fr; }
 	uint32_t h_bounds[6];
 	CK(cudaMemcpyAsync(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost, st));
-	cudaFreeAsync(d_bounds, st);
 	CK(cudaEventRecord(e1, st));
 	CK(cudaEventSynchronize(e1));
 	float ms = 0.0f;
 	CK(cudaEventElapsedTime(&ms, e0, e1));
-	cudaEventDestroy(e0); cudaEventDestroy(e1);
 	s->build_device_ms = ms;
 	float amax = 0.0f;
 	for (int k = 0; k < 3; k++) {

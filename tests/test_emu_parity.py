@@ -83,3 +83,18 @@ def test_deep_stack_spills(emu_lib, orc):
 
 def test_host_batch_many_chunks(emu_lib, orc):
     pc.case_host_batch_chunks(emu_lib, orc, nrays=30000, chunk_log2=12)
+
+
+def test_randomised_adversarial_scenes(emu_lib, orc):
+    """a fixed slice of tools/fuzz_emu.py (slivers, degenerate and duplicated triangles, lattice-aligned
+    geometry, rays through vertices / along axes / starting on surfaces, tight t windows; both
+    builders, with and without a triangle filter, closest hit and occlusion)"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+    import fuzz_emu
+    hits = 0
+    for seed in range(1000, 1040):
+        hits += fuzz_emu.one(emu_lib, seed)[2]
+    assert hits > 500
+    emu_lib.rtk_cuda_set_build_mode(1)                  # back to the default (binned SAH)

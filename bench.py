@@ -632,6 +632,29 @@ def main():
            "ms_per_step": e2e_s * 1e3, "api": "rtk_trace_rays (host rtk_ray[] in, rtk_hit[] + mask out, pinned)",
            "hits_per_step": int(nh), "rows_equal_device_path": same_rows, "rows_compared": k}
 
+    # ---- the same batch with compact results (rtk_trace_rays_compact: 16-byte records, no host-side
+    # row placement), reported beside the headline e2e; single GPU only, and never at the measurement's cost
+    e2e_compact = None
+    if world == 1:
+        try:
+            h_h16 = torch.empty((n, 16), dtype=torch.uint8).pin_memory()
+
+            def compact_step():
+                if lib.rtk_trace_rays_compact(sc.ptr, h_rays.data_ptr(), h_h16.data_ptr(), n) != 0:
+                    raise RuntimeError(lib.last_error())
+            compact_step()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                compact_step()
+            torch.cuda.synchronize()
+            c_s = (time.perf_counter() - t0) / args.e2e_steps
+            e2e_compact = {"value": n / c_s / 1e6, "unit": UNIT, "ms_per_step": c_s * 1e3,
+                           "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 16 * n,
+                           "api": "rtk_trace_rays_compact (host rtk_ray[] in, 16-byte (t,u,v,triangle) record per ray out, pinned)",
+                           "records_equal_device_path": bool(torch.equal(h_h16[:k], d_h16[:k].cpu()))}
+        except Exception as ex:
+            e2e_compact = {"error": str(ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -648,7 +671,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload,
-        "e2e": e2e, "gpu_launches": 2 * args.steps,
+        "e2e": e2e, "e2e_compact": e2e_compact, "gpu_launches": 2 * args.steps,
         "kernels_ms": {"k_trace": trace_ms, "k_resolve": resolve_ms},
         "roofline": {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,

@@ -108,6 +108,14 @@ int  rtk_cuda_measure_read_bandwidth(size_t bytes, int passes, double *gb_per_s)
  * Returns the number of hits, or (size_t)-1 on error. */
 size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits, uint8_t *hit_mask, size_t n);
 
+/* Host buffers, compact results: hits[i] is a 16-byte record for EVERY ray --
+ * t, u, v and the global triangle number, or prim == RTK_CUDA_MISS (t, u, v = 0)
+ * -- for callers that look the vertices up themselves (or only need
+ * distances / visibility).  Half the bytes of the rays come back and nothing is
+ * repacked on the host, so the batch is bound by the upload of the rays alone.
+ * Returns 0 or a negative rtk_cuda_status. */
+int rtk_trace_rays_compact(const rtk_scene *scene, const rtk_ray *rays, rtk_cuda_hit16 *hits, size_t n);
+
 /* Device buffers (16-byte aligned), asynchronous on `stream`.  d_hits[i] is
  * written only where d_hit_mask[i] != 0.  One batch per scene may be in flight. */
 int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hits, void *d_hit_mask, size_t n, void *stream);

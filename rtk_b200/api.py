@@ -136,6 +136,7 @@ SYMBOLS = {
     "rtk_cuda_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "rtk_cuda_measure_read_bandwidth": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "rtk_trace_rays": (C.c_size_t, [_P, _P, _P, _P, C.c_size_t]),
+    "rtk_trace_rays_compact": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "rtk_trace_rays_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
     "rtk_trace_rays_compact_device": (C.c_int, [_P, _P, _P, C.c_size_t, _P]),
     "rtk_resolve_hits_device": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P]),
@@ -305,6 +306,16 @@ class Scene:
         if r == C.c_size_t(-1).value:
             raise RtkError("rtk_trace_rays failed: " + self.lib.last_error())
         return hits, mask, int(r)
+
+    def trace_rays_compact(self, rays, out=None):
+        """rtk_trace_rays_compact with host arrays -> HIT16_DTYPE record per ray."""
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        if out is None:
+            out = np.zeros(len(rays), dtype=HIT16_DTYPE)
+        r = self.lib.rtk_trace_rays_compact(self.ptr, rays.ctypes.data, out.ctypes.data, len(rays))
+        if r:
+            raise RtkError("rtk_trace_rays_compact failed: " + self.lib.last_error())
+        return out
 
     def set_triangle_filter(self, keep):
         """rtk_cuda_set_triangle_filter: `keep` is a boolean array over the scene's global triangle

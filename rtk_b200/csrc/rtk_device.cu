@@ -1070,6 +1070,63 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 	return rc == RTKD_OK ? total : -1;
 }
 
+// Host-buffer batch with COMPACT results: rays up, one 16-byte record (t, u, v, global triangle
+// number or RTKD miss) per ray down, straight into the caller's array -- no dense packing, no row
+// placement by host threads.  32 bytes per ray go up and 16 come down, on the two directions of the
+// link, so the batch is bound by the upload alone.  Same staging, same chunking, same upload stream
+// running ahead as rtkd_trace_host; each chunk's stream carries k_trace and the copy of its records.
+extern "C" int rtkd_trace_host_compact(rtkd_scene *s, const void *rays, void *hit16, size_t n)
+{
+	if (!n) return RTKD_OK;
+	pthread_mutex_lock(&g_stage_lock);
+	int rc = stage_prepare(n);
+	if (rc == RTKD_OK) rc = ensure_scratch(s);
+	host_stage &G = g_stage;
+	if (rc == RTKD_OK && G.rays_cap < n) {
+		if (G.d_rays) cudaFree(G.d_rays);
+		G.d_rays = NULL; G.rays_cap = 0;
+		if (cudaMalloc(&G.d_rays, 32 * n) != cudaSuccess) { rtkd_set_error("out of device memory for %zu rays", n); rc = RTKD_ERR_MEMORY; }
+		else G.rays_cap = n;
+	}
+	if (rc != RTKD_OK) { pthread_mutex_unlock(&g_stage_lock); return rc; }
+	const size_t chunk = G.chunk;
+	const size_t nchunks = (n + chunk - 1) / chunk;
+	cudaEvent_t prev_traced = NULL;
+	size_t uploads = 0;
+	for (size_t it = 0; it < nchunks && rc == RTKD_OK; it++) {
+		for (; uploads < nchunks && uploads <= it + RTKD_HOST_AHEAD; uploads++) {
+			const size_t off = uploads * chunk, cnt = n - off < chunk ? n - off : chunk;
+			cudaError_t e = cudaMemcpyAsync(G.d_rays + 2 * off, (const char*)rays + 32 * off, 32 * cnt, cudaMemcpyHostToDevice, G.up);
+			if (e == cudaSuccess) e = cudaEventRecord(G.uploaded[uploads % RTKD_HOST_RING], G.up);
+			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays_compact: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
+		}
+		if (rc != RTKD_OK) break;
+		// the chunk's stream still holds the copy of the chunk that used this buffer before: stream
+		// order keeps the new traversal from overwriting records that have not left yet
+		host_buf &B = G.b[it % RTKD_HOST_BUFS];
+		const size_t off = it * chunk, cnt = n - off < chunk ? n - off : chunk;
+		cudaError_t e = cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0);
+		if (e == cudaSuccess && prev_traced) e = cudaStreamWaitEvent(B.st, prev_traced, 0);   // the traversal scratch is the scene's
+		if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays_compact: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
+		rc = rtkd_trace(s, G.d_rays + 2 * off, B.d_h16, cnt, 1, NULL, B.st);
+		if (rc) break;
+		e = cudaEventRecord(B.traced, B.st);
+		prev_traced = B.traced;
+		if (e == cudaSuccess) e = cudaMemcpyAsync((char*)hit16 + 16 * off, B.d_h16, 16 * cnt, cudaMemcpyDeviceToHost, B.st);
+		if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays_compact: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
+	}
+	for (int k = 0; k < RTKD_HOST_BUFS; k++) if (cudaStreamSynchronize(G.b[k].st) != cudaSuccess && rc == RTKD_OK) rc = RTKD_ERR_CUDA;
+	if (cudaStreamSynchronize(G.up) != cudaSuccess && rc == RTKD_OK) rc = RTKD_ERR_CUDA;
+	if (rc == RTKD_OK) {
+		uint32_t herr = 0;
+		if (cudaMemcpy(&herr, (unsigned char*)s->scratch + 192, sizeof(herr), cudaMemcpyDeviceToHost) != cudaSuccess) rc = RTKD_ERR_CUDA;
+		if (herr & 2u) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
+	}
+	if (rc == RTKD_ERR_CUDA && !g_err[0]) rtkd_set_error("CUDA failure in rtk_trace_rays_compact");
+	pthread_mutex_unlock(&g_stage_lock);
+	return rc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // serialisation
 // ---------------------------------------------------------------------------------------------

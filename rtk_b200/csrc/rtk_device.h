@@ -104,6 +104,9 @@ int rtkd_gen_bounce(rtkd_scene *s, const void *d_rays_in, const void *d_hit16, v
 /* host-buffer batch: H2D, trace, resolve, D2H; returns hits or -1 */
 long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n);
 
+/* host-buffer batch with compact results: one 16-byte record per ray straight into the caller's array */
+int rtkd_trace_host_compact(rtkd_scene *s, const void *rays, void *hit16, size_t n);
+
 /* host placement of dense hit rows (rtk_place.c): for every ray i of the chunk with mask[i] != 0
  * the next 68-byte row of its 128-ray block -- block b's rows start at rows[block_base[b]] --
  * is copied to hits[first_ray + i]; mask_out (may be NULL) receives the mask bytes. */

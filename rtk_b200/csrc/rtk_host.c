@@ -651,6 +651,16 @@ size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits
 	return (size_t)r;
 }
 
+int rtk_trace_rays_compact(const rtk_scene *scene, const rtk_ray *rays, rtk_cuda_hit16 *hits, size_t n)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return RTK_CUDA_ERR_SCENE;
+	if (n && (!rays || !hits)) { rtkd_set_error("rays / hits is NULL"); return RTK_CUDA_ERR_ARGUMENT; }
+	int r = rtkd_trace_host_compact(dev, rays, hits, n);
+	if (r) warn_once();
+	return r;
+}
+
 int rtk_trace_rays_compact_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream)
 {
 	rtkd_scene *dev = scene_device(scene);

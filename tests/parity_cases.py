@@ -868,4 +868,20 @@ def case_host_batch_chunks(lib, orc, nrays=30000, chunk_log2=12):
     assert hits3[m].tobytes() == hits2[m].tobytes()
     k = min(nrays, 1500)
     assert_same(api.hits_to_hit16(hits2, mask2, s["mesh_first"])[:k], orc.trace_brute(s["tris"], rays[:k]), "chunked host batch")
+    # compact results (rtk_trace_rays_compact): a record for every ray, one chunk and many chunks
+    full = api.hits_to_hit16(hits2, mask2, s["mesh_first"])
+    c1 = sc.trace_rays_compact(rays)
+    os.environ["RTK_B200_HOST_CHUNK_LOG2"] = str(chunk_log2)
+    try:
+        c2 = sc.trace_rays_compact(rays, out=np.full(nrays, 0x5A5A5A5A, dtype=np.uint32).repeat(4).view(api.HIT16_DTYPE))
+        c3 = sc.trace_rays_compact(rays[:nrays - 37])                           # ragged last chunk
+    finally:
+        os.environ.pop("RTK_B200_HOST_CHUNK_LOG2", None)
+        if old is not None:
+            os.environ["RTK_B200_HOST_CHUNK_LOG2"] = old
+    assert_same(c1, full, "compact host batch")
+    assert_same(c2, full, "compact host batch, many chunks")
+    assert_same(c3, full[:nrays - 37], "compact host batch, ragged")
+    assert len(sc.trace_rays_compact(rays[:0])) == 0
+    assert lib.rtk_trace_rays_compact(sc.ptr, None, None, 5) != 0
     sc.free()

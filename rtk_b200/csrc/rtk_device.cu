@@ -891,6 +891,7 @@ extern "C" void *rtkd_scene_hit16(rtkd_scene *s, size_t n)
 #define RTKD_HOST_BUFS 4
 #define RTKD_HOST_AHEAD 4
 #define RTKD_HOST_RING 8             // upload events: more than RTKD_HOST_AHEAD + 1
+#define RTKD_HOST_SMALL ((size_t)2048)  // batches up to this size take the one-stream, one-synchronisation path
 
 struct host_buf {
 	cudaStream_t st;
@@ -1013,6 +1014,36 @@ extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits
 	const size_t mask_bytes = (chunk + 15) & ~(size_t)15;
 	rtkd_arrays a;
 	fill_arrays(s, a);
+	if (rc == RTKD_OK && n <= RTKD_HOST_SMALL) {
+		// Small batches -- rtk_trace_ray is a batch of one -- are bound by latency, not by bytes: one
+		// stream, rows expanded in place (no dense packing, no worker threads), ONE synchronisation.
+		host_buf &B = G.b[0];
+		cudaError_t e = cudaMemcpyAsync(G.d_rays, rays, 32 * n, cudaMemcpyHostToDevice, B.st);
+		if (e == cudaSuccess) rc = rtkd_trace(s, G.d_rays, B.d_h16, n, 1, NULL, B.st);
+		if (e == cudaSuccess && rc == RTKD_OK) {
+			RTK_LAUNCH(k_resolve<false>, (unsigned)((n + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, B.st,
+			           a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)n, (unsigned long long*)NULL, (uint32_t*)NULL);
+			e = cudaGetLastError();
+			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_rows, B.d_rows, 68 * n, cudaMemcpyDeviceToHost, B.st);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_meta, B.d_mask, n, cudaMemcpyDeviceToHost, B.st);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_meta + mask_bytes, (unsigned char*)s->scratch + 192, 4, cudaMemcpyDeviceToHost, B.st);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(B.st);
+		}
+		if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; }
+		if (rc == RTKD_OK) {
+			uint32_t herr = 0;
+			memcpy(&herr, B.h_meta + mask_bytes, 4);
+			if (herr & 2u) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
+		}
+		if (rc == RTKD_OK) {
+			for (size_t i = 0; i < n; i++) {
+				if (B.h_meta[i]) { memcpy((char*)hits + 68 * i, B.h_rows + 68 * i, 68); total++; }    // rows of misses stay untouched (rtk.c:571-576)
+			}
+			if (mask) memcpy(mask, B.h_meta, n);
+		}
+		pthread_mutex_unlock(&g_stage_lock);
+		return rc == RTKD_OK ? total : -1;
+	}
 	cudaEvent_t prev_traced = NULL;
 	size_t uploads = 0;                 // chunks whose upload has been enqueued
 	// chunk ci enters stage A in iteration ci, stage B in iteration ci+1, stage C in iteration ci+2

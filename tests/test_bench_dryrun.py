@@ -1,0 +1,19 @@
+"""bench.py's control flow, executed without a GPU (tools/bench_emu.py): the emulator build of the
+library, host stand-ins for torch's CUDA entry points, gloo instead of NCCL.  Checks that every leg
+runs, that the self-checks inside the bench pass (oracle parity, gather content, host paths against
+the device path) and that the one JSON line has the contract's keys.  Nothing here is a measurement."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_bench_dry_run(world):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_emu.py"), str(world)],
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert f"dry run ok (world {world})" in r.stdout

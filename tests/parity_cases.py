@@ -804,6 +804,54 @@ def case_instancing(lib, orc, dev):
     sc.free()
 
 
+def case_pathological(lib, orc):
+    """scenes a builder can trip over: zero-extent bounds (all points / all collinear / all coplanar),
+    one triangle that dwarfs the rest, coordinates whose products overflow or underflow fp32, signed
+    zeros, two clusters a million units apart -- both builders, hits bit-exact as everywhere else"""
+    rng = np.random.default_rng(5)
+    n = 500
+
+    def rays_for(tris, count=250):
+        flat = tris.reshape(-1, 3).astype(np.float64)
+        lo, hi = flat.min(0), flat.max(0)
+        ext = np.maximum(hi - lo, max(np.abs(hi).max() * 1e-3, 1e-3))
+        r = np.zeros(count, dtype=api.RAY_DTYPE)
+        o = lo + (rng.random((count, 3)) * 3 - 1) * ext
+        tgt = tris[rng.integers(0, len(tris), count)].astype(np.float64).mean(1)
+        d = (tgt - o).astype(np.float32)
+        d[np.abs(d).max(1) == 0] = (0, 0, 1)
+        r["o"], r["d"], r["max_t"] = o.astype(np.float32), d, api.RTK_INF
+        return r
+    cases = {}
+    cases["all points at one place"] = np.repeat(np.repeat(rng.random((1, 1, 3)), 3, 1), n, 0)
+    line = np.zeros((n, 3, 3))
+    line[:, :, 0] = rng.random((n, 3))
+    cases["all collinear on the x axis"] = line
+    plane = rng.random((n, 3, 3))
+    plane[:, :, 1] = 0.25
+    cases["all in one plane"] = plane
+    big = rng.random((n, 1, 3)) + 0.01 * rng.random((n, 3, 3))
+    big[0] = [(-50, -50, 0.5), (50, -50, 0.5), (0, 80, 0.5)]
+    cases["one huge triangle"] = big
+    cases["1e15 coordinates"] = rng.random((n, 3, 3)) * 1e15
+    cases["1e-20 coordinates"] = rng.random((n, 3, 3)) * 1e-20
+    neg = rng.random((n, 1, 3)) - 0.5 + 0.05 * rng.random((n, 3, 3))
+    neg[::3, :, 2] = -0.0
+    cases["signed zeros"] = neg
+    cases["two far clusters"] = np.concatenate([rng.random((n // 2, 3, 3)), rng.random((n // 2, 3, 3)) + 1e6])
+    total = 0
+    for mode in (api.RTK_CUDA_BUILD_LBVH, api.RTK_CUDA_BUILD_SAH):
+        for name, tris in cases.items():
+            tris = np.ascontiguousarray(tris.astype(np.float32))
+            r = rays_for(tris)
+            got, _, _ = trace_hit16(lib, soup_mesh(tris), r, mode=mode)
+            want = orc.trace_brute(tris, r)
+            assert_same(got, want, f"{name} (build mode {mode})")
+            total += int((want["prim"] != api.RTK_CUDA_MISS).sum())
+    assert total > 1000
+    lib.rtk_cuda_set_build_mode(api.RTK_CUDA_BUILD_SAH)
+
+
 def case_deep_stack(lib, orc, dev=None):
     """Thousands of coincident triangles: the builder cannot separate them (forced halving,
     rtk.c:1429-1443), every box overlaps every other, so a ray has to visit all of them: the

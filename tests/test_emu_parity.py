@@ -65,6 +65,10 @@ def test_baked_instancing(emu_lib, orc):
     pc.case_instancing(emu_lib, orc, pc.HostDevice())
 
 
+def test_pathological_scenes(emu_lib, orc):
+    pc.case_pathological(emu_lib, orc)
+
+
 def test_triangle_filter(emu_lib, orc):
     pc.case_triangle_filter(emu_lib, orc, pc.HostDevice())
 

@@ -218,3 +218,7 @@ def test_concurrent_host_threads(gpu_lib, orc):
 
 def test_baked_instancing(gpu_lib, orc):
     pc.case_instancing(gpu_lib, orc, TorchDevice())
+
+
+def test_pathological_scenes(gpu_lib, orc):
+    pc.case_pathological(gpu_lib, orc)

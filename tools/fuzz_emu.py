@@ -133,6 +133,49 @@ def one(lib, seed):
     return len(tris), len(rays), int((want["prim"] != api.RTK_CUDA_MISS).sum())
 
 
+def one_update(lib, seed):
+    """device-mesh build (indexed, shared vertices), then vertex perturbations with refit / rebuild,
+    optionally under a triangle filter -- against the oracle on the moved triangles"""
+    rng = np.random.default_rng(seed)
+    g = int(rng.integers(3, 14))
+    xs, ys = np.meshgrid(np.arange(g) / (g - 1), np.arange(g) / (g - 1))
+    pos = np.stack([xs.ravel(), 0.2 * rng.random(g * g), ys.ravel()], -1).astype(np.float32)
+    quads = [(j * g + i, j * g + i + 1, (j + 1) * g + i, (j + 1) * g + i + 1) for j in range(g - 1) for i in range(g - 1)]
+    idx = np.array([t for a, b, c, d in quads for t in ((a, b, c), (b, d, c))], dtype=np.uint32)
+    meshes = (api.rtk_cuda_mesh * 1)()
+    ix = np.ascontiguousarray(idx)
+    meshes[0].d_indices, meshes[0].num_vertices, meshes[0].num_triangles = ix.ctypes.data, len(pos), len(idx)
+    p0 = np.ascontiguousarray(pos)
+    meshes[0].d_positions = p0.ctypes.data
+    lib.rtk_cuda_set_build_mode(int(rng.integers(0, 2)))
+    ptr = lib.rtk_cuda_build_scene(meshes, 1, None)
+    assert ptr, lib.last_error()
+    sc = api.Scene(lib, ptr)
+    hits_total = 0
+    try:
+        keep = None
+        if rng.random() < 0.4:
+            keep = rng.random(len(idx)) < 0.7
+            sc.set_triangle_filter(keep)
+        for step in range(3):
+            cur = (pos + (rng.random(pos.shape) - 0.5) * np.float32(rng.choice([1e-3, 0.05, 0.5]))).astype(np.float32)
+            if rng.random() < 0.3:
+                cur *= np.float32(rng.choice([0.01, 7.0]))
+            cur = np.ascontiguousarray(cur)
+            meshes[0].d_positions = cur.ctypes.data
+            mode = int(rng.integers(0, 2))
+            assert lib.rtk_cuda_update_scene(sc.ptr, meshes, 1, mode, None) == 0, lib.last_error()
+            tris = np.ascontiguousarray(cur[idx.astype(np.int64)])
+            rays = make_rays(rng, tris, int(rng.choice([33, 150])))
+            want = pc.filtered_oracle(orc, tris, rays, keep) if keep is not None else orc.trace_brute(tris, rays)
+            got = sc.trace_rays_compact(rays)
+            pc.assert_same(got, want, f"update seed {seed} step {step} mode {mode} filter {keep is not None}")
+            hits_total += int((want["prim"] != api.RTK_CUDA_MISS).sum())
+    finally:
+        sc.free()
+    return len(idx), 0, hits_total
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -141,7 +184,7 @@ def main():
     t0, n, hits, rays = time.time(), 0, 0, 0
     while time.time() - t0 < budget:
         try:
-            _, r, h = one(lib, seed)
+            _, r, h = one_update(lib, seed) if seed % 4 == 3 else one(lib, seed)
         except AssertionError as ex:
             print("MISMATCH", ex)
             return 1

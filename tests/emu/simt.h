@@ -288,18 +288,27 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 	p->multiProcessorCount = 2; p->l2CacheSize = 1 << 20; p->totalGlobalMem = (size_t)8 << 30; p->major = 10;
 	return cudaSuccess;
 }
+// With SIMT_SHM_MALLOC=1 in the environment "device memory" comes from named POSIX shared memory, so
+// that another emulated process can map it through the fake CUDA IPC calls below (the two-process
+// dry run of the peer-memory gather).  Otherwise it is plain heap memory.
+struct simt_shm_block { void *ptr; size_t size; char name[40]; };
+simt_shm_block *simt_shm_find(const void *p);
+void *simt_shm_alloc(size_t n);
+bool simt_shm_release(void *p);
 template <typename T> static inline cudaError_t cudaMalloc(T **p, size_t n)
 {
 	void *q = NULL;
-	if (posix_memalign(&q, 256, n ? n : 256)) return cudaErrorMemoryAllocation;
+	static const bool shm = getenv("SIMT_SHM_MALLOC") && atoi(getenv("SIMT_SHM_MALLOC")) != 0;
+	if (shm) { q = simt_shm_alloc(n ? n : 256); if (!q) return cudaErrorMemoryAllocation; }
+	else if (posix_memalign(&q, 256, n ? n : 256)) return cudaErrorMemoryAllocation;
 	memset(q, 0xCD, n);   // poison: device memory is uninitialised
 	*p = (T*)q;
 	return cudaSuccess;
 }
 template <typename T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void *p) { if (!simt_shm_release(p)) free(p); return cudaSuccess; }
 template <typename T> static inline cudaError_t cudaMallocAsync(T **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
 static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
@@ -335,12 +344,14 @@ struct cudaPointerAttributes { int type; void *devicePointer; void *hostPointer;
 #define cudaMemoryTypeDevice 2
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = 0; a->devicePointer = 0; a->hostPointer = 0; return cudaSuccess; }
 
-// CUDA IPC: the emulated "other process" is this process, a handle is the pointer itself
+// CUDA IPC.  Heap-backed memory: the emulated "other process" is this process and a handle is the
+// pointer itself.  Shared-memory-backed memory (SIMT_SHM_MALLOC): a handle carries the name and size
+// of the block and another process maps it.
 struct cudaIpcMemHandle_t { char reserved[64]; };
 #define cudaIpcMemLazyEnablePeerAccess 1
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
-static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return *p ? cudaSuccess : cudaErrorInvalidValue; }
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p);
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags);
+cudaError_t cudaIpcCloseMemHandle(void *p);
 
 // kernel launch: RTK_LAUNCH(kernel, grid, block, stream, args...)
 #define RTK_LAUNCH(kernel, grid, block, stream, ...) \
@@ -480,4 +491,89 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body)
 	cur = NULL;
 }
 } // namespace simt
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+static std::mutex g_shm_lock;
+static std::vector<simt_shm_block> g_shm_blocks;     // blocks this process created
+static std::vector<simt_shm_block> g_shm_mapped;     // blocks of other processes mapped here
+// whatever the process still holds at exit (staging buffers, scenes nobody freed) must not stay in /dev/shm
+static struct simt_shm_cleanup {
+	~simt_shm_cleanup() { for (auto &b : g_shm_blocks) shm_unlink(b.name); }
+} g_shm_cleanup;
+simt_shm_block *simt_shm_find(const void *p)
+{
+	for (auto &b : g_shm_blocks) if (b.ptr == p) return &b;
+	return NULL;
+}
+void *simt_shm_alloc(size_t n)
+{
+	std::lock_guard<std::mutex> guard(g_shm_lock);
+	static unsigned counter = 0;
+	simt_shm_block b;
+	snprintf(b.name, sizeof(b.name), "/simt_%d_%u", (int)getpid(), counter++);
+	b.size = (n + 4095) & ~(size_t)4095;
+	int fd = shm_open(b.name, O_CREAT | O_EXCL | O_RDWR, 0600);
+	if (fd < 0) return NULL;
+	if (ftruncate(fd, (off_t)b.size) != 0) { close(fd); shm_unlink(b.name); return NULL; }
+	b.ptr = mmap(NULL, b.size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (b.ptr == MAP_FAILED) { shm_unlink(b.name); return NULL; }
+	g_shm_blocks.push_back(b);
+	return b.ptr;
+}
+bool simt_shm_release(void *p)
+{
+	std::lock_guard<std::mutex> guard(g_shm_lock);
+	for (size_t i = 0; i < g_shm_blocks.size(); i++) if (g_shm_blocks[i].ptr == p) {
+		munmap(p, g_shm_blocks[i].size);
+		shm_unlink(g_shm_blocks[i].name);
+		g_shm_blocks.erase(g_shm_blocks.begin() + (long)i);
+		return true;
+	}
+	return false;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p)
+{
+	std::lock_guard<std::mutex> guard(g_shm_lock);
+	memset(h, 0, sizeof(*h));
+	if (simt_shm_block *b = simt_shm_find(p)) {
+		h->reserved[0] = 'S';
+		memcpy(h->reserved + 8, &b->size, sizeof(size_t));
+		memcpy(h->reserved + 16, b->name, sizeof(b->name));
+	} else {
+		h->reserved[0] = 'P';
+		memcpy(h->reserved + 8, &p, sizeof(p));
+	}
+	return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned)
+{
+	std::lock_guard<std::mutex> guard(g_shm_lock);
+	if (h.reserved[0] == 'P') { memcpy(p, h.reserved + 8, sizeof(*p)); return *p ? cudaSuccess : cudaErrorInvalidValue; }
+	if (h.reserved[0] != 'S') return cudaErrorInvalidValue;
+	simt_shm_block b;
+	memcpy(&b.size, h.reserved + 8, sizeof(size_t));
+	memcpy(b.name, h.reserved + 16, sizeof(b.name));
+	b.name[sizeof(b.name) - 1] = 0;
+	int fd = shm_open(b.name, O_RDWR, 0600);
+	if (fd < 0) return cudaErrorInvalidValue;
+	b.ptr = mmap(NULL, b.size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (b.ptr == MAP_FAILED) return cudaErrorInvalidValue;
+	g_shm_mapped.push_back(b);
+	*p = b.ptr;
+	return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void *p)
+{
+	std::lock_guard<std::mutex> guard(g_shm_lock);
+	for (size_t i = 0; i < g_shm_mapped.size(); i++) if (g_shm_mapped[i].ptr == p) {
+		munmap(p, g_shm_mapped[i].size);
+		g_shm_mapped.erase(g_shm_mapped.begin() + (long)i);
+		return cudaSuccess;
+	}
+	return cudaSuccess;      // heap-backed "mapping": nothing to undo
+}
 #endif

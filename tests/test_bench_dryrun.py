@@ -11,9 +11,11 @@ import pytest
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_bench_dry_run(world):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_emu.py"), str(world)],
+@pytest.mark.parametrize("world,extra", [(1, []), (2, []), (2, ["--gather", "p2p"])])
+def test_bench_dry_run(world, extra):
+    """the third case is the peer-memory gather between two real processes: the emulator then backs
+    'device memory' with POSIX shared memory and its CUDA IPC calls map the window for real"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_emu.py"), str(world)] + extra,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert f"dry run ok (world {world})" in r.stdout

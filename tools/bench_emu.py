@@ -8,6 +8,9 @@ torch's CUDA entry points are replaced by host stand-ins, and NCCL by gloo.  Not
 run is a measurement -- the line is checked for shape only.  TEST INFRASTRUCTURE.
 
     python tools/bench_emu.py [world] [bench.py arguments...]
+    python tools/bench_emu.py 2 --gather p2p      # peer-memory gather: emulated device memory is then
+                                                  # POSIX shared memory, the window really is mapped by
+                                                  # the other process
 """
 import json
 import os
@@ -97,7 +100,7 @@ def main():
         port = s.getsockname()[1]
     procs = []
     for rank in range(world):
-        env = dict(os.environ, RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
+        env = dict(os.environ, SIMT_SHM_MALLOC="1" if "p2p" in extra else "0", RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--child", "x"] + args, env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
@@ -127,6 +130,7 @@ def main():
         assert line["occlusion"]["agrees_with_closest_hit_mask"]
     else:
         assert line["gather_check"].get("equal") is True, line["gather_check"]
+        assert line["config"]["gather"] == ("p2p" if "p2p" in extra else "nccl")
     print(json.dumps(line)[:3000])
     print(f"dry run ok (world {world}); nothing above is a measurement")
     return 0

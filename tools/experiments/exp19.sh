@@ -1,5 +1,5 @@
 # Round 2, first call (1 GPU, ~3 min of box time): everything written after round 1's GPU budget ran out.
-#   gpurun --timeout 420 -- 'sh tools/exp19.sh'
+#   gpurun --timeout 420 -- 'sh tools/experiments/exp19.sh'
 # 1. the whole GPU tier (new cases: baked instancing, concurrent host threads, pathological scenes,
 #    compact host batch, small-batch path);  2. the default bench line (look at e2e_compact and
 #    e2e);  3. latency of rtk_trace_ray on the small-batch path.

@@ -1,5 +1,5 @@
 # Round 2 (2 GPUs, then 8): NCCL gather against the peer-memory gather (copy-engine pushes).
-#   gpurun --gpus 2 --timeout 600 -- 'sh tools/exp20.sh 2'      (then the same with 8)
+#   gpurun --gpus 2 --timeout 600 -- 'sh tools/experiments/exp20.sh 2'      (then the same with 8)
 # gather_check.equal must be true in both modes.
 N=${1:-2}
 mkdir -p gpurun_out

@@ -112,7 +112,13 @@ static int ensure_init(void)
 }
 extern "C" int rtkd_bind_thread(void) { return ensure_init(); }
 
-extern "C" void rtkd_shutdown(void) { g_device = -1; g_sm_count = 0; }
+static void stage_shutdown(void);          // host-batch staging (defined with the pipeline below)
+extern "C" void rtkd_shutdown(void)
+{
+	// scenes are the caller's to free first; what the library itself holds on the device goes here
+	if (g_sm_count) { ensure_init(); cudaDeviceSynchronize(); stage_shutdown(); }
+	g_device = -1; g_sm_count = 0;
+}
 
 extern "C" int rtkd_reserve_sms(int sms)
 {
@@ -923,6 +929,26 @@ static void stage_release(void)
 		cudaFreeHost(B.h_meta); cudaFreeHost(B.h_rows);
 		B.d_h16 = NULL; B.d_rows = B.d_base = NULL; B.d_mask = NULL; B.h_meta = B.h_rows = NULL;
 	}
+}
+
+static void stage_shutdown(void)
+{
+	pthread_mutex_lock(&g_stage_lock);
+	if (g_stage.ready || g_stage.up) {
+		stage_release();
+		for (int k = 0; k < RTKD_HOST_BUFS; k++) {
+			host_buf &B = g_stage.b[k];
+			if (B.st) cudaStreamDestroy(B.st);
+			if (B.traced) cudaEventDestroy(B.traced);
+			if (B.meta_done) cudaEventDestroy(B.meta_done);
+			if (B.rows_done) cudaEventDestroy(B.rows_done);
+		}
+		if (g_stage.up) cudaStreamDestroy(g_stage.up);
+		for (int k = 0; k < RTKD_HOST_RING; k++) if (g_stage.uploaded[k]) cudaEventDestroy(g_stage.uploaded[k]);
+	}
+	if (g_stage.d_rays) cudaFree(g_stage.d_rays);
+	memset(&g_stage, 0, sizeof(g_stage));
+	pthread_mutex_unlock(&g_stage_lock);
 }
 
 static int stage_prepare(size_t want)

@@ -386,6 +386,15 @@ def case_api_semantics(lib, orc):
     hits, mask, _ = sc.trace_rays(rays)
     assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want, "finish_build")
     sc.free()
+    # rtk_cuda_shutdown releases the library's own device memory (staging of the host batches);
+    # the next call initialises again by itself
+    lib.rtk_cuda_shutdown()
+    got, _, _ = trace_hit16(lib, s, rays)
+    assert_same(got, want, "after shutdown and implicit re-initialisation")
+    lib.rtk_cuda_shutdown()
+    assert lib.rtk_cuda_init(0) == 0
+    got, _, _ = trace_hit16(lib, s, rays)
+    assert_same(got, want, "after shutdown and rtk_cuda_init")
 
 
 def case_threads(lib, orc, nthreads=4):

@@ -74,8 +74,13 @@ typedef struct rtk_cuda_trace_stats {
 /* ---- device selection ------------------------------------------------- */
 
 /* Bind the calling process to one CUDA device (one process per GPU).  Called
- * implicitly with device 0 by the first entry point that needs a device. */
+ * implicitly with device 0 by the first entry point that needs a device.  CUDA's
+ * current device is per host thread: every entry point makes the library's device
+ * current on the thread that calls it, so worker threads need no set-up of their own. */
 int  rtk_cuda_init(int device);
+/* Releases what the library itself holds on the device (streams, events, device and pinned
+ * staging of the host batches).  Scenes are the caller's: free them first.  A later call
+ * initialises the library again. */
 void rtk_cuda_shutdown(void);
 const char *rtk_cuda_last_error(void);
 int  rtk_cuda_set_build_mode(int mode);

@@ -916,7 +916,8 @@ struct host_stage {
 	cudaStream_t up;                    // upload stream
 	cudaEvent_t uploaded[RTKD_HOST_RING];
 	float4 *d_rays; size_t rays_cap;    // the whole batch's rays (grow-only)
-	bool ready;
+	bool ready;                         // buffers allocated for `chunk`
+	bool streams;                       // streams and events exist (they outlive a change of chunk size)
 };
 static host_stage g_stage;
 static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;
@@ -934,7 +935,7 @@ static void stage_release(void)
 static void stage_shutdown(void)
 {
 	pthread_mutex_lock(&g_stage_lock);
-	if (g_stage.ready || g_stage.up) {
+	if (g_stage.ready || g_stage.streams) {
 		stage_release();
 		for (int k = 0; k < RTKD_HOST_BUFS; k++) {
 			host_buf &B = g_stage.b[k];
@@ -963,8 +964,8 @@ static int stage_prepare(size_t want)
 	size_t chunk = want < max_chunk ? want : max_chunk;
 	if (chunk < 4096) chunk = 4096;
 	if (g_stage.ready && (forced ? g_stage.chunk == chunk : g_stage.chunk >= chunk)) return RTKD_OK;
-	if (g_stage.ready) stage_release();
-	else {
+	stage_release();                     // also what an earlier, failed attempt left behind
+	if (!g_stage.streams) {
 		for (int k = 0; k < RTKD_HOST_BUFS; k++) {
 			host_buf &B = g_stage.b[k];
 			CK(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking));
@@ -974,6 +975,7 @@ static int stage_prepare(size_t want)
 		}
 		CK(cudaStreamCreateWithFlags(&g_stage.up, cudaStreamNonBlocking));
 		for (int k = 0; k < RTKD_HOST_RING; k++) CK(cudaEventCreateWithFlags(&g_stage.uploaded[k], cudaEventDisableTiming));
+		g_stage.streams = true;
 	}
 	g_stage.ready = false;
 	g_stage.chunk = chunk;

@@ -194,6 +194,8 @@ def run_wavefront(args, workload, lib, api, scene, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     W, H, SPP, BOUNCES, BANDS = 3840, 2160, 16, 4, 8
+    if args.wf_frame:                                       # dry runs only: the workload is the 4K frame
+        W, H, SPP = (int(v) for v in args.wf_frame.split("x"))
     band = (rank % BANDS) if world > 1 else 0
     rows = H // BANDS
     npx = W * rows
@@ -335,6 +337,7 @@ def main():
                          "overlapped with the next step.  p2p: copy-engine pushes into a peer-memory window on rank 0 "
                          "(rtk_cuda_peer_*, CUDA IPC over NVLink; no NCCL kernels beside the persistent traversal grid)")
     ap.add_argument("--lib", default=None, help="experiment: alternative build of librtk_b200 (same ABI)")
+    ap.add_argument("--wf-frame", default=None, help="C5 dry runs on the emulator only: WIDTHxHEIGHTxSPP instead of 3840x2160x16")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 

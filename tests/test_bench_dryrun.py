@@ -11,7 +11,10 @@ import pytest
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-@pytest.mark.parametrize("world,extra", [(1, []), (2, []), (2, ["--gather", "p2p"])])
+WF = ["--workload", "C5", "--wf-frame", "64x32x2", "--scale", "0.0005"]      # the wavefront leg on a toy frame
+
+
+@pytest.mark.parametrize("world,extra", [(1, []), (2, []), (2, ["--gather", "p2p"]), (1, WF), (2, WF)])
 def test_bench_dry_run(world, extra):
     """the third case is the peer-memory gather between two real processes: the emulator then backs
     'device memory' with POSIX shared memory and its CUDA IPC calls map the window for real"""

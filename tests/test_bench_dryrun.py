@@ -21,4 +21,4 @@ def test_bench_dry_run(world, extra):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_emu.py"), str(world)] + extra,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert f"dry run ok (world {world})" in r.stdout
+    assert f"dry run ok (world {world}" in r.stdout

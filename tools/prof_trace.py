@@ -1,4 +1,4 @@
-"""One workload, N identical k_trace launches: the command profiled with ncu (tools/exp*.sh).
+"""One workload, N identical k_trace launches: the command profiled with ncu (tools/experiments/exp*.sh).
 usage: python tools/prof_trace.py [workload] [launches] [rays]"""
 import os
 import sys

@@ -681,7 +681,8 @@ def main():
                      # dram__bytes_read.sum + dram__bytes_write.sum of one k_trace launch on this very
                      # workload (profiles/r1e_k_trace_raw.csv); unknown for any other workload
                      "traffic": 1.728e9 if (args.workload == "C3" and n == FULL_RAYS and args.scale == 1.0 and args.build_mode == "sah") else None,
-                     "traffic_unit": "bytes per launch (ncu, profiles/r1e_k_trace_raw.csv)",
+                     "traffic_unit": "bytes per launch (ncu, profiles/r1e_k_trace_raw.csv; captured before the collapse rule "
+                                     "that absorbs small subtrees, i.e. on a tree with a third more wide nodes)",
                      "peak_source": peak_src,
                      "l2": {"achieved": achieved, "peak": l2_gbs.value, "unit": "GB/s",
                             "frac": achieved / l2_gbs.value if l2_gbs.value else None,

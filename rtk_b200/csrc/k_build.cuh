@@ -410,19 +410,47 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 	slot[0] = t.left[root]; slot[1] = t.right[root];
 #define RTK_OPENABLE(c) ((c) >= 0 && (t.last[c] - t.first[c] + 1) > RTK_LEAF_MAX)
 #define RTK_BIDX(c) ((c) >= 0 ? (c) : (n - 1) + ~(c))
-	for (int k = 0; k < 2; k++)
+	// nleaf[k]: number of leaves (maximal subtrees of at most RTK_LEAF_MAX triangles) below an openable
+	// slot when that is at most RTK_WIDE, else 0.  Only subtrees of at most RTK_WIDE * RTK_LEAF_MAX
+	// triangles can qualify, so the walk is short.
+	int nleaf[RTK_WIDE];
+#define RTK_COUNT_LEAVES(k) do { \
+		nleaf[k] = 0; \
+		const int c0 = slot[k]; \
+		if (area[k] >= 0.0f && (t.last[c0] - t.first[c0] + 1) <= RTK_LEAF_MAX * RTK_WIDE) { \
+			int todo[2 * RTK_WIDE + 2], ntodo = 0, leaves = 0; \
+			todo[ntodo++] = c0; \
+			while (ntodo > 0 && leaves + ntodo <= RTK_WIDE) { \
+				const int c1 = todo[--ntodo]; \
+				if (c1 >= 0 && (t.last[c1] - t.first[c1] + 1) > RTK_LEAF_MAX) { todo[ntodo++] = t.left[c1]; todo[ntodo++] = t.right[c1]; } \
+				else leaves++; \
+			} \
+			if (ntodo == 0) nleaf[k] = leaves; \
+		} \
+	} while (0)
+	for (int k = 0; k < 2; k++) {
 		area[k] = RTK_OPENABLE(slot[k]) ? rtk_half_area(t.blo[slot[k]], t.bhi[slot[k]]) : -1.0f;
+		RTK_COUNT_LEAVES(k);
+	}
 	while (ns < RTK_WIDE) {
+		// A subtree whose leaves ALL fit into the free slots is absorbed whole, largest area first: the
+		// wide node it would have become -- with few children, near the bottom of the tree, where most
+		// nodes are -- disappears (a third fewer wide nodes, 3 % fewer node visits per ray on the
+		// terrain and 10 % on the soup, counted by the statistics kernel).  Otherwise the child with the
+		// largest area is opened, as before.
 		int best = -1; float ba = -1.0f;
-		for (int k = 0; k < ns; k++) if (area[k] > ba) { ba = area[k]; best = k; }
+		for (int k = 0; k < ns; k++) if (nleaf[k] && nleaf[k] <= RTK_WIDE - ns + 1 && area[k] > ba) { ba = area[k]; best = k; }
+		if (best < 0) for (int k = 0; k < ns; k++) if (area[k] > ba) { ba = area[k]; best = k; }
 		if (best < 0) break;
 		int c = slot[best];
 		int l = t.left[c], r = t.right[c];
 		slot[best] = l; slot[ns] = r;
 		area[best] = RTK_OPENABLE(l) ? rtk_half_area(t.blo[l], t.bhi[l]) : -1.0f;
 		area[ns] = RTK_OPENABLE(r) ? rtk_half_area(t.blo[r], t.bhi[r]) : -1.0f;
+		RTK_COUNT_LEAVES(best); RTK_COUNT_LEAVES(ns);
 		ns++;
 	}
+#undef RTK_COUNT_LEAVES
 	float4 *node = a.nodes + 16ull * dst;
 	double cost = 0.0;
 	for (int k = 0; k < RTK_WIDE; k++) {

@@ -78,6 +78,24 @@ typedef struct rtk_cuda_trace_stats {
  * current device is per host thread: every entry point makes the library's device
  * current on the thread that calls it, so worker threads need no set-up of their own. */
 int  rtk_cuda_init(int device);
+/* Drive SEVERAL devices from this one process, the way a reference user gets the whole machine from one
+ * rtk_build_scene / rtk_trace_ray call site (rtk.h:126-129): devices[0] builds every scene, the scene is
+ * copied to the other devices (device to device, NVLink between peers) by rtk_build_scene, host batches
+ * (rtk_trace_rays, rtk_trace_rays_compact) are split into contiguous ranges over all of them -- one upload
+ * stream, one chunk pipeline and one worker thread per device -- and every device entry point runs on
+ * the device that owns the caller's ray buffer.  rtk_free_scene frees the copies on every device.  The
+ * devices must be of one kind.  rtk_cuda_init(d) is the list {d}; a different list needs
+ * rtk_cuda_shutdown() first. */
+int  rtk_cuda_init_devices(const int *devices, int num_devices);
+int  rtk_cuda_device_count(void);
+/* Page-locked host memory every device of the list reads and WRITES in place.  When the hits / hit_mask
+ * arrays given to rtk_trace_rays are page-locked (these calls, cudaHostAlloc, cudaHostRegister, ...) the
+ * rows of the rays that hit travel straight from the resolve kernel into the caller's array: no staging
+ * copy, no host threads.  Pageable arrays work too, through pinned staging and a pool of host threads. */
+void *rtk_cuda_host_alloc(size_t bytes);
+void  rtk_cuda_host_free(void *p);
+int   rtk_cuda_host_register(void *p, size_t bytes);
+int   rtk_cuda_host_unregister(void *p);
 /* Releases what the library itself holds on the device (streams, events, device and pinned
  * staging of the host batches).  Scenes are the caller's: free them first.  A later call
  * initialises the library again. */
@@ -100,6 +118,13 @@ int  rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *trace_ctas_per_s
  * times with 16-byte loads.  A buffer well below the L2 size measures L2 read bandwidth, one well
  * above it HBM read bandwidth. */
 int  rtk_cuda_measure_read_bandwidth(size_t bytes, int passes, double *gb_per_s);
+/* The access pattern of the traversal rather than of a copy: warps gather `record_bytes`-sized records
+ * (256 = a wide node, 128 = one line of a leaf slot) at hashed offsets of a `bytes`-sized buffer.  With
+ * the buffer inside the L2 this is the denominator of the L2 roofline. */
+int  rtk_cuda_measure_gather_bandwidth(size_t bytes, size_t record_bytes, int passes, double *gb_per_s);
+/* Ceiling of the host-buffer path: aggregate GB/s of concurrent copies between pinned host memory and the
+ * first num_devices devices of the list; directions: 1 host-to-device, 2 device-to-host, 3 both at once. */
+int  rtk_cuda_measure_host_link(int num_devices, size_t bytes_per_device, int directions, int passes, double *gb_per_s);
 
 /* ---- batched closest hit (replaces a user loop over rtk_trace_ray) ----- */
 
@@ -108,8 +133,9 @@ int  rtk_cuda_measure_read_bandwidth(size_t bytes, int passes, double *gb_per_s)
  * the miss rule of rtk.c:571-576.  hit_mask may be NULL.  The batch runs as a
  * pipeline over 1M-ray chunks: rays go up, only the rows of rays that hit
  * (plus one mask byte per ray) come back, and a few library threads
- * (RTK_B200_HOST_THREADS, default 3/4 of the CPUs, at most 16) copy each row to hits[i].  Pinned
- * (page-locked) caller buffers let the uploads overlap the kernels.
+ * (RTK_B200_HOST_THREADS, default 3/4 of the CPUs, at most 16) copy each row to hits[i] -- unless hits
+ * and hit_mask are page-locked (see rtk_cuda_host_alloc), in which case the device writes the rows
+ * straight into them.  With several devices in use the batch is split over all of them.
  * Returns the number of hits, or (size_t)-1 on error. */
 size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits, uint8_t *hit_mask, size_t n);
 
@@ -122,13 +148,33 @@ size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits
 int rtk_trace_rays_compact(const rtk_scene *scene, const rtk_ray *rays, rtk_cuda_hit16 *hits, size_t n);
 
 /* Device buffers (16-byte aligned), asynchronous on `stream`.  d_hits[i] is
- * written only where d_hit_mask[i] != 0.  One batch per scene may be in flight. */
+ * written only where d_hit_mask[i] != 0.
+ *
+ * Concurrency of every *_device query below: like rtk_trace_ray (rtk.h:129) they are re-entrant on a
+ * scene -- any number of host threads and streams may query one scene at once; each launch takes its
+ * own cursor / stack scratch from the scene.  With several devices in use (rtk_cuda_init_devices) the
+ * call runs on the device that owns d_rays; `stream` must belong to that device.  What must NOT overlap
+ * a query, exactly as freeing a reference scene under a running rtk_trace_ray must not: rtk_free_scene,
+ * rtk_cuda_rebuild_scene / update / set_triangle_filter on the same scene.  rtk_trace_rays_device
+ * additionally uses one scene-owned buffer of compact records: one such call per scene at a time (use
+ * the two halves below with your own buffer otherwise).  A traversal that ran out of stack sets a sticky
+ * flag instead of returning wrong hits silently: rtk_cuda_scene_status reads it. */
 int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hits, void *d_hit_mask, size_t n, void *stream);
 
 /* The two halves of the call above: traversal to compact records
  * (rtk.c:390-539 + 181-388), then expansion to rtk_hit (rtk.c:371-381). */
 int rtk_trace_rays_compact_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream);
 int rtk_resolve_hits_device(const rtk_scene *scene, const void *d_hit16, void *d_hits, void *d_hit_mask, size_t n, void *stream);
+
+/* RTK_CUDA_OK, or RTK_CUDA_ERR_OVERFLOW when some traversal on this scene exhausted its stack since the
+ * scene was last built (cannot happen for trees this library builds: the stack is sized from the tree's
+ * depth; a defence for blobs).  Meaningful once the caller has synchronised the streams it queried on;
+ * the host-buffer entry points check it themselves. */
+int rtk_cuda_scene_status(const rtk_scene *scene);
+
+/* Test hook: cap the global-memory part of the traversal stack at `entries` per ray (0 = sized from the
+ * tree depth, the default) so that the overflow report can be exercised. */
+int rtk_cuda_debug_limit_stack(int entries);
 
 /* Occlusion (shadow-ray) query: d_occluded[i] = 1 iff some triangle is hit in
  * (min_t, max_t), i.e. exactly where the closest-hit query reports a hit; the

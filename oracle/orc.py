@@ -43,6 +43,8 @@ def lib():
         L = C.CDLL(LIBORC)
         L.orc_trace_brute.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
         L.orc_trace_brute.restype = None
+        L.orc_trace_brute_blocked.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        L.orc_trace_brute_blocked.restype = C.c_int
         L.orc_ray_triangle.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.POINTER(C.c_float),
                                        C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_ray_triangle.restype = C.c_int
@@ -77,11 +79,18 @@ def _rays(rays):
     return a
 
 
-def trace_brute(tris, rays, threads=0):
-    """Canonical brute force: (ntris,3,3) float32, rays RAY_DTYPE -> HIT16_DTYPE array."""
+def trace_brute(tris, rays, threads=0, blocked=None):
+    """Canonical brute force: (ntris,3,3) float32, rays RAY_DTYPE -> HIT16_DTYPE array.
+    Big jobs (>= 2^26 ray-triangle pairs) take the blocked, pre-filtered loop, which gives the same
+    answers (the scalar code stays the arbiter of every hit; tests/test_oracle.py compares the two)."""
     t9, r = _tri9(tris), _rays(rays)
     out = np.zeros(len(r), dtype=HIT16_DTYPE)
-    lib().orc_trace_brute(t9.ctypes.data, len(t9), r.ctypes.data, len(r), out.ctypes.data, threads)
+    if blocked is None:
+        blocked = len(t9) * len(r) >= (1 << 26)
+    if blocked:
+        lib().orc_trace_brute_blocked(t9.ctypes.data, len(t9), r.ctypes.data, len(r), out.ctypes.data, threads)
+    else:
+        lib().orc_trace_brute(t9.ctypes.data, len(t9), r.ctypes.data, len(r), out.ctypes.data, threads)
     return out
 
 

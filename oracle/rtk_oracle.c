@@ -189,6 +189,122 @@ void orc_trace_brute(const float *tri9, size_t ntris, const orc_ray *rays, size_
 	run_jobs(brute_worker, jobs, sizeof(brute_job), threads);
 }
 
+/* ---- the same brute force, blocked and pre-filtered --------------------- */
+/* For the big scenes (1M and 10M triangles) the plain loop above is minutes of CPU per thousand
+ * rays.  This variant gives the SAME answers: the scalar orc_tri() above stays the only arbiter of
+ * every hit; a vector pre-filter merely skips triangles that orc_tri() would reject at its sign
+ * test (rtk.c:340-344).  The filter evaluates the three fp32 edge values of 8 triangles at a time
+ * with the very operations of orc_tri (separate multiplies and adds/subtracts, minps/maxps
+ * semantics) and drops a triangle only when none of them is exactly zero, the smallest is < 0 and
+ * the largest is > 0 -- the case in which orc_tri returns 0 before looking at t.  Everything else
+ * (exact zeros, NaNs, same-sign values) goes to orc_tri in triangle order, so ties still resolve
+ * to the lowest id.  Triangles are transposed to SoA once and visited block by block for a batch
+ * of rays, which keeps a block in cache.  tests/test_oracle.py checks it against orc_trace_brute. */
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define ORC_TB 2048             /* triangles per block: 9 x 8 KB */
+#define ORC_RB 32               /* rays per batch */
+
+typedef struct {
+	const float *tri9; const float *soa; size_t ntris, npad;
+	const orc_ray *rays; orc_hit *out;
+	size_t begin, end;
+} fast_job;
+
+__attribute__((target("avx2")))
+static void fast_block(const fast_job *j, size_t i0, size_t i1, const orc_ray *ray, const orc_setup *s,
+                       float *best, orc_hit *h)
+{
+	const size_t np = j->npad;
+	const float *c0x = j->soa + (0 + s->kx) * np, *c0y = j->soa + (0 + s->ky) * np, *c0z = j->soa + (0 + s->kz) * np;
+	const float *c1x = j->soa + (3 + s->kx) * np, *c1y = j->soa + (3 + s->ky) * np, *c1z = j->soa + (3 + s->kz) * np;
+	const float *c2x = j->soa + (6 + s->kx) * np, *c2y = j->soa + (6 + s->ky) * np, *c2z = j->soa + (6 + s->kz) * np;
+	const __m256 ox = _mm256_set1_ps(s->ox), oy = _mm256_set1_ps(s->oy), oz = _mm256_set1_ps(s->oz);
+	const __m256 sx = _mm256_set1_ps(s->sx), sy = _mm256_set1_ps(s->sy), zero = _mm256_setzero_ps();
+	for (size_t i = i0; i < i1; i += 8) {
+		__m256 a0z = _mm256_sub_ps(_mm256_loadu_ps(c0z + i), oz), a1z = _mm256_sub_ps(_mm256_loadu_ps(c1z + i), oz), a2z = _mm256_sub_ps(_mm256_loadu_ps(c2z + i), oz);
+		__m256 x0 = _mm256_add_ps(_mm256_sub_ps(_mm256_loadu_ps(c0x + i), ox), _mm256_mul_ps(sx, a0z));
+		__m256 y0 = _mm256_add_ps(_mm256_sub_ps(_mm256_loadu_ps(c0y + i), oy), _mm256_mul_ps(sy, a0z));
+		__m256 x1 = _mm256_add_ps(_mm256_sub_ps(_mm256_loadu_ps(c1x + i), ox), _mm256_mul_ps(sx, a1z));
+		__m256 y1 = _mm256_add_ps(_mm256_sub_ps(_mm256_loadu_ps(c1y + i), oy), _mm256_mul_ps(sy, a1z));
+		__m256 x2 = _mm256_add_ps(_mm256_sub_ps(_mm256_loadu_ps(c2x + i), ox), _mm256_mul_ps(sx, a2z));
+		__m256 y2 = _mm256_add_ps(_mm256_sub_ps(_mm256_loadu_ps(c2y + i), oy), _mm256_mul_ps(sy, a2z));
+		__m256 u = _mm256_sub_ps(_mm256_mul_ps(x1, y2), _mm256_mul_ps(y1, x2));
+		__m256 v = _mm256_sub_ps(_mm256_mul_ps(x2, y0), _mm256_mul_ps(y2, x0));
+		__m256 w = _mm256_sub_ps(_mm256_mul_ps(x0, y1), _mm256_mul_ps(y0, x1));
+		__m256 anyz = _mm256_or_ps(_mm256_or_ps(_mm256_cmp_ps(u, zero, _CMP_EQ_OQ), _mm256_cmp_ps(v, zero, _CMP_EQ_OQ)), _mm256_cmp_ps(w, zero, _CMP_EQ_OQ));
+		__m256 neg = _mm256_cmp_ps(_mm256_min_ps(_mm256_min_ps(u, v), w), zero, _CMP_LT_OQ);
+		__m256 pos = _mm256_cmp_ps(_mm256_max_ps(_mm256_max_ps(u, v), w), zero, _CMP_GT_OQ);
+		int reject = _mm256_movemask_ps(_mm256_andnot_ps(anyz, _mm256_and_ps(neg, pos)));
+		int keep = ~reject & 0xff;
+		while (keep) {
+			int k = __builtin_ctz((unsigned)keep);
+			keep &= keep - 1;
+			size_t id = i + (size_t)k;
+			if (id >= j->ntris) break;
+			float t, uu, vv;
+			if (orc_tri(s, j->tri9 + 9 * id, ray->min_t, *best, &t, &uu, &vv)) {
+				*best = t;
+				h->t = t; h->u = uu; h->v = vv; h->prim = (uint32_t)id;
+			}
+		}
+	}
+}
+
+static void *fast_worker(void *arg)
+{
+	fast_job *j = (fast_job*)arg;
+	for (size_t r0 = j->begin; r0 < j->end; r0 += ORC_RB) {
+		size_t nr = j->end - r0 < ORC_RB ? j->end - r0 : ORC_RB;
+		orc_setup st[ORC_RB];
+		float best[ORC_RB];
+		orc_hit h[ORC_RB];
+		for (size_t q = 0; q < nr; q++) {
+			orc_ray_setup(&j->rays[r0 + q], &st[q]);
+			best[q] = j->rays[r0 + q].max_t;
+			h[q].t = h[q].u = h[q].v = 0.0f; h[q].prim = 0xffffffffu;
+		}
+		for (size_t i0 = 0; i0 < j->ntris; i0 += ORC_TB) {
+			size_t i1 = i0 + ORC_TB < j->npad ? i0 + ORC_TB : j->npad;
+			for (size_t q = 0; q < nr; q++) fast_block(j, i0, i1, &j->rays[r0 + q], &st[q], &best[q], &h[q]);
+		}
+		for (size_t q = 0; q < nr; q++) j->out[r0 + q] = h[q];
+	}
+	return NULL;
+}
+#endif
+
+int orc_trace_brute_blocked(const float *tri9, size_t ntris, const orc_ray *rays, size_t nrays,
+                            orc_hit *out, int threads)
+{
+#if defined(__x86_64__)
+	if (!__builtin_cpu_supports("avx2") || !ntris) { orc_trace_brute(tri9, ntris, rays, nrays, out, threads); return 0; }
+	size_t npad = (ntris + 7) & ~(size_t)7;
+	float *soa = NULL;
+	if (posix_memalign((void**)&soa, 64, sizeof(float) * 9 * npad)) { orc_trace_brute(tri9, ntris, rays, nrays, out, threads); return 0; }
+	for (size_t c = 0; c < 9; c++) {
+		float *d = soa + c * npad;
+		for (size_t i = 0; i < ntris; i++) d[i] = tri9[9 * i + c];
+		for (size_t i = ntris; i < npad; i++) d[i] = 0.0f;          /* padding never reaches orc_tri (id >= ntris) */
+	}
+	threads = pick_threads(threads, (nrays + ORC_RB - 1) / ORC_RB);
+	fast_job jobs[256];
+	size_t batches = (nrays + ORC_RB - 1) / ORC_RB;
+	for (int i = 0; i < threads; i++) {
+		jobs[i].tri9 = tri9; jobs[i].soa = soa; jobs[i].ntris = ntris; jobs[i].npad = npad; jobs[i].rays = rays; jobs[i].out = out;
+		jobs[i].begin = batches * (size_t)i / (size_t)threads * ORC_RB;
+		jobs[i].end = batches * (size_t)(i + 1) / (size_t)threads * ORC_RB;
+		if (jobs[i].end > nrays) jobs[i].end = nrays;
+	}
+	run_jobs(fast_worker, jobs, sizeof(fast_job), threads);
+	free(soa);
+	return 1;
+#else
+	orc_trace_brute(tri9, ntris, rays, nrays, out, threads);
+	return 0;
+#endif
+}
+
 /* ---------------------------------------------------------------------- */
 /* Reference blob structures (layout facts: rtk.c:69-86, rtk.h:78-89)      */
 /* ---------------------------------------------------------------------- */

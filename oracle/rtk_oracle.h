@@ -37,6 +37,12 @@ typedef struct orc_hit { float t, u, v; uint32_t prim; } orc_hit;
 void orc_trace_brute(const float *tri9, size_t ntris, const orc_ray *rays, size_t nrays,
                      orc_hit *out, int threads);
 
+/* The same answers, faster (blocked over triangles, AVX2 pre-filter of the sign test; the scalar
+ * code remains the arbiter of every hit -- see rtk_oracle.c).  Returns 1 when the vector path ran,
+ * 0 when it fell back to orc_trace_brute (no AVX2). */
+int orc_trace_brute_blocked(const float *tri9, size_t ntris, const orc_ray *rays, size_t nrays,
+                            orc_hit *out, int threads);
+
 /* A single ray/triangle evaluation: returns 1 and fills t,u,v when the
  * triangle is accepted for (min_t, max_t). */
 int orc_ray_triangle(const orc_ray *ray, const float *tri9, float max_t, float *t, float *u, float *v);

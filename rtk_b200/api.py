@@ -18,6 +18,8 @@ RTK_INF = np.float32(3.402823e+38)
 RTK_CUDA_MISS = 0xFFFFFFFF
 (RTK_TYPE_DEFAULT, RTK_TYPE_F32, RTK_TYPE_F64, RTK_TYPE_REAL, RTK_TYPE_U16, RTK_TYPE_U32) = range(6)
 RTK_CUDA_BUILD_LBVH, RTK_CUDA_BUILD_SAH = 0, 1
+(RTK_CUDA_OK, RTK_CUDA_ERR_NO_DEVICE, RTK_CUDA_ERR_CUDA, RTK_CUDA_ERR_ARGUMENT, RTK_CUDA_ERR_SCENE,
+ RTK_CUDA_ERR_MEMORY, RTK_CUDA_ERR_OVERFLOW) = (0, -1, -2, -3, -4, -5, -6)
 
 
 class rtk_vec3(C.Structure):
@@ -128,6 +130,16 @@ SYMBOLS = {
     "rtk_trace_ray_filter": (C.c_bool, [_P, C.POINTER(rtk_ray), C.POINTER(rtk_hit), rtk_filter_fn, _P]),
     # rtk_cuda.h
     "rtk_cuda_init": (C.c_int, [C.c_int]),
+    "rtk_cuda_init_devices": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
+    "rtk_cuda_device_count": (C.c_int, []),
+    "rtk_cuda_host_alloc": (_P, [C.c_size_t]),
+    "rtk_cuda_host_free": (None, [_P]),
+    "rtk_cuda_host_register": (C.c_int, [_P, C.c_size_t]),
+    "rtk_cuda_host_unregister": (C.c_int, [_P]),
+    "rtk_cuda_scene_status": (C.c_int, [_P]),
+    "rtk_cuda_debug_limit_stack": (C.c_int, [C.c_int]),
+    "rtk_cuda_measure_gather_bandwidth": (C.c_int, [C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
+    "rtk_cuda_measure_host_link": (C.c_int, [C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "rtk_cuda_shutdown": (None, []),
     "rtk_cuda_last_error": (C.c_char_p, []),
     "rtk_cuda_set_build_mode": (C.c_int, [C.c_int]),

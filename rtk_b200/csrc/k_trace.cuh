@@ -64,7 +64,7 @@ struct rtkd_trace_args {
 	uint32_t *counter;           // global ray cursor (zeroed before launch)
 	uint2 *overflow;             // [groups_in_grid * ovf_entries] stack spill
 	uint32_t ovf_entries;
-	uint32_t *err;               // bit 1: stack exhausted
+	uint32_t *status;            // the scene's sticky status word (host-mapped): bit 1 = stack exhausted
 	unsigned long long *stats;   // [6] when STATS
 };
 
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 		int _p = (pos); \
 		if (_p < RTK_STACK_SMEM) s_stack[_p][gcta] = (val); \
 		else if ((uint32_t)(_p - RTK_STACK_SMEM) < p.ovf_entries) p.overflow[gglobal * p.ovf_entries + (uint32_t)(_p - RTK_STACK_SMEM)] = (val); \
-		else atomicOr(p.err, 2u); \
+		else *(volatile uint32_t*)p.status = 2u; \
 	} while (0)
 #define RTK_STACK_POP() do { \
 		cur_ref = RTK_REF_EMPTY; \

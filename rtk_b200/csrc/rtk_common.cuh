@@ -12,6 +12,26 @@
 #include <string.h>
 #define RTK_LAUNCH(kernel, grid, block, stream, ...) \
 	kernel<<<dim3(grid), dim3(block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__)
+// launch with an L2 access-policy window: [win_base, win_base + win_bytes) is fetched as PERSISTING
+// (a fraction win_ratio of it when it exceeds the set-aside part of the L2)
+#define RTK_LAUNCH_WIN(kernel, grid, block, strm_, win_base, win_bytes, win_ratio, ...) do { \
+	cudaLaunchConfig_t _cfg; memset(&_cfg, 0, sizeof(_cfg)); \
+	_cfg.gridDim = dim3(grid); _cfg.blockDim = dim3(block); _cfg.stream = (cudaStream_t)(strm_); \
+	cudaLaunchAttribute _at[1]; memset(_at, 0, sizeof(_at)); \
+	if ((win_base) && (win_bytes)) { \
+		_at[0].id = cudaLaunchAttributeAccessPolicyWindow; \
+		_at[0].val.accessPolicyWindow.base_ptr = (void*)(win_base); \
+		_at[0].val.accessPolicyWindow.num_bytes = (size_t)(win_bytes); \
+		_at[0].val.accessPolicyWindow.hitRatio = (win_ratio); \
+		_at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; \
+		_at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal; \
+		_cfg.attrs = _at; _cfg.numAttrs = 1; \
+	} \
+	cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__); \
+} while (0)
+#else
+#define RTK_LAUNCH_WIN(kernel, grid, block, stream, win_base, win_bytes, win_ratio, ...) \
+	RTK_LAUNCH(kernel, grid, block, stream, __VA_ARGS__)
 #endif
 
 #define RTK_DEV __device__ __forceinline__

@@ -20,10 +20,16 @@
 #define RTKD_ERR_OVERFLOW (-6)
 
 static __thread char g_err[512];
-static int g_device = -1;
+
 static int g_sm_count = 0, g_trace_ctas = 0, g_trace_lanes = RTK_TRACE_LANES, g_trace_pd = 1;
 static int g_reserved_sms = 0;      // SMs the persistent traversal grid leaves free (for concurrent NCCL kernels)
 static size_t g_l2_bytes = 0;
+static size_t g_l2_window_max = 0;  // largest access-policy window the device accepts (0: no L2 persistence)
+static size_t g_l2_setaside = 0;    // L2 bytes set aside for persisting lines
+static int g_l2_persist = 1;        // RTK_B200_L2_PERSIST=0 switches the persisting window off
+static int g_host_direct = 1;       // RTK_B200_HOST_DIRECT=0: rows always travel through pinned staging
+static size_t g_min_share = (size_t)1 << 18;   // a device joins a host batch only for at least this many rays (RTK_B200_HOST_MIN_SHARE_LOG2)
+static int g_stack_limit = 0;       // test hook (rtkd_debug_limit_stack): spill entries per ray, 0 = sized from the tree
 static uint64_t g_next_id = 1;
 
 extern "C" const char *rtkd_last_error(void) { return g_err; }
@@ -52,9 +58,69 @@ struct async_free {
 	~async_free() { if (ptr) cudaFreeAsync(ptr, st); }
 };
 
-extern "C" int rtkd_init(int device)
+// ---------------------------------------------------------------------------------------------
+// devices.  The library drives a LIST of devices from one process (rtk_cuda_init_devices): scenes are
+// built on the first and replicated to the others, host batches are split over all of them, device
+// entry points run on whichever of them owns the caller's buffers.  rtk_cuda_init(d) is the list {d}.
+// Everything a host batch needs on one device (streams, staging, its worker thread) is in dev_ctx.
+// ---------------------------------------------------------------------------------------------
+
+#define RTKD_HOST_BUFS 4
+#define RTKD_HOST_RING 8             // upload events: more than RTKD_HOST_AHEAD + 1
+
+struct host_buf {
+	cudaStream_t st;
+	cudaEvent_t traced, meta_done, rows_done;
+	float4 *d_h16;
+	uint32_t *d_rows, *d_base;          // d_base: [blocks] block bases, then the 64-bit hit count
+	unsigned char *d_mask;
+	unsigned char *h_meta;              // pinned: mask bytes | block bases | hit count
+	unsigned char *h_rows;              // pinned: dense rows
+	size_t off, cnt, hits;              // the chunk this buffer currently carries
+	int ticket, state;                  // state: 0 free, 1 stage A queued, 2 stage B queued, 3 placing
+};
+struct host_stage {
+	size_t chunk, blocks, meta_bytes;
+	host_buf b[RTKD_HOST_BUFS];
+	cudaStream_t up;                    // upload stream
+	cudaEvent_t uploaded[RTKD_HOST_RING];
+	float4 *d_rays; size_t rays_cap;    // the rays of this device's share of the batch (grow-only)
+	unsigned long long *d_count;        // hit counter of a batch whose rows go straight to the caller's memory
+	bool ready;                         // device buffers allocated for `chunk`
+	bool staged;                        // ... and the pinned staging of the placement path as well
+	bool streams;                       // streams and events exist (they outlive a change of chunk size)
+	// the small-batch path (rtk_trace_ray) has its own few kilobytes
+	cudaStream_t sm_st;
+	float4 *sm_d_rays, *sm_d_h16; uint32_t *sm_d_rows; unsigned char *sm_d_mask;
+	unsigned char *sm_h_rows, *sm_h_mask;
+};
+
+struct batch_job;
+struct dev_ctx {
+	int device;                         // CUDA ordinal
+	pthread_mutex_t lock;               // one host batch at a time per device
+	host_stage stage;
+	// worker thread: runs this device's share of a multi-device batch (the caller's thread runs the first share)
+	pthread_t thread; bool thread_up, quit;
+	pthread_mutex_t jm; pthread_cond_t jc;
+	batch_job *job; bool job_done;
+};
+static dev_ctx g_ctx[RTKD_MAX_DEVICES];
+static int g_ndev = 0;
+static pthread_mutex_t g_init_lock = PTHREAD_MUTEX_INITIALIZER;
+
+static int bind_index(int k)
 {
-	if (g_device == device && g_sm_count) { CK(cudaSetDevice(device)); return RTKD_OK; }   // another host thread binding itself
+	int cur = -1;
+	if (cudaGetDevice(&cur) != cudaSuccess || cur != g_ctx[k].device) CK(cudaSetDevice(g_ctx[k].device));
+	return RTKD_OK;
+}
+
+static void *ctx_worker(void *arg);
+static void stage_shutdown(dev_ctx &X);          // host-batch staging (defined with the pipeline below)
+
+static int init_devices_locked(const int *devices, int n)
+{
 	int count = 0;
 	cudaError_t e = cudaGetDeviceCount(&count);
 	if (e != cudaSuccess || count <= 0) {
@@ -62,12 +128,62 @@ extern "C" int rtkd_init(int device)
 		               e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
 		return RTKD_ERR_NO_DEVICE;
 	}
-	if (device < 0 || device >= count) { rtkd_set_error("device %d out of range (0..%d)", device, count - 1); return RTKD_ERR_ARGUMENT; }
-	CK(cudaSetDevice(device));
-	cudaDeviceProp prop;
-	CK(cudaGetDeviceProperties(&prop, device));
-	g_sm_count = prop.multiProcessorCount;
-	g_l2_bytes = (size_t)prop.l2CacheSize;
+	if (n < 1 || n > RTKD_MAX_DEVICES || !devices) { rtkd_set_error("device list must name 1..%d devices", RTKD_MAX_DEVICES); return RTKD_ERR_ARGUMENT; }
+	for (int i = 0; i < n; i++) {
+		if (devices[i] < 0 || devices[i] >= count) { rtkd_set_error("device %d out of range (0..%d)", devices[i], count - 1); return RTKD_ERR_ARGUMENT; }
+		// (test hook: RTK_B200_TEST_DUP_DEVICES=1 lets one physical device appear several times, so that the
+		// whole multi-device layer -- replicas, worker threads, range split -- runs on a one-GPU box)
+		const char *dup = getenv("RTK_B200_TEST_DUP_DEVICES");
+		for (int j = 0; j < i; j++) if (devices[j] == devices[i] && !(dup && atoi(dup))) { rtkd_set_error("device %d named twice", devices[i]); return RTKD_ERR_ARGUMENT; }
+	}
+	if (g_ndev) {
+		// already up: the same list is a no-op (another host thread binding itself), a different one is refused
+		bool same = n == g_ndev;
+		for (int i = 0; same && i < n; i++) same = g_ctx[i].device == devices[i];
+		if (same) return bind_index(0);
+		rtkd_set_error("rtk_b200 is already bound to %d device(s) starting at device %d: call rtk_cuda_shutdown() first", g_ndev, g_ctx[0].device);
+		return RTKD_ERR_ARGUMENT;
+	}
+	int sm = 0;
+	size_t l2 = 0;
+	for (int i = 0; i < n; i++) {
+		cudaDeviceProp prop;
+		CK(cudaSetDevice(devices[i]));
+		CK(cudaGetDeviceProperties(&prop, devices[i]));
+		if (i == 0) { sm = prop.multiProcessorCount; l2 = (size_t)prop.l2CacheSize; }
+		else if (prop.multiProcessorCount != sm) { rtkd_set_error("devices %d and %d differ (%d vs %d SMs): the device list must be homogeneous", devices[0], devices[i], sm, prop.multiProcessorCount); return RTKD_ERR_ARGUMENT; }
+#ifndef RTK_SIMT_EMU
+		{
+			// keep freed scratch in the stream-ordered pool: the build allocates its temporaries
+			// with cudaMallocAsync on every (re)build
+			cudaMemPool_t pool;
+			if (cudaDeviceGetDefaultMemPool(&pool, devices[i]) == cudaSuccess) {
+				unsigned long long thr = ~0ull;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+			}
+		}
+#endif
+		// L2 persistence: the traversal working set (nodes + leaf slots) gets a persisting access-policy
+		// window so that the ray / hit streams do not evict it
+		int maxp = 0, maxw = 0;
+		if (cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, devices[i]) == cudaSuccess && maxp > 0) {
+			cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
+			cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, devices[i]);
+			if (i == 0) { g_l2_window_max = (size_t)(maxw > 0 ? maxw : 0); g_l2_setaside = (size_t)maxp; }
+		}
+		cudaGetLastError();
+	}
+	// peers: replicas are copied device to device (NVLink when the devices are peers)
+	for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) if (i != j) {
+		int can = 0;
+		if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can) {
+			cudaSetDevice(devices[i]);
+			cudaDeviceEnablePeerAccess(devices[j], 0);
+			cudaGetLastError();                         // "already enabled" is fine
+		}
+	}
+	CK(cudaSetDevice(devices[0]));
+	g_sm_count = sm; g_l2_bytes = l2;
 	{
 		const char *e = getenv("RTK_B200_LANES");          // experiment knob: lanes per ray
 		if (e && (atoi(e) == 8 || atoi(e) == 4 || atoi(e) == 2)) g_trace_lanes = atoi(e);
@@ -77,6 +193,9 @@ extern "C" int rtkd_init(int device)
 		if (e) g_trace_pd = atoi(e) != 0;
 		if (g_trace_lanes == 8) g_trace_pd = 0;
 	}
+	{ const char *e = getenv("RTK_B200_L2_PERSIST"); if (e) g_l2_persist = atoi(e) != 0; }
+	{ const char *e = getenv("RTK_B200_HOST_DIRECT"); if (e) g_host_direct = atoi(e) != 0; }
+	{ const char *e = getenv("RTK_B200_HOST_MIN_SHARE_LOG2"); if (e && atoi(e) >= 7 && atoi(e) <= 30) g_min_share = (size_t)1 << atoi(e); }
 	int ctas = 0;
 	if (g_trace_lanes == 8) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<8, 1, false>, RTK_TRACE_THREADS, 0));
 	else if (g_trace_lanes == 4 && g_trace_pd) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<4, 1, false, false, true>, RTK_TRACE_THREADS, 0));
@@ -84,40 +203,67 @@ extern "C" int rtkd_init(int device)
 	else if (g_trace_pd) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<2, 1, false, false, true>, RTK_TRACE_THREADS, 0));
 	else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_trace<2, 1, false>, RTK_TRACE_THREADS, 0));
 	g_trace_ctas = ctas > 0 ? ctas : 1;
-#ifndef RTK_SIMT_EMU
-	{
-		// keep freed scratch in the stream-ordered pool: the build allocates its temporaries
-		// with cudaMallocAsync on every (re)build
-		cudaMemPool_t pool;
-		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-			unsigned long long thr = ~0ull;
-			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-		}
+	for (int i = 0; i < n; i++) {
+		dev_ctx &X = g_ctx[i];
+		memset(&X, 0, sizeof(X));
+		X.device = devices[i];
+		pthread_mutex_init(&X.lock, NULL);
+		pthread_mutex_init(&X.jm, NULL);
+		pthread_cond_init(&X.jc, NULL);
 	}
-#endif
-	g_device = device;
+
+	__atomic_store_n(&g_ndev, n, __ATOMIC_RELEASE);
+	// one worker per further device; they sleep on a condition variable between batches
+	for (int i = 1; i < n; i++) {
+		if (pthread_create(&g_ctx[i].thread, NULL, ctx_worker, &g_ctx[i]) == 0) g_ctx[i].thread_up = true;
+		else { rtkd_set_error("cannot start the worker thread of device %d", devices[i]); return RTKD_ERR_MEMORY; }
+	}
 	return RTKD_OK;
 }
 
-// Every entry point passes through here (directly or via rtkd_bind_thread): the library is bound to
-// ONE device per process, but CUDA's current device is per host thread and starts at 0 -- a worker
-// thread of the caller that traces against a scene on device 3 must be switched to device 3 first
-// (the reference's rtk_trace_ray is called from many user threads, rtk.h:129).
+extern "C" int rtkd_init_devices(const int *devices, int n)
+{
+	pthread_mutex_lock(&g_init_lock);
+	int r = init_devices_locked(devices, n);
+	pthread_mutex_unlock(&g_init_lock);
+	return r;
+}
+
+extern "C" int rtkd_init(int device) { return rtkd_init_devices(&device, 1); }
+extern "C" int rtkd_device_count(void) { return g_ndev; }
+
+// Every entry point passes through here (directly or via rtkd_bind_thread): CUDA's current device is
+// per host thread and starts at 0 -- a worker thread of the caller that traces against a scene on
+// device 3 must be switched to device 3 first (the reference's rtk_trace_ray is called from many user
+// threads, rtk.h:129).
 static int ensure_init(void)
 {
-	if (!g_sm_count) return rtkd_init(0);
-	int cur = -1;
-	if (cudaGetDevice(&cur) != cudaSuccess || cur != g_device) CK(cudaSetDevice(g_device));
-	return RTKD_OK;
+	if (!__atomic_load_n(&g_ndev, __ATOMIC_ACQUIRE)) { int d = 0; return rtkd_init_devices(&d, 1); }
+	return bind_index(0);
 }
 extern "C" int rtkd_bind_thread(void) { return ensure_init(); }
 
-static void stage_shutdown(void);          // host-batch staging (defined with the pipeline below)
 extern "C" void rtkd_shutdown(void)
 {
-	// scenes are the caller's to free first; what the library itself holds on the device goes here
-	if (g_sm_count) { ensure_init(); cudaDeviceSynchronize(); stage_shutdown(); }
-	g_device = -1; g_sm_count = 0;
+	// scenes are the caller's to free first; what the library itself holds on the devices goes here
+	pthread_mutex_lock(&g_init_lock);
+	const int n = g_ndev;
+	for (int i = 1; i < n; i++) {
+		dev_ctx &X = g_ctx[i];
+		if (!X.thread_up) continue;
+		pthread_mutex_lock(&X.jm); X.quit = true; pthread_cond_broadcast(&X.jc); pthread_mutex_unlock(&X.jm);
+		pthread_join(X.thread, NULL);
+		X.thread_up = false;
+	}
+	for (int i = 0; i < n; i++) {
+		dev_ctx &X = g_ctx[i];
+		if (cudaSetDevice(X.device) == cudaSuccess) { cudaDeviceSynchronize(); stage_shutdown(X); }
+		pthread_mutex_destroy(&X.lock); pthread_mutex_destroy(&X.jm); pthread_cond_destroy(&X.jc);
+	}
+	if (n) cudaSetDevice(g_ctx[0].device);
+	g_sm_count = 0;
+	__atomic_store_n(&g_ndev, 0, __ATOMIC_RELEASE);
+	pthread_mutex_unlock(&g_init_lock);
 }
 
 extern "C" int rtkd_reserve_sms(int sms)
@@ -137,6 +283,31 @@ extern "C" int rtkd_device_info(int *sm_count, size_t *l2_bytes, int *ctas_per_s
 	if (l2_bytes) *l2_bytes = g_l2_bytes;
 	if (ctas_per_sm) *ctas_per_sm = g_trace_ctas;
 	if (threads_per_cta) *threads_per_cta = RTK_TRACE_THREADS;
+	return RTKD_OK;
+}
+
+extern "C" int rtkd_debug_limit_stack(int entries) { g_stack_limit = entries > 0 ? entries : 0; return RTKD_OK; }
+
+// page-locked host memory that every device of the list can read and write in place
+extern "C" void *rtkd_host_alloc(size_t bytes)
+{
+	if (ensure_init()) return NULL;
+	void *p = NULL;
+	CKP(cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable | cudaHostAllocMapped));
+	return p;
+}
+extern "C" void rtkd_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" int rtkd_host_register(void *p, size_t bytes)
+{
+	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
+	if (!p || !bytes) { rtkd_set_error("nothing to register"); return RTKD_ERR_ARGUMENT; }
+	CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+	return RTKD_OK;
+}
+extern "C" int rtkd_host_unregister(void *p)
+{
+	if (!p) return RTKD_OK;
+	CK(cudaHostUnregister(p));
 	return RTKD_OK;
 }
 
@@ -189,22 +360,142 @@ extern "C" int rtkd_read_bandwidth(size_t bytes, int passes, double *gbs)
 	return RTKD_OK;
 }
 
+// Random-gather probe: the access pattern of the traversal, not of a copy.  Every warp reads
+// `record_bytes`-sized records (256 = a wide node: 8 lanes x LDG.256; 128 = one leaf-slot line: 8 lanes
+// x LDG.128) at hashed offsets of a `bytes`-sized buffer, four independent records in flight per lane
+// group.  With the buffer inside the L2 this is the L2 bandwidth the traversal can hope for, which is
+// what roofline.l2 divides by; a streaming probe flatters that denominator.
+__global__ void __launch_bounds__(256) k_gather_probe(const float4 *buf, uint32_t nrec, uint32_t rec16, int iters, float *sink)
+{
+	float acc = 0.0f;
+	const uint32_t lane = threadIdx.x & 31, sub = lane & 7, grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+	uint32_t x = grp * 0x9E3779B9u + 0x7F4A7C15u;
+	for (int it = 0; it < iters; it++) {
+		float4 a[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			x ^= x << 13; x ^= x >> 17; x ^= x << 5;                       // xorshift32, one record per 8 lanes
+			const float4 *r = buf + (size_t)(x % nrec) * rec16;
+			a[j] = __ldg(r + sub);
+			if (rec16 > 8) { float4 b = __ldg(r + 8 + sub); a[j].x += b.y; }
+		}
+		acc += (a[0].x + a[1].y) + (a[2].z + a[3].w);
+	}
+	if (acc == 123.456f) *sink = acc;
+}
+
+extern "C" int rtkd_gather_bandwidth(size_t bytes, size_t record_bytes, int passes, double *gbs)
+{
+	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
+	if (bytes < 65536 || (record_bytes != 128 && record_bytes != 256) || passes < 1 || !gbs) { rtkd_set_error("bad probe arguments"); return RTKD_ERR_ARGUMENT; }
+	float4 *buf = NULL;
+	float *sink = NULL;
+	struct dev_free { void *p = NULL; ~dev_free() { if (p) cudaFree(p); } } buf_guard, sink_guard;
+	CK(cudaMalloc(&buf, bytes));
+	buf_guard.p = buf;
+	CK(cudaMalloc(&sink, 4));
+	sink_guard.p = sink;
+	CK(cudaMemset(buf, 0, bytes));
+	event_pair ev;
+	CK(cudaEventCreate(&ev.e0)); CK(cudaEventCreate(&ev.e1));
+	const uint32_t nrec = (uint32_t)(bytes / record_bytes), rec16 = (uint32_t)(record_bytes / 16);
+	const unsigned grid = (unsigned)g_sm_count * 8;
+	const int iters = 64;
+	RTK_LAUNCH(k_gather_probe, grid, 256, 0, (const float4*)buf, nrec, rec16, iters, sink);      // warm the cache
+	CK(cudaEventRecord(ev.e0, 0));
+	for (int p = 0; p < passes; p++) RTK_LAUNCH(k_gather_probe, grid, 256, 0, (const float4*)buf, nrec, rec16, iters, sink);
+	CK(cudaEventRecord(ev.e1, 0));
+	CK(cudaEventSynchronize(ev.e1));
+	float ms = 0.0f;
+	CK(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+	const double total = (double)grid * 256 / 8 * iters * 4 * (double)record_bytes * passes;
+	*gbs = ms > 0.0f ? total / (ms * 1e-3) / 1e9 : 0.0;
+	return RTKD_OK;
+}
+
+// Host-link probe: the ceiling of the host-buffer path.  On each of the first `ndev` devices of the list
+// one copy stream moves `bytes_per_device` from pinned host memory up (dir & 1) and another one the
+// same amount down (dir & 2), all devices at once, `passes` times; the result is the aggregate GB/s of
+// the directions asked for (PCIe links, root complexes and host DRAM all included).
+extern "C" int rtkd_link_bandwidth(int ndev, size_t bytes_per_device, int dir, int passes, double *gbs)
+{
+	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
+	if (ndev < 1 || ndev > g_ndev || !bytes_per_device || !(dir & 3) || passes < 1 || !gbs) { rtkd_set_error("bad link probe arguments"); return RTKD_ERR_ARGUMENT; }
+	struct leg { void *h_up = NULL, *h_dn = NULL, *d_up = NULL, *d_dn = NULL; cudaStream_t su = NULL, sd = NULL; };
+	leg L[RTKD_MAX_DEVICES];
+	int rc = RTKD_OK;
+	cudaError_t e = cudaSuccess;
+	for (int i = 0; i < ndev && e == cudaSuccess; i++) {
+		e = cudaSetDevice(g_ctx[i].device);
+		if (e == cudaSuccess && (dir & 1)) { e = cudaHostAlloc(&L[i].h_up, bytes_per_device, cudaHostAllocPortable); if (e == cudaSuccess) e = cudaMalloc(&L[i].d_up, bytes_per_device); }
+		if (e == cudaSuccess && (dir & 2)) { e = cudaHostAlloc(&L[i].h_dn, bytes_per_device, cudaHostAllocPortable); if (e == cudaSuccess) e = cudaMalloc(&L[i].d_dn, bytes_per_device); }
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&L[i].su, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&L[i].sd, cudaStreamNonBlocking);
+		if (e == cudaSuccess && L[i].h_up) memset(L[i].h_up, 1, bytes_per_device);      // touch: the pages exist before the clock starts
+		if (e == cudaSuccess && L[i].h_dn) memset(L[i].h_dn, 1, bytes_per_device);
+	}
+	double best = 0.0;
+	for (int rep = 0; rep < 2 && e == cudaSuccess; rep++) {          // first repetition warms up
+		struct timespec t0, t1;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		for (int p = 0; p < passes && e == cudaSuccess; p++)
+			for (int i = 0; i < ndev && e == cudaSuccess; i++) {
+				e = cudaSetDevice(g_ctx[i].device);
+				if (e == cudaSuccess && (dir & 1)) e = cudaMemcpyAsync(L[i].d_up, L[i].h_up, bytes_per_device, cudaMemcpyHostToDevice, L[i].su);
+				if (e == cudaSuccess && (dir & 2)) e = cudaMemcpyAsync(L[i].h_dn, L[i].d_dn, bytes_per_device, cudaMemcpyDeviceToHost, L[i].sd);
+			}
+		for (int i = 0; i < ndev && e == cudaSuccess; i++) {
+			e = cudaSetDevice(g_ctx[i].device);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(L[i].su);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(L[i].sd);
+		}
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		const double sec = (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9;
+		const double total = (double)bytes_per_device * passes * ndev * (((dir & 1) ? 1 : 0) + ((dir & 2) ? 1 : 0));
+		if (sec > 0.0) best = total / sec / 1e9;
+	}
+	if (e != cudaSuccess) { rtkd_set_error("link probe: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; }
+	for (int i = 0; i < ndev; i++) {
+		cudaSetDevice(g_ctx[i].device);
+		if (L[i].su) cudaStreamDestroy(L[i].su);
+		if (L[i].sd) cudaStreamDestroy(L[i].sd);
+		cudaFree(L[i].d_up); cudaFree(L[i].d_dn);
+		cudaFreeHost(L[i].h_up); cudaFreeHost(L[i].h_dn);
+	}
+	bind_index(0);
+	*gbs = best;
+	return rc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // scene lifetime
 // ---------------------------------------------------------------------------------------------
 
-extern "C" rtkd_scene *rtkd_scene_new(uint32_t num_tris, uint32_t num_meshes, const uint32_t *mesh_first)
+static rtkd_scene *scene_alloc_on(int dev_index, uint32_t num_tris, uint32_t num_meshes, const uint32_t *mesh_first)
 {
-	if (ensure_init()) return NULL;
+	if (bind_index(dev_index)) return NULL;
 	rtkd_scene *s = (rtkd_scene*)calloc(1, sizeof(rtkd_scene));
 	if (!s) { rtkd_set_error("out of host memory"); return NULL; }
-	s->id = ((uint64_t)time(NULL) << 20) ^ (__atomic_fetch_add(&g_next_id, 1, __ATOMIC_RELAXED) * 0x9E3779B97F4A7C15ull);   // scenes may be built from several host threads
+	s->dev_index = dev_index;
 	s->num_tris = num_tris; s->num_meshes = num_meshes;
 	s->h_mesh_first = (uint32_t*)malloc(sizeof(uint32_t) * (num_meshes + 1));
+	pthread_mutex_t *m = (pthread_mutex_t*)malloc(sizeof(pthread_mutex_t));
+	if (!s->h_mesh_first || !m) { free(s->h_mesh_first); free(m); free(s); rtkd_set_error("out of host memory"); return NULL; }
+	pthread_mutex_init(m, NULL);
+	s->slot_lock = m;
 	memcpy(s->h_mesh_first, mesh_first, sizeof(uint32_t) * (num_meshes + 1));
 	cudaError_t e = cudaMalloc((float4**)&s->tri_orig, sizeof(float4) * 3 * (size_t)(num_tris ? num_tris : 1));
 	if (e == cudaSuccess) e = cudaMalloc((uint32_t**)&s->mesh_first, sizeof(uint32_t) * (num_meshes + 1));
 	if (e == cudaSuccess) e = cudaMemcpy(s->mesh_first, mesh_first, sizeof(uint32_t) * (num_meshes + 1), cudaMemcpyHostToDevice);
+	// the status word lives in pinned host memory the device writes to directly: the host reads it
+	// without a copy once it has synchronised with the query
+	if (e == cudaSuccess) e = cudaHostAlloc((uint32_t**)&s->h_status, 64, cudaHostAllocPortable | cudaHostAllocMapped);
+	if (e == cudaSuccess) {
+		*s->h_status = 0;
+		cudaPointerAttributes a;
+		if (cudaPointerGetAttributes(&a, s->h_status) == cudaSuccess && a.devicePointer) s->d_status = (uint32_t*)a.devicePointer;
+		else s->d_status = s->h_status;
+	}
 	if (e != cudaSuccess) {
 		rtkd_set_error("scene allocation failed: %s", cudaGetErrorString(e));
 		rtkd_scene_free(s);
@@ -213,24 +504,133 @@ extern "C" rtkd_scene *rtkd_scene_new(uint32_t num_tris, uint32_t num_meshes, co
 	return s;
 }
 
+extern "C" rtkd_scene *rtkd_scene_new(uint32_t num_tris, uint32_t num_meshes, const uint32_t *mesh_first)
+{
+	if (ensure_init()) return NULL;
+	rtkd_scene *s = scene_alloc_on(0, num_tris, num_meshes, mesh_first);
+	if (s) s->id = ((uint64_t)time(NULL) << 20) ^ (__atomic_fetch_add(&g_next_id, 1, __ATOMIC_RELAXED) * 0x9E3779B97F4A7C15ull);   // scenes may be built from several host threads
+	return s;
+}
+
+static void scene_free_slots(rtkd_scene *s)
+{
+	for (int k = 0; k < RTKD_TRACE_SLOTS; k++) {
+		rtkd_trace_slot &T = s->slot[k];
+		if (T.scratch) cudaFree(T.scratch);
+		if (T.overflow) cudaFree(T.overflow);
+		if (T.done) cudaEventDestroy((cudaEvent_t)T.done);
+		memset(&T, 0, sizeof(T));
+	}
+}
+
 extern "C" void rtkd_scene_free(rtkd_scene *s)
 {
 	if (!s) return;
-	if (g_sm_count) ensure_init();           // the freeing thread may not be the one that built the scene
+	for (int k = 1; k < RTKD_MAX_DEVICES; k++) if (s->replica[k]) { rtkd_scene_free(s->replica[k]); s->replica[k] = NULL; }
+	if (g_ndev && s->dev_index < g_ndev) bind_index(s->dev_index);      // the freeing thread may not be the one that built the scene
 	cudaDeviceSynchronize();
 	if (s->tri_orig) cudaFree(s->tri_orig);
-	if (s->tv0) cudaFree(s->tv0);
-	if (s->tv1) cudaFree(s->tv1);
-	if (s->tv2) cudaFree(s->tv2);
-	if (s->nodes) cudaFree(s->nodes);
+	if (s->arena) cudaFree(s->arena);
 	if (s->node_level) cudaFree(s->node_level);
 	if (s->mesh_first) cudaFree(s->mesh_first);
-	if (s->scratch) cudaFree(s->scratch);
-	if (s->overflow) cudaFree(s->overflow);
+	scene_free_slots(s);
+	if (s->h_status) cudaFreeHost(s->h_status);
 	if (s->hit16) cudaFree(s->hit16);
 	if (s->filter_bits) cudaFree(s->filter_bits);
+	if (s->slot_lock) { pthread_mutex_destroy((pthread_mutex_t*)s->slot_lock); free(s->slot_lock); }
 	free(s->h_mesh_first);
 	free(s);
+	if (g_ndev) bind_index(0);
+}
+
+// nodes | tv0 | tv1 | tv2 in one allocation (256-byte aligned sections); grows with some slack so that
+// rebuilds of a deforming mesh rarely need a new allocation
+static size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
+static int scene_arena_layout(rtkd_scene *s, uint32_t num_nodes, uint32_t num_tv, bool slack)
+{
+	const size_t nb = a256(256 * (size_t)(num_nodes ? num_nodes : 1)), tb = a256(16 * (size_t)(num_tv ? num_tv : 8));
+	const size_t need = nb + 3 * tb;
+	if (!s->arena || s->arena_cap < need) {
+		if (s->arena) cudaFree(s->arena);
+		s->arena = NULL; s->arena_cap = 0;
+		const size_t cap = slack ? need + need / 16 + 4096 : need;
+		CK(cudaMalloc((unsigned char**)&s->arena, cap));
+		s->arena_cap = cap;
+	}
+	unsigned char *b = (unsigned char*)s->arena;
+	s->nodes = b; s->tv0 = b + nb; s->tv1 = b + nb + tb; s->tv2 = b + nb + 2 * tb;
+	s->arena_used = need;
+	return RTKD_OK;
+}
+
+// Replicas: the scene as built on the first device, copied array by array to every further device of
+// the list (device-to-device; NVLink between peers).  A 10M-triangle scene is 1.1 GB, i.e. a couple of
+// milliseconds per replica, all replicas in flight at once -- cheaper than building it again on every
+// device (15 ms) or pushing the meshes through PCIe once more.
+extern "C" int rtkd_sync_replicas(rtkd_scene *s)
+{
+	if (g_ndev <= 1 || s->dev_index != 0) return RTKD_OK;
+	pthread_mutex_t *m = (pthread_mutex_t*)s->slot_lock;
+	pthread_mutex_lock(m);
+	if (s->replica_epoch == s->epoch && s->replica[1]) { pthread_mutex_unlock(m); return RTKD_OK; }
+	int rc = RTKD_OK;
+	const int src = g_ctx[0].device;
+	cudaStream_t st[RTKD_MAX_DEVICES] = { NULL };
+	for (int k = 1; k < g_ndev && rc == RTKD_OK; k++) {
+		rtkd_scene *r = s->replica[k];
+		if (r && (r->num_tris != s->num_tris || r->num_meshes != s->num_meshes)) { rtkd_scene_free(r); r = s->replica[k] = NULL; }
+		if (!r) {
+			r = scene_alloc_on(k, s->num_tris, s->num_meshes, s->h_mesh_first);
+			if (!r) { rc = RTKD_ERR_MEMORY; break; }
+			s->replica[k] = r;
+		}
+		if (bind_index(k)) { rc = RTKD_ERR_CUDA; break; }
+		r->id = s->id;
+		r->num_nodes = s->num_nodes; r->num_leaves = s->num_leaves; r->depth = s->depth; r->build_mode = s->build_mode;
+		r->num_tv = s->num_tv;
+		memcpy(r->bounds_min, s->bounds_min, 12); memcpy(r->bounds_max, s->bounds_max, 12);
+		r->abs_max = s->abs_max; r->sah_cost = s->sah_cost;
+		r->build_device_ms = s->build_device_ms; r->build_total_ms = s->build_total_ms;
+		*r->h_status = 0;
+		rc = scene_arena_layout(r, s->num_nodes, s->num_tv, false);
+		if (rc) break;
+		const int dst = g_ctx[k].device;
+		cudaError_t e = cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking);
+		if (e == cudaSuccess && s->num_tris) e = cudaMemcpyPeerAsync(r->tri_orig, dst, s->tri_orig, src, 48 * (size_t)s->num_tris, st[k]);
+		if (e == cudaSuccess && s->arena_used && s->arena) e = cudaMemcpyPeerAsync(r->arena, dst, s->arena, src, s->arena_used, st[k]);
+		if (e != cudaSuccess) { rtkd_set_error("scene replication to device %d failed: %s", dst, cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; }
+	}
+	for (int k = 1; k < g_ndev; k++) if (st[k]) {
+		bind_index(k);
+		if (cudaStreamSynchronize(st[k]) != cudaSuccess && rc == RTKD_OK) { rtkd_set_error("scene replication failed"); rc = RTKD_ERR_CUDA; }
+		cudaStreamDestroy(st[k]);
+	}
+	bind_index(0);
+	if (rc == RTKD_OK) s->replica_epoch = s->epoch;
+	pthread_mutex_unlock(m);
+	return rc;
+}
+
+extern "C" rtkd_scene *rtkd_scene_for_pointer(rtkd_scene *s, const void *p)
+{
+	if (g_ndev <= 1) { if (bind_index(0)) return NULL; return s; }
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); rtkd_set_error("cannot tell which device owns the buffer"); return NULL; }
+	if (a.type != cudaMemoryTypeDevice) { if (bind_index(0)) return NULL; return s; }      // managed / mapped host memory: the first device serves it
+	int k = -1;
+	for (int i = 0; i < g_ndev; i++) if (g_ctx[i].device == a.device) k = i;
+	if (k < 0) { rtkd_set_error("the buffer lives on device %d, which is not in the library's device list", a.device); return NULL; }
+	if (k == 0) { if (bind_index(0)) return NULL; return s; }
+	if (rtkd_sync_replicas(s)) return NULL;
+	if (bind_index(k)) return NULL;
+	return s->replica[k];
+}
+
+extern "C" uint32_t rtkd_scene_status(rtkd_scene *s)
+{
+	uint32_t v = s->h_status ? *(volatile uint32_t*)s->h_status : 0u;
+	for (int k = 1; k < RTKD_MAX_DEVICES; k++) if (s->replica[k] && s->replica[k]->h_status) v |= *(volatile uint32_t*)s->replica[k]->h_status;
+	return v;
 }
 
 extern "C" void *rtkd_upload(const void *host, size_t bytes, void *stream)
@@ -272,6 +672,8 @@ extern "C" int rtkd_decode_mesh_xf(rtkd_scene *s, uint32_t first_prim, uint32_t 
                                    const float *xf12, void *stream)
 {
 	if (!ntris) return RTKD_OK;
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
+	s->epoch++;
 	if ((size_t)first_prim + ntris > s->num_tris) { rtkd_set_error("decode range outside the scene"); return RTKD_ERR_ARGUMENT; }
 	rtkd_decode_args a;
 	a.pos = (const unsigned char*)d_pos; a.idx = (const unsigned char*)d_idx;
@@ -408,6 +810,7 @@ static int apply_filter(rtkd_scene *s, cudaStream_t st)
 
 extern "C" int rtkd_set_filter(rtkd_scene *s, const void *bits, size_t num_words, int on_device, void *stream)
 {
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	cudaStream_t st = (cudaStream_t)stream;
 	const size_t words = ((size_t)s->num_tris + 31) / 32;
 	if (!bits) {
@@ -418,6 +821,7 @@ extern "C" int rtkd_set_filter(rtkd_scene *s, const void *bits, size_t num_words
 		int r = apply_filter(s, st);
 		CK(cudaStreamSynchronize(st));
 		cudaFree(old);
+		s->epoch++;
 		return r;
 	}
 	if (num_words < words) { rtkd_set_error("triangle filter needs %zu words for %u triangles, got %zu", words, s->num_tris, num_words); return RTKD_ERR_ARGUMENT; }
@@ -427,11 +831,13 @@ extern "C" int rtkd_set_filter(rtkd_scene *s, const void *bits, size_t num_words
 	int r = apply_filter(s, st);
 	// filters change rarely: return with the pass done, whatever stream the next query uses
 	CK(cudaStreamSynchronize(st));
+	s->epoch++;
 	return r;
 }
 
 extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 {
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	cudaStream_t st = (cudaStream_t)stream;
 	const uint32_t n = s->num_tris;
 	s->build_mode = (uint32_t)mode;
@@ -541,30 +947,22 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		CK(cudaMemcpyAsync(&h_cost, B.d_cost, sizeof(double), cudaMemcpyDeviceToHost, st));
 	}
 
-	// node array: reuse the previous allocation when it is large enough
-	if (!s->nodes || s->nodes_cap < num_nodes) {
-		if (s->nodes) cudaFree(s->nodes);
-		s->nodes = NULL;
-		CK(cudaMalloc((float4**)&s->nodes, sizeof(float4) * 16 * (size_t)num_nodes));
+	// node array and traversal triangles (one 8-entry slot per leaf, sized now that the leaves are
+	// counted): one arena, reused when it is large enough
+	const uint32_t num_tv = num_leaves * RTK_LEAF_MAX;
+	{
+		int ar = scene_arena_layout(s, num_nodes, num_tv, true);
+		if (ar) return ar;
+	}
+	if (!s->node_level || s->node_level_cap < num_nodes) {
 		if (s->node_level) cudaFree(s->node_level);
 		s->node_level = NULL;
-		CK(cudaMalloc((unsigned char**)&s->node_level, (size_t)num_nodes));
-		s->nodes_cap = num_nodes;
+		const uint32_t cap = num_nodes + num_nodes / 16 + 64;
+		CK(cudaMalloc((unsigned char**)&s->node_level, (size_t)cap));
+		s->node_level_cap = cap;
 	}
-	if (!s->node_level) CK(cudaMalloc((unsigned char**)&s->node_level, (size_t)s->nodes_cap));
 	CK(cudaMemcpyAsync(s->node_level, B.node_level, (size_t)num_nodes, cudaMemcpyDeviceToDevice, st));
 	CK(cudaMemcpyAsync(s->nodes, B.wide, sizeof(float4) * 16 * (size_t)num_nodes, cudaMemcpyDeviceToDevice, st));
-	// traversal triangles: one 8-entry slot per leaf, sized now that the leaves are counted
-	const uint32_t num_tv = num_leaves * RTK_LEAF_MAX;
-	if (!s->tv0 || s->tv_cap < num_tv) {
-		if (s->tv0) { cudaFree(s->tv0); cudaFree(s->tv1); cudaFree(s->tv2); }
-		s->tv0 = s->tv1 = s->tv2 = NULL;
-		const uint32_t cap = num_tv + num_tv / 16 + 64;        // rebuilds of a deforming mesh rarely need a new allocation
-		CK(cudaMalloc((float4**)&s->tv0, sizeof(float4) * (size_t)cap));
-		CK(cudaMalloc((float4**)&s->tv1, sizeof(float4) * (size_t)cap));
-		CK(cudaMalloc((float4**)&s->tv2, sizeof(float4) * (size_t)cap));
-		s->tv_cap = cap;
-	}
 	RTK_LAUNCH(k_emit_leaves, (num_tv + 255) / 256, 256, st, tri, svals, (const uint2*)B.leaf_list, num_leaves,
 	           (float4*)s->tv0, (float4*)s->tv1, (float4*)s->tv2); CK_LAUNCH();
 	s->num_tv = num_tv;
@@ -577,6 +975,8 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 
 	s->num_nodes = num_nodes; s->num_leaves = num_leaves; s->depth = depth;
 	s->build_device_ms = ms;
+	s->epoch++;
+	if (s->h_status) *s->h_status = 0;          // a new tree: whatever the old one could not hold is history
 	float amax = 0.0f;
 	for (int k = 0; k < 3; k++) {
 		uint32_t u = h_bounds[k], v = h_bounds[3 + k];
@@ -600,6 +1000,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 // new scene bounds.  Valid after rtkd_decode_mesh rewrote the corners of a scene built here.
 extern "C" int rtkd_refit(rtkd_scene *s, void *stream)
 {
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	cudaStream_t st = (cudaStream_t)stream;
 	if (!s->num_tris || !s->num_nodes) return RTKD_OK;
 	if (!s->node_level) { rtkd_set_error("this scene carries no level table (loaded from a blob): rebuild it instead"); return RTKD_ERR_SCENE; }
@@ -633,6 +1034,8 @@ extern "C" int rtkd_refit(rtkd_scene *s, void *stream)
 	float ms = 0.0f;
 	CK(cudaEventElapsedTime(&ms, e0, e1));
 	s->build_device_ms = ms;
+	s->epoch++;
+	if (s->h_status) *s->h_status = 0;
 	float amax = 0.0f;
 	for (int k = 0; k < 3; k++) {
 		uint32_t u = h_bounds[k], v = h_bounds[3 + k];
@@ -661,48 +1064,85 @@ static void fill_arrays(const rtkd_scene *s, rtkd_arrays &a)
 	a.abs_max = s->abs_max;
 }
 
-static int ensure_scratch(rtkd_scene *s)
+// A traversal launch takes one of the scene's slots (ray cursor, statistics, spill slab of the stack).
+// slot_acquire returns with the scene's slot lock HELD; slot_release records the slot's event on the
+// stream and drops the lock, so that nobody can pick the slot between the choice and the launch.
+static int slot_acquire(rtkd_scene *s, cudaStream_t st, rtkd_trace_slot **out)
 {
-	// scratch layout: +0 ray cursor | +64 stats[6] | +128 hit counter | +192 sticky error flags
-	if (!s->scratch) {
-		CK(cudaMalloc((unsigned char**)&s->scratch, 256));
-		CK(cudaMemset(s->scratch, 0, 256));
-	}
-	size_t groups = (size_t)g_sm_count * g_trace_ctas * RTK_TRACE_WARPS * (32 / g_trace_lanes);
-	size_t need = (size_t)7 * s->depth + 8;
+	pthread_mutex_t *m = (pthread_mutex_t*)s->slot_lock;
+	const size_t groups = (size_t)g_sm_count * g_trace_ctas * RTK_TRACE_WARPS * (32 / g_trace_lanes);
+	const size_t need = (size_t)7 * s->depth + 8;            // at most 7 pushes per level of wide nodes
 	size_t entries = need > RTK_STACK_SMEM ? need - RTK_STACK_SMEM : 0;
 	if (entries < 8) entries = 8;
-	if (!s->overflow || s->overflow_entries < entries || s->overflow_groups < groups) {
-		if (s->overflow) cudaFree(s->overflow);
-		s->overflow = NULL;
-		CK(cudaMalloc((uint2**)&s->overflow, sizeof(uint2) * entries * groups));
-		s->overflow_entries = entries; s->overflow_groups = groups;
+	if (g_stack_limit > 0) entries = (size_t)g_stack_limit;
+	pthread_mutex_lock(m);
+	int pick = -1;
+	// (1) the slot this stream used last: stream order protects it
+	for (int k = 0; k < RTKD_TRACE_SLOTS && pick < 0; k++) if (s->slot[k].used && s->slot[k].last_stream == (void*)st) pick = k;
+	// (2) a slot whose last launch has finished  (3) a slot nobody has used yet
+	for (int k = 0; k < RTKD_TRACE_SLOTS && pick < 0; k++) if (s->slot[k].used && cudaEventQuery((cudaEvent_t)s->slot[k].done) == cudaSuccess) pick = k;
+	for (int k = 0; k < RTKD_TRACE_SLOTS && pick < 0; k++) if (!s->slot[k].used) pick = k;
+	cudaGetLastError();                                      // cudaErrorNotReady of the queries above
+	cudaError_t e = cudaSuccess;
+	if (pick < 0) {
+		// (4) every slot is busy on another stream: queue behind one of them
+		static unsigned rr = 0;
+		pick = (int)(__atomic_fetch_add(&rr, 1u, __ATOMIC_RELAXED) % RTKD_TRACE_SLOTS);
+		e = cudaStreamWaitEvent(st, (cudaEvent_t)s->slot[pick].done, 0);
 	}
+	rtkd_trace_slot &T = s->slot[pick];
+	if (e == cudaSuccess && !T.scratch) {
+		e = cudaMalloc((unsigned char**)&T.scratch, 256);
+		if (e == cudaSuccess) e = cudaMemset(T.scratch, 0, 256);
+		cudaEvent_t ev = NULL;
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+		T.done = ev;
+	}
+	if (e == cudaSuccess && (!T.overflow || (g_stack_limit > 0 ? T.overflow_entries != entries : T.overflow_entries < entries) || T.overflow_groups < groups)) {
+		// the tree got deeper since the slab was sized (cudaFree waits for whatever still reads it)
+		if (T.overflow) cudaFree(T.overflow);
+		T.overflow = NULL;
+		e = cudaMalloc((uint2**)&T.overflow, sizeof(uint2) * entries * groups);
+		T.overflow_entries = entries; T.overflow_groups = groups;
+	}
+	if (e != cudaSuccess) {
+		rtkd_set_error("traversal scratch: %s", cudaGetErrorString(e));
+		pthread_mutex_unlock(m);
+		return e == cudaErrorMemoryAllocation ? RTKD_ERR_MEMORY : RTKD_ERR_CUDA;
+	}
+	T.used = 1; T.last_stream = (void*)st;
+	*out = &T;
 	return RTKD_OK;
 }
+static void slot_release(rtkd_scene *s, rtkd_trace_slot *T, cudaStream_t st)
+{
+	cudaEventRecord((cudaEvent_t)T->done, st);
+	pthread_mutex_unlock((pthread_mutex_t*)s->slot_lock);
+}
 
-// one instantiation per (lanes per ray, cull mode, statistics, any-hit, leaf-phase variant)
+// one instantiation per (lanes per ray, cull mode, statistics, any-hit, leaf-phase variant); every launch
+// carries the scene's access-policy window (RTK_LAUNCH_WIN: nodes + leaf slots persist in L2)
 template <int L, bool PD>
-static void launch_trace_l(int cull_mode, bool stats, unsigned grid, cudaStream_t st, const rtkd_trace_args &p)
+static void launch_trace_l(int cull_mode, bool stats, unsigned grid, cudaStream_t st, const rtkd_trace_args &p, void *wb, size_t wn, float wr)
 {
 	const bool c1 = (cull_mode & 1) != 0;
 	if (cull_mode & 2) {
 		// occlusion query (any hit): the output is a byte per ray
-		if (c1) { RTK_LAUNCH((k_trace<L, 1, false, true, PD>), grid, RTK_TRACE_THREADS, st, p); }
-		else { RTK_LAUNCH((k_trace<L, 0, false, true, PD>), grid, RTK_TRACE_THREADS, st, p); }
+		if (c1) { RTK_LAUNCH_WIN((k_trace<L, 1, false, true, PD>), grid, RTK_TRACE_THREADS, st, wb, wn, wr, p); }
+		else { RTK_LAUNCH_WIN((k_trace<L, 0, false, true, PD>), grid, RTK_TRACE_THREADS, st, wb, wn, wr, p); }
 	} else if (stats) {
-		if (c1) { RTK_LAUNCH((k_trace<L, 1, true, false, PD>), grid, RTK_TRACE_THREADS, st, p); }
-		else { RTK_LAUNCH((k_trace<L, 0, true, false, PD>), grid, RTK_TRACE_THREADS, st, p); }
+		if (c1) { RTK_LAUNCH_WIN((k_trace<L, 1, true, false, PD>), grid, RTK_TRACE_THREADS, st, wb, wn, wr, p); }
+		else { RTK_LAUNCH_WIN((k_trace<L, 0, true, false, PD>), grid, RTK_TRACE_THREADS, st, wb, wn, wr, p); }
 	} else {
-		if (c1) { RTK_LAUNCH((k_trace<L, 1, false, false, PD>), grid, RTK_TRACE_THREADS, st, p); }
-		else { RTK_LAUNCH((k_trace<L, 0, false, false, PD>), grid, RTK_TRACE_THREADS, st, p); }
+		if (c1) { RTK_LAUNCH_WIN((k_trace<L, 1, false, false, PD>), grid, RTK_TRACE_THREADS, st, wb, wn, wr, p); }
+		else { RTK_LAUNCH_WIN((k_trace<L, 0, false, false, PD>), grid, RTK_TRACE_THREADS, st, wb, wn, wr, p); }
 	}
 }
-static void launch_trace(int lanes, int cull_mode, bool stats, bool pd, unsigned grid, cudaStream_t st, const rtkd_trace_args &p)
+static void launch_trace(int lanes, int cull_mode, bool stats, bool pd, unsigned grid, cudaStream_t st, const rtkd_trace_args &p, void *wb, size_t wn, float wr)
 {
-	if (lanes == 8) launch_trace_l<8, false>(cull_mode, stats, grid, st, p);
-	else if (lanes == 4) { if (pd) launch_trace_l<4, true>(cull_mode, stats, grid, st, p); else launch_trace_l<4, false>(cull_mode, stats, grid, st, p); }
-	else { if (pd) launch_trace_l<2, true>(cull_mode, stats, grid, st, p); else launch_trace_l<2, false>(cull_mode, stats, grid, st, p); }
+	if (lanes == 8) launch_trace_l<8, false>(cull_mode, stats, grid, st, p, wb, wn, wr);
+	else if (lanes == 4) { if (pd) launch_trace_l<4, true>(cull_mode, stats, grid, st, p, wb, wn, wr); else launch_trace_l<4, false>(cull_mode, stats, grid, st, p, wb, wn, wr); }
+	else { if (pd) launch_trace_l<2, true>(cull_mode, stats, grid, st, p, wb, wn, wr); else launch_trace_l<2, false>(cull_mode, stats, grid, st, p, wb, wn, wr); }
 }
 
 extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, int cull_mode,
@@ -712,38 +1152,59 @@ extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size
 	if (n > 0xfffffff0ull) { rtkd_set_error("batch too large (%zu rays); split it", n); return RTKD_ERR_ARGUMENT; }
 	if (((uintptr_t)d_rays & 15) || (!(cull_mode & 2) && ((uintptr_t)d_hit16 & 15))) { rtkd_set_error("device ray / hit buffers must be 16-byte aligned"); return RTKD_ERR_ARGUMENT; }
 	if ((cull_mode & 2) && stats) { rtkd_set_error("no statistics variant of the occlusion query"); return RTKD_ERR_ARGUMENT; }
-	int r = ensure_scratch(s);
-	if (r) return r;
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	cudaStream_t st = (cudaStream_t)stream;
-	CK(cudaMemsetAsync(s->scratch, 0, 128, st));
+	rtkd_trace_slot *T = NULL;
+	int r = slot_acquire(s, st, &T);
+	if (r) return r;
+	cudaError_t e = cudaMemsetAsync(T->scratch, 0, 128, st);
 	rtkd_trace_args p;
 	fill_arrays(s, p.sc);
 	p.rays = (const float4*)d_rays; p.out = (float4*)d_hit16; p.nrays = (uint32_t)n;
-	p.counter = (uint32_t*)s->scratch; p.err = (uint32_t*)((unsigned char*)s->scratch + 192);
-	p.stats = (unsigned long long*)((unsigned char*)s->scratch + 64);
-	p.overflow = (uint2*)s->overflow; p.ovf_entries = (uint32_t)s->overflow_entries;
+	p.counter = (uint32_t*)T->scratch; p.status = s->d_status;
+	p.stats = (unsigned long long*)((unsigned char*)T->scratch + 64);
+	p.overflow = (uint2*)T->overflow; p.ovf_entries = (uint32_t)T->overflow_entries;
 	// persistent grid: one wave of resident CTAs, never more CTAs than ray batches
 	size_t batches = (n + RTK_RAY_BATCH - 1) / RTK_RAY_BATCH;
 	size_t ctas = (size_t)(g_sm_count - g_reserved_sms) * g_trace_ctas;
 	size_t want = (batches + RTK_TRACE_WARPS - 1) / RTK_TRACE_WARPS;
 	unsigned grid = (unsigned)(want < ctas ? want : ctas);
-	launch_trace(g_trace_lanes, cull_mode, stats != NULL, g_trace_pd != 0, grid, st, p);
-	CK_LAUNCH();
+	// L2 window: the arena (nodes first, then the leaf slots) as far as the device allows
+	void *wb = NULL; size_t wn = 0; float wr = 1.0f;
+	if (g_l2_persist && g_l2_window_max && s->arena && s->arena_used) {
+		wb = s->arena;
+		wn = s->arena_used < g_l2_window_max ? s->arena_used : g_l2_window_max;
+		const size_t setaside = g_l2_setaside;
+		wr = wn <= setaside ? 1.0f : (float)((double)setaside / (double)wn);
+	}
+	if (e == cudaSuccess) {
+		launch_trace(g_trace_lanes, cull_mode, stats != NULL, g_trace_pd != 0, grid, st, p, wb, wn, wr);
+		e = cudaGetLastError();
+	}
+	if (e != cudaSuccess) {
+		rtkd_set_error("k_trace launch: %s", cudaGetErrorString(e));
+		slot_release(s, T, st);
+		return RTKD_ERR_CUDA;
+	}
 	if (stats) {
+		// slow path: the counters are read before the slot can go to anybody else
 		unsigned long long h[8];
-		uint32_t herr = 0;
-		CK(cudaMemcpyAsync(h, p.stats, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost, st));
-		CK(cudaMemcpyAsync(&herr, p.err, sizeof(herr), cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
+		e = cudaMemcpyAsync(h, p.stats, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost, st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		slot_release(s, T, st);
+		if (e != cudaSuccess) { rtkd_set_error("trace statistics: %s", cudaGetErrorString(e)); return RTKD_ERR_CUDA; }
 		stats->rays = n; stats->hits = h[1]; stats->node_visits = h[2]; stats->leaf_visits = h[3];
 		stats->tri_tests = h[4]; stats->stack_max = h[5];
-		if (herr & 2u) { rtkd_set_error("traversal stack exhausted"); return RTKD_ERR_OVERFLOW; }
+		if (*(volatile uint32_t*)s->h_status & 2u) { rtkd_set_error("traversal stack exhausted"); return RTKD_ERR_OVERFLOW; }
+		return RTKD_OK;
 	}
+	slot_release(s, T, st);
 	return RTKD_OK;
 }
 
 extern "C" int rtkd_trace_brute(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, void *stream)
 {
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	if (!n) return RTKD_OK;
 	rtkd_arrays a;
 	fill_arrays(s, a);
@@ -755,14 +1216,11 @@ extern "C" int rtkd_trace_brute(rtkd_scene *s, const void *d_rays, void *d_hit16
 extern "C" int rtkd_resolve(rtkd_scene *s, const void *d_hit16, void *d_hits, void *d_mask, size_t n, void *stream)
 {
 	if (!n) return RTKD_OK;
-	int r = ensure_scratch(s);
-	if (r) return r;
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	rtkd_arrays a;
 	fill_arrays(s, a);
-	unsigned long long *cnt = (unsigned long long*)((unsigned char*)s->scratch + 128);
-	CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), (cudaStream_t)stream));
 	RTK_LAUNCH(k_resolve<false>, (unsigned)((n + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, stream,
-	           a, (const float4*)d_hit16, (uint32_t*)d_hits, (unsigned char*)d_mask, (uint32_t)n, cnt, (uint32_t*)NULL);
+	           a, (const float4*)d_hit16, (uint32_t*)d_hits, (unsigned char*)d_mask, (uint32_t)n, (unsigned long long*)NULL, (uint32_t*)NULL);
 	CK_LAUNCH();
 	return RTKD_OK;
 }
@@ -857,6 +1315,7 @@ extern "C" int rtkd_gen_bounce(rtkd_scene *s, const void *d_rays_in, const void 
 {
 	if (!n) return RTKD_OK;
 	if (n > 0xfffffff0ull) { rtkd_set_error("batch too large"); return RTKD_ERR_ARGUMENT; }
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	rtkd_arrays a;
 	fill_arrays(s, a);
 	// push the new origin off the surface by 2^-13 of the scene's largest coordinate
@@ -869,6 +1328,7 @@ extern "C" int rtkd_gen_bounce(rtkd_scene *s, const void *d_rays_in, const void 
 
 extern "C" void *rtkd_scene_hit16(rtkd_scene *s, size_t n)
 {
+	if (bind_index(s->dev_index)) return NULL;
 	if (s->hit16_cap < n) {
 		if (s->hit16) cudaFree(s->hit16);
 		s->hit16 = NULL; s->hit16_cap = 0;
@@ -879,80 +1339,78 @@ extern "C" void *rtkd_scene_hit16(rtkd_scene *s, size_t n)
 	return s->hit16;
 }
 
-// Host-buffer batch: a three-stage pipeline over chunks of RTKD_HOST_CHUNK rays, RTKD_HOST_BUFS chunks
-// in flight on their own streams.
-//   upload             the rays of the whole batch go to one device buffer, chunk by chunk on a
-//                      copy stream of their own that runs RTKD_HOST_AHEAD chunks ahead of the
-//                      kernels, so the H2D engine -- the bottleneck resource of the batch: 32 bytes
-//                      per ray up against ~26 down -- never waits for the host
-//   stage A (enqueue)  k_trace -> k_resolve<dense> -> D2H of the chunk's mask bytes, block bases
-//                      and hit count into pinned staging
-//   stage B            once the count is known: D2H of exactly the rows of the rays that hit
-//   stage C            the host worker pool (rtk_place.c) copies each row to hits[i]
-// Only hit rows cross PCIe (68 bytes per HIT plus 1 byte per ray instead of 69 bytes per ray), and
-// rows of rays that missed are left untouched in the caller's array, the reference's miss rule
-// (rtk.c:571-576).  The traversal scratch (ray cursor, overflow slab) belongs to the scene, so the
-// TRAVERSALS of consecutive chunks are serialised with an event; everything else overlaps.
+// ---------------------------------------------------------------------------------------------
+// Host-buffer batches (rtk_trace_rays / rtk_trace_rays_compact): the reference's contract is that ONE
+// process calls the library and gets the machine (rtk.h:126-129), so a batch is split into contiguous
+// ranges over every device of the list; each device runs its range as a pipeline over chunks of
+// RTKD_HOST_CHUNK rays, RTKD_HOST_BUFS chunks in flight on their own streams, driven by the device's
+// worker thread (the caller's thread drives the first device).
+//
+//   upload     the rays of the range go to one device buffer, chunk by chunk on a copy stream of
+//              their own that runs RTKD_HOST_AHEAD chunks ahead of the kernels
+//   rows, DIRECT (the caller's hits / mask arrays are page-locked: cudaHostAlloc, cudaHostRegister,
+//              rtk_cuda_host_alloc, torch pin_memory ...): k_trace -> k_resolve writes the 68-byte rows of
+//              the rays that hit, and the mask bytes, STRAIGHT INTO THE CALLER'S ARRAYS over PCIe.
+//              No staging, no host threads, nothing for the CPUs to do: the links are the limit, and
+//              there is one per GPU.  Rows of rays that missed are never touched (rtk.c:571-576).
+//   rows, STAGED (pageable arrays): k_trace -> k_resolve<dense> -> D2H of the mask bytes, block bases and
+//              hit count -> D2H of exactly the hit rows -> the host worker pool (rtk_place.c) copies
+//              each row to hits[i].
+//   compact    k_trace -> D2H of the chunk's 16-byte records into the caller's array.
+// Every traversal launch takes its own slot of the scene, so the chunks of a batch -- and batches of
+// different host threads -- overlap freely.
+// ---------------------------------------------------------------------------------------------
 #define RTKD_HOST_CHUNK ((size_t)1 << 20)
-#define RTKD_HOST_BUFS 4
 #define RTKD_HOST_AHEAD 4
-#define RTKD_HOST_RING 8             // upload events: more than RTKD_HOST_AHEAD + 1
-#define RTKD_HOST_SMALL ((size_t)2048)  // batches up to this size take the one-stream, one-synchronisation path
+#define RTKD_HOST_SMALL ((size_t)2048)          // batches up to this size take the one-stream, one-synchronisation path
 
-struct host_buf {
-	cudaStream_t st;
-	cudaEvent_t traced, meta_done, rows_done;
-	float4 *d_h16;
-	uint32_t *d_rows, *d_base;          // d_base: [blocks] block bases, then the 64-bit hit count
-	unsigned char *d_mask;
-	unsigned char *h_meta;              // pinned: mask bytes | block bases | hit count
-	unsigned char *h_rows;              // pinned: dense rows
-	size_t off, cnt, hits;              // the chunk this buffer currently carries
-	int ticket, state;                  // state: 0 free, 1 stage A queued, 2 stage B queued, 3 placing
+struct batch_job {
+	rtkd_scene *s;                      // the copy of the scene on this device
+	const char *rays; char *hits; unsigned char *mask;     // the caller's WHOLE arrays
+	size_t first, n;                    // this device's range of them
+	int mode;                           // 0: rtk_hit rows + mask, 1: compact records (hits = rtk_cuda_hit16[])
+	long long found;                    // rays that hit (mode 0)
+	int rc;
+	char err[320];
 };
-struct host_stage {
-	size_t chunk, blocks, meta_bytes;
-	host_buf b[RTKD_HOST_BUFS];
-	cudaStream_t up;                    // upload stream
-	cudaEvent_t uploaded[RTKD_HOST_RING];
-	float4 *d_rays; size_t rays_cap;    // the whole batch's rays (grow-only)
-	bool ready;                         // buffers allocated for `chunk`
-	bool streams;                       // streams and events exist (they outlive a change of chunk size)
-};
-static host_stage g_stage;
-static pthread_mutex_t g_stage_lock = PTHREAD_MUTEX_INITIALIZER;
 
-static void stage_release(void)
+static void stage_release(host_stage &G)
 {
 	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
-		host_buf &B = g_stage.b[k];
+		host_buf &B = G.b[k];
 		cudaFree(B.d_h16); cudaFree(B.d_rows); cudaFree(B.d_base); cudaFree(B.d_mask);
 		cudaFreeHost(B.h_meta); cudaFreeHost(B.h_rows);
 		B.d_h16 = NULL; B.d_rows = B.d_base = NULL; B.d_mask = NULL; B.h_meta = B.h_rows = NULL;
 	}
+	G.ready = G.staged = false;
 }
 
-static void stage_shutdown(void)
+static void stage_shutdown(dev_ctx &X)
 {
-	pthread_mutex_lock(&g_stage_lock);
-	if (g_stage.ready || g_stage.streams) {
-		stage_release();
+	host_stage &G = X.stage;
+	stage_release(G);
+	if (G.streams) {
 		for (int k = 0; k < RTKD_HOST_BUFS; k++) {
-			host_buf &B = g_stage.b[k];
+			host_buf &B = G.b[k];
 			if (B.st) cudaStreamDestroy(B.st);
 			if (B.traced) cudaEventDestroy(B.traced);
 			if (B.meta_done) cudaEventDestroy(B.meta_done);
 			if (B.rows_done) cudaEventDestroy(B.rows_done);
 		}
-		if (g_stage.up) cudaStreamDestroy(g_stage.up);
-		for (int k = 0; k < RTKD_HOST_RING; k++) if (g_stage.uploaded[k]) cudaEventDestroy(g_stage.uploaded[k]);
+		if (G.up) cudaStreamDestroy(G.up);
+		for (int k = 0; k < RTKD_HOST_RING; k++) if (G.uploaded[k]) cudaEventDestroy(G.uploaded[k]);
 	}
-	if (g_stage.d_rays) cudaFree(g_stage.d_rays);
-	memset(&g_stage, 0, sizeof(g_stage));
-	pthread_mutex_unlock(&g_stage_lock);
+	if (G.d_rays) cudaFree(G.d_rays);
+	if (G.d_count) cudaFree(G.d_count);
+	if (G.sm_st) cudaStreamDestroy(G.sm_st);
+	cudaFree(G.sm_d_rays); cudaFree(G.sm_d_h16); cudaFree(G.sm_d_rows); cudaFree(G.sm_d_mask);
+	cudaFreeHost(G.sm_h_rows); cudaFreeHost(G.sm_h_mask);
+	memset(&G, 0, sizeof(G));
 }
 
-static int stage_prepare(size_t want)
+// buffers of one device for chunks of up to `want` rays; `staged` adds the dense-row buffers and the
+// pinned staging that only the placement path needs
+static int stage_prepare(host_stage &G, size_t want, bool staged)
 {
 	size_t max_chunk = RTKD_HOST_CHUNK;
 	bool forced = false;
@@ -963,45 +1421,127 @@ static int stage_prepare(size_t want)
 	}
 	size_t chunk = want < max_chunk ? want : max_chunk;
 	if (chunk < 4096) chunk = 4096;
-	if (g_stage.ready && (forced ? g_stage.chunk == chunk : g_stage.chunk >= chunk)) return RTKD_OK;
-	stage_release();                     // also what an earlier, failed attempt left behind
-	if (!g_stage.streams) {
+	const bool fits = G.ready && (forced ? G.chunk == chunk : G.chunk >= chunk);
+	if (fits && (!staged || G.staged)) return RTKD_OK;
+	if (!fits) stage_release(G);             // also what an earlier, failed attempt left behind
+	else chunk = G.chunk;                    // only the staging half is missing
+	if (!G.streams) {
 		for (int k = 0; k < RTKD_HOST_BUFS; k++) {
-			host_buf &B = g_stage.b[k];
+			host_buf &B = G.b[k];
 			CK(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking));
 			CK(cudaEventCreateWithFlags(&B.traced, cudaEventDisableTiming));
 			CK(cudaEventCreateWithFlags(&B.meta_done, cudaEventDisableTiming));
 			CK(cudaEventCreateWithFlags(&B.rows_done, cudaEventDisableTiming));
 		}
-		CK(cudaStreamCreateWithFlags(&g_stage.up, cudaStreamNonBlocking));
-		for (int k = 0; k < RTKD_HOST_RING; k++) CK(cudaEventCreateWithFlags(&g_stage.uploaded[k], cudaEventDisableTiming));
-		g_stage.streams = true;
+		CK(cudaStreamCreateWithFlags(&G.up, cudaStreamNonBlocking));
+		for (int k = 0; k < RTKD_HOST_RING; k++) CK(cudaEventCreateWithFlags(&G.uploaded[k], cudaEventDisableTiming));
+		CK(cudaMalloc(&G.d_count, 64));
+		G.streams = true;
 	}
-	g_stage.ready = false;
-	g_stage.chunk = chunk;
-	g_stage.blocks = ((chunk + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS + 3) & ~(size_t)3;   // the 64-bit count follows: keep it aligned
-	g_stage.meta_bytes = ((chunk + 15) & ~(size_t)15) + 4 * g_stage.blocks + 16;
+	G.chunk = chunk;
+	G.blocks = ((chunk + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS + 3) & ~(size_t)3;   // the 64-bit count follows: keep it aligned
+	G.meta_bytes = ((chunk + 15) & ~(size_t)15) + 4 * G.blocks + 16;
 	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
-		host_buf &B = g_stage.b[k];
-		CK(cudaMalloc(&B.d_h16, 16 * chunk));
-		CK(cudaMalloc(&B.d_rows, 68 * chunk));
-		CK(cudaMalloc(&B.d_base, 4 * g_stage.blocks + 16));
-		CK(cudaMalloc(&B.d_mask, (chunk + 15) & ~(size_t)15));
-		CK(cudaMallocHost(&B.h_meta, g_stage.meta_bytes));
-		CK(cudaMallocHost(&B.h_rows, 68 * chunk));
+		host_buf &B = G.b[k];
+		if (!B.d_h16) CK(cudaMalloc(&B.d_h16, 16 * chunk));
+		if (!B.d_mask) CK(cudaMalloc(&B.d_mask, (chunk + 15) & ~(size_t)15));
+		if (staged) {
+			if (!B.d_rows) CK(cudaMalloc(&B.d_rows, 68 * chunk));
+			if (!B.d_base) CK(cudaMalloc(&B.d_base, 4 * G.blocks + 16));
+			if (!B.h_meta) CK(cudaMallocHost(&B.h_meta, G.meta_bytes));
+			if (!B.h_rows) CK(cudaMallocHost(&B.h_rows, 68 * chunk));
+		}
 		B.state = 0; B.ticket = -1;
 	}
-	g_stage.ready = true;
+	G.ready = true;
+	if (staged) G.staged = true;
 	return RTKD_OK;
 }
 
+static int stage_rays(host_stage &G, size_t n)
+{
+	if (G.rays_cap >= n) return RTKD_OK;
+	if (G.d_rays) cudaFree(G.d_rays);
+	G.d_rays = NULL; G.rays_cap = 0;
+	if (cudaMalloc(&G.d_rays, 32 * n) != cudaSuccess) { cudaGetLastError(); rtkd_set_error("out of device memory for %zu rays", n); return RTKD_ERR_MEMORY; }
+	G.rays_cap = n;
+	return RTKD_OK;
+}
+
+// device-visible address of page-locked host memory [p, p + bytes), or NULL when the range is pageable
+static void *host_mapped(const void *p, size_t bytes)
+{
+	if (!p || !bytes) return NULL;
+	cudaPointerAttributes a, b;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess || cudaPointerGetAttributes(&b, (const char*)p + bytes - 1) != cudaSuccess) { cudaGetLastError(); return NULL; }
+	if (a.type != cudaMemoryTypeHost || b.type != cudaMemoryTypeHost || !a.devicePointer) return NULL;
+	return a.devicePointer;
+}
+
+#define PIPE_CK(call, what) do { cudaError_t _e = (call); if (_e != cudaSuccess) { rtkd_set_error("%s: %s", what, cudaGetErrorString(_e)); rc = RTKD_ERR_CUDA; } } while (0)
+
+// keep the upload stream RTKD_HOST_AHEAD chunks ahead of the kernels
+static int pipe_uploads(host_stage &G, const batch_job &J, size_t it, size_t nchunks, size_t &uploads, const char *what)
+{
+	int rc = RTKD_OK;
+	for (; uploads < nchunks && uploads <= it + RTKD_HOST_AHEAD && rc == RTKD_OK; uploads++) {
+		const size_t off = uploads * G.chunk, cnt = J.n - off < G.chunk ? J.n - off : G.chunk;
+		PIPE_CK(cudaMemcpyAsync(G.d_rays + 2 * off, J.rays + 32 * (J.first + off), 32 * cnt, cudaMemcpyHostToDevice, G.up), what);
+		if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(G.uploaded[uploads % RTKD_HOST_RING], G.up), what);
+	}
+	return rc;
+}
+
+static int pipe_finish(dev_ctx &X, const batch_job &J, int rc, const char *what)
+{
+	host_stage &G = X.stage;
+	for (int k = 0; k < RTKD_HOST_BUFS; k++) if (cudaStreamSynchronize(G.b[k].st) != cudaSuccess && rc == RTKD_OK) { rtkd_set_error("%s: device failure", what); rc = RTKD_ERR_CUDA; }
+	if (cudaStreamSynchronize(G.up) != cudaSuccess && rc == RTKD_OK) { rtkd_set_error("%s: device failure", what); rc = RTKD_ERR_CUDA; }
+	if (rc == RTKD_OK && (*(volatile uint32_t*)J.s->h_status & 2u)) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
+	return rc;
+}
+
+// rows straight into the caller's page-locked arrays (m_hits / m_mask: their device-visible addresses)
+static int pipeline_rows_direct(dev_ctx &X, batch_job &J, uint32_t *m_hits, unsigned char *m_mask)
+{
+	static const char *what = "rtk_trace_rays";
+	host_stage &G = X.stage;
+	const size_t chunk = G.chunk, nchunks = (J.n + chunk - 1) / chunk;
+	rtkd_arrays a;
+	fill_arrays(J.s, a);
+	int rc = RTKD_OK;
+	PIPE_CK(cudaMemsetAsync(G.d_count, 0, 8, G.up), what);          // ahead of the first upload event
+	size_t uploads = 0;
+	for (size_t it = 0; it < nchunks && rc == RTKD_OK; it++) {
+		rc = pipe_uploads(G, J, it, nchunks, uploads, what);
+		if (rc) break;
+		host_buf &B = G.b[it % RTKD_HOST_BUFS];
+		const size_t off = it * chunk, cnt = J.n - off < chunk ? J.n - off : chunk;
+		PIPE_CK(cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0), what);
+		if (rc) break;
+		rc = rtkd_trace(J.s, G.d_rays + 2 * off, B.d_h16, cnt, 1, NULL, B.st);
+		if (rc) break;
+		const unsigned blocks = (unsigned)((cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS);
+		RTK_LAUNCH(k_resolve<false>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, m_hits + 17 * (J.first + off),
+		           m_mask ? m_mask + J.first + off : B.d_mask, (uint32_t)cnt, G.d_count, (uint32_t*)NULL);
+		PIPE_CK(cudaGetLastError(), what);
+	}
+	rc = pipe_finish(X, J, rc, what);
+	if (rc == RTKD_OK) {
+		unsigned long long hc = 0;
+		PIPE_CK(cudaMemcpy(&hc, G.d_count, sizeof(hc), cudaMemcpyDeviceToHost), what);
+		J.found = (long long)hc;
+	}
+	return rc;
+}
+
 // stage B of one buffer: wait for the chunk's count, then fetch exactly its rows
-static int host_stage_b(host_buf &B)
+static int host_stage_b(host_stage &G, host_buf &B)
 {
 	CK(cudaEventSynchronize(B.meta_done));
-	const size_t mask_bytes = (g_stage.chunk + 15) & ~(size_t)15;
+	const size_t mask_bytes = (G.chunk + 15) & ~(size_t)15;
 	unsigned long long hc = 0;
-	memcpy(&hc, B.h_meta + mask_bytes + 4 * g_stage.blocks, sizeof(hc));
+	memcpy(&hc, B.h_meta + mask_bytes + 4 * G.blocks, sizeof(hc));
 	B.hits = (size_t)hc;
 	if (B.hits) CK(cudaMemcpyAsync(B.h_rows, B.d_rows, 68 * B.hits, cudaMemcpyDeviceToHost, B.st));
 	CK(cudaEventRecord(B.rows_done, B.st));
@@ -1010,180 +1550,257 @@ static int host_stage_b(host_buf &B)
 }
 
 // stage C: hand the rows to the placement workers
-static int host_stage_c(host_buf &B, void *hits, unsigned char *mask)
+static int host_stage_c(host_stage &G, host_buf &B, const batch_job &J)
 {
 	CK(cudaEventSynchronize(B.rows_done));
-	const size_t mask_bytes = (g_stage.chunk + 15) & ~(size_t)15;
+	const size_t mask_bytes = (G.chunk + 15) & ~(size_t)15;
 	rtkd_place_desc d;
-	d.hits = hits; d.mask_out = mask;
+	d.hits = J.hits; d.mask_out = J.mask;
 	d.rows = B.h_rows; d.mask = B.h_meta; d.block_base = (const uint32_t*)(B.h_meta + mask_bytes);
-	d.first_ray = B.off; d.nrays = B.cnt;
+	d.first_ray = J.first + B.off; d.nrays = B.cnt;
 	B.ticket = rtkd_place_submit(&d);
 	B.state = 3;
 	return RTKD_OK;
 }
 
-extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n)
+// rows through pinned staging and the placement workers (pageable caller arrays)
+static int pipeline_rows_staged(dev_ctx &X, batch_job &J)
 {
-	if (!n) return 0;
-	pthread_mutex_lock(&g_stage_lock);
-	long long total = 0;
-	int rc = stage_prepare(n);
-	if (rc == RTKD_OK) rc = ensure_scratch(s);
-	host_stage &G = g_stage;
-	if (rc == RTKD_OK && G.rays_cap < n) {
-		if (G.d_rays) cudaFree(G.d_rays);
-		G.d_rays = NULL; G.rays_cap = 0;
-		if (cudaMalloc(&G.d_rays, 32 * n) != cudaSuccess) { rtkd_set_error("out of device memory for %zu rays", n); rc = RTKD_ERR_MEMORY; }
-		else G.rays_cap = n;
-	}
-	const size_t chunk = G.chunk;
-	const size_t nchunks = (n + chunk - 1) / chunk;
+	static const char *what = "rtk_trace_rays";
+	host_stage &G = X.stage;
+	const size_t chunk = G.chunk, nchunks = (J.n + chunk - 1) / chunk;
 	const size_t mask_bytes = (chunk + 15) & ~(size_t)15;
 	rtkd_arrays a;
-	fill_arrays(s, a);
-	if (rc == RTKD_OK && n <= RTKD_HOST_SMALL) {
-		// Small batches -- rtk_trace_ray is a batch of one -- are bound by latency, not by bytes: one
-		// stream, rows expanded in place (no dense packing, no worker threads), ONE synchronisation.
-		host_buf &B = G.b[0];
-		cudaError_t e = cudaMemcpyAsync(G.d_rays, rays, 32 * n, cudaMemcpyHostToDevice, B.st);
-		if (e == cudaSuccess) rc = rtkd_trace(s, G.d_rays, B.d_h16, n, 1, NULL, B.st);
-		if (e == cudaSuccess && rc == RTKD_OK) {
-			RTK_LAUNCH(k_resolve<false>, (unsigned)((n + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, B.st,
-			           a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)n, (unsigned long long*)NULL, (uint32_t*)NULL);
-			e = cudaGetLastError();
-			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_rows, B.d_rows, 68 * n, cudaMemcpyDeviceToHost, B.st);
-			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_meta, B.d_mask, n, cudaMemcpyDeviceToHost, B.st);
-			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_meta + mask_bytes, (unsigned char*)s->scratch + 192, 4, cudaMemcpyDeviceToHost, B.st);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(B.st);
-		}
-		if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; }
-		if (rc == RTKD_OK) {
-			uint32_t herr = 0;
-			memcpy(&herr, B.h_meta + mask_bytes, 4);
-			if (herr & 2u) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
-		}
-		if (rc == RTKD_OK) {
-			for (size_t i = 0; i < n; i++) {
-				if (B.h_meta[i]) { memcpy((char*)hits + 68 * i, B.h_rows + 68 * i, 68); total++; }    // rows of misses stay untouched (rtk.c:571-576)
-			}
-			if (mask) memcpy(mask, B.h_meta, n);
-		}
-		pthread_mutex_unlock(&g_stage_lock);
-		return rc == RTKD_OK ? total : -1;
-	}
-	cudaEvent_t prev_traced = NULL;
-	size_t uploads = 0;                 // chunks whose upload has been enqueued
+	fill_arrays(J.s, a);
+	int rc = RTKD_OK;
+	long long total = 0;
+	size_t uploads = 0;
 	// chunk ci enters stage A in iteration ci, stage B in iteration ci+1, stage C in iteration ci+2
 	// and its buffer is reused in iteration ci + RTKD_HOST_BUFS
 	for (size_t it = 0; it < nchunks + 2 && rc == RTKD_OK; it++) {
-		// keep the upload stream RTKD_HOST_AHEAD chunks ahead of the kernels
-		for (; uploads < nchunks && uploads <= it + RTKD_HOST_AHEAD; uploads++) {
-			const size_t off = uploads * chunk, cnt = n - off < chunk ? n - off : chunk;
-			cudaError_t e = cudaMemcpyAsync(G.d_rays + 2 * off, (const char*)rays + 32 * off, 32 * cnt, cudaMemcpyHostToDevice, G.up);
-			if (e == cudaSuccess) e = cudaEventRecord(G.uploaded[uploads % RTKD_HOST_RING], G.up);
-			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
-		}
-		if (rc != RTKD_OK) break;
+		rc = pipe_uploads(G, J, it, nchunks, uploads, what);
+		if (rc) break;
 		if (it < nchunks) {
 			host_buf &B = G.b[it % RTKD_HOST_BUFS];
 			if (B.state == 3) { rtkd_place_wait(B.ticket); total += (long long)B.hits; B.state = 0; }
-			B.off = it * chunk; B.cnt = n - B.off < chunk ? n - B.off : chunk;
+			B.off = it * chunk; B.cnt = J.n - B.off < chunk ? J.n - B.off : chunk;
 			unsigned long long *d_count = (unsigned long long*)((unsigned char*)B.d_base + 4 * G.blocks);
-			cudaError_t e = cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0);
-			if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, 16, B.st);
-			if (e == cudaSuccess && prev_traced) e = cudaStreamWaitEvent(B.st, prev_traced, 0);
-			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
-			rc = rtkd_trace(s, G.d_rays + 2 * B.off, B.d_h16, B.cnt, 1, NULL, B.st);
+			PIPE_CK(cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0), what);
+			if (rc == RTKD_OK) PIPE_CK(cudaMemsetAsync(d_count, 0, 16, B.st), what);
 			if (rc) break;
-			cudaEventRecord(B.traced, B.st);
-			prev_traced = B.traced;
+			rc = rtkd_trace(J.s, G.d_rays + 2 * B.off, B.d_h16, B.cnt, 1, NULL, B.st);
+			if (rc) break;
 			const unsigned blocks = (unsigned)((B.cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS);
 			RTK_LAUNCH(k_resolve<true>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)B.cnt, d_count, B.d_base);
-			e = cudaGetLastError();
+			PIPE_CK(cudaGetLastError(), what);
 			// mask bytes and bases+count land in one pinned block: [mask | bases | count]
-			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_meta, B.d_mask, B.cnt, cudaMemcpyDeviceToHost, B.st);
-			if (e == cudaSuccess) e = cudaMemcpyAsync(B.h_meta + mask_bytes, B.d_base, 4 * G.blocks + 16, cudaMemcpyDeviceToHost, B.st);
-			if (e == cudaSuccess) e = cudaEventRecord(B.meta_done, B.st);
-			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
+			if (rc == RTKD_OK) PIPE_CK(cudaMemcpyAsync(B.h_meta, B.d_mask, B.cnt, cudaMemcpyDeviceToHost, B.st), what);
+			if (rc == RTKD_OK) PIPE_CK(cudaMemcpyAsync(B.h_meta + mask_bytes, B.d_base, 4 * G.blocks + 16, cudaMemcpyDeviceToHost, B.st), what);
+			if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.meta_done, B.st), what);
+			if (rc) break;
 			B.state = 1;
 		}
-		if (it >= 1 && it - 1 < nchunks) rc = host_stage_b(G.b[(it - 1) % RTKD_HOST_BUFS]);
-		if (rc == RTKD_OK && it >= 2 && it - 2 < nchunks) rc = host_stage_c(G.b[(it - 2) % RTKD_HOST_BUFS], hits, mask);
+		if (it >= 1 && it - 1 < nchunks) rc = host_stage_b(G, G.b[(it - 1) % RTKD_HOST_BUFS]);
+		if (rc == RTKD_OK && it >= 2 && it - 2 < nchunks) rc = host_stage_c(G, G.b[(it - 2) % RTKD_HOST_BUFS], J);
 	}
 	// drain: placements still running, and -- after an error -- whatever is still queued
 	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
 		host_buf &B = G.b[k];
 		if (B.state == 3) { rtkd_place_wait(B.ticket); total += (long long)B.hits; }
-		else if (B.state) cudaStreamSynchronize(B.st);
 		B.state = 0; B.ticket = -1;
 	}
-	if (rc != RTKD_OK) cudaStreamSynchronize(G.up);
-	if (rc == RTKD_OK) {
-		uint32_t herr = 0;
-		if (cudaMemcpy(&herr, (unsigned char*)s->scratch + 192, sizeof(herr), cudaMemcpyDeviceToHost) != cudaSuccess) rc = RTKD_ERR_CUDA;
-		if (herr & 2u) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
+	rc = pipe_finish(X, J, rc, what);
+	J.found = total;
+	return rc;
+}
+
+// compact records: the copy engine puts each chunk's records straight into the caller's array
+static int pipeline_compact(dev_ctx &X, batch_job &J)
+{
+	static const char *what = "rtk_trace_rays_compact";
+	host_stage &G = X.stage;
+	const size_t chunk = G.chunk, nchunks = (J.n + chunk - 1) / chunk;
+	int rc = RTKD_OK;
+	size_t uploads = 0;
+	for (size_t it = 0; it < nchunks && rc == RTKD_OK; it++) {
+		rc = pipe_uploads(G, J, it, nchunks, uploads, what);
+		if (rc) break;
+		// the chunk's stream still holds the copy of the chunk that used this buffer before: stream
+		// order keeps the new traversal from overwriting records that have not left yet
+		host_buf &B = G.b[it % RTKD_HOST_BUFS];
+		const size_t off = it * chunk, cnt = J.n - off < chunk ? J.n - off : chunk;
+		PIPE_CK(cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0), what);
+		if (rc) break;
+		rc = rtkd_trace(J.s, G.d_rays + 2 * off, B.d_h16, cnt, 1, NULL, B.st);
+		if (rc) break;
+		PIPE_CK(cudaMemcpyAsync(J.hits + 16 * (J.first + off), B.d_h16, 16 * cnt, cudaMemcpyDeviceToHost, B.st), what);
 	}
-	if (rc == RTKD_ERR_CUDA && !g_err[0]) rtkd_set_error("CUDA failure in rtk_trace_rays");
-	pthread_mutex_unlock(&g_stage_lock);
+	return pipe_finish(X, J, rc, what);
+}
+
+// one device's share of a batch, on the thread that drives that device
+static void run_job(dev_ctx &X, batch_job &J)
+{
+	int rc = bind_index((int)(&X - g_ctx));
+	uint32_t *m_hits = NULL;
+	unsigned char *m_mask = NULL;
+	bool direct = false;
+	if (rc == RTKD_OK && J.mode == 0 && g_host_direct) {
+		m_hits = (uint32_t*)host_mapped(J.hits, 68 * (J.first + J.n));
+		m_mask = J.mask ? (unsigned char*)host_mapped(J.mask, J.first + J.n) : NULL;
+		direct = m_hits && (!J.mask || m_mask);
+	}
+	if (rc == RTKD_OK) rc = stage_prepare(X.stage, J.n, J.mode == 0 && !direct);
+	if (rc == RTKD_OK) rc = stage_rays(X.stage, J.n);
+	if (rc == RTKD_OK) {
+		if (J.mode == 1) rc = pipeline_compact(X, J);
+		else if (direct) rc = pipeline_rows_direct(X, J, m_hits, m_mask);
+		else rc = pipeline_rows_staged(X, J);
+	}
+	if (rc == RTKD_ERR_CUDA && !g_err[0]) rtkd_set_error("CUDA failure in a host batch");
+	J.rc = rc;
+	if (rc) { strncpy(J.err, g_err, sizeof(J.err) - 1); J.err[sizeof(J.err) - 1] = 0; }
+}
+
+static void *ctx_worker(void *arg)
+{
+	dev_ctx &X = *(dev_ctx*)arg;
+	cudaSetDevice(X.device);
+	pthread_mutex_lock(&X.jm);
+	for (;;) {
+		while (!X.quit && !(X.job && !X.job_done)) pthread_cond_wait(&X.jc, &X.jm);
+		if (X.quit) break;
+		batch_job *J = X.job;
+		pthread_mutex_unlock(&X.jm);
+		run_job(X, *J);
+		pthread_mutex_lock(&X.jm);
+		X.job_done = true;
+		pthread_cond_broadcast(&X.jc);
+	}
+	pthread_mutex_unlock(&X.jm);
+	return NULL;
+}
+
+// split [0, n) over the devices, run the shares, merge
+static long long run_batch(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n, int mode)
+{
+	int use = g_ndev;
+	while (use > 1 && n / (size_t)use < g_min_share) use--;
+	if (use > 1 && rtkd_sync_replicas(s) != RTKD_OK) return -1;
+	batch_job J[RTKD_MAX_DEVICES];
+	// contiguous ranges, multiples of the resolve block (128 rays = 68 full 128-byte lines of rows)
+	size_t per = (n / (size_t)use + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS * RTK_RESOLVE_THREADS;
+	size_t first = 0;
+	int used = 0;
+	for (int k = 0; k < use && first < n; k++, used++) {
+		batch_job &j = J[k];
+		memset(&j, 0, sizeof(j));
+		j.s = k == 0 ? s : s->replica[k];
+		j.rays = (const char*)rays; j.hits = (char*)hits; j.mask = mask;
+		j.first = first; j.n = (k == use - 1 || n - first < per) ? n - first : per;
+		j.mode = mode;
+		first += j.n;
+	}
+	for (int k = 0; k < used; k++) pthread_mutex_lock(&g_ctx[k].lock);      // ascending order: no deadlock between batches
+	for (int k = 1; k < used; k++) {
+		dev_ctx &X = g_ctx[k];
+		pthread_mutex_lock(&X.jm);
+		X.job = &J[k]; X.job_done = false;
+		pthread_cond_broadcast(&X.jc);
+		pthread_mutex_unlock(&X.jm);
+	}
+	run_job(g_ctx[0], J[0]);
+	for (int k = 1; k < used; k++) {
+		dev_ctx &X = g_ctx[k];
+		pthread_mutex_lock(&X.jm);
+		while (!X.job_done) pthread_cond_wait(&X.jc, &X.jm);
+		X.job = NULL;
+		pthread_mutex_unlock(&X.jm);
+	}
+	for (int k = used - 1; k >= 0; k--) pthread_mutex_unlock(&g_ctx[k].lock);
+	bind_index(0);
+	long long total = 0;
+	for (int k = 0; k < used; k++) {
+		if (J[k].rc) { rtkd_set_error("%s (device %d)", J[k].err, g_ctx[k].device); return -1; }
+		total += J[k].found;
+	}
+	return total;
+}
+
+// Small batches -- rtk_trace_ray is a batch of one -- are bound by latency, not by bytes: one stream,
+// rows expanded in place (no dense packing, no worker threads), ONE synchronisation.  Concurrent small
+// batches of different host threads go to different devices of the list when there are several.
+static int small_prepare(host_stage &G)
+{
+	if (G.sm_st) return RTKD_OK;
+	CK(cudaMalloc(&G.sm_d_rays, 32 * RTKD_HOST_SMALL));
+	CK(cudaMalloc(&G.sm_d_h16, 16 * RTKD_HOST_SMALL));
+	CK(cudaMalloc(&G.sm_d_rows, 68 * RTKD_HOST_SMALL));
+	CK(cudaMalloc(&G.sm_d_mask, RTKD_HOST_SMALL));
+	CK(cudaMallocHost(&G.sm_h_rows, 68 * RTKD_HOST_SMALL));
+	CK(cudaMallocHost(&G.sm_h_mask, RTKD_HOST_SMALL));
+	CK(cudaStreamCreateWithFlags(&G.sm_st, cudaStreamNonBlocking));
+	return RTKD_OK;
+}
+
+static long long small_batch(rtkd_scene *s0, const void *rays, void *hits, unsigned char *mask, size_t n)
+{
+	int k = 0;
+	bool locked = false;
+	for (int i = 0; i < g_ndev && !locked; i++) if (pthread_mutex_trylock(&g_ctx[i].lock) == 0) { k = i; locked = true; }
+	if (!locked) { k = 0; pthread_mutex_lock(&g_ctx[0].lock); }
+	dev_ctx &X = g_ctx[k];
+	host_stage &G = X.stage;
+	rtkd_scene *s = s0;
+	int rc = RTKD_OK;
+	if (k > 0) { rc = rtkd_sync_replicas(s0); s = s0->replica[k]; }
+	if (rc == RTKD_OK) rc = bind_index(k);
+	if (rc == RTKD_OK) rc = small_prepare(G);
+	long long total = 0;
+	if (rc == RTKD_OK) {
+		rtkd_arrays a;
+		fill_arrays(s, a);
+		cudaStream_t st = G.sm_st;
+		cudaError_t e = cudaMemcpyAsync(G.sm_d_rays, rays, 32 * n, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) rc = rtkd_trace(s, G.sm_d_rays, G.sm_d_h16, n, 1, NULL, st);
+		if (e == cudaSuccess && rc == RTKD_OK) {
+			RTK_LAUNCH(k_resolve<false>, (unsigned)((n + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS), RTK_RESOLVE_THREADS, st,
+			           a, (const float4*)G.sm_d_h16, G.sm_d_rows, G.sm_d_mask, (uint32_t)n, (unsigned long long*)NULL, (uint32_t*)NULL);
+			e = cudaGetLastError();
+			if (e == cudaSuccess) e = cudaMemcpyAsync(G.sm_h_rows, G.sm_d_rows, 68 * n, cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(G.sm_h_mask, G.sm_d_mask, n, cudaMemcpyDeviceToHost, st);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		}
+		if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; }
+		if (rc == RTKD_OK && (*(volatile uint32_t*)s->h_status & 2u)) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
+		if (rc == RTKD_OK) {
+			for (size_t i = 0; i < n; i++) {
+				if (G.sm_h_mask[i]) { memcpy((char*)hits + 68 * i, G.sm_h_rows + 68 * i, 68); total++; }    // rows of misses stay untouched (rtk.c:571-576)
+			}
+			if (mask) memcpy(mask, G.sm_h_mask, n);
+		}
+	}
+	pthread_mutex_unlock(&X.lock);
+	bind_index(0);
 	return rc == RTKD_OK ? total : -1;
+}
+
+extern "C" long long rtkd_trace_host(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n)
+{
+	if (!n) return 0;
+	if (ensure_init()) return -1;
+	if (n <= RTKD_HOST_SMALL) return small_batch(s, rays, hits, mask, n);
+	return run_batch(s, rays, hits, mask, n, 0);
 }
 
 // Host-buffer batch with COMPACT results: rays up, one 16-byte record (t, u, v, global triangle
 // number or RTKD miss) per ray down, straight into the caller's array -- no dense packing, no row
-// placement by host threads.  32 bytes per ray go up and 16 come down, on the two directions of the
-// link, so the batch is bound by the upload alone.  Same staging, same chunking, same upload stream
-// running ahead as rtkd_trace_host; each chunk's stream carries k_trace and the copy of its records.
+// placement.  32 bytes per ray go up and 16 come down, on the two directions of the link.
 extern "C" int rtkd_trace_host_compact(rtkd_scene *s, const void *rays, void *hit16, size_t n)
 {
 	if (!n) return RTKD_OK;
-	pthread_mutex_lock(&g_stage_lock);
-	int rc = stage_prepare(n);
-	if (rc == RTKD_OK) rc = ensure_scratch(s);
-	host_stage &G = g_stage;
-	if (rc == RTKD_OK && G.rays_cap < n) {
-		if (G.d_rays) cudaFree(G.d_rays);
-		G.d_rays = NULL; G.rays_cap = 0;
-		if (cudaMalloc(&G.d_rays, 32 * n) != cudaSuccess) { rtkd_set_error("out of device memory for %zu rays", n); rc = RTKD_ERR_MEMORY; }
-		else G.rays_cap = n;
-	}
-	if (rc != RTKD_OK) { pthread_mutex_unlock(&g_stage_lock); return rc; }
-	const size_t chunk = G.chunk;
-	const size_t nchunks = (n + chunk - 1) / chunk;
-	cudaEvent_t prev_traced = NULL;
-	size_t uploads = 0;
-	for (size_t it = 0; it < nchunks && rc == RTKD_OK; it++) {
-		for (; uploads < nchunks && uploads <= it + RTKD_HOST_AHEAD; uploads++) {
-			const size_t off = uploads * chunk, cnt = n - off < chunk ? n - off : chunk;
-			cudaError_t e = cudaMemcpyAsync(G.d_rays + 2 * off, (const char*)rays + 32 * off, 32 * cnt, cudaMemcpyHostToDevice, G.up);
-			if (e == cudaSuccess) e = cudaEventRecord(G.uploaded[uploads % RTKD_HOST_RING], G.up);
-			if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays_compact: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
-		}
-		if (rc != RTKD_OK) break;
-		// the chunk's stream still holds the copy of the chunk that used this buffer before: stream
-		// order keeps the new traversal from overwriting records that have not left yet
-		host_buf &B = G.b[it % RTKD_HOST_BUFS];
-		const size_t off = it * chunk, cnt = n - off < chunk ? n - off : chunk;
-		cudaError_t e = cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0);
-		if (e == cudaSuccess && prev_traced) e = cudaStreamWaitEvent(B.st, prev_traced, 0);   // the traversal scratch is the scene's
-		if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays_compact: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
-		rc = rtkd_trace(s, G.d_rays + 2 * off, B.d_h16, cnt, 1, NULL, B.st);
-		if (rc) break;
-		e = cudaEventRecord(B.traced, B.st);
-		prev_traced = B.traced;
-		if (e == cudaSuccess) e = cudaMemcpyAsync((char*)hit16 + 16 * off, B.d_h16, 16 * cnt, cudaMemcpyDeviceToHost, B.st);
-		if (e != cudaSuccess) { rtkd_set_error("rtk_trace_rays_compact: %s", cudaGetErrorString(e)); rc = RTKD_ERR_CUDA; break; }
-	}
-	for (int k = 0; k < RTKD_HOST_BUFS; k++) if (cudaStreamSynchronize(G.b[k].st) != cudaSuccess && rc == RTKD_OK) rc = RTKD_ERR_CUDA;
-	if (cudaStreamSynchronize(G.up) != cudaSuccess && rc == RTKD_OK) rc = RTKD_ERR_CUDA;
-	if (rc == RTKD_OK) {
-		uint32_t herr = 0;
-		if (cudaMemcpy(&herr, (unsigned char*)s->scratch + 192, sizeof(herr), cudaMemcpyDeviceToHost) != cudaSuccess) rc = RTKD_ERR_CUDA;
-		if (herr & 2u) { rtkd_set_error("traversal stack exhausted"); rc = RTKD_ERR_OVERFLOW; }
-	}
-	if (rc == RTKD_ERR_CUDA && !g_err[0]) rtkd_set_error("CUDA failure in rtk_trace_rays_compact");
-	pthread_mutex_unlock(&g_stage_lock);
-	return rc;
+	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
+	return run_batch(s, rays, hit16, NULL, n, 1) < 0 ? RTKD_ERR_CUDA : RTKD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1222,6 +1839,7 @@ extern "C" size_t rtkd_blob_payload_size(const rtkd_scene *s)
 
 extern "C" int rtkd_blob_write(const rtkd_scene *s, void *payload)
 {
+	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	rtkd_blob_sub b;
 	memset(&b, 0, sizeof(b));
 	memcpy(&b.magic2, "B200RTK3", 8);
@@ -1246,40 +1864,89 @@ extern "C" int rtkd_blob_write(const rtkd_scene *s, void *payload)
 	return RTKD_OK;
 }
 
+// Blobs come from disk: nothing in one is trusted.  The host checks the section table, this kernel
+// checks every reference the traversal and the resolve kernel would follow: a child is a leaf inside
+// the slot array, or a node with a HIGHER index than its parent (the builder allocates children after
+// their parents, so a well-formed tree has no other kind -- and a blob with a cycle cannot hang the
+// traversal), and every triangle number of a leaf slot is inside the corner array.
+__global__ void __launch_bounds__(256) k_validate_blob(const float4 *nodes, uint32_t num_nodes, const float4 *tv0, uint32_t num_tv,
+                                                       uint32_t num_tris, uint32_t *bad)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < num_nodes * RTK_WIDE) {
+		const uint32_t ref = __float_as_uint(nodes[2ull * i].w), parent = i / RTK_WIDE;
+		if (ref != RTK_REF_EMPTY) {
+			if (rtk_ref_is_leaf(ref)) {
+				const uint32_t first = rtk_leaf_first(ref);
+				if ((first & 7u) || first + RTK_LEAF_MAX > num_tv) atomicOr(bad, 1u);
+			} else if (ref >= num_nodes || ref <= parent) atomicOr(bad, 2u);
+		}
+	}
+	if (i < num_tv) {
+		const uint32_t id = __float_as_uint(tv0[i].w);
+		if (id != RTK_MISS && id >= num_tris) atomicOr(bad, 4u);
+	}
+}
+
 extern "C" rtkd_scene *rtkd_blob_read(const void *payload, size_t payload_size)
 {
 	if (ensure_init()) return NULL;
 	rtkd_blob_sub b;
-	if (payload_size < sizeof(b)) { rtkd_set_error("scene blob truncated"); return NULL; }
+	if (payload_size < a128(sizeof(b))) { rtkd_set_error("scene blob truncated"); return NULL; }
 	memcpy(&b, payload, sizeof(b));
 	if (memcmp(&b.magic2, "B200RTK3", 8) != 0) { rtkd_set_error("blob was not written by rtk_b200 (device-layout magic missing)"); return NULL; }
-	if (b.off_mesh + 4 * ((size_t)b.num_meshes + 1) > payload_size) { rtkd_set_error("scene blob truncated"); return NULL; }
+	// section table: ordered, 128-byte aligned, inside the payload, sized by the counts
+	{
+		const uint64_t off[7] = { b.off_nodes, b.off_tv0, b.off_tv1, b.off_tv2, b.off_orig, b.off_mesh, (uint64_t)payload_size };
+		const uint64_t len[6] = { 256ull * b.num_nodes, 16ull * b.num_tv, 16ull * b.num_tv, 16ull * b.num_tv, 48ull * b.num_tris, 4ull * ((uint64_t)b.num_meshes + 1) };
+		bool ok = off[0] >= a128(sizeof(b));
+		for (int k = 0; k < 6 && ok; k++) ok = (off[k] & 127) == 0 && off[k] <= off[k + 1] && len[k] <= off[k + 1] - off[k];
+		if (ok) ok = b.num_tv == (uint64_t)b.num_leaves * RTK_LEAF_MAX && b.num_leaves <= RTK_MAX_LEAVES && b.num_tris <= 0x0fffffffu &&
+		             b.depth <= RTKD_COLLAPSE_LEVELS && b.num_nodes <= 0x7fffffffu && (b.num_tris == 0 || (b.num_nodes >= 1 && b.depth >= 1)) &&
+		             b.num_leaves <= b.num_tris && (b.num_tris == 0 || b.num_leaves >= 1);
+		if (!ok) { rtkd_set_error("scene blob is corrupt or truncated (section table)"); return NULL; }
+		const uint32_t *mf = (const uint32_t*)((const char*)payload + b.off_mesh);
+		bool mok = mf[0] == 0 && mf[b.num_meshes] == b.num_tris;
+		for (uint32_t m = 0; m < b.num_meshes && mok; m++) mok = mf[m] <= mf[m + 1];
+		if (!mok) { rtkd_set_error("scene blob is corrupt (mesh table)"); return NULL; }
+		for (int k = 0; k < 3; k++) if (!(b.bounds_min[k] <= b.bounds_max[k]) && b.num_tris) { rtkd_set_error("scene blob is corrupt (bounds)"); return NULL; }
+		if (!(b.abs_max >= 0.0f) || !isfinite(b.abs_max)) { rtkd_set_error("scene blob is corrupt (bounds)"); return NULL; }
+	}
 	const char *p = (const char*)payload;
 	rtkd_scene *s = rtkd_scene_new(b.num_tris, b.num_meshes, (const uint32_t*)(p + b.off_mesh));
 	if (!s) return NULL;
 	s->id = b.id;
 	s->num_nodes = b.num_nodes; s->num_leaves = b.num_leaves; s->depth = b.depth; s->build_mode = b.build_mode;
 	memcpy(s->bounds_min, b.bounds_min, 12); memcpy(s->bounds_max, b.bounds_max, 12);
-	s->abs_max = b.abs_max; s->sah_cost = b.sah_cost; s->num_tv = b.num_tv; s->tv_cap = b.num_tv;
+	s->abs_max = b.abs_max; s->sah_cost = b.sah_cost; s->num_tv = b.num_tv;
 	cudaError_t e = cudaSuccess;
+	if (scene_arena_layout(s, b.num_nodes, b.num_tv, false) != RTKD_OK) { rtkd_scene_free(s); return NULL; }
 	if (b.num_tris) {
 		e = cudaMemcpy(s->tri_orig, p + b.off_orig, 48 * (size_t)b.num_tris, cudaMemcpyHostToDevice);
-		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv0, 16 * (size_t)b.num_tv);
-		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv1, 16 * (size_t)b.num_tv);
-		if (e == cudaSuccess) e = cudaMalloc((float4**)&s->tv2, 16 * (size_t)b.num_tv);
 		if (e == cudaSuccess) e = cudaMemcpy(s->tv0, p + b.off_tv0, 16 * (size_t)b.num_tv, cudaMemcpyHostToDevice);
 		if (e == cudaSuccess) e = cudaMemcpy(s->tv1, p + b.off_tv1, 16 * (size_t)b.num_tv, cudaMemcpyHostToDevice);
 		if (e == cudaSuccess) e = cudaMemcpy(s->tv2, p + b.off_tv2, 16 * (size_t)b.num_tv, cudaMemcpyHostToDevice);
 	}
-	if (e == cudaSuccess && b.num_nodes) {
-		e = cudaMalloc((float4**)&s->nodes, 256 * (size_t)b.num_nodes);
-		s->nodes_cap = b.num_nodes;
-		if (e == cudaSuccess) e = cudaMemcpy(s->nodes, p + b.off_nodes, 256 * (size_t)b.num_nodes, cudaMemcpyHostToDevice);
+	if (e == cudaSuccess && b.num_nodes) e = cudaMemcpy(s->nodes, p + b.off_nodes, 256 * (size_t)b.num_nodes, cudaMemcpyHostToDevice);
+	uint32_t bad = 0;
+	if (e == cudaSuccess && (b.num_nodes || b.num_tv)) {
+		uint32_t *d_bad = NULL;
+		e = cudaMalloc(&d_bad, sizeof(uint32_t));
+		if (e == cudaSuccess) e = cudaMemset(d_bad, 0, sizeof(uint32_t));
+		if (e == cudaSuccess) {
+			const size_t items = (size_t)b.num_nodes * RTK_WIDE > b.num_tv ? (size_t)b.num_nodes * RTK_WIDE : b.num_tv;
+			RTK_LAUNCH(k_validate_blob, (unsigned)((items + 255) / 256), 256, 0, (const float4*)s->nodes, b.num_nodes, (const float4*)s->tv0, b.num_tv, b.num_tris, d_bad);
+			e = cudaGetLastError();
+		}
+		if (e == cudaSuccess) e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+		cudaFree(d_bad);
 	}
-	if (e != cudaSuccess) {
-		rtkd_set_error("scene upload failed: %s", cudaGetErrorString(e));
+	if (e != cudaSuccess || bad) {
+		if (bad) rtkd_set_error("scene blob is corrupt (%s)", (bad & 2u) ? "child reference outside the tree" : (bad & 1u) ? "leaf reference outside the triangle slots" : "triangle number outside the scene");
+		else rtkd_set_error("scene upload failed: %s", cudaGetErrorString(e));
 		rtkd_scene_free(s);
 		return NULL;
 	}
+	s->epoch++;
 	return s;
 }

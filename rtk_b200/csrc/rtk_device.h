@@ -13,25 +13,52 @@
 extern "C" {
 #endif
 
-/* A scene resident on the current device.  Pointers are device pointers. */
+#define RTKD_MAX_DEVICES 16
+#define RTKD_TRACE_SLOTS 4
+
+/* What one traversal launch needs for itself: ray cursor, statistics, the global-memory part of the
+ * traversal stack.  A scene owns a few of them so that queries from different streams and host
+ * threads never share mutable state (rtk_trace_ray is re-entrant on a const scene, rtk.h:129). */
+typedef struct rtkd_trace_slot {
+	void *scratch;               /* 256 bytes: +0 ray cursor | +64 stats[6] | +128 hit counter */
+	void *overflow; size_t overflow_entries, overflow_groups;
+	void *done;                  /* cudaEvent_t: recorded after the slot's last launch */
+	void *last_stream;           /* stream of that launch */
+	int   used;
+} rtkd_trace_slot;
+
+/* A scene resident on ONE device.  Pointers are device pointers.  With several devices in use
+ * (rtk_cuda_init_devices) the scene built on the first device carries one replica per further
+ * device: the same struct with that device's pointers. */
 typedef struct rtkd_scene {
 	uint64_t id;                 /* unique per process, also stored in serialised blobs */
 	uint32_t num_tris, num_meshes, num_nodes, num_leaves, depth, build_mode;
 	void *tri_orig;              /* float4[3*num_tris] */
-	void *tv0, *tv1, *tv2;       /* float4[num_tv] each: one 8-entry slot per leaf */
-	uint32_t num_tv, tv_cap;
+	/* what the traversal kernel reads lives in ONE allocation (nodes | tv0 | tv1 | tv2), so that one
+	 * L2 access-policy window covers it */
+	void *arena; size_t arena_cap, arena_used;
 	void *nodes;                 /* float4[16*num_nodes] */
-	uint32_t nodes_cap;
+	void *tv0, *tv1, *tv2;       /* float4[num_tv] each: one 8-entry slot per leaf */
+	uint32_t num_tv;
 	unsigned char *node_level;   /* uint8[num_nodes]: depth of each wide node (NULL for a scene loaded from a blob) */
+	uint32_t node_level_cap;
 	void *mesh_first;            /* uint32[num_meshes+1] */
 	uint32_t *h_mesh_first;      /* host copy */
 	float bounds_min[3], bounds_max[3], abs_max;
 	double build_device_ms, build_total_ms, sah_cost;
+	double upload_ms;            /* host-to-device part of build_total_ms */
 	/* traversal scratch, created on first use */
-	void *scratch;               /* counter, err, stats */
-	void *overflow; size_t overflow_entries, overflow_groups;
+	rtkd_trace_slot slot[RTKD_TRACE_SLOTS];
+	void *slot_lock;             /* pthread_mutex_t* */
+	uint32_t *h_status;          /* pinned + mapped: bit 1 = traversal stack exhausted (sticky until the next build) */
+	uint32_t *d_status;          /* device view of h_status */
 	void *hit16; size_t hit16_cap;   /* compact hits of rtk_trace_rays_device */
 	void *filter_bits;           /* uint32[(num_tris+31)/32] or NULL: triangle filter baked into the leaf slots */
+	/* multi-device */
+	int dev_index;               /* index into the library's device list (0 = the device the scene was built on) */
+	uint64_t epoch;              /* bumped by every change of the device arrays */
+	struct rtkd_scene *replica[RTKD_MAX_DEVICES];   /* [k] = copy on device k (k >= 1), or NULL */
+	uint64_t replica_epoch;      /* epoch the replicas were copied at */
 } rtkd_scene;
 
 typedef struct rtkd_trace_stats {
@@ -39,6 +66,8 @@ typedef struct rtkd_trace_stats {
 } rtkd_trace_stats;
 
 int         rtkd_init(int device);           /* 0 or negative rtk_cuda_status */
+int         rtkd_init_devices(const int *devices, int n);   /* devices[0] builds; host batches are split over all n */
+int         rtkd_device_count(void);         /* devices in use (0 before initialisation) */
 int         rtkd_bind_thread(void);          /* make the library's device current on the calling thread (initialises device 0 if needed) */
 void        rtkd_shutdown(void);
 const char *rtkd_last_error(void);
@@ -47,6 +76,15 @@ int         rtkd_reserve_sms(int sms);       /* the traversal grid leaves this m
 int         rtkd_device_info(int *sm_count, size_t *l2_bytes, int *ctas_per_sm, int *threads_per_cta);
 
 int         rtkd_read_bandwidth(size_t bytes, int passes, double *gbs);   /* read probe: L2 (small buffer) or HBM */
+int         rtkd_gather_bandwidth(size_t bytes, size_t record_bytes, int passes, double *gbs);   /* random record gathers */
+/* host link probe: concurrent pinned-memory copies on the first `ndev` devices; dir 1 = up, 2 = down, 3 = both */
+int         rtkd_link_bandwidth(int ndev, size_t bytes_per_device, int dir, int passes, double *gbs);
+
+/* page-locked host memory the devices can read and WRITE directly (rows of rtk_trace_rays land in it without staging) */
+void       *rtkd_host_alloc(size_t bytes);
+void        rtkd_host_free(void *p);
+int         rtkd_host_register(void *p, size_t bytes);
+int         rtkd_host_unregister(void *p);
 
 rtkd_scene *rtkd_scene_new(uint32_t num_tris, uint32_t num_meshes, const uint32_t *mesh_first);
 void        rtkd_scene_free(rtkd_scene *s);
@@ -86,6 +124,12 @@ int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, int c
 int rtkd_trace_brute(rtkd_scene *s, const void *d_rays, void *d_hit16, size_t n, void *stream);
 int rtkd_resolve(rtkd_scene *s, const void *d_hit16, void *d_hits, void *d_mask, size_t n, void *stream);
 void *rtkd_scene_hit16(rtkd_scene *s, size_t n);   /* scene-owned compact hit buffer of >= n records */
+/* the copy of the scene on the device that owns device pointer `p` (replicas are brought up to date);
+ * that device becomes current on the calling thread.  NULL: p belongs to no device in use */
+rtkd_scene *rtkd_scene_for_pointer(rtkd_scene *s, const void *p);
+int   rtkd_sync_replicas(rtkd_scene *s);           /* copy the scene to every further device in use */
+uint32_t rtkd_scene_status(rtkd_scene *s);         /* sticky error bits of the scene on all its devices */
+int   rtkd_debug_limit_stack(int entries);         /* test hook: global-memory stack entries per ray (0 = sized from the tree) */
 
 /* hit gather over NVLink peer memory (CUDA IPC): a window owned by the gathering process, opened
  * by the others, filled with copy-engine pushes.  handle64 is a cudaIpcMemHandle_t. */

@@ -70,6 +70,17 @@ int rtk_cuda_init(int device)
 	if (r) warn_once();
 	return r;
 }
+int rtk_cuda_init_devices(const int *devices, int num_devices)
+{
+	int r = rtkd_init_devices(devices, num_devices);
+	if (r) warn_once();
+	return r;
+}
+int rtk_cuda_device_count(void) { return rtkd_device_count(); }
+void *rtk_cuda_host_alloc(size_t bytes) { return rtkd_host_alloc(bytes); }
+void rtk_cuda_host_free(void *p) { rtkd_host_free(p); }
+int rtk_cuda_host_register(void *p, size_t bytes) { return rtkd_host_register(p, bytes); }
+int rtk_cuda_host_unregister(void *p) { return rtkd_host_unregister(p); }
 void rtk_cuda_shutdown(void) { rtkd_shutdown(); }
 int rtk_cuda_device_info(int *sm_count, size_t *l2_bytes, int *ctas, int *threads)
 {
@@ -81,6 +92,14 @@ int rtk_cuda_reserve_sms(int sms) { return rtkd_reserve_sms(sms); }
 int rtk_cuda_measure_read_bandwidth(size_t bytes, int passes, double *gb_per_s)
 {
 	return rtkd_read_bandwidth(bytes, passes, gb_per_s);
+}
+int rtk_cuda_measure_gather_bandwidth(size_t bytes, size_t record_bytes, int passes, double *gb_per_s)
+{
+	return rtkd_gather_bandwidth(bytes, record_bytes, passes, gb_per_s);
+}
+int rtk_cuda_measure_host_link(int num_devices, size_t bytes_per_device, int directions, int passes, double *gb_per_s)
+{
+	return rtkd_link_bandwidth(num_devices, bytes_per_device, directions, passes, gb_per_s);
 }
 
 /* ---------------------------------------------------------------------------------------- */
@@ -152,7 +171,8 @@ static rtkd_scene *scene_device(const rtk_scene *scene)
 			rtkd_set_error("scene handle is not resident on this device (handles from rtk_build_scene cannot be copied; use rtk_finish_build_to for a relocatable blob)");
 		} else {
 			if (e) { rtkd_scene_free(e->dev); table_remove(e); }       /* a different blob now lives at this address */
-			dev = rtkd_blob_read((const char*)scene + HEADER_BLOCK, (size_t)scene->size_in_bytes - HEADER_BLOCK);
+			if (scene->size_in_bytes < HEADER_BLOCK) rtkd_set_error("scene blob truncated");
+			else dev = rtkd_blob_read((const char*)scene + HEADER_BLOCK, (size_t)scene->size_in_bytes - HEADER_BLOCK);
 			if (dev && table_add(scene, dev, 0) != 0) { rtkd_scene_free(dev); dev = NULL; rtkd_set_error("out of host memory"); }
 		}
 	}
@@ -160,6 +180,26 @@ static rtkd_scene *scene_device(const rtk_scene *scene)
 	if (!dev) warn_once();
 	return dev;
 }
+
+/* the copy of the scene on the device that owns the caller's device buffer (several devices in use) */
+static rtkd_scene *scene_on_device_of(const rtk_scene *scene, const void *d_ptr)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return NULL;
+	rtkd_scene *r = rtkd_scene_for_pointer(dev, d_ptr);
+	if (!r) warn_once();
+	return r;
+}
+
+int rtk_cuda_scene_status(const rtk_scene *scene)
+{
+	rtkd_scene *dev = scene_device(scene);
+	if (!dev) return RTK_CUDA_ERR_SCENE;
+	if (rtkd_scene_status(dev) & 2u) { rtkd_set_error("traversal stack exhausted"); return RTK_CUDA_ERR_OVERFLOW; }
+	return RTK_CUDA_OK;
+}
+
+int rtk_cuda_debug_limit_stack(int entries) { return rtkd_debug_limit_stack(entries); }
 
 int rtk_cuda_attach_scene(const rtk_scene *scene) { return scene_device(scene) ? RTK_CUDA_OK : RTK_CUDA_ERR_SCENE; }
 
@@ -489,6 +529,8 @@ rtk_scene *rtk_build_scene(const rtk_scene_desc *desc)
 	rtkd_scene *dev = b->dev;
 	b->dev = NULL;
 	build_free(b);
+	/* "upload + build + replicate": with several devices in use every one of them gets its copy now */
+	if (dev && rtkd_sync_replicas(dev) != RTK_CUDA_OK) { warn_once(); rtkd_scene_free(dev); return NULL; }
 	return dev ? make_handle(dev) : NULL;
 }
 
@@ -663,21 +705,21 @@ int rtk_trace_rays_compact(const rtk_scene *scene, const rtk_ray *rays, rtk_cuda
 
 int rtk_trace_rays_compact_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream)
 {
-	rtkd_scene *dev = scene_device(scene);
+	rtkd_scene *dev = scene_on_device_of(scene, d_rays);
 	if (!dev) return RTK_CUDA_ERR_SCENE;
 	return rtkd_trace(dev, d_rays, d_hit16, n, g_cull_mode, NULL, stream);
 }
 
 int rtk_resolve_hits_device(const rtk_scene *scene, const void *d_hit16, void *d_hits, void *d_hit_mask, size_t n, void *stream)
 {
-	rtkd_scene *dev = scene_device(scene);
+	rtkd_scene *dev = scene_on_device_of(scene, d_hit16);
 	if (!dev) return RTK_CUDA_ERR_SCENE;
 	return rtkd_resolve(dev, d_hit16, d_hits, d_hit_mask, n, stream);
 }
 
 int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hits, void *d_hit_mask, size_t n, void *stream)
 {
-	rtkd_scene *dev = scene_device(scene);
+	rtkd_scene *dev = scene_on_device_of(scene, d_rays);
 	if (!dev) return RTK_CUDA_ERR_SCENE;
 	void *h16 = rtkd_scene_hit16(dev, n);
 	if (!h16 && n) return RTK_CUDA_ERR_MEMORY;
@@ -688,7 +730,7 @@ int rtk_trace_rays_device(const rtk_scene *scene, const void *d_rays, void *d_hi
 
 int rtk_occluded_rays_device(const rtk_scene *scene, const void *d_rays, void *d_occluded, size_t n, void *stream)
 {
-	rtkd_scene *dev = scene_device(scene);
+	rtkd_scene *dev = scene_on_device_of(scene, d_rays);
 	if (!dev) return RTK_CUDA_ERR_SCENE;
 	return rtkd_trace(dev, d_rays, d_occluded, n, g_cull_mode | 2, NULL, stream);
 }
@@ -734,7 +776,7 @@ int rtk_cuda_generate_primary_rays(const rtk_cuda_camera *camera, uint64_t seed,
 int rtk_cuda_generate_bounce_rays(const rtk_scene *scene, const void *d_rays_in, const void *d_hit16, void *d_rays_out,
                                   void *d_alive, size_t n, uint64_t seed, uint32_t bounce, uint64_t first_ray, uint32_t flags, void *stream)
 {
-	rtkd_scene *dev = scene_device(scene);
+	rtkd_scene *dev = scene_on_device_of(scene, d_rays_in);
 	if (!dev) return RTK_CUDA_ERR_SCENE;
 	if (bounce >= 16) { rtkd_set_error("bounce number must be below 16"); return RTK_CUDA_ERR_ARGUMENT; }
 	return rtkd_gen_bounce(dev, d_rays_in, d_hit16, d_rays_out, d_alive, n, seed, bounce, first_ray, flags, stream);
@@ -742,15 +784,15 @@ int rtk_cuda_generate_bounce_rays(const rtk_scene *scene, const void *d_rays_in,
 
 int rtk_trace_rays_bruteforce_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, void *stream)
 {
-	rtkd_scene *dev = scene_device(scene);
+	rtkd_scene *dev = scene_on_device_of(scene, d_rays);
 	if (!dev) return RTK_CUDA_ERR_SCENE;
 	return rtkd_trace_brute(dev, d_rays, d_hit16, n, stream);
 }
 
 int rtk_trace_stats_device(const rtk_scene *scene, const void *d_rays, void *d_hit16, size_t n, rtk_cuda_trace_stats *stats, void *stream)
 {
-	rtkd_scene *dev = scene_device(scene);
-	if (!dev || !stats) return RTK_CUDA_ERR_SCENE;
+	rtkd_scene *dev = stats ? scene_on_device_of(scene, d_rays) : NULL;
+	if (!dev) return RTK_CUDA_ERR_SCENE;
 	rtkd_trace_stats st;
 	int r = rtkd_trace(dev, d_rays, d_hit16, n, g_cull_mode, &st, stream);
 	stats->rays = st.rays; stats->hits = st.hits; stats->node_visits = st.node_visits;

@@ -278,9 +278,18 @@ struct cudaDeviceProp { char name[256]; int multiProcessorCount; int l2CacheSize
 static inline const char *cudaGetErrorString(cudaError_t e) { return e == 0 ? "no error" : "emulated CUDA error"; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
-static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+// SIMT_DEVICES=n in the environment emulates n devices (the in-library multi-GPU layer): the current
+// device is per host thread as in CUDA, "device memory" remembers the device it was allocated on
+// (cudaPointerGetAttributes reports it), peer copies are plain copies.
+static inline int simt_device_count() { static const int n = getenv("SIMT_DEVICES") && atoi(getenv("SIMT_DEVICES")) > 0 ? atoi(getenv("SIMT_DEVICES")) : 1; return n; }
+extern __thread int simt_cur_device;
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = simt_device_count(); return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= simt_device_count()) return cudaErrorInvalidValue; simt_cur_device = d; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int *d) { *d = simt_cur_device; return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+void simt_track_alloc(void *p, size_t n, int kind);      // kind: 2 device, 1 pinned host
+void simt_track_free(void *p);
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int)
 {
 	memset(p, 0, sizeof(*p));
@@ -302,16 +311,33 @@ template <typename T> static inline cudaError_t cudaMalloc(T **p, size_t n)
 	if (shm) { q = simt_shm_alloc(n ? n : 256); if (!q) return cudaErrorMemoryAllocation; }
 	else if (posix_memalign(&q, 256, n ? n : 256)) return cudaErrorMemoryAllocation;
 	memset(q, 0xCD, n);   // poison: device memory is uninitialised
+	simt_track_alloc(q, n ? n : 256, 2);
 	*p = (T*)q;
 	return cudaSuccess;
 }
-template <typename T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { return cudaMalloc(p, n); }
-static inline cudaError_t cudaFree(void *p) { if (!simt_shm_release(p)) free(p); return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMallocHost(T **p, size_t n)
+{
+	void *q = NULL;
+	if (posix_memalign(&q, 256, n ? n : 256)) return cudaErrorMemoryAllocation;
+	memset(q, 0xCD, n);
+	simt_track_alloc(q, n ? n : 256, 1);
+	*p = (T*)q;
+	return cudaSuccess;
+}
+#define cudaHostAllocDefault 0
+#define cudaHostAllocPortable 1
+#define cudaHostAllocMapped 2
+template <typename T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { return cudaMallocHost(p, n); }
+static inline cudaError_t cudaFree(void *p) { if (!p) return cudaSuccess; simt_track_free(p); if (!simt_shm_release(p)) free(p); return cudaSuccess; }
 template <typename T> static inline cudaError_t cudaMallocAsync(T **p, size_t n, cudaStream_t) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeAsync(void *p, cudaStream_t) { return cudaFree(p); }
-static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
-static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
-static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+#define cudaHostRegisterDefault 0
+#define cudaHostRegisterPortable 1
+#define cudaHostRegisterMapped 2
+static inline cudaError_t cudaHostRegister(void *p, size_t n, unsigned) { simt_track_alloc(p, n, 1); return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *p) { simt_track_free(p); return cudaSuccess; }
+static inline cudaError_t cudaFreeHost(void *p) { if (!p) return cudaSuccess; simt_track_free(p); free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void *d, int, const void *s, int, size_t n, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
@@ -333,16 +359,24 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = 0)
 	return cudaSuccess;
 }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 2; return cudaSuccess; }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
 #define cudaFuncAttributePreferredSharedMemoryCarveout 9
-struct cudaPointerAttributes { int type; void *devicePointer; void *hostPointer; };
+struct cudaPointerAttributes { int type; int device; void *devicePointer; void *hostPointer; };
+#define cudaMemoryTypeUnregistered 0
 #define cudaMemoryTypeHost 1
 #define cudaMemoryTypeDevice 2
-static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *) { a->type = 0; a->devicePointer = 0; a->hostPointer = 0; return cudaSuccess; }
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p);
+// L2 persistence controls: accepted and ignored
+#define cudaLimitPersistingL2CacheSize 6
+static inline cudaError_t cudaDeviceSetLimit(int, size_t) { return cudaSuccess; }
+#define cudaDevAttrMaxPersistingL2CacheSize 108
+#define cudaDevAttrMaxAccessPolicyWindowSize 109
+static inline cudaError_t cudaDeviceGetAttribute(int *v, int, int) { *v = 0; return cudaSuccess; }
 
 // CUDA IPC.  Heap-backed memory: the emulated "other process" is this process and a handle is the
 // pointer itself.  Shared-memory-backed memory (SIMT_SHM_MALLOC): a handle carries the name and size
@@ -495,6 +529,36 @@ void launch(dim3 grid, dim3 block, const std::function<void()> &body)
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <unistd.h>
+#include <map>
+__thread int simt_cur_device = 0;
+// allocation table behind cudaPointerGetAttributes: base -> (size, kind, device)
+struct simt_alloc_rec { size_t size; int kind, device; };
+static std::mutex g_alloc_lock;
+static std::map<uintptr_t, simt_alloc_rec> g_allocs;
+void simt_track_alloc(void *p, size_t n, int kind)
+{
+	std::lock_guard<std::mutex> guard(g_alloc_lock);
+	simt_alloc_rec r = { n, kind, simt_cur_device };
+	g_allocs[(uintptr_t)p] = r;
+}
+void simt_track_free(void *p)
+{
+	std::lock_guard<std::mutex> guard(g_alloc_lock);
+	g_allocs.erase((uintptr_t)p);
+}
+cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p)
+{
+	std::lock_guard<std::mutex> guard(g_alloc_lock);
+	a->type = cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = 0; a->hostPointer = 0;
+	auto it = g_allocs.upper_bound((uintptr_t)p);
+	if (it == g_allocs.begin()) return cudaSuccess;
+	--it;
+	if ((uintptr_t)p >= it->first + it->second.size) return cudaSuccess;
+	a->type = it->second.kind; a->device = it->second.device;
+	a->devicePointer = (void*)p;
+	a->hostPointer = it->second.kind == cudaMemoryTypeHost ? (void*)p : 0;
+	return cudaSuccess;
+}
 static std::mutex g_shm_lock;
 static std::vector<simt_shm_block> g_shm_blocks;     // blocks this process created
 static std::vector<simt_shm_block> g_shm_mapped;     // blocks of other processes mapped here

@@ -484,6 +484,9 @@ class HostDevice:
     def get(self, handle, dtype, count):
         return handle[:count * np.dtype(dtype).itemsize].copy().view(dtype)
 
+    def sync(self):
+        pass
+
 
 def case_wavefront(lib, orc, dev):
     """primary rays and bounce rays generated on the device, traced without leaving
@@ -942,3 +945,292 @@ def case_host_batch_chunks(lib, orc, nrays=30000, chunk_log2=12):
     assert len(sc.trace_rays_compact(rays[:0])) == 0
     assert lib.rtk_trace_rays_compact(sc.ptr, None, None, 5) != 0
     sc.free()
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: page-locked caller arrays (rows written in place by the device), several devices behind
+# one process, concurrent streams on one scene, blob validation, the overflow report
+# ---------------------------------------------------------------------------------------------
+
+class PinnedArrays:
+    """numpy views of rtk_cuda_host_alloc memory (page-locked, device-writable)"""
+
+    def __init__(self, lib):
+        self.lib, self.ptrs = lib, []
+
+    def empty(self, n, dtype, fill=None):
+        dt = np.dtype(dtype)
+        nbytes = max(n * dt.itemsize, 16)
+        p = self.lib.rtk_cuda_host_alloc(nbytes)
+        assert p, self.lib.last_error()
+        self.ptrs.append(p)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(nbytes,))[:n * dt.itemsize].view(dt)
+        if fill is not None:
+            a.view(np.uint8)[:] = fill
+        return a
+
+    def free(self):
+        for p in self.ptrs:
+            self.lib.rtk_cuda_host_free(p)
+        self.ptrs = []
+
+
+def case_direct_rows(lib, orc, nrays=30000, chunk_log2=12):
+    """rtk_trace_rays with page-locked hits / mask arrays: the resolve kernel writes the rows of the rays
+    that hit straight into the caller's memory.  Must equal the staged path (pageable arrays) byte for
+    byte, leave the rows of misses untouched (rtk.c:571-576), survive many chunks and ragged tails, and
+    agree with the oracle."""
+    s = scenes.config_scene("C3", 0.004)
+    rays = scenes.bounce_rays(s, nrays)
+    sc = lib.build_scene(s["meshes"])
+    pin = PinnedArrays(lib)
+    old = os.environ.pop("RTK_B200_HOST_CHUNK_LOG2", None)
+    try:
+        hits0 = np.zeros(nrays, dtype=api.HIT_DTYPE)
+        hits0.view(np.uint8)[:] = 0x5A
+        _, mask0, n0 = sc.trace_rays(rays, hits=hits0)                       # pageable: staged path
+        p_rays = pin.empty(nrays, api.RAY_DTYPE)
+        p_rays[:] = rays
+        for log2 in (None, chunk_log2):
+            if log2 is not None:
+                os.environ["RTK_B200_HOST_CHUNK_LOG2"] = str(log2)
+            p_hits = pin.empty(nrays, api.HIT_DTYPE, fill=0x5A)
+            p_mask = pin.empty(nrays, np.uint8, fill=0x77)
+            r = lib.rtk_trace_rays(sc.ptr, p_rays.ctypes.data, p_hits.ctypes.data, p_mask.ctypes.data, nrays)
+            assert r == n0, (r, n0, lib.last_error())
+            assert np.array_equal(p_mask, mask0)
+            assert p_hits.tobytes() == hits0.tobytes(), "direct rows differ from the staged rows"
+            # no mask requested, pageable rays, ragged count
+            p_hits2 = pin.empty(nrays, api.HIT_DTYPE, fill=0x5A)
+            k = nrays - 37
+            r = lib.rtk_trace_rays(sc.ptr, rays.ctypes.data, p_hits2.ctypes.data, None, k)
+            assert r == int(mask0[:k].sum())
+            assert p_hits2[:k].tobytes() == hits0[:k].tobytes()
+            assert (p_hits2[k:].view(np.uint8) == 0x5A).all()
+        m = mask0.astype(bool)
+        assert 0 < m.sum() < nrays
+        assert (hits0.view(np.uint8).reshape(-1, 68)[~m] == 0x5A).all()
+        kk = min(nrays, 1500)
+        assert_same(api.hits_to_hit16(p_hits, p_mask, s["mesh_first"])[:kk], orc.trace_brute(s["tris"], rays[:kk]), "direct rows")
+    finally:
+        os.environ.pop("RTK_B200_HOST_CHUNK_LOG2", None)
+        if old is not None:
+            os.environ["RTK_B200_HOST_CHUNK_LOG2"] = old
+        pin.free()
+        sc.free()
+
+
+def case_multi_device(lib, orc, ndev, dev=None, nrays=600000, oracle_rays=1200):
+    """`lib` was initialised with rtk_cuda_init_devices over `ndev` devices.  One rtk_build_scene, one
+    rtk_trace_rays: the batch is split over the devices and the result must be what a single device
+    gives -- rows, mask, count, compact records -- and the oracle's on a sample.  Small batches, pageable
+    and page-locked arrays, the triangle filter and a rebuild all have to reach every replica."""
+    assert lib.rtk_cuda_device_count() == ndev
+    s = scenes.config_scene("C3", 0.004)
+    rays = scenes.bounce_rays(s, nrays)
+    sc = lib.build_scene(s["meshes"])
+    pin = PinnedArrays(lib)
+    try:
+        # reference result: compact records of the whole batch through the device entry point on the
+        # first device (single-device code path), expanded on the host side of the test
+        want16 = sc.trace_rays_compact(rays)                   # split over the devices as well ...
+        idx = np.linspace(0, nrays - 1, oracle_rays).astype(np.int64)
+        assert_same(want16[idx], orc.trace_brute(s["tris"], rays[idx]), "multi-device compact records")
+        # every share's boundary region against the oracle too (off-by-one in the range split)
+        per = (nrays // ndev + 127) // 128 * 128
+        edges = np.unique(np.clip(np.concatenate([np.arange(k * per - 3, k * per + 3) for k in range(1, ndev)] + [np.arange(nrays - 4, nrays)]), 0, nrays - 1))
+        assert_same(want16[edges], orc.trace_brute(s["tris"], rays[edges]), "multi-device share boundaries")
+        # rows, pageable arrays (staged path on every device)
+        hits = np.zeros(nrays, dtype=api.HIT_DTYPE)
+        hits.view(np.uint8)[:] = 0x5A
+        _, mask, nh = sc.trace_rays(rays, hits=hits)
+        assert nh == int(mask.sum()) == int((want16["prim"] != api.RTK_CUDA_MISS).sum())
+        assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want16, "multi-device rows (staged)")
+        assert (hits.view(np.uint8).reshape(-1, 68)[~mask.astype(bool)] == 0x5A).all()
+        # rows, page-locked arrays (written in place by every device)
+        p_rays = pin.empty(nrays, api.RAY_DTYPE)
+        p_rays[:] = rays
+        p_hits = pin.empty(nrays, api.HIT_DTYPE, fill=0x5A)
+        p_mask = pin.empty(nrays, np.uint8, fill=0x77)
+        r = lib.rtk_trace_rays(sc.ptr, p_rays.ctypes.data, p_hits.ctypes.data, p_mask.ctypes.data, nrays)
+        assert r == nh, (r, nh, lib.last_error())
+        assert p_hits.tobytes() == hits.tobytes() and np.array_equal(p_mask, mask)
+        # single rays from several threads land on different devices
+        import threading
+        errors = []
+
+        def single(tid):
+            try:
+                for i in range(tid, 64, 4):
+                    h = sc.trace_ray(rays[i])
+                    if want16["prim"][i] == api.RTK_CUDA_MISS:
+                        assert h is None
+                    else:
+                        assert h is not None and h["t"] == want16["t"][i]
+            except Exception as ex:                                   # noqa: BLE001
+                errors.append(ex)
+        th = [threading.Thread(target=single, args=(t,)) for t in range(4)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if errors:
+            raise errors[0]
+        # a filter and a rebuild must reach the replicas
+        keep = np.ones(len(s["tris"]), dtype=bool)
+        keep[want16["prim"][want16["prim"] != api.RTK_CUDA_MISS]] = False       # switch off every first hit
+        sc.set_triangle_filter(keep)
+        got = sc.trace_rays_compact(rays)
+        hitm = got["prim"] != api.RTK_CUDA_MISS
+        assert not np.isin(got["prim"][hitm], np.nonzero(~keep)[0]).any(), "a replica still traces switched-off triangles"
+        k = 400
+        tr = s["tris"].copy()
+        tr[~keep] = np.nan
+        assert_same(got[idx[:k]], orc.trace_brute(tr, rays[idx[:k]]), "filtered, multi-device")
+        sc.set_triangle_filter(None)
+        assert lib.rtk_cuda_rebuild_scene(sc.ptr, None) == 0, lib.last_error()
+        assert_same(sc.trace_rays_compact(rays), want16, "after filter removal and rebuild")
+        assert lib.rtk_cuda_scene_status(sc.ptr) == 0
+        # device entry points follow the buffer: a buffer on device k is traced by device k's replica
+        if dev is not None and hasattr(dev, "on_device"):
+            for k in range(ndev):
+                with dev.on_device(k):
+                    h_r, d_r = dev.put(rays[:5000])
+                    h_o, d_o = dev.empty(16 * 5000)
+                    assert lib.rtk_trace_rays_compact_device(sc.ptr, d_r, d_o, 5000, dev.stream) == 0, lib.last_error()
+                    assert_same(dev.get(h_o, api.HIT16_DTYPE, 5000), want16[:5000], f"device entry point on device {k}")
+    finally:
+        pin.free()
+        sc.free()
+
+
+def case_two_streams(lib, orc, dev, make_stream=None):
+    """Two queries on ONE scene in flight at once on different streams (and from two host threads): each
+    launch has its own ray cursor and stack scratch, so neither may skip or repeat rays."""
+    import threading
+    s = scenes.config_scene("C3", 0.004)
+    n = 200000
+    rays = scenes.bounce_rays(s, n)
+    sc = lib.build_scene(s["meshes"])
+    want = sc.trace_rays_compact(rays)
+    k = 800
+    assert_same(want[:k], orc.trace_brute(s["tris"], rays[:k]), "reference run")
+    h_r, d_r = dev.put(rays)
+    streams = [make_stream() if make_stream else None for _ in range(2)]
+    outs = [dev.empty(16 * n, fill=0x11) for _ in range(4)]
+    errors = []
+
+    def worker(t):
+        try:
+            for rep in range(2):
+                h_o, d_o = outs[2 * t + rep]
+                if lib.rtk_trace_rays_compact_device(sc.ptr, d_r, d_o, n, streams[t]) != 0:
+                    raise RuntimeError(lib.last_error())
+        except Exception as ex:                                   # noqa: BLE001
+            errors.append(ex)
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    if errors:
+        raise errors[0]
+    dev.sync()
+    for i, (h_o, _) in enumerate(outs):
+        assert_same(dev.get(h_o, api.HIT16_DTYPE, n), want, f"concurrent query {i}")
+    sc.free()
+
+
+def case_blob_validation(lib, orc):
+    """Blobs come from disk: truncated or corrupted ones are refused with a reason instead of being
+    uploaded (host out-of-bounds reads) or traced (device out-of-bounds reads, endless loops)."""
+    s = scenes.config_scene("C3", 0.002)
+    rays = scenes.bounce_rays(s, 500)
+    sc, blob = lib.build_blob(s["meshes"])
+    want = sc.trace_rays_compact(rays)
+    size = len(blob)
+    good = blob.copy()
+    sc.free()
+
+    def attempt(mutate, what):
+        buf = np.zeros(size + 256, dtype=np.uint8)
+        off = (-buf.ctypes.data) % 128
+        buf[off:off + size] = good
+        view = buf[off:off + size]
+        mutate(view)
+        hits = np.zeros(len(rays), dtype=api.HIT_DTYPE)
+        r = lib.rtk_trace_rays(buf.ctypes.data + off, rays.ctypes.data, hits.ctypes.data, None, len(rays))
+        if r != C.c_size_t(-1).value:
+            lib.rtk_cuda_detach_scene(buf.ctypes.data + off)
+        return r, lib.last_error(), buf
+
+    r, err, buf = attempt(lambda v: None, "untouched")
+    assert r == int((want["prim"] != api.RTK_CUDA_MISS).sum()), err
+    hdr = api.rtk_scene.from_buffer(good)          # header block: 128 bytes; payload table follows
+    sub = good[128:256].view(np.uint64)             # magic2, id, 3 x u32 pairs ..., offsets at the end
+    u32 = good[128:256].view(np.uint32)
+
+    def set_size(v):
+        v[24:32] = np.frombuffer(np.uint64(64).tobytes(), dtype=np.uint8)          # size_in_bytes < header block
+    r, err, _ = attempt(set_size, "size below the header")
+    assert r == C.c_size_t(-1).value and "truncated" in err, err
+
+    def cut(v):
+        v[24:32] = np.frombuffer(np.uint64(size // 2).tobytes(), dtype=np.uint8)    # claims half its size
+    r, err, _ = attempt(cut, "truncated")
+    assert r == C.c_size_t(-1).value and ("corrupt" in err or "truncated" in err), err
+
+    def big_nodes(v):
+        v[128 + 24:128 + 28] = np.frombuffer(np.uint32(0x7fffff00).tobytes(), dtype=np.uint8)   # num_nodes
+    r, err, _ = attempt(big_nodes, "node count")
+    assert r == C.c_size_t(-1).value and "corrupt" in err, err
+
+    # child reference of the root pointing at the root itself: a cycle
+    off_nodes = int(good[128:256].view(np.uint64)[10])
+
+    def cycle(v):
+        node0 = v[128 + off_nodes:128 + off_nodes + 256].view(np.uint32)
+        k = [j for j in range(8) if node0[8 * j + 3] != 0xffffffff and not (node0[8 * j + 3] & 0x80000000)]
+        assert k, "root has no internal child in this scene"
+        node0[8 * k[0] + 3] = 0
+    r, err, _ = attempt(cycle, "cycle")
+    assert r == C.c_size_t(-1).value and "child reference" in err, err
+
+    off_tv0 = int(good[128:256].view(np.uint64)[11])
+
+    def bad_prim(v):
+        v[128 + off_tv0 + 12:128 + off_tv0 + 16] = np.frombuffer(np.uint32(0x0ffffff0).tobytes(), dtype=np.uint8)
+    r, err, _ = attempt(bad_prim, "triangle number")
+    assert r == C.c_size_t(-1).value and "triangle number" in err, err
+
+
+def case_overflow_report(lib, orc, dev):
+    """A traversal that runs out of stack is REPORTED: host entry points fail with RTK_CUDA_ERR_OVERFLOW,
+    the device path raises the scene's sticky status, and a rebuild clears it."""
+    base = np.array([[(0, 0, 1), (1, 0, 1), (0, 1, 1)]], dtype=np.float32)
+    tris = np.repeat(base, 9000, axis=0)               # coincident: every box overlaps every other
+    rays = np.zeros(2100, dtype=api.RAY_DTYPE)
+    rng = np.random.default_rng(5)
+    rays["o"] = np.concatenate([rng.random((2100, 2)) * 0.6, np.zeros((2100, 1))], axis=1).astype(np.float32)
+    rays["d"] = (0, 0, 1)
+    rays["max_t"] = api.RTK_INF
+    sc = lib.build_scene(soup_mesh(tris))
+    try:
+        want = sc.trace_rays_compact(rays)
+        assert lib.rtk_cuda_scene_status(sc.ptr) == 0
+        assert lib.rtk_cuda_debug_limit_stack(1) == 0           # 16 entries in shared memory + 1: far too few here
+        hits = np.zeros(len(rays), dtype=api.HIT_DTYPE)
+        r = lib.rtk_trace_rays(sc.ptr, rays.ctypes.data, hits.ctypes.data, None, len(rays))
+        assert r == C.c_size_t(-1).value and "stack" in lib.last_error(), (r, lib.last_error())
+        assert lib.rtk_cuda_scene_status(sc.ptr) == api.RTK_CUDA_ERR_OVERFLOW
+        # device path: returns OK (asynchronous), the status tells
+        h_r, d_r = dev.put(rays)
+        h_o, d_o = dev.empty(16 * len(rays))
+        assert lib.rtk_trace_rays_compact_device(sc.ptr, d_r, d_o, len(rays), dev.stream) == 0
+        dev.sync()
+        assert lib.rtk_cuda_scene_status(sc.ptr) == api.RTK_CUDA_ERR_OVERFLOW
+        # back to automatic sizing + rebuild: the flag is cleared and the answers are right again
+        assert lib.rtk_cuda_debug_limit_stack(0) == 0
+        assert lib.rtk_cuda_rebuild_scene(sc.ptr, None) == 0
+        assert lib.rtk_cuda_scene_status(sc.ptr) == 0
+        assert_same(sc.trace_rays_compact(rays), want, "after the rebuild")
+        assert lib.rtk_cuda_scene_status(sc.ptr) == 0
+    finally:
+        lib.rtk_cuda_debug_limit_stack(0)
+        sc.free()

@@ -102,3 +102,63 @@ def test_randomised_adversarial_scenes(emu_lib, orc):
         hits += fuzz_emu.one(emu_lib, seed)[2]
     assert hits > 500
     emu_lib.rtk_cuda_set_build_mode(1)                  # back to the default (binned SAH)
+
+
+# ---- round 2 ------------------------------------------------------------------------------------
+
+def test_direct_rows_into_page_locked_arrays(emu_lib, orc):
+    pc.case_direct_rows(emu_lib, orc, nrays=20000, chunk_log2=12)
+
+
+def test_two_streams_one_scene(emu_lib, orc):
+    pc.case_two_streams(emu_lib, orc, pc.HostDevice())
+
+
+def test_blob_validation(emu_lib, orc):
+    pc.case_blob_validation(emu_lib, orc)
+
+
+def test_overflow_is_reported(emu_lib, orc):
+    pc.case_overflow_report(emu_lib, orc, pc.HostDevice())
+
+
+def test_probes(emu_lib):
+    import ctypes as C
+    g = C.c_double(0)
+    assert emu_lib.rtk_cuda_measure_gather_bandwidth(1 << 18, 256, 1, C.byref(g)) == 0 and g.value > 0
+    assert emu_lib.rtk_cuda_measure_gather_bandwidth(1 << 18, 128, 1, C.byref(g)) == 0 and g.value > 0
+    assert emu_lib.rtk_cuda_measure_gather_bandwidth(1 << 18, 100, 1, C.byref(g)) != 0
+    assert emu_lib.rtk_cuda_measure_host_link(1, 1 << 16, 3, 2, C.byref(g)) == 0 and g.value > 0
+    assert emu_lib.rtk_cuda_measure_host_link(2, 1 << 16, 3, 2, C.byref(g)) != 0          # one device in use
+
+
+def test_multi_device_in_one_process():
+    """rtk_cuda_init_devices over 3 emulated devices (SIMT_DEVICES=3): a process of its own, because the
+    device list of a process is fixed at initialisation."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    code = (
+        "import os, sys, ctypes as C\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r}); sys.path.insert(0, {os.path.join(root, 'tests', 'emu')!r})\n"
+        "import build_emu, parity_cases as pc\n"
+        "from rtk_b200 import api\n"
+        "from oracle import orc\n"
+        "lib = api.Library(build_emu.build())\n"
+        "devs = (C.c_int * 3)(0, 1, 2)\n"
+        "assert lib.rtk_cuda_init_devices(devs, 3) == 0, lib.last_error()\n"
+        "assert lib.rtk_cuda_init_devices(devs, 3) == 0\n"
+        "assert lib.rtk_cuda_init(1) != 0 and 'already bound' in lib.last_error()\n"
+        "g = C.c_double(0)\n"
+        "assert lib.rtk_cuda_measure_host_link(3, 1 << 16, 3, 2, C.byref(g)) == 0 and g.value > 0\n"
+        "pc.case_multi_device(lib, orc, 3, pc.HostDevice(), nrays=3 * (1 << 14) + 1000, oracle_rays=500)\n"
+        "lib.rtk_cuda_shutdown()\n"
+        "two = (C.c_int * 2)(2, 0)\n"
+        "assert lib.rtk_cuda_init_devices(two, 2) == 0, lib.last_error()\n"
+        "pc.case_multi_device(lib, orc, 2, None, nrays=2 * (1 << 14), oracle_rays=200)\n"
+        "print('multi-device ok')\n"
+    )
+    env = dict(os.environ, SIMT_DEVICES="3", RTK_B200_HOST_MIN_SHARE_LOG2="14", RTK_B200_HOST_CHUNK_LOG2="12")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "multi-device ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -75,3 +75,40 @@ def test_scene_generators_are_deterministic():
     assert len(c1["tris"]) == 992 and c1["meshes"][0]["indices"].dtype == np.uint16
     c4 = scenes.config_scene("C4", 0.001)
     assert len(c4["meshes"]) == 2 and c4["mesh_first"][-1] == len(c4["tris"])
+
+
+def test_blocked_brute_force_equals_plain_brute_force(orc):
+    """orc.trace_brute switches to the blocked, pre-filtered loop for big jobs; the scalar code stays the
+    arbiter of every hit there, so the two must agree bit for bit -- on random soups, on the exactly
+    coplanar grid (fp64 promotion, shared edges and vertices, ties), on degenerate and NaN triangles,
+    and on counts that are not multiples of the vector width or the block size."""
+    rng = np.random.default_rng(11)
+    for ntris, nrays in ((4099, 333), (2048, 64), (7, 40), (1, 9), (20001, 70)):
+        tris = (rng.random((ntris, 1, 3)) + 0.08 * (rng.random((ntris, 3, 3)) * 2 - 1)).astype(np.float32)
+        if ntris > 100:
+            tris[5] = tris[4]                                  # duplicate: a tie in t
+            tris[17, 2] = tris[17, 1]                          # degenerate
+            tris[33, 0, 1] = np.nan
+        rays = np.zeros(nrays, dtype=orc.RAY_DTYPE)
+        rays["o"] = rng.random((nrays, 3)).astype(np.float32)
+        rays["d"] = rng.normal(size=(nrays, 3)).astype(np.float32)
+        rays["d"][::7, 1] = 0.0
+        rays["max_t"] = 3.402823e38
+        rays["max_t"][::5] = 0.4
+        rays["min_t"][::3] = 0.1
+        a = orc.trace_brute(tris, rays, blocked=False)
+        b = orc.trace_brute(tris, rays, blocked=True)
+        pc.assert_same(b, a, f"blocked vs plain, {ntris} triangles")
+    g = scenes._quad_grid((0, 0, 1), (1, 0, 0), (0, 1, 0), 16, 16)
+    grid = g[0][g[1].astype(np.int64)]
+    gx, gy = np.meshgrid(np.arange(0, 65) / 64.0, np.arange(0, 65) / 64.0)
+    r2 = np.zeros(gx.size, dtype=orc.RAY_DTYPE)
+    r2["o"] = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], -1)
+    r2["d"] = (0, 0, 1)
+    r2["max_t"] = 3.402823e38
+    a, b = orc.trace_brute(grid, r2, blocked=False), orc.trace_brute(grid, r2, blocked=True)
+    assert (a["prim"] != orc.MISS).all()
+    pc.assert_same(b, a, "blocked vs plain, coplanar grid")
+    s = scenes.config_scene("C1")
+    rays = scenes.config_rays("C1", s)[::97]
+    pc.assert_same(orc.trace_brute(s["tris"], rays, blocked=True), orc.trace_brute(s["tris"], rays, blocked=False), "C1")

@@ -47,7 +47,7 @@ def _build(force, verbose, defines):
          "-c", os.path.join(CSRC, "rtk_device.cu"), "-o", dev_o],
         ["gcc", "-O2", "-fPIC", "-Wall", "-std=gnu11", "-c", os.path.join(CSRC, "rtk_host.c"), "-o", host_o],
         ["gcc", "-O2", "-fPIC", "-Wall", "-std=gnu11", "-c", os.path.join(CSRC, "rtk_place.c"), "-o", place_o],
-        [NVCC, *ARCH, "-shared", "-o", OUT, dev_o, host_o, place_o, "-lpthread"],
+        [NVCC, *ARCH, "-shared", "-o", OUT, dev_o, host_o, place_o, "-lpthread", "-ldl"],
     ]
     for c in cmds:
         r = subprocess.run(c, capture_output=True, text=True)

@@ -36,6 +36,18 @@
 
 #define RTK_DEV __device__ __forceinline__
 
+// NVTX ranges around the host-side stages (build phases, the chunks of a host batch, replication): they
+// show up in Nsight timelines and cost nothing when no tool is attached
+#ifndef RTK_SIMT_EMU
+#include <nvtx3/nvToolsExt.h>
+struct rtk_nvtx_range { rtk_nvtx_range(const char *n) { nvtxRangePushA(n); } ~rtk_nvtx_range() { nvtxRangePop(); } };
+#else
+struct rtk_nvtx_range { rtk_nvtx_range(const char *) {} };
+#endif
+#define RTK_NVTX_CAT2(a, b) a##b
+#define RTK_NVTX_CAT(a, b) RTK_NVTX_CAT2(a, b)
+#define RTK_NVTX(name) rtk_nvtx_range RTK_NVTX_CAT(_nvtx_, __LINE__)(name)
+
 #define RTK_MISS 0xffffffffu
 #define RTK_INF_F 3.402823e+38f          // RTK_INF, reference rtk.h:11
 

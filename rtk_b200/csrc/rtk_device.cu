@@ -571,6 +571,7 @@ extern "C" int rtkd_sync_replicas(rtkd_scene *s)
 {
 	if (g_ndev <= 1 || s->dev_index != 0) return RTKD_OK;
 	pthread_mutex_t *m = (pthread_mutex_t*)s->slot_lock;
+	RTK_NVTX("rtk_b200 scene replication");
 	pthread_mutex_lock(m);
 	if (s->replica_epoch == s->epoch && s->replica[1]) { pthread_mutex_unlock(m); return RTKD_OK; }
 	int rc = RTKD_OK;
@@ -768,6 +769,7 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 // binned-SAH binary tree (k_sah.cuh): one host synchronisation per level of large nodes
 static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, build_bufs &B, uint32_t n)
 {
+	RTK_NVTX("rtk_b200 build: binned SAH levels");
 	rtkd_sah &h = B.h;
 	RTK_LAUNCH(k_sah_prim_bounds, (n + 255) / 256, 256, st, tri, svals, n, (float4*)h.pb, h.idx0); CK_LAUNCH();
 	RTK_LAUNCH(k_sah_root, 1, 32, st, h, (const uint32_t*)B.d_bounds, n); CK_LAUNCH();
@@ -840,6 +842,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	if (bind_index(s->dev_index)) return RTKD_ERR_CUDA;
 	cudaStream_t st = (cudaStream_t)stream;
 	const uint32_t n = s->num_tris;
+	RTK_NVTX("rtk_b200 build");
 	s->build_mode = (uint32_t)mode;
 	event_pair ev;
 	CK(cudaEventCreate(&ev.e0)); CK(cudaEventCreate(&ev.e1));
@@ -1513,6 +1516,7 @@ static int pipeline_rows_direct(dev_ctx &X, batch_job &J, uint32_t *m_hits, unsi
 	PIPE_CK(cudaMemsetAsync(G.d_count, 0, 8, G.up), what);          // ahead of the first upload event
 	size_t uploads = 0;
 	for (size_t it = 0; it < nchunks && rc == RTKD_OK; it++) {
+		RTK_NVTX("rtk_b200 host batch: enqueue chunk (direct rows)");
 		rc = pipe_uploads(G, J, it, nchunks, uploads, what);
 		if (rc) break;
 		host_buf &B = G.b[it % RTKD_HOST_BUFS];
@@ -1641,6 +1645,7 @@ static int pipeline_compact(dev_ctx &X, batch_job &J)
 // one device's share of a batch, on the thread that drives that device
 static void run_job(dev_ctx &X, batch_job &J)
 {
+	RTK_NVTX("rtk_b200 host batch: one device's share");
 	int rc = bind_index((int)(&X - g_ctx));
 	uint32_t *m_hits = NULL;
 	unsigned char *m_mask = NULL;

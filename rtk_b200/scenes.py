@@ -264,11 +264,18 @@ def bounce_rays(scene, n, seed=0xD3, first=0, up=(0.0, 1.0, 0.0)):
     return make_rays(o.astype(np.float32), d.astype(np.float32))
 
 
+def scene_bounds(scene):
+    """(lo, hi) float32 corners of the scene's bounding box; computed once per scene dict"""
+    if "_bounds" not in scene:
+        t = scene["tris"].reshape(-1, 3)
+        scene["_bounds"] = (t.min(0), t.max(0))
+    return scene["_bounds"]
+
+
 def segment_rays(scene, n, seed=0xD4, first=0, length=0.25):
     """Uniform segments: origin ~U(bbox), direction ~U(sphere) * length * diag, max_t = 1."""
-    tris = scene["tris"]
-    lo = tris.reshape(-1, 3).min(0).astype(np.float64)
-    hi = tris.reshape(-1, 3).max(0).astype(np.float64)
+    lo, hi = scene_bounds(scene)
+    lo, hi = lo.astype(np.float64), hi.astype(np.float64)
     idx = np.arange(first, first + n, dtype=np.uint64)
 
     def s(k):
@@ -281,10 +288,10 @@ def segment_rays(scene, n, seed=0xD4, first=0, length=0.25):
     return make_rays(o.astype(np.float32), d.astype(np.float32), 0.0, 1.0)
 
 
-def terrain_primary_rays(scene, width, height):
-    """Coherent camera rays looking down onto the terrain from above one corner."""
-    tris = scene["tris"].reshape(-1, 3)
-    lo, hi = tris.min(0), tris.max(0)
+def terrain_primary_rays(scene, width, height, first=0, count=None):
+    """Coherent camera rays looking down onto the terrain from above one corner: pixels
+    [first, first + count) of the width x height image, row-major (default: all of them)."""
+    lo, hi = scene_bounds(scene)
     c = (lo + hi) / 2
     eye = np.array([c[0], hi[1] + 0.8 * (hi[2] - lo[2]), lo[2] - 0.6 * (hi[2] - lo[2])], dtype=np.float32)
     fwd = c - eye
@@ -292,33 +299,50 @@ def terrain_primary_rays(scene, width, height):
     right = np.cross([0.0, 1.0, 0.0], fwd)
     right /= np.linalg.norm(right)
     upv = np.cross(fwd, right)
-    py, px = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    if count is None:
+        count = width * height - first
+    pix = np.arange(first, first + count, dtype=np.int64)
+    py, px = pix // width, pix % width
     th = np.tan(np.radians(50.0) / 2)
     sx = ((px + 0.5) / width * 2 - 1) * th * (width / height)
     sy = (1 - (py + 0.5) / height * 2) * th
-    d = fwd[None, None, :] + sx[..., None] * right + sy[..., None] * upv
+    d = fwd[None, :] + sx[..., None] * right + sy[..., None] * upv
     d = d.reshape(-1, 3).astype(np.float32)
     return make_rays(np.broadcast_to(eye, d.shape), d)
 
 
-def mixed_rays(scene, n, seed=0xD4, block=65536):
-    """C4: thirds of coherent primary / bounce / segment rays interleaved in blocks of `block`."""
+def mixed_rays(scene, n, seed=0xD4, block=65536, first=0, count=None, threads=1):
+    """C4: thirds of coherent primary / bounce / segment rays interleaved in blocks of `block`.
+    Rays [first, first + count) of the n-ray set (first a multiple of `block`; default: all of them):
+    every block regenerates alone, so ranks and worker threads can each make their own part."""
     nb = (n + block - 1) // block
-    out = np.zeros(n, dtype=RAY_DTYPE)
+    if count is None:
+        count = n - first
+    assert first % block == 0 and first + count <= n
+    out = np.zeros(count, dtype=RAY_DTYPE)
     n_prim = sum(min(block, n - b * block) for b in range(0, nb, 3))
     side = int(np.ceil(np.sqrt(max(n_prim, 1))))
-    prim = terrain_primary_rays(scene, side, side)
-    pp = 0
-    for b in range(nb):
-        lo, hi = b * block, min(n, (b + 1) * block)
+    scene_bounds(scene)
+
+    def one(b):
+        lo, hi = b * block, min(n, (b + 1) * block, first + count)
         k = b % 3
         if k == 0:
-            out[lo:hi] = prim[pp:pp + (hi - lo)]
-            pp += hi - lo
+            pp = sum(min(block, n - bb * block) for bb in range(0, b, 3))
+            r = terrain_primary_rays(scene, side, side, pp, hi - lo)
         elif k == 1:
-            out[lo:hi] = bounce_rays(scene, hi - lo, seed=seed, first=lo)
+            r = bounce_rays(scene, hi - lo, seed=seed, first=lo)
         else:
-            out[lo:hi] = segment_rays(scene, hi - lo, seed=seed ^ 0x55, first=lo)
+            r = segment_rays(scene, hi - lo, seed=seed ^ 0x55, first=lo)
+        out[lo - first:hi - first] = r
+    blocks = range(first // block, (first + count + block - 1) // block)
+    if threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, blocks))
+    else:
+        for b in blocks:
+            one(b)
     return out
 
 

@@ -488,6 +488,35 @@ class HostDevice:
         pass
 
 
+class TorchDevice:
+    """device buffers for the shared cases on a real GPU: torch owns the memory, the library sees raw pointers"""
+    stream = None
+
+    def put(self, arr):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).cuda()
+        return t, t.data_ptr()
+
+    def empty(self, nbytes, fill=0):
+        import torch
+        t = torch.full((max(nbytes, 16),), fill, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        return t, t.data_ptr()
+
+    def get(self, handle, dtype, count):
+        import torch
+        torch.cuda.synchronize(handle.device)
+        return handle[:count * np.dtype(dtype).itemsize].cpu().numpy().view(dtype)
+
+    def sync(self):
+        import torch
+        torch.cuda.synchronize()
+
+    def on_device(self, k):
+        import torch
+        return torch.cuda.device(k)
+
+
 def case_wavefront(lib, orc, dev):
     """primary rays and bounce rays generated on the device, traced without leaving
     it.  Generators against the numpy restatement (oracle/wavefront_ref.py): primary rays bit for

@@ -171,25 +171,7 @@ def test_occlusion_query(gpu_lib, orc):
     pc.case_occlusion(gpu_lib, orc, alloc)
 
 
-class TorchDevice:
-    """device buffers for the shared cases: torch owns the memory, the library sees raw pointers"""
-    stream = None
-
-    def put(self, arr):
-        import torch
-        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1).copy()).cuda()
-        return t, t.data_ptr()
-
-    def empty(self, nbytes, fill=0):
-        import torch
-        t = torch.full((max(nbytes, 16),), fill, dtype=torch.uint8, device="cuda")
-        torch.cuda.synchronize()
-        return t, t.data_ptr()
-
-    def get(self, handle, dtype, count):
-        import torch
-        torch.cuda.synchronize()
-        return handle[:count * np.dtype(dtype).itemsize].cpu().numpy().view(dtype)
+TorchDevice = pc.TorchDevice
 
 
 def test_wavefront_generators(gpu_lib, orc):
@@ -222,3 +204,136 @@ def test_baked_instancing(gpu_lib, orc):
 
 def test_pathological_scenes(gpu_lib, orc):
     pc.case_pathological(gpu_lib, orc)
+
+
+# ---- round 2 ------------------------------------------------------------------------------------
+
+def test_direct_rows_into_page_locked_arrays(gpu_lib, orc):
+    pc.case_direct_rows(gpu_lib, orc, nrays=300000, chunk_log2=14)
+
+
+def test_two_streams_one_scene(gpu_lib, orc):
+    import torch
+    streams = []
+
+    def make_stream():
+        streams.append(torch.cuda.Stream())
+        return streams[-1].cuda_stream
+    pc.case_two_streams(gpu_lib, orc, TorchDevice(), make_stream)
+
+
+def test_blob_validation(gpu_lib, orc):
+    pc.case_blob_validation(gpu_lib, orc)
+
+
+def test_overflow_is_reported(gpu_lib, orc):
+    pc.case_overflow_report(gpu_lib, orc, TorchDevice())
+
+
+def test_probes(gpu_lib):
+    g = C.c_double(0)
+    assert gpu_lib.rtk_cuda_measure_gather_bandwidth(96 << 20, 256, 3, C.byref(g)) == 0 and g.value > 500, g.value
+    assert gpu_lib.rtk_cuda_measure_host_link(1, 64 << 20, 3, 2, C.byref(g)) == 0 and g.value > 5, g.value
+
+
+def test_multi_device_in_one_process():
+    """rtk_cuda_init_devices: ONE process drives several GPUs behind rtk_build_scene / rtk_trace_rays.
+    On a box with 2+ GPUs the real ones (up to 4); on a one-GPU box the same physical device twice
+    (test hook RTK_B200_TEST_DUP_DEVICES), which still runs every line of the multi-device layer:
+    replicas, per-device worker threads and pipelines, range split, merge.  A process of its own, because
+    a process's device list is fixed at initialisation."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    have = torch.cuda.device_count()
+    devs = list(range(min(have, 4))) if have >= 2 else [0, 0]
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    code = (
+        "import os, sys, ctypes as C\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "import parity_cases as pc\n"
+        "from rtk_b200 import api\n"
+        "from oracle import orc\n"
+        "lib = api.load()\n"
+        f"devs = (C.c_int * {len(devs)})({', '.join(str(d) for d in devs)})\n"
+        f"assert lib.rtk_cuda_init_devices(devs, {len(devs)}) == 0, lib.last_error()\n"
+        "g = C.c_double(0)\n"
+        f"assert lib.rtk_cuda_measure_host_link({len(devs)}, 32 << 20, 3, 2, C.byref(g)) == 0 and g.value > 5, g.value\n"
+        f"pc.case_multi_device(lib, orc, {len(devs)}, {'pc.TorchDevice()' if have >= 2 else 'None'}, nrays={len(devs)} * 700000 + 999, oracle_rays=2000)\n"
+        "print('multi-device ok')\n"
+    )
+    env = dict(os.environ)
+    if have < 2:
+        env["RTK_B200_TEST_DUP_DEVICES"] = "1"
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "multi-device ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_full_size_c4_and_one_c5_band(gpu_lib, orc):
+    """BASELINE configs 4 and 5 at FULL size: the 10M-triangle terrain in two meshes.
+    C4: 2^21 mixed rays (coherent / bounce / short segments) -- 2048 sampled rays against the CPU oracle
+    (mesh_index / triangle_index through the host entry point included), 65536 rays against the
+    exhaustive GPU kernel.  C5: one band of the 4K frame (3840 x 270 pixels x 16 spp = 16.6M rays) generated
+    on the device and followed for 4 bounces; the bounce-3 rays, as the device produced them, against the
+    oracle (512) and the exhaustive kernel (16384)."""
+    import torch
+    s = scenes.config_scene("C4")
+    assert len(s["tris"]) == 10_000_000 and len(s["meshes"]) == 2
+    sc = gpu_lib.build_scene(s["meshes"])
+    info = sc.info()
+    assert info.num_triangles == 10_000_000 and info.num_meshes == 2
+    n = 1 << 21
+    rays = scenes.mixed_rays(s, n, seed=0xD4)
+    trav = _device_trace(gpu_lib, sc, rays)
+    assert 0.2 < (trav["prim"] != api.RTK_CUDA_MISS).mean() < 0.999
+    idx = np.sort(np.random.default_rng(4).choice(n, 2048, replace=False))
+    want = orc.trace_brute(s["tris"], rays[idx])
+    pc.assert_same(trav[idx], want, "C4 full size vs CPU oracle")
+    kb = 65536
+    sub = np.ascontiguousarray(rays[::n // kb][:kb])
+    pc.assert_same(_device_trace(gpu_lib, sc, sub), _device_trace(gpu_lib, sc, sub, brute=True), "C4 full size vs exhaustive GPU kernel")
+    # host entry point: mesh_index / triangle_index of the two 5M-triangle meshes
+    hits, mask, nh = sc.trace_rays(np.ascontiguousarray(rays[idx]))
+    pc.assert_same(api.hits_to_hit16(hits, mask, s["mesh_first"]), want, "C4 rows vs oracle")
+    m = mask.astype(bool)
+    assert set(np.unique(hits["mesh_index"][m])) <= {0, 1} and len(np.unique(hits["mesh_index"][m])) == 2
+    assert (hits["triangle_index"][m] < 5_000_000).all()
+    # ---- C5: one band, rays never leave the device ----
+    W, H, SPP, BOUNCES, BANDS = 3840, 2160, 16, 4, 8
+    npx = W * (H // BANDS)
+    nr = npx * SPP
+    tris = s["tris"].reshape(-1, 3)
+    lo, hi = tris.min(0), tris.max(0)
+    c = (lo + hi) / 2
+    eye = np.array([c[0], hi[1] + 0.8 * (hi[2] - lo[2]), lo[2] - 0.6 * (hi[2] - lo[2])], dtype=np.float32)
+    fwd = (c - eye) / np.linalg.norm(c - eye)
+    right = np.cross([0.0, 1.0, 0.0], fwd)
+    right /= np.linalg.norm(right)
+    up = np.cross(fwd, right)
+    cam = api.rtk_cuda_camera()
+    cam.eye[:], cam.forward[:], cam.right[:], cam.up[:] = [float(x) for x in eye], [float(x) for x in fwd], [float(x) for x in right], [float(x) for x in up]
+    cam.tan_half_fov, cam.width, cam.height = float(np.tan(np.radians(50.0) / 2)), W, H
+    st = torch.cuda.current_stream().cuda_stream
+    bufs = [torch.empty((nr, 32), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    h16 = torch.empty((nr, 16), dtype=torch.uint8, device="cuda")
+    band = 3
+    for sp in range(SPP):
+        assert gpu_lib.rtk_cuda_generate_primary_rays(C.byref(cam), 0xD5, sp, band * npx, npx, bufs[0].data_ptr() + 32 * npx * sp, st) == 0
+    cur = 0
+    for b in range(BOUNCES):
+        assert gpu_lib.rtk_trace_rays_compact_device(sc.ptr, bufs[cur].data_ptr(), h16.data_ptr(), nr, st) == 0, gpu_lib.last_error()
+        if b + 1 < BOUNCES:
+            assert gpu_lib.rtk_cuda_generate_bounce_rays(sc.ptr, bufs[cur].data_ptr(), h16.data_ptr(), bufs[cur ^ 1].data_ptr(), None, nr,
+                                                         0xD5, b, band * nr, api.RTK_CUDA_BOUNCE_RELAUNCH, st) == 0
+            cur ^= 1
+    torch.cuda.synchronize()
+    got = h16.cpu().numpy().view(api.HIT16_DTYPE).reshape(-1)
+    last = bufs[cur]
+    pick = np.sort(np.random.default_rng(5).choice(nr, 16384, replace=False))
+    r_last = last.cpu().numpy().view(api.RAY_DTYPE).reshape(-1)[pick]
+    assert (got["prim"] != api.RTK_CUDA_MISS).mean() > 0.5
+    pc.assert_same(got[pick], _device_trace(gpu_lib, sc, r_last, brute=True), "C5 bounce 3 vs exhaustive GPU kernel")
+    pc.assert_same(got[pick[:512]], orc.trace_brute(s["tris"], r_last[:512]), "C5 bounce 3 vs CPU oracle")
+    assert gpu_lib.rtk_cuda_scene_status(sc.ptr) == 0
+    sc.free()

@@ -72,9 +72,11 @@ def install_shims():
 
     def lib_init(self, path):
         real_lib_init(self, path)
-        probe = self.rtk_cuda_measure_read_bandwidth
-        # the emulator streams a buffer with fibers: keep the probe tiny
+        probe, gprobe, lprobe = self.rtk_cuda_measure_read_bandwidth, self.rtk_cuda_measure_gather_bandwidth, self.rtk_cuda_measure_host_link
+        # the emulator streams a buffer with fibers: keep the probes tiny
         self.rtk_cuda_measure_read_bandwidth = lambda nbytes, passes, out: probe(1 << 16, 1, out)
+        self.rtk_cuda_measure_gather_bandwidth = lambda nbytes, rec, passes, out: gprobe(1 << 16, rec, 1, out)
+        self.rtk_cuda_measure_host_link = lambda ndev, nbytes, d, passes, out: lprobe(ndev, 1 << 16, d, 1, out)
     api.Library.__init__ = lib_init
 
 
@@ -94,13 +96,14 @@ def main():
     import build_emu
     lib = build_emu.build()
     args = ["--gpus", str(world), "--steps", "2", "--warmup", "1", "--rays", "4096", "--scale", "0.004",
-            "--lib", lib, "--e2e-steps", "1", "--parity-rays", "256", "--cpu-sample", "4096"] + extra
+            "--lib", lib, "--e2e-steps", "1", "--parity-rays", "256", "--cpu-sample", "4096",
+            "--legs", "c4,e2e", "--c4-rays", "6000", "--c4-scale", "0.0004", "--c4-steps", "1"] + extra
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     procs = []
     for rank in range(world):
-        env = dict(os.environ, SIMT_SHM_MALLOC="1" if "p2p" in extra else "0", RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
+        env = dict(os.environ, SIMT_SHM_MALLOC="1" if "p2p" in extra else "0", SIMT_DEVICES=str(world), RTK_B200_HOST_MIN_SHARE_LOG2="10", RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--child", "x"] + args, env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
@@ -133,9 +136,15 @@ def main():
     for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert key in line["roofline"], key
     assert line["e2e"]["rows_equal_device_path"], line["e2e"]
+    assert line["e2e"]["devices"] == world and line["e2e"]["rays_per_step"] == 4096 * world, line["e2e"]
+    assert line["e2e_compact"].get("records_equal_device_path") is True, line["e2e_compact"]
+    assert line["e2e_pageable"]["rows_equal_pinned_path"], line["e2e_pageable"]
+    assert line["c4"]["parity"]["bit_exact"] and line["c4"]["parity"]["gpu_bruteforce_bit_exact"], line["c4"]["parity"]
+    assert line["c4"]["scaling"] == "strong" and line["c4"]["rays_total"] == 6000
+    assert line["build"]["roofline"]["frac"] > 0
+    assert line["parity"]["gpu_bruteforce_bit_exact"]
     if world == 1:
         assert line["cpu_baseline"]["kind"] in ("reference", "unavailable"), line["cpu_baseline"]
-        assert line["e2e_compact"].get("records_equal_device_path") is True, line["e2e_compact"]
         assert line["occlusion"]["agrees_with_closest_hit_mask"]
     else:
         assert line["gather_check"].get("equal") is True, line["gather_check"]

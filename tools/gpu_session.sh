@@ -1,0 +1,59 @@
+#!/bin/sh
+# One parametrised entry for every gpurun call of the round (see tools/experiments/README.md).
+# usage: sh tools/gpu_session.sh <tag> <stage> [stage args] [-- <stage> ...]
+# Stages run in order; a failing stage does not stop the later ones (each writes its own log).
+TAG="$1"; shift
+OUT=gpurun_out
+mkdir -p $OUT
+run_stage() {
+	stage="$1"; shift
+	echo "=== stage $stage $* ($(date +%T))"
+	case "$stage" in
+	tests)
+		timeout 1200 python -m pytest tests -m gpu -x -q "$@" > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/${TAG}_pytest.log ;;
+	bench)
+		name="$1"; shift
+		timeout 1500 python bench.py "$@" > $OUT/${TAG}_bench_${name}.json 2> $OUT/${TAG}_bench_${name}.err; echo "bench exit $?"
+		tail -c 600 $OUT/${TAG}_bench_${name}.err; head -c 1500 $OUT/${TAG}_bench_${name}.json; echo ;;
+	ab)
+		for v in 1 0; do RTK_B200_L2_PERSIST=$v timeout 300 python tools/prof_trace.py C3 6 2>&1 | tail -1 | sed "s/^/L2_PERSIST=$v /"; done
+		for v in 1 0; do RTK_B200_L2_PERSIST=$v timeout 600 python tools/prof_trace.py C4 4 33554432 2>&1 | tail -1 | sed "s/^/L2_PERSIST=$v /"; done
+		for v in 1 0; do RTK_B200_HOST_DIRECT=$v timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | tail -12 | sed "s/^/HOST_DIRECT=$v /"; done ;;
+	ncu)
+		w="$1"; n="${2:-16777216}"
+		timeout 600 python tools/prof_trace.py $w 4 $n > $OUT/${TAG}_prof_${w}_plain.log 2>&1 &&
+		timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 2 -c 1 -f -o $OUT/${TAG}_k_trace_${w} \
+			python tools/prof_trace.py $w 4 $n > $OUT/${TAG}_prof_${w}_ncu.log 2>&1
+		echo "ncu exit $?"; tail -2 $OUT/${TAG}_prof_${w}_plain.log ;;
+	launches)
+		timeout 900 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --parity-rays 0 --legs e2e > $OUT/${TAG}_launch_plain.log 2>&1 &&
+		timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/${TAG}_launches_bench.csv \
+			python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --parity-rays 0 --legs e2e > $OUT/${TAG}_launch_ncu.log 2>&1
+		echo "launch list exit $?" ;;
+	build)
+		timeout 600 python tools/build_profile.py --config C3 --rebuilds 4 2>&1 | tail -6
+		timeout 600 python tools/build_profile.py --config C4 --rebuilds 3 2>&1 | tail -5 ;;
+	buildncu)
+		timeout 600 python tools/prof_build.py ${1:-C3} sah > $OUT/${TAG}_pb_plain.log 2>&1 &&
+		timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/${TAG}_launches_build_${1:-C3}.csv \
+			python tools/prof_build.py ${1:-C3} sah > $OUT/${TAG}_pb_ncu.log 2>&1
+		echo "build launch list exit $?"; tail -1 $OUT/${TAG}_pb_plain.log ;;
+	scale)
+		N="$1"; shift
+		for g in nccl p2p; do
+			timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
+				bench.py --gpus $N --steps 30 --warmup 3 --gather $g "$@" > $OUT/${TAG}_scale_${N}_${g}.json 2> $OUT/${TAG}_scale_${N}_${g}.err
+			echo "scale $N $g exit $?"; tail -c 400 $OUT/${TAG}_scale_${N}_${g}.err; head -c 1200 $OUT/${TAG}_scale_${N}_${g}.json; echo
+		done ;;
+	e2e)
+		N="$1"; timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 4 2>&1 | tail -14 ;;
+	*) echo "unknown stage $stage" ;;
+	esac
+}
+args=""
+while [ $# -gt 0 ]; do
+	if [ "$1" = "--" ]; then run_stage $args; args=""; else args="$args $1"; fi
+	shift
+done
+[ -n "$args" ] && run_stage $args
+echo "=== done ($(date +%T))"

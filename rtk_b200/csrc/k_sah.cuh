@@ -49,6 +49,7 @@ struct rtkd_sah {
 	int4 *split;                  // per active node: axis (-1: equal split), bin, n_left, first child
 	uint32_t *cursor;             // per active node: left / right write cursors
 	uint32_t node_cap;
+	uint32_t act_cap, small_cap;  // capacities of act_in / act_out and small_list (never reached: see carve(); guarded all the same)
 };
 
 // bin of a triangle on one axis, rtk.c:892-902
@@ -401,8 +402,13 @@ RTK_DEV void rtk_sah_emit_children(rtkd_sah &s, uint32_t node, const rtk_sah_cho
 		uint32_t cnt = k == 0 ? c.n_left : (last - first + 1) - c.n_left;
 		s.left[id] = -1; s.right[id] = -1; s.ndepth[id] = depth + 1;
 		if (child_buf >= 0) {
-			if (cnt > RTK_SAH_SMALL) s.act_out[atomicAdd(&s.counters[1], 1u)] = id;
-			else s.small_list[atomicAdd(&s.counters[2], 1u)] = id | ((uint32_t)child_buf << 31);
+			if (cnt > RTK_SAH_SMALL) {
+				const uint32_t at = atomicAdd(&s.counters[1], 1u);
+				if (at < s.act_cap) s.act_out[at] = id; else atomicOr(&s.counters[3], 2u);
+			} else {
+				const uint32_t at = atomicAdd(&s.counters[2], 1u);
+				if (at < s.small_cap) s.small_list[at] = id | ((uint32_t)child_buf << 31); else atomicOr(&s.counters[3], 4u);
+			}
 		}
 	}
 	atomicMax(&s.counters[4], depth + 1);

@@ -634,3 +634,36 @@ __global__ void __launch_bounds__(RTK_RESOLVE_THREADS) k_resolve(rtkd_arrays sc,
 		}
 	}
 }
+
+// ---------------------------------------------------------------------------------------------
+// Row push of the direct host path: rows expanded in device memory (k_resolve, rows in place at a
+// 68-byte pitch) go to the caller's page-locked rtk_hit array, hit rows only, and the mask bytes to the
+// caller's mask array.  A handful of persistent CTAs (they run on the SMs the traversal grid leaves
+// free) loop over the chunk's 128-ray blocks; a block's 2176 words are written 32 consecutive words
+// per warp instruction -- one aligned 128-byte line of host memory, minus the words of rays that missed.
+// ---------------------------------------------------------------------------------------------
+
+#define RTK_PUSH_THREADS 256
+
+__global__ void __launch_bounds__(RTK_PUSH_THREADS) k_push_rows(const uint32_t *rows, const unsigned char *mask, uint32_t *host_hits,
+                                                                unsigned char *host_mask, uint32_t nrays)
+{
+	__shared__ unsigned char s_m[RTK_RESOLVE_THREADS];
+	const uint32_t nblocks = (nrays + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS;
+	for (uint32_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+		const uint32_t base = b * RTK_RESOLVE_THREADS;
+		const uint32_t cnt = rtk_umin(RTK_RESOLVE_THREADS, nrays - base);
+		__syncthreads();
+		if (threadIdx.x < RTK_RESOLVE_THREADS) {
+			const unsigned char m = threadIdx.x < cnt ? mask[base + threadIdx.x] : (unsigned char)0;
+			s_m[threadIdx.x] = m;
+			if (host_mask && threadIdx.x < cnt) host_mask[base + threadIdx.x] = m;
+		}
+		__syncthreads();
+		const uint32_t *src = rows + 17ull * base;
+		uint32_t *dst = host_hits + 17ull * base;
+		for (uint32_t w = threadIdx.x; w < cnt * 17u; w += RTK_PUSH_THREADS) {
+			if (s_m[w / 17u]) dst[w] = src[w];
+		}
+	}
+}

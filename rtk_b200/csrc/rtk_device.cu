@@ -26,7 +26,11 @@ static int g_reserved_sms = 0;      // SMs the persistent traversal grid leaves 
 static size_t g_l2_bytes = 0;
 static size_t g_l2_window_max = 0;  // largest access-policy window the device accepts (0: no L2 persistence)
 static size_t g_l2_setaside = 0;    // L2 bytes set aside for persisting lines
-static int g_l2_persist = 1;        // RTK_B200_L2_PERSIST=0 switches the persisting window off
+static int g_l2_persist = 0;        // RTK_B200_L2_PERSIST=1: persisting L2 window over nodes + leaf slots.  Off by default --
+                                    // measured on C3/C4: k_trace gains nothing (1705 vs 1704 Mrays/s), while k_resolve, whose
+                                    // corner gathers lose the set-aside part of the L2, goes from 0.47 to 1.10 ms per batch
+static int g_push_sms = 8;          // RTK_B200_PUSH_SMS: SMs the traversal grid leaves to the row-push kernel of the direct host path
+static __thread int t_reserve_extra = 0;   // set by the direct host pipeline around its traversal launches
 static int g_host_direct = 1;       // RTK_B200_HOST_DIRECT=0: rows always travel through pinned staging
 static size_t g_min_share = (size_t)1 << 18;   // a device joins a host batch only for at least this many rays (RTK_B200_HOST_MIN_SHARE_LOG2)
 static int g_stack_limit = 0;       // test hook (rtkd_debug_limit_stack): spill entries per ray, 0 = sized from the tree
@@ -83,6 +87,7 @@ struct host_stage {
 	size_t chunk, blocks, meta_bytes;
 	host_buf b[RTKD_HOST_BUFS];
 	cudaStream_t up;                    // upload stream
+	cudaStream_t push;                  // direct host path: the stream of the row-push kernel
 	cudaEvent_t uploaded[RTKD_HOST_RING];
 	float4 *d_rays; size_t rays_cap;    // the rays of this device's share of the batch (grow-only)
 	unsigned long long *d_count;        // hit counter of a batch whose rows go straight to the caller's memory
@@ -166,7 +171,8 @@ static int init_devices_locked(const int *devices, int n)
 		// L2 persistence: the traversal working set (nodes + leaf slots) gets a persisting access-policy
 		// window so that the ray / hit streams do not evict it
 		int maxp = 0, maxw = 0;
-		if (cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, devices[i]) == cudaSuccess && maxp > 0) {
+		{ const char *e = getenv("RTK_B200_L2_PERSIST"); if (e) g_l2_persist = atoi(e) != 0; }
+		if (g_l2_persist && cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, devices[i]) == cudaSuccess && maxp > 0) {
 			cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)maxp);
 			cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, devices[i]);
 			if (i == 0) { g_l2_window_max = (size_t)(maxw > 0 ? maxw : 0); g_l2_setaside = (size_t)maxp; }
@@ -193,7 +199,7 @@ static int init_devices_locked(const int *devices, int n)
 		if (e) g_trace_pd = atoi(e) != 0;
 		if (g_trace_lanes == 8) g_trace_pd = 0;
 	}
-	{ const char *e = getenv("RTK_B200_L2_PERSIST"); if (e) g_l2_persist = atoi(e) != 0; }
+	{ const char *e = getenv("RTK_B200_PUSH_SMS"); if (e && atoi(e) >= 0 && atoi(e) < sm) g_push_sms = atoi(e); }
 	{ const char *e = getenv("RTK_B200_HOST_DIRECT"); if (e) g_host_direct = atoi(e) != 0; }
 	{ const char *e = getenv("RTK_B200_HOST_MIN_SHARE_LOG2"); if (e && atoi(e) >= 7 && atoi(e) <= 30) g_min_share = (size_t)1 << atoi(e); }
 	int ctas = 0;
@@ -738,7 +744,10 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 	if (use_sah) {
 		const size_t cap2 = 2 * (size_t)n + 2;
 		B.act_cap = n / RTK_SAH_SMALL + 4;
-		B.small_cap = 4 * (size_t)(n / RTK_SAH_SMALL) + 8;
+		// small subtrees are disjoint, non-empty triangle ranges: there can never be more than n of them,
+		// however skewed the splits are (a peeling split emits one per level); active large nodes are
+		// disjoint ranges of more than RTK_SAH_SMALL triangles each, so fewer than n / RTK_SAH_SMALL
+		B.small_cap = (size_t)n + 8;
 		B.h.pb = A.take<float4>(2 * (size_t)n);
 		B.h.idx0 = A.take<uint32_t>(n); B.h.idx1 = A.take<uint32_t>(n); B.h.idx_final = A.take<uint32_t>(n);
 		B.h.left = A.take<int>(cap2); B.h.right = A.take<int>(cap2); B.h.first = A.take<int>(cap2); B.h.last = A.take<int>(cap2);
@@ -750,6 +759,7 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 		B.h.bins = A.take<uint32_t>(B.act_cap * RTK_SAH_NODEBINS);
 		B.h.split = A.take<int4>(B.act_cap); B.h.cursor = A.take<uint32_t>(2 * B.act_cap);
 		B.h.node_cap = (uint32_t)cap2;
+		B.h.act_cap = (uint32_t)B.act_cap; B.h.small_cap = (uint32_t)B.small_cap;
 		B.order = A.take<uint32_t>(n);
 	} else if (n > 1) {
 		B.t.left = A.take<int>(n - 1); B.t.right = A.take<int>(n - 1);
@@ -794,7 +804,7 @@ static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, 
 		src_buf ^= 1;
 		depth++;
 	}
-	if (hc[2] > B.small_cap) { rtkd_set_error("SAH small-subtree list overflow"); return RTKD_ERR_MEMORY; }
+	if (hc[2] > B.small_cap || hc[3]) { rtkd_set_error("SAH builder ran out of list space (flags %u)", hc[3]); return RTKD_ERR_MEMORY; }
 	if (hc[2]) { RTK_LAUNCH(k_sah_small, hc[2], RTK_SAH_SMALL_THREADS, st, h, hc[2]); CK_LAUNCH(); }
 	RTK_LAUNCH(k_sah_compose, (n + 255) / 256, 256, st, (const uint32_t*)h.idx_final, svals, n, B.order); CK_LAUNCH();
 	return RTKD_OK;
@@ -1169,7 +1179,9 @@ extern "C" int rtkd_trace(rtkd_scene *s, const void *d_rays, void *d_hit16, size
 	p.overflow = (uint2*)T->overflow; p.ovf_entries = (uint32_t)T->overflow_entries;
 	// persistent grid: one wave of resident CTAs, never more CTAs than ray batches
 	size_t batches = (n + RTK_RAY_BATCH - 1) / RTK_RAY_BATCH;
-	size_t ctas = (size_t)(g_sm_count - g_reserved_sms) * g_trace_ctas;
+	int reserved = g_reserved_sms + t_reserve_extra;
+	if (reserved >= g_sm_count) reserved = g_sm_count - 1;
+	size_t ctas = (size_t)(g_sm_count - reserved) * g_trace_ctas;
 	size_t want = (batches + RTK_TRACE_WARPS - 1) / RTK_TRACE_WARPS;
 	unsigned grid = (unsigned)(want < ctas ? want : ctas);
 	// L2 window: the arena (nodes first, then the leaf slots) as far as the device allows
@@ -1401,6 +1413,7 @@ static void stage_shutdown(dev_ctx &X)
 			if (B.rows_done) cudaEventDestroy(B.rows_done);
 		}
 		if (G.up) cudaStreamDestroy(G.up);
+		if (G.push) cudaStreamDestroy(G.push);
 		for (int k = 0; k < RTKD_HOST_RING; k++) if (G.uploaded[k]) cudaEventDestroy(G.uploaded[k]);
 	}
 	if (G.d_rays) cudaFree(G.d_rays);
@@ -1437,6 +1450,7 @@ static int stage_prepare(host_stage &G, size_t want, bool staged)
 			CK(cudaEventCreateWithFlags(&B.rows_done, cudaEventDisableTiming));
 		}
 		CK(cudaStreamCreateWithFlags(&G.up, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&G.push, cudaStreamNonBlocking));
 		for (int k = 0; k < RTKD_HOST_RING; k++) CK(cudaEventCreateWithFlags(&G.uploaded[k], cudaEventDisableTiming));
 		CK(cudaMalloc(&G.d_count, 64));
 		G.streams = true;
@@ -1448,8 +1462,8 @@ static int stage_prepare(host_stage &G, size_t want, bool staged)
 		host_buf &B = G.b[k];
 		if (!B.d_h16) CK(cudaMalloc(&B.d_h16, 16 * chunk));
 		if (!B.d_mask) CK(cudaMalloc(&B.d_mask, (chunk + 15) & ~(size_t)15));
+		if (!B.d_rows) CK(cudaMalloc(&B.d_rows, 68 * chunk));
 		if (staged) {
-			if (!B.d_rows) CK(cudaMalloc(&B.d_rows, 68 * chunk));
 			if (!B.d_base) CK(cudaMalloc(&B.d_base, 4 * G.blocks + 16));
 			if (!B.h_meta) CK(cudaMallocHost(&B.h_meta, G.meta_bytes));
 			if (!B.h_rows) CK(cudaMallocHost(&B.h_rows, 68 * chunk));
@@ -1504,7 +1518,13 @@ static int pipe_finish(dev_ctx &X, const batch_job &J, int rc, const char *what)
 	return rc;
 }
 
-// rows straight into the caller's page-locked arrays (m_hits / m_mask: their device-visible addresses)
+// Rows straight into the caller's page-locked arrays (m_hits / m_mask: their device-visible addresses).
+// A write to host memory is a PCIe transaction the writing warp waits for, and the rows of an incoherent
+// batch are scattered 68-byte pieces: a resolve kernel that wrote them itself would sit on the SMs at
+// PCIe speed between two traversals (measured: 26 ms per 16.7M rays instead of 10).  So k_resolve expands
+// the chunk's rows in DEVICE memory (70 us), and k_push_rows -- a few CTAs on SMs that the traversal grid
+// leaves free for it, on a stream of its own -- streams the rows of the rays that hit, and the mask
+// bytes, into the caller's arrays while the next chunks are traced.
 static int pipeline_rows_direct(dev_ctx &X, batch_job &J, uint32_t *m_hits, unsigned char *m_mask)
 {
 	static const char *what = "rtk_trace_rays";
@@ -1515,6 +1535,8 @@ static int pipeline_rows_direct(dev_ctx &X, batch_job &J, uint32_t *m_hits, unsi
 	int rc = RTKD_OK;
 	PIPE_CK(cudaMemsetAsync(G.d_count, 0, 8, G.up), what);          // ahead of the first upload event
 	size_t uploads = 0;
+	const unsigned push_ctas = (unsigned)((g_push_sms > 0 ? g_push_sms : 1) * (2048 / RTK_PUSH_THREADS));
+	t_reserve_extra = g_push_sms;
 	for (size_t it = 0; it < nchunks && rc == RTKD_OK; it++) {
 		RTK_NVTX("rtk_b200 host batch: enqueue chunk (direct rows)");
 		rc = pipe_uploads(G, J, it, nchunks, uploads, what);
@@ -1522,14 +1544,23 @@ static int pipeline_rows_direct(dev_ctx &X, batch_job &J, uint32_t *m_hits, unsi
 		host_buf &B = G.b[it % RTKD_HOST_BUFS];
 		const size_t off = it * chunk, cnt = J.n - off < chunk ? J.n - off : chunk;
 		PIPE_CK(cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0), what);
+		if (rc == RTKD_OK && it >= RTKD_HOST_BUFS) PIPE_CK(cudaStreamWaitEvent(B.st, B.rows_done, 0), what);   // the push of the chunk that had this buffer
 		if (rc) break;
 		rc = rtkd_trace(J.s, G.d_rays + 2 * off, B.d_h16, cnt, 1, NULL, B.st);
 		if (rc) break;
 		const unsigned blocks = (unsigned)((cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS);
-		RTK_LAUNCH(k_resolve<false>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, m_hits + 17 * (J.first + off),
-		           m_mask ? m_mask + J.first + off : B.d_mask, (uint32_t)cnt, G.d_count, (uint32_t*)NULL);
+		RTK_LAUNCH(k_resolve<false>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)cnt, G.d_count, (uint32_t*)NULL);
 		PIPE_CK(cudaGetLastError(), what);
+		if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.traced, B.st), what);
+		if (rc == RTKD_OK) PIPE_CK(cudaStreamWaitEvent(G.push, B.traced, 0), what);
+		if (rc) break;
+		RTK_LAUNCH(k_push_rows, push_ctas < blocks ? push_ctas : blocks, RTK_PUSH_THREADS, G.push, (const uint32_t*)B.d_rows, (const unsigned char*)B.d_mask,
+		           m_hits + 17 * (J.first + off), m_mask ? m_mask + J.first + off : (unsigned char*)NULL, (uint32_t)cnt);
+		PIPE_CK(cudaGetLastError(), what);
+		if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.rows_done, G.push), what);
 	}
+	t_reserve_extra = 0;
+	if (cudaStreamSynchronize(G.push) != cudaSuccess && rc == RTKD_OK) { rtkd_set_error("%s: device failure", what); rc = RTKD_ERR_CUDA; }
 	rc = pipe_finish(X, J, rc, what);
 	if (rc == RTKD_OK) {
 		unsigned long long hc = 0;

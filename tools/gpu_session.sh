@@ -39,14 +39,29 @@ run_stage() {
 			python tools/prof_build.py ${1:-C3} sah > $OUT/${TAG}_pb_ncu.log 2>&1
 		echo "build launch list exit $?"; tail -1 $OUT/${TAG}_pb_plain.log ;;
 	scale)
+		# the N-rank line with the NCCL gather (all legs) and with the peer-memory gather (headline only)
 		N="$1"; shift
 		for g in nccl p2p; do
+			legs="--legs c4,e2e"; [ "$g" = p2p ] && legs="--legs none --parity-rays 0"
 			timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
-				bench.py --gpus $N --steps 30 --warmup 3 --gather $g "$@" > $OUT/${TAG}_scale_${N}_${g}.json 2> $OUT/${TAG}_scale_${N}_${g}.err
-			echo "scale $N $g exit $?"; tail -c 400 $OUT/${TAG}_scale_${N}_${g}.err; head -c 1200 $OUT/${TAG}_scale_${N}_${g}.json; echo
+				bench.py --gpus $N --steps 30 --warmup 3 --gather $g $legs "$@" > $OUT/${TAG}_scale_${N}_${g}.json 2> $OUT/${TAG}_scale_${N}_${g}.err
+			echo "scale $N $g exit $?"; tail -c 400 $OUT/${TAG}_scale_${N}_${g}.err; head -c 600 $OUT/${TAG}_scale_${N}_${g}.json; echo
 		done ;;
 	e2e)
-		N="$1"; timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 4 2>&1 | tail -14 ;;
+		# one process, N devices: rows direct / staged, compact, link ceilings
+		N="$1"
+		timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 4 2>&1 | tail -14
+		RTK_B200_HOST_DIRECT=0 timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 4 2>&1 | grep -E "rows " | sed "s/^/HOST_DIRECT=0 /" ;;
+	variants)
+		# k_trace of every variant library rtk_b200/librtk_b200_<name>.so on one workload: "variants C3 base v00 v10 ..."
+		w="$1"; shift
+		for v in "$@"; do
+			lib=rtk_b200/librtk_b200_$v.so; [ "$v" = main ] && lib=rtk_b200/librtk_b200.so
+			RTK_LIB=$lib timeout 300 python tools/prof_trace.py $w 6 2>&1 | tail -1 | sed "s/^/$v /"
+		done ;;
+	hostab)
+		for v in 1 0; do RTK_B200_HOST_DIRECT=$v timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows|compact" | sed "s/^/HOST_DIRECT=$v /"; done
+		for r in 2 8; do RTK_B200_PUSH_SMS=$r timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows " | sed "s/^/PUSH_SMS=$r /"; done ;;
 	*) echo "unknown stage $stage" ;;
 	esac
 }

@@ -959,10 +959,12 @@ def main():
                     parts = [rays_np] + [np.load(shm_path(r)).view(api.RAY_DTYPE).reshape(-1) for r in range(1, world)]
                     rays_all = np.concatenate(parts)
                     del parts
+                    lib.build_scene(scene["meshes"]).free()                    # contexts, modules and peer mappings of all devices exist after this
                     t0 = time.perf_counter()
                     sc_all = lib.build_scene(scene["meshes"])                  # builds on device 0, replicates to the others
+                    rep_ms = (time.perf_counter() - t0) * 1e3
                     e2e_out = e2e_legs(lib, api, sc_all, scene, rays_all, args.e2e_steps, world, check16)
-                    e2e_out["e2e"]["build_and_replicate_ms"] = (time.perf_counter() - t0) * 1e3 - 0.0
+                    e2e_out["e2e"]["build_and_replicate_ms"] = rep_ms
                     e2e_out["e2e"]["single_link"] = link_ceiling(lib, 1)
                     sc_all.free()
                     del rays_all

@@ -29,6 +29,7 @@ static size_t g_l2_setaside = 0;    // L2 bytes set aside for persisting lines
 static int g_l2_persist = 0;        // RTK_B200_L2_PERSIST=1: persisting L2 window over nodes + leaf slots.  Off by default --
                                     // measured on C3/C4: k_trace gains nothing (1705 vs 1704 Mrays/s), while k_resolve, whose
                                     // corner gathers lose the set-aside part of the L2, goes from 0.47 to 1.10 ms per batch
+static int g_host_mix = -1;         // RTK_B200_HOST_MIX: every k-th chunk of a direct batch takes the staged route (-1: 2 x devices)
 static int g_push_sms = 8;          // RTK_B200_PUSH_SMS: SMs the traversal grid leaves to the row-push kernel of the direct host path
 static __thread int t_reserve_extra = 0;   // set by the direct host pipeline around its traversal launches
 static int g_host_direct = 1;       // RTK_B200_HOST_DIRECT=0: rows always travel through pinned staging
@@ -200,6 +201,7 @@ static int init_devices_locked(const int *devices, int n)
 		if (g_trace_lanes == 8) g_trace_pd = 0;
 	}
 	{ const char *e = getenv("RTK_B200_PUSH_SMS"); if (e && atoi(e) >= 0 && atoi(e) < sm) g_push_sms = atoi(e); }
+	{ const char *e = getenv("RTK_B200_HOST_MIX"); if (e && atoi(e) >= 0) g_host_mix = atoi(e); }
 	{ const char *e = getenv("RTK_B200_HOST_DIRECT"); if (e) g_host_direct = atoi(e) != 0; }
 	{ const char *e = getenv("RTK_B200_HOST_MIN_SHARE_LOG2"); if (e && atoi(e) >= 7 && atoi(e) <= 30) g_min_share = (size_t)1 << atoi(e); }
 	int ctas = 0;
@@ -1384,6 +1386,7 @@ struct batch_job {
 	const char *rays; char *hits; unsigned char *mask;     // the caller's WHOLE arrays
 	size_t first, n;                    // this device's range of them
 	int mode;                           // 0: rtk_hit rows + mask, 1: compact records (hits = rtk_cuda_hit16[])
+	int ndev;                           // devices that share this batch
 	long long found;                    // rays that hit (mode 0)
 	int rc;
 	char err[320];
@@ -1518,58 +1521,6 @@ static int pipe_finish(dev_ctx &X, const batch_job &J, int rc, const char *what)
 	return rc;
 }
 
-// Rows straight into the caller's page-locked arrays (m_hits / m_mask: their device-visible addresses).
-// A write to host memory is a PCIe transaction the writing warp waits for, and the rows of an incoherent
-// batch are scattered 68-byte pieces: a resolve kernel that wrote them itself would sit on the SMs at
-// PCIe speed between two traversals (measured: 26 ms per 16.7M rays instead of 10).  So k_resolve expands
-// the chunk's rows in DEVICE memory (70 us), and k_push_rows -- a few CTAs on SMs that the traversal grid
-// leaves free for it, on a stream of its own -- streams the rows of the rays that hit, and the mask
-// bytes, into the caller's arrays while the next chunks are traced.
-static int pipeline_rows_direct(dev_ctx &X, batch_job &J, uint32_t *m_hits, unsigned char *m_mask)
-{
-	static const char *what = "rtk_trace_rays";
-	host_stage &G = X.stage;
-	const size_t chunk = G.chunk, nchunks = (J.n + chunk - 1) / chunk;
-	rtkd_arrays a;
-	fill_arrays(J.s, a);
-	int rc = RTKD_OK;
-	PIPE_CK(cudaMemsetAsync(G.d_count, 0, 8, G.up), what);          // ahead of the first upload event
-	size_t uploads = 0;
-	const unsigned push_ctas = (unsigned)((g_push_sms > 0 ? g_push_sms : 1) * (2048 / RTK_PUSH_THREADS));
-	t_reserve_extra = g_push_sms;
-	for (size_t it = 0; it < nchunks && rc == RTKD_OK; it++) {
-		RTK_NVTX("rtk_b200 host batch: enqueue chunk (direct rows)");
-		rc = pipe_uploads(G, J, it, nchunks, uploads, what);
-		if (rc) break;
-		host_buf &B = G.b[it % RTKD_HOST_BUFS];
-		const size_t off = it * chunk, cnt = J.n - off < chunk ? J.n - off : chunk;
-		PIPE_CK(cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0), what);
-		if (rc == RTKD_OK && it >= RTKD_HOST_BUFS) PIPE_CK(cudaStreamWaitEvent(B.st, B.rows_done, 0), what);   // the push of the chunk that had this buffer
-		if (rc) break;
-		rc = rtkd_trace(J.s, G.d_rays + 2 * off, B.d_h16, cnt, 1, NULL, B.st);
-		if (rc) break;
-		const unsigned blocks = (unsigned)((cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS);
-		RTK_LAUNCH(k_resolve<false>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)cnt, G.d_count, (uint32_t*)NULL);
-		PIPE_CK(cudaGetLastError(), what);
-		if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.traced, B.st), what);
-		if (rc == RTKD_OK) PIPE_CK(cudaStreamWaitEvent(G.push, B.traced, 0), what);
-		if (rc) break;
-		RTK_LAUNCH(k_push_rows, push_ctas < blocks ? push_ctas : blocks, RTK_PUSH_THREADS, G.push, (const uint32_t*)B.d_rows, (const unsigned char*)B.d_mask,
-		           m_hits + 17 * (J.first + off), m_mask ? m_mask + J.first + off : (unsigned char*)NULL, (uint32_t)cnt);
-		PIPE_CK(cudaGetLastError(), what);
-		if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.rows_done, G.push), what);
-	}
-	t_reserve_extra = 0;
-	if (cudaStreamSynchronize(G.push) != cudaSuccess && rc == RTKD_OK) { rtkd_set_error("%s: device failure", what); rc = RTKD_ERR_CUDA; }
-	rc = pipe_finish(X, J, rc, what);
-	if (rc == RTKD_OK) {
-		unsigned long long hc = 0;
-		PIPE_CK(cudaMemcpy(&hc, G.d_count, sizeof(hc), cudaMemcpyDeviceToHost), what);
-		J.found = (long long)hc;
-	}
-	return rc;
-}
-
 // stage B of one buffer: wait for the chunk's count, then fetch exactly its rows
 static int host_stage_b(host_stage &G, host_buf &B)
 {
@@ -1598,8 +1549,23 @@ static int host_stage_c(host_stage &G, host_buf &B, const batch_job &J)
 	return RTKD_OK;
 }
 
-// rows through pinned staging and the placement workers (pageable caller arrays)
-static int pipeline_rows_staged(dev_ctx &X, batch_job &J)
+// The rows of a host batch reach the caller's rtk_hit array in one of two ways, chosen CHUNK BY CHUNK:
+//
+//   direct   (needs page-locked caller arrays; m_hits / m_mask are their device-visible addresses)
+//            k_resolve expands the chunk's rows in DEVICE memory; k_push_rows -- a few CTAs on SMs that the
+//            traversal grid leaves free, on a stream of its own -- writes the rows of the rays that hit, and the
+//            mask bytes, straight into the caller's arrays while the next chunks are traced.  No staging, no
+//            host threads; but scattered 68-byte pieces cross PCIe at about 45 % efficiency (~25 GB/s measured),
+//            and a warp that writes to host memory waits for the link, which is why the push is not done by the
+//            resolve kernel itself (that was measured: 26 ms per 16.7M rays instead of 18).
+//   staged   k_resolve<dense> packs the rows, the copy engine brings exactly those back at full link speed
+//            (55 GB/s), and the host worker pool (rtk_place.c) puts each row where it belongs -- bound by the
+//            host's memory system, a resource all devices share.
+//
+// staged_every = 0: every chunk direct; 1: every chunk staged (pageable arrays); k > 1: every k-th chunk
+// staged, so that link and host threads both work: one device alone is fastest at k = 2, and the staged
+// share shrinks with the number of devices that share the host.
+static int pipeline_rows(dev_ctx &X, batch_job &J, uint32_t *m_hits, unsigned char *m_mask, unsigned staged_every)
 {
 	static const char *what = "rtk_trace_rays";
 	host_stage &G = X.stage;
@@ -1610,41 +1576,72 @@ static int pipeline_rows_staged(dev_ctx &X, batch_job &J)
 	int rc = RTKD_OK;
 	long long total = 0;
 	size_t uploads = 0;
-	// chunk ci enters stage A in iteration ci, stage B in iteration ci+1, stage C in iteration ci+2
-	// and its buffer is reused in iteration ci + RTKD_HOST_BUFS
+	const unsigned push_ctas = (unsigned)((g_push_sms > 0 ? g_push_sms : 1) * (2048 / RTK_PUSH_THREADS));
+	bool staged_of[RTKD_HOST_BUFS] = { false, false, false, false };     // mode of the chunk each buffer carries
+	bool used[RTKD_HOST_BUFS] = { false, false, false, false };
+	PIPE_CK(cudaMemsetAsync(G.d_count, 0, 8, G.up), what);          // ahead of the first upload event
+	if (staged_every != 1) t_reserve_extra = g_push_sms;
+	// chunk ci is enqueued in iteration ci; a staged chunk enters stage B in iteration ci+1 and stage C in
+	// iteration ci+2; its buffer is reused in iteration ci + RTKD_HOST_BUFS
 	for (size_t it = 0; it < nchunks + 2 && rc == RTKD_OK; it++) {
+		RTK_NVTX("rtk_b200 host batch: chunk");
 		rc = pipe_uploads(G, J, it, nchunks, uploads, what);
 		if (rc) break;
 		if (it < nchunks) {
-			host_buf &B = G.b[it % RTKD_HOST_BUFS];
+			const int bi = (int)(it % RTKD_HOST_BUFS);
+			host_buf &B = G.b[bi];
 			if (B.state == 3) { rtkd_place_wait(B.ticket); total += (long long)B.hits; B.state = 0; }
+			const bool staged = staged_every == 1 || (staged_every > 1 && it % staged_every == staged_every - 1);
 			B.off = it * chunk; B.cnt = J.n - B.off < chunk ? J.n - B.off : chunk;
-			unsigned long long *d_count = (unsigned long long*)((unsigned char*)B.d_base + 4 * G.blocks);
 			PIPE_CK(cudaStreamWaitEvent(B.st, G.uploaded[it % RTKD_HOST_RING], 0), what);
-			if (rc == RTKD_OK) PIPE_CK(cudaMemsetAsync(d_count, 0, 16, B.st), what);
+			// the buffer's previous chunk: a staged one left through B.st itself, a direct one through the push stream
+			if (rc == RTKD_OK && used[bi] && !staged_of[bi]) PIPE_CK(cudaStreamWaitEvent(B.st, B.rows_done, 0), what);
 			if (rc) break;
 			rc = rtkd_trace(J.s, G.d_rays + 2 * B.off, B.d_h16, B.cnt, 1, NULL, B.st);
 			if (rc) break;
 			const unsigned blocks = (unsigned)((B.cnt + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS);
-			RTK_LAUNCH(k_resolve<true>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)B.cnt, d_count, B.d_base);
-			PIPE_CK(cudaGetLastError(), what);
-			// mask bytes and bases+count land in one pinned block: [mask | bases | count]
-			if (rc == RTKD_OK) PIPE_CK(cudaMemcpyAsync(B.h_meta, B.d_mask, B.cnt, cudaMemcpyDeviceToHost, B.st), what);
-			if (rc == RTKD_OK) PIPE_CK(cudaMemcpyAsync(B.h_meta + mask_bytes, B.d_base, 4 * G.blocks + 16, cudaMemcpyDeviceToHost, B.st), what);
-			if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.meta_done, B.st), what);
-			if (rc) break;
-			B.state = 1;
+			if (staged) {
+				unsigned long long *d_count = (unsigned long long*)((unsigned char*)B.d_base + 4 * G.blocks);
+				PIPE_CK(cudaMemsetAsync(d_count, 0, 16, B.st), what);
+				RTK_LAUNCH(k_resolve<true>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)B.cnt, d_count, B.d_base);
+				PIPE_CK(cudaGetLastError(), what);
+				// mask bytes and bases+count land in one pinned block: [mask | bases | count]
+				if (rc == RTKD_OK) PIPE_CK(cudaMemcpyAsync(B.h_meta, B.d_mask, B.cnt, cudaMemcpyDeviceToHost, B.st), what);
+				if (rc == RTKD_OK) PIPE_CK(cudaMemcpyAsync(B.h_meta + mask_bytes, B.d_base, 4 * G.blocks + 16, cudaMemcpyDeviceToHost, B.st), what);
+				if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.meta_done, B.st), what);
+				if (rc) break;
+				B.state = 1;
+			} else {
+				RTK_LAUNCH(k_resolve<false>, blocks, RTK_RESOLVE_THREADS, B.st, a, (const float4*)B.d_h16, B.d_rows, B.d_mask, (uint32_t)B.cnt, G.d_count, (uint32_t*)NULL);
+				PIPE_CK(cudaGetLastError(), what);
+				if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.traced, B.st), what);
+				if (rc == RTKD_OK) PIPE_CK(cudaStreamWaitEvent(G.push, B.traced, 0), what);
+				if (rc) break;
+				RTK_LAUNCH(k_push_rows, push_ctas < blocks ? push_ctas : blocks, RTK_PUSH_THREADS, G.push, (const uint32_t*)B.d_rows, (const unsigned char*)B.d_mask,
+				           m_hits + 17 * (J.first + B.off), m_mask ? m_mask + J.first + B.off : (unsigned char*)NULL, (uint32_t)B.cnt);
+				PIPE_CK(cudaGetLastError(), what);
+				if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(B.rows_done, G.push), what);
+				B.state = 0;
+			}
+			staged_of[bi] = staged; used[bi] = true;
 		}
-		if (it >= 1 && it - 1 < nchunks) rc = host_stage_b(G, G.b[(it - 1) % RTKD_HOST_BUFS]);
-		if (rc == RTKD_OK && it >= 2 && it - 2 < nchunks) rc = host_stage_c(G, G.b[(it - 2) % RTKD_HOST_BUFS], J);
+		if (it >= 1 && it - 1 < nchunks && G.b[(it - 1) % RTKD_HOST_BUFS].state == 1) rc = host_stage_b(G, G.b[(it - 1) % RTKD_HOST_BUFS]);
+		if (rc == RTKD_OK && it >= 2 && it - 2 < nchunks && G.b[(it - 2) % RTKD_HOST_BUFS].state == 2) rc = host_stage_c(G, G.b[(it - 2) % RTKD_HOST_BUFS], J);
 	}
+	t_reserve_extra = 0;
 	// drain: placements still running, and -- after an error -- whatever is still queued
 	for (int k = 0; k < RTKD_HOST_BUFS; k++) {
 		host_buf &B = G.b[k];
 		if (B.state == 3) { rtkd_place_wait(B.ticket); total += (long long)B.hits; }
 		B.state = 0; B.ticket = -1;
 	}
+	if (cudaStreamSynchronize(G.push) != cudaSuccess && rc == RTKD_OK) { rtkd_set_error("%s: device failure", what); rc = RTKD_ERR_CUDA; }
 	rc = pipe_finish(X, J, rc, what);
+	if (rc == RTKD_OK && staged_every != 1) {
+		unsigned long long hc = 0;
+		PIPE_CK(cudaMemcpy(&hc, G.d_count, sizeof(hc), cudaMemcpyDeviceToHost), what);
+		total += (long long)hc;
+	}
 	J.found = total;
 	return rc;
 }
@@ -1686,12 +1683,15 @@ static void run_job(dev_ctx &X, batch_job &J)
 		m_mask = J.mask ? (unsigned char*)host_mapped(J.mask, J.first + J.n) : NULL;
 		direct = m_hits && (!J.mask || m_mask);
 	}
-	if (rc == RTKD_OK) rc = stage_prepare(X.stage, J.n, J.mode == 0 && !direct);
+	// direct and staged chunks are mixed when the arrays allow direct writes: every (2 x devices in the batch)-th
+	// chunk is staged (RTK_B200_HOST_MIX=k: every k-th; 0: none), i.e. about half a device's rows for the host threads
+	unsigned staged_every = 1;
+	if (direct) staged_every = g_host_mix >= 0 ? (unsigned)g_host_mix : 2u * (unsigned)(J.ndev > 0 ? J.ndev : 1);
+	if (rc == RTKD_OK) rc = stage_prepare(X.stage, J.n, J.mode == 0 && staged_every != 0);
 	if (rc == RTKD_OK) rc = stage_rays(X.stage, J.n);
 	if (rc == RTKD_OK) {
 		if (J.mode == 1) rc = pipeline_compact(X, J);
-		else if (direct) rc = pipeline_rows_direct(X, J, m_hits, m_mask);
-		else rc = pipeline_rows_staged(X, J);
+		else rc = pipeline_rows(X, J, m_hits, m_mask, staged_every);
 	}
 	if (rc == RTKD_ERR_CUDA && !g_err[0]) rtkd_set_error("CUDA failure in a host batch");
 	J.rc = rc;
@@ -1734,7 +1734,7 @@ static long long run_batch(rtkd_scene *s, const void *rays, void *hits, unsigned
 		j.s = k == 0 ? s : s->replica[k];
 		j.rays = (const char*)rays; j.hits = (char*)hits; j.mask = mask;
 		j.first = first; j.n = (k == use - 1 || n - first < per) ? n - first : per;
-		j.mode = mode;
+		j.mode = mode; j.ndev = use;
 		first += j.n;
 	}
 	for (int k = 0; k < used; k++) pthread_mutex_lock(&g_ctx[k].lock);      // ascending order: no deadlock between batches

@@ -94,6 +94,11 @@ int  rtk_cuda_device_count(void);
  * copy, no host threads.  Pageable arrays work too, through pinned staging and a pool of host threads. */
 void *rtk_cuda_host_alloc(size_t bytes);
 void  rtk_cuda_host_free(void *p);
+/* The same for an array that rtk_trace_rays / rtk_trace_rays_compact will split over SEVERAL devices: an
+ * array of `count` elements (rays: 32 bytes, rtk_hit: 68, mask: 1, rtk_cuda_hit16: 16) whose part for
+ * device k -- the split a batch of `count` rays gets -- is placed on device k's NUMA node before it is
+ * page-locked, so that each link reads and writes the memory of its own socket.  Free with rtk_cuda_host_free. */
+void *rtk_cuda_host_alloc_batch(size_t element_bytes, size_t count);
 int   rtk_cuda_host_register(void *p, size_t bytes);
 int   rtk_cuda_host_unregister(void *p);
 /* Releases what the library itself holds on the device (streams, events, device and pinned

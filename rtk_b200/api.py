@@ -134,6 +134,7 @@ SYMBOLS = {
     "rtk_cuda_device_count": (C.c_int, []),
     "rtk_cuda_host_alloc": (_P, [C.c_size_t]),
     "rtk_cuda_host_free": (None, [_P]),
+    "rtk_cuda_host_alloc_batch": (_P, [C.c_size_t, C.c_size_t]),
     "rtk_cuda_host_register": (C.c_int, [_P, C.c_size_t]),
     "rtk_cuda_host_unregister": (C.c_int, [_P]),
     "rtk_cuda_scene_status": (C.c_int, [_P]),

@@ -10,6 +10,11 @@
 #include "k_wavefront.cuh"
 #include <stdarg.h>
 #include <pthread.h>
+#ifndef RTK_SIMT_EMU
+#include <sched.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#endif
 
 #define RTKD_OK 0
 #define RTKD_ERR_NO_DEVICE (-1)
@@ -304,7 +309,8 @@ extern "C" void *rtkd_host_alloc(size_t bytes)
 	CKP(cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocPortable | cudaHostAllocMapped));
 	return p;
 }
-extern "C" void rtkd_host_free(void *p) { if (p) cudaFreeHost(p); }
+extern "C" void rtkd_host_free_any(void *p);
+extern "C" void rtkd_host_free(void *p) { rtkd_host_free_any(p); }
 extern "C" int rtkd_host_register(void *p, size_t bytes)
 {
 	if (ensure_init()) return RTKD_ERR_NO_DEVICE;
@@ -317,6 +323,158 @@ extern "C" int rtkd_host_unregister(void *p)
 	if (!p) return RTKD_OK;
 	CK(cudaHostUnregister(p));
 	return RTKD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host arrays for batches that are split over several devices.  cudaHostAlloc puts every page on the NUMA
+// node of the calling thread; on a two-socket box all eight links then read and write ONE socket's memory
+// (measured on the 8-GPU box: 8 devices reach 96 GB/s device-to-host against 56 GB/s for one).  A batch
+// array is therefore allocated share by share: the part of the array that device k will read or write
+// (the very split run_batch makes) is first touched by a thread pinned to the CPUs of that device's NUMA
+// node, then the whole array is page-locked.  Linux only; anything that cannot be found out (no NUMA
+// information, a container without the sysfs files) degrades to a plain page-locked allocation.
+// ---------------------------------------------------------------------------------------------
+
+struct batch_alloc { void *p; size_t bytes; bool mapped; };
+static batch_alloc g_ballocs[64];
+static pthread_mutex_t g_balloc_lock = PTHREAD_MUTEX_INITIALIZER;
+static int g_numa_policy = 1;       // RTK_B200_NUMA: 0 plain allocations, 1 device-local shares (default), 2 round-robin over the nodes
+
+static void batch_split(size_t n, int *use_out, size_t *per_out)
+{
+	int use = g_ndev > 0 ? g_ndev : 1;
+	while (use > 1 && n / (size_t)use < g_min_share) use--;
+	*use_out = use;
+	*per_out = (n / (size_t)use + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS * RTK_RESOLVE_THREADS;
+}
+
+#ifndef RTK_SIMT_EMU
+static int numa_node_count(void)
+{
+	int n = 0;
+	char path[96];
+	for (; n < 64; n++) { snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", n); if (access(path, R_OK) != 0) break; }
+	return n;
+}
+static bool numa_node_cpus(int node, cpu_set_t *set)
+{
+	char path[96], buf[4096];
+	snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+	FILE *f = fopen(path, "r");
+	if (!f) return false;
+	const bool ok = fgets(buf, sizeof(buf), f) != NULL;
+	fclose(f);
+	if (!ok) return false;
+	CPU_ZERO(set);
+	int any = 0;
+	for (char *q = buf; *q; ) {                               // "0-15,32-47"
+		char *e; long a = strtol(q, &e, 10); if (e == q) break;
+		long b = a; if (*e == '-') { q = e + 1; b = strtol(q, &e, 10); }
+		for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, set); any = 1; }
+		q = *e == ',' ? e + 1 : e; if (*e != ',' ) break;
+	}
+	return any != 0;
+}
+static int numa_node_of_device(int ordinal)
+{
+	char bus[32] = { 0 }, path[128];
+	if (cudaDeviceGetPCIBusId(bus, sizeof(bus), ordinal) != cudaSuccess) { cudaGetLastError(); return -1; }
+	for (char *q = bus; *q; q++) if (*q >= 'A' && *q <= 'Z') *q = (char)(*q - 'A' + 'a');
+	snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+	FILE *f = fopen(path, "r");
+	if (!f) return -1;
+	int node = -1;
+	if (fscanf(f, "%d", &node) != 1) node = -1;
+	fclose(f);
+	return node;
+}
+struct touch_job { char *p; size_t bytes; int node; };
+static void *touch_worker(void *arg)
+{
+	touch_job *j = (touch_job*)arg;
+	cpu_set_t set;
+	if (j->node >= 0 && numa_node_cpus(j->node, &set)) {
+		cpu_set_t allowed;                                    // stay inside the process's own cpuset
+		if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) { CPU_AND(&set, &set, &allowed); }
+		if (CPU_COUNT(&set) > 0) sched_setaffinity(0, sizeof(set), &set);
+	}
+	for (size_t off = 0; off < j->bytes; off += 4096) j->p[off] = 0;           // first touch: the page lands on this thread's node
+	return NULL;
+}
+#endif
+
+// page-locked memory of share_bytes[0] + ... + share_bytes[use-1] bytes, share k placed on device k's NUMA node
+static void *numa_alloc_shares(const size_t *share_bytes, int use)
+{
+	size_t bytes = 0;
+	for (int k = 0; k < use; k++) bytes += share_bytes[k];
+	if (!bytes) bytes = 16;
+#ifndef RTK_SIMT_EMU
+	{ const char *e = getenv("RTK_B200_NUMA"); if (e) g_numa_policy = atoi(e); }
+	const int nodes = numa_node_count();
+	if (g_numa_policy > 0 && nodes > 1 && use > 1) {
+		const size_t total = (bytes + 4095) & ~(size_t)4095;
+		char *p = (char*)mmap(NULL, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+		if (p != (char*)MAP_FAILED) {
+			touch_job jobs[RTKD_MAX_DEVICES];
+			pthread_t th[RTKD_MAX_DEVICES];
+			bool up[RTKD_MAX_DEVICES];
+			size_t begin = 0, acc = 0;
+			for (int k = 0; k < use; k++) {
+				acc += share_bytes[k];
+				size_t end = k == use - 1 ? total : acc & ~(size_t)4095;
+				if (end > total) end = total;
+				int node = g_numa_policy == 1 ? numa_node_of_device(g_ctx[k].device) : -1;
+				if (node < 0 || node >= nodes) node = (int)((size_t)k * (size_t)nodes / (size_t)use);
+				jobs[k].p = p + begin; jobs[k].bytes = end > begin ? end - begin : 0; jobs[k].node = node;
+				up[k] = jobs[k].bytes && pthread_create(&th[k], NULL, touch_worker, &jobs[k]) == 0;
+				if (!up[k] && jobs[k].bytes) touch_worker(&jobs[k]);
+				begin = end;
+			}
+			for (int k = 0; k < use; k++) if (up[k]) pthread_join(th[k], NULL);
+			if (cudaHostRegister(p, total, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
+				pthread_mutex_lock(&g_balloc_lock);
+				for (int i = 0; i < 64; i++) if (!g_ballocs[i].p) { g_ballocs[i].p = p; g_ballocs[i].bytes = total; g_ballocs[i].mapped = true; break; }
+				pthread_mutex_unlock(&g_balloc_lock);
+				return p;
+			}
+			cudaGetLastError();
+			munmap(p, total);
+		}
+	}
+#endif
+	return rtkd_host_alloc(bytes);
+}
+
+// page-locked array of `count` elements of `elem_bytes` for batches of `count` rays: the elements device k
+// will read or write (run_batch's split) are placed on device k's NUMA node
+extern "C" void *rtkd_host_alloc_batch(size_t elem_bytes, size_t count)
+{
+	if (ensure_init()) return NULL;
+	int use = 1; size_t per = count;
+	batch_split(count, &use, &per);
+	size_t shares[RTKD_MAX_DEVICES];
+	size_t left = count;
+	for (int k = 0; k < use; k++) { size_t c = k == use - 1 ? left : (left < per ? left : per); shares[k] = c * elem_bytes; left -= c; }
+	return numa_alloc_shares(shares, use);
+}
+
+extern "C" void rtkd_host_free_any(void *p)
+{
+	if (!p) return;
+#ifndef RTK_SIMT_EMU
+	pthread_mutex_lock(&g_balloc_lock);
+	for (int i = 0; i < 64; i++) if (g_ballocs[i].p == p) {
+		const size_t bytes = g_ballocs[i].bytes;
+		g_ballocs[i].p = NULL;
+		pthread_mutex_unlock(&g_balloc_lock);
+		cudaHostUnregister(p);
+		munmap(p, bytes);
+		return;
+	}
+	pthread_mutex_unlock(&g_balloc_lock);
+#endif
+	cudaFreeHost(p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -431,12 +589,17 @@ extern "C" int rtkd_link_bandwidth(int ndev, size_t bytes_per_device, int dir, i
 	if (ndev < 1 || ndev > g_ndev || !bytes_per_device || !(dir & 3) || passes < 1 || !gbs) { rtkd_set_error("bad link probe arguments"); return RTKD_ERR_ARGUMENT; }
 	struct leg { void *h_up = NULL, *h_dn = NULL, *d_up = NULL, *d_dn = NULL; cudaStream_t su = NULL, sd = NULL; };
 	leg L[RTKD_MAX_DEVICES];
+	size_t shares[RTKD_MAX_DEVICES];
+	for (int i = 0; i < ndev; i++) shares[i] = bytes_per_device;
+	char *h_up_all = (dir & 1) ? (char*)numa_alloc_shares(shares, ndev) : NULL;
+	char *h_dn_all = (dir & 2) ? (char*)numa_alloc_shares(shares, ndev) : NULL;
 	int rc = RTKD_OK;
 	cudaError_t e = cudaSuccess;
 	for (int i = 0; i < ndev && e == cudaSuccess; i++) {
 		e = cudaSetDevice(g_ctx[i].device);
-		if (e == cudaSuccess && (dir & 1)) { e = cudaHostAlloc(&L[i].h_up, bytes_per_device, cudaHostAllocPortable); if (e == cudaSuccess) e = cudaMalloc(&L[i].d_up, bytes_per_device); }
-		if (e == cudaSuccess && (dir & 2)) { e = cudaHostAlloc(&L[i].h_dn, bytes_per_device, cudaHostAllocPortable); if (e == cudaSuccess) e = cudaMalloc(&L[i].d_dn, bytes_per_device); }
+		// the host side of every leg is ONE array of ndev shares, placed like a batch array (share i near device i)
+		if (e == cudaSuccess && (dir & 1)) { L[i].h_up = h_up_all ? h_up_all + (size_t)i * bytes_per_device : NULL; if (!L[i].h_up) e = cudaErrorMemoryAllocation; if (e == cudaSuccess) e = cudaMalloc(&L[i].d_up, bytes_per_device); }
+		if (e == cudaSuccess && (dir & 2)) { L[i].h_dn = h_dn_all ? h_dn_all + (size_t)i * bytes_per_device : NULL; if (!L[i].h_dn) e = cudaErrorMemoryAllocation; if (e == cudaSuccess) e = cudaMalloc(&L[i].d_dn, bytes_per_device); }
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&L[i].su, cudaStreamNonBlocking);
 		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&L[i].sd, cudaStreamNonBlocking);
 		if (e == cudaSuccess && L[i].h_up) memset(L[i].h_up, 1, bytes_per_device);      // touch: the pages exist before the clock starts
@@ -468,8 +631,8 @@ extern "C" int rtkd_link_bandwidth(int ndev, size_t bytes_per_device, int dir, i
 		if (L[i].su) cudaStreamDestroy(L[i].su);
 		if (L[i].sd) cudaStreamDestroy(L[i].sd);
 		cudaFree(L[i].d_up); cudaFree(L[i].d_dn);
-		cudaFreeHost(L[i].h_up); cudaFreeHost(L[i].h_dn);
 	}
+	rtkd_host_free(h_up_all); rtkd_host_free(h_dn_all);
 	bind_index(0);
 	*gbs = best;
 	return rc;
@@ -1720,12 +1883,12 @@ static void *ctx_worker(void *arg)
 // split [0, n) over the devices, run the shares, merge
 static long long run_batch(rtkd_scene *s, const void *rays, void *hits, unsigned char *mask, size_t n, int mode)
 {
-	int use = g_ndev;
-	while (use > 1 && n / (size_t)use < g_min_share) use--;
+	int use = 1;
+	size_t per = n;
+	// contiguous ranges, multiples of the resolve block (128 rays = 68 full 128-byte lines of rows)
+	batch_split(n, &use, &per);
 	if (use > 1 && rtkd_sync_replicas(s) != RTKD_OK) return -1;
 	batch_job J[RTKD_MAX_DEVICES];
-	// contiguous ranges, multiples of the resolve block (128 rays = 68 full 128-byte lines of rows)
-	size_t per = (n / (size_t)use + RTK_RESOLVE_THREADS - 1) / RTK_RESOLVE_THREADS * RTK_RESOLVE_THREADS;
 	size_t first = 0;
 	int used = 0;
 	for (int k = 0; k < use && first < n; k++, used++) {

@@ -83,6 +83,7 @@ int         rtkd_link_bandwidth(int ndev, size_t bytes_per_device, int dir, int 
 /* page-locked host memory the devices can read and WRITE directly (rows of rtk_trace_rays land in it without staging) */
 void       *rtkd_host_alloc(size_t bytes);
 void        rtkd_host_free(void *p);
+void       *rtkd_host_alloc_batch(size_t elem_bytes, size_t count);   /* array for batches of `count` rays: each device's share on its NUMA node */
 int         rtkd_host_register(void *p, size_t bytes);
 int         rtkd_host_unregister(void *p);
 

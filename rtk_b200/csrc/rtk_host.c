@@ -79,6 +79,7 @@ int rtk_cuda_init_devices(const int *devices, int num_devices)
 int rtk_cuda_device_count(void) { return rtkd_device_count(); }
 void *rtk_cuda_host_alloc(size_t bytes) { return rtkd_host_alloc(bytes); }
 void rtk_cuda_host_free(void *p) { rtkd_host_free(p); }
+void *rtk_cuda_host_alloc_batch(size_t element_bytes, size_t count) { return rtkd_host_alloc_batch(element_bytes, count); }
 int rtk_cuda_host_register(void *p, size_t bytes) { return rtkd_host_register(p, bytes); }
 int rtk_cuda_host_unregister(void *p) { return rtkd_host_unregister(p); }
 void rtk_cuda_shutdown(void) { rtkd_shutdown(); }

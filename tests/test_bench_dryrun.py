@@ -14,10 +14,11 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 WF = ["--workload", "C5", "--wf-frame", "64x32x2", "--scale", "0.0005"]      # the wavefront leg on a toy frame
 
 
-@pytest.mark.parametrize("world,extra", [(1, []), (2, []), (2, ["--gather", "p2p"]), (1, WF), (2, WF)])
+@pytest.mark.parametrize("world,extra", [(1, []), (2, []), (2, ["--gather", "nccl"]), (1, WF), (2, WF)])
 def test_bench_dry_run(world, extra):
-    """the third case is the peer-memory gather between two real processes: the emulator then backs
-    'device memory' with POSIX shared memory and its CUDA IPC calls map the window for real"""
+    """the second case is the peer-memory gather (the default) between two real processes: the emulator then
+    backs 'device memory' with POSIX shared memory and its CUDA IPC calls map the window for real; the third is
+    the torch.distributed gather"""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_emu.py"), str(world)] + extra,
                        capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]

@@ -8,9 +8,9 @@ torch's CUDA entry points are replaced by host stand-ins, and NCCL by gloo.  Not
 run is a measurement -- the line is checked for shape only.  TEST INFRASTRUCTURE.
 
     python tools/bench_emu.py [world] [bench.py arguments...]
-    python tools/bench_emu.py 2 --gather p2p      # peer-memory gather: emulated device memory is then
-                                                  # POSIX shared memory, the window really is mapped by
-                                                  # the other process
+    python tools/bench_emu.py 2                   # peer-memory gather (the default): emulated device memory is
+                                                  # POSIX shared memory, the window really is mapped by the other process
+    python tools/bench_emu.py 2 --gather nccl     # torch.distributed gather (gloo here)
 """
 import json
 import os
@@ -103,7 +103,7 @@ def main():
         port = s.getsockname()[1]
     procs = []
     for rank in range(world):
-        env = dict(os.environ, SIMT_SHM_MALLOC="1" if "p2p" in extra else "0", SIMT_DEVICES=str(world), RTK_B200_HOST_MIN_SHARE_LOG2="10", RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
+        env = dict(os.environ, SIMT_SHM_MALLOC="0" if "nccl" in extra else "1", SIMT_DEVICES=str(world), RTK_B200_HOST_MIN_SHARE_LOG2="10", RANK=str(rank), LOCAL_RANK="0", WORLD_SIZE=str(world), LOCAL_WORLD_SIZE=str(world),
                    MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--child", "x"] + args, env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
@@ -148,7 +148,7 @@ def main():
         assert line["occlusion"]["agrees_with_closest_hit_mask"]
     else:
         assert line["gather_check"].get("equal") is True, line["gather_check"]
-        assert line["config"]["gather"] == ("p2p" if "p2p" in extra else "nccl")
+        assert line["config"]["gather"] == ("nccl" if "nccl" in extra else "p2p")
     print(json.dumps(line)[:3000])
     print(f"dry run ok (world {world}); nothing above is a measurement")
     return 0

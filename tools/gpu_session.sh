@@ -62,6 +62,18 @@ run_stage() {
 	hostab)
 		for v in 1 0; do RTK_B200_HOST_DIRECT=$v timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows|compact" | sed "s/^/HOST_DIRECT=$v /"; done
 		for r in 2 8; do RTK_B200_PUSH_SMS=$r timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows " | sed "s/^/PUSH_SMS=$r /"; done ;;
+	topo)
+		# what the host looks like: sockets, NUMA nodes, which node each GPU hangs off, the cpuset of this container
+		lscpu | grep -E "Model name|Socket|NUMA|^CPU\(s\)|Thread|Core" ; nproc
+		for n in /sys/devices/system/node/node*; do echo "$n: cpus $(cat $n/cpulist) $(grep MemTotal $n/meminfo | tr -s ' ')"; done
+		for d in $(nvidia-smi --query-gpu=pci.bus_id --format=csv,noheader | tr 'A-Z' 'a-z' | sed 's/^0000//'); do echo "gpu $d numa_node $(cat /sys/bus/pci/devices/$d/numa_node 2>/dev/null)"; done
+		nvidia-smi topo -m 2>&1 | head -14
+		grep -E "Cpus_allowed_list|Mems_allowed_list" /proc/self/status ;;
+	numa)
+		# host link ceilings and the row path under the three placement policies of the batch arrays
+		N="$1"
+		for v in 1 0 2; do RTK_B200_NUMA=$v timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 3 2>&1 | grep -E "rows  |compact|host link, $N" | sed "s/^/NUMA=$v /"; done
+		for m in 4 8; do RTK_B200_HOST_MIX=$m timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 3 2>&1 | grep -E "rows  " | sed "s/^/MIX=$m /"; done ;;
 	*) echo "unknown stage $stage" ;;
 	esac
 }

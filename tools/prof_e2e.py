@@ -24,7 +24,7 @@ one = scenes.bounce_rays(s, min(n, 1 << 22)) if workload == "C3" else scenes.mix
 
 def pinned(count, dtype):
     dt = np.dtype(dtype)
-    p = lib.rtk_cuda_host_alloc(count * dt.itemsize)
+    p = lib.rtk_cuda_host_alloc_batch(dt.itemsize, count)
     assert p, lib.last_error()
     return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(count * dt.itemsize,)).view(dt)
 
@@ -46,8 +46,9 @@ for name, fn in (("rows", lambda: lib.rtk_trace_rays(sc.ptr, rays.ctypes.data, h
         r = fn()
         ms.append((time.perf_counter() - t0) * 1e3)
         assert r != C.c_size_t(-1).value and r >= 0, lib.last_error()
-    print("%-14s %d rays on %d device(s), direct=%s: ms %s | best %.1f Mrays/s" %
-          (name, n, ndev, os.environ.get("RTK_B200_HOST_DIRECT", "1"), " ".join("%.2f" % m for m in ms), n / min(ms) / 1e3))
+    print("%-14s %d rays on %d device(s), direct=%s mix=%s numa=%s: ms %s | best %.1f Mrays/s" %
+          (name, n, ndev, os.environ.get("RTK_B200_HOST_DIRECT", "1"), os.environ.get("RTK_B200_HOST_MIX", "auto"), os.environ.get("RTK_B200_NUMA", "1"),
+           " ".join("%.2f" % m for m in ms), n / min(ms) / 1e3))
 for d in (1, 2, 3):
     for k in sorted(set([1, ndev])):
         g = C.c_double(0)

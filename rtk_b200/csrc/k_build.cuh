@@ -395,7 +395,33 @@ struct rtkd_collapse_args {
 	float4 *nodes;
 	int n;                       // triangles
 	uint32_t *err;
+	const unsigned char *nleaf;  // [binary node] from k_count_leaves
 };
+
+// nleaf[c] for every binary node c: the number of leaves (maximal subtrees of at most RTK_LEAF_MAX triangles)
+// below c when c must be opened and that number is at most RTK_WIDE, else 0.  k_collapse asks this of every
+// slot each time it opens one; walking the subtree there (a local-memory stack per thread, up to a dozen walks
+// per wide node) had doubled the kernel's time -- one pass over the binary nodes up front, walks only where at
+// most RTK_LEAF_MAX * RTK_WIDE triangles hang below, costs a tenth of that.
+__global__ void k_count_leaves(rtkd_bvh2 t, const uint32_t *num_nodes_dev, uint32_t num_nodes_host, unsigned char *nleaf)
+{
+	const uint32_t c0 = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t num = num_nodes_dev ? *num_nodes_dev : num_nodes_host;
+	if (c0 >= num) return;
+	unsigned char out = 0;
+	const int span = t.last[c0] - t.first[c0] + 1;
+	if (span > RTK_LEAF_MAX && span <= RTK_LEAF_MAX * RTK_WIDE) {
+		int todo[2 * RTK_WIDE + 2], ntodo = 0, leaves = 0;
+		todo[ntodo++] = (int)c0;
+		while (ntodo > 0 && leaves + ntodo <= RTK_WIDE) {
+			const int c1 = todo[--ntodo];
+			if (c1 >= 0 && (t.last[c1] - t.first[c1] + 1) > RTK_LEAF_MAX) { todo[ntodo++] = t.left[c1]; todo[ntodo++] = t.right[c1]; }
+			else leaves++;
+		}
+		if (ntodo == 0) out = (unsigned char)leaves;
+	}
+	nleaf[c0] = out;
+}
 
 __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 {
@@ -414,20 +440,7 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 	// slot when that is at most RTK_WIDE, else 0.  Only subtrees of at most RTK_WIDE * RTK_LEAF_MAX
 	// triangles can qualify, so the walk is short.
 	int nleaf[RTK_WIDE];
-#define RTK_COUNT_LEAVES(k) do { \
-		nleaf[k] = 0; \
-		const int c0 = slot[k]; \
-		if (area[k] >= 0.0f && (t.last[c0] - t.first[c0] + 1) <= RTK_LEAF_MAX * RTK_WIDE) { \
-			int todo[2 * RTK_WIDE + 2], ntodo = 0, leaves = 0; \
-			todo[ntodo++] = c0; \
-			while (ntodo > 0 && leaves + ntodo <= RTK_WIDE) { \
-				const int c1 = todo[--ntodo]; \
-				if (c1 >= 0 && (t.last[c1] - t.first[c1] + 1) > RTK_LEAF_MAX) { todo[ntodo++] = t.left[c1]; todo[ntodo++] = t.right[c1]; } \
-				else leaves++; \
-			} \
-			if (ntodo == 0) nleaf[k] = leaves; \
-		} \
-	} while (0)
+#define RTK_COUNT_LEAVES(k) do { nleaf[k] = area[k] >= 0.0f ? (int)a.nleaf[slot[k]] : 0; } while (0)
 	for (int k = 0; k < 2; k++) {
 		area[k] = RTK_OPENABLE(slot[k]) ? rtk_half_area(t.blo[slot[k]], t.bhi[slot[k]]) : -1.0f;
 		RTK_COUNT_LEAVES(k);

@@ -41,7 +41,7 @@ struct rtkd_sah {
 	int *left, *right, *first, *last;
 	float4 *blo, *bhi;
 	uint32_t *ndepth;
-	uint32_t *counters;           // [0] node_alloc [1] n_act_out [2] n_small [3] err [4] max depth
+	uint32_t *counters;           // [0] node_alloc [1] n_act_out [2] n_small [3] err [4] max depth [5] chunks, [6] nodes of the level
 	uint32_t *act_in, *act_out;   // large nodes of this / the next level
 	uint32_t *small_list;         // node id | (buffer << 31)
 	uint32_t *chunk_base;         // [n_act + 1] exclusive scan of chunk counts
@@ -277,7 +277,7 @@ __global__ void k_sah_root(rtkd_sah s, const uint32_t *bounds, uint32_t n)
 	s.blo[0] = make_float4(rtk_ord2f(bounds[0]), rtk_ord2f(bounds[1]), rtk_ord2f(bounds[2]), 0.0f);
 	s.bhi[0] = make_float4(rtk_ord2f(bounds[3]), rtk_ord2f(bounds[4]), rtk_ord2f(bounds[5]), 0.0f);
 	s.counters[0] = 1; s.counters[1] = 0; s.counters[2] = 0; s.counters[3] = 0; s.counters[4] = 0;
-	s.counters[5] = 0;
+	s.counters[5] = 0; s.counters[6] = 0;
 	if (n > RTK_SAH_SMALL) { s.act_in[0] = 0; s.counters[1] = 1; }
 	else { s.small_list[0] = 0; s.counters[2] = 1; }
 }
@@ -287,8 +287,8 @@ __global__ void k_sah_root(rtkd_sah s, const uint32_t *bounds, uint32_t n)
 // ---------------------------------------------------------------------------------------------
 
 // chunk table of the level about to run: chunk_base[a] = first chunk of active node a.  Single
-// block; reads the number of active nodes from counters[1] and leaves the chunk total in
-// counters[5] so that the host needs one read-back per level.
+// block; reads the number of active nodes from counters[1] and leaves it in counters[6], the chunk
+// total in counters[5].
 __global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, const uint32_t *act)
 {
 	__shared__ uint32_t s_warp[32];
@@ -320,7 +320,10 @@ __global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, const uint32_t *a
 		if (threadIdx.x == 1023) s_carry = carry + woff + x;
 		__syncthreads();
 	}
-	if (threadIdx.x == 0) { s.chunk_base[n_act] = s_carry; s.counters[5] = s_carry; }
+	// counters[6] / [5]: nodes and chunks of the level about to run (the kernels of the level read them on the
+	// device: the host launches upper-bound grids and does not wait for them); counters[1] starts the next list
+	__syncthreads();
+	if (threadIdx.x == 0) { s.chunk_base[n_act] = s_carry; s.counters[5] = s_carry; s.counters[6] = n_act; s.counters[1] = 0; }
 }
 
 RTK_DEV uint32_t rtk_sah_find_node(const uint32_t *chunk_base, uint32_t n_act, uint32_t chunk)
@@ -333,15 +336,18 @@ RTK_DEV uint32_t rtk_sah_find_node(const uint32_t *chunk_base, uint32_t n_act, u
 	return lo;
 }
 
-__global__ void k_sah_bins_clear(rtkd_sah s, uint32_t n_act)
+__global__ void k_sah_bins_clear(rtkd_sah s)
 {
+	if (blockIdx.x >= s.counters[6]) return;
 	rtk_sah_bins_clear(s.bins + (size_t)blockIdx.x * RTK_SAH_NODEBINS, threadIdx.x, blockDim.x);
 }
 
-__global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, uint32_t n_act, int src_buf)
+__global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf)
 {
 	__shared__ uint32_t s_bins[RTK_SAH_NODEBINS];
 	__shared__ uint32_t s_a;
+	if (blockIdx.x >= s.counters[5]) return;                 // the grid is an upper bound on the level's chunks
+	const uint32_t n_act = s.counters[6];
 	if (threadIdx.x == 0) s_a = rtk_sah_find_node(s.chunk_base, n_act, blockIdx.x);
 	rtk_sah_bins_clear(s_bins, threadIdx.x, 256);
 	__syncthreads();
@@ -415,10 +421,10 @@ RTK_DEV void rtk_sah_emit_children(rtkd_sah &s, uint32_t node, const rtk_sah_cho
 }
 
 // one warp per active large node
-__global__ void __launch_bounds__(128) k_sah_split_large(rtkd_sah s, uint32_t n_act, uint32_t depth, int dst_buf)
+__global__ void __launch_bounds__(128) k_sah_split_large(rtkd_sah s, uint32_t depth, int dst_buf)
 {
 	const uint32_t a = blockIdx.x * 4 + (threadIdx.x >> 5);
-	if (a >= n_act) return;
+	if (a >= s.counters[6]) return;
 	const int lane = threadIdx.x & 31;
 	const uint32_t node = s.act_in[a];
 	const uint32_t count = (uint32_t)(s.last[node] - s.first[node] + 1);
@@ -438,9 +444,11 @@ __global__ void __launch_bounds__(128) k_sah_split_large(rtkd_sah s, uint32_t n_
 	}
 }
 
-__global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, uint32_t n_act, int src_buf)
+__global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, int src_buf)
 {
 	__shared__ uint32_t s_a, s_cntl[8], s_basel, s_baser;
+	if (blockIdx.x >= s.counters[5]) return;
+	const uint32_t n_act = s.counters[6];
 	if (threadIdx.x == 0) s_a = rtk_sah_find_node(s.chunk_base, n_act, blockIdx.x);
 	__syncthreads();
 	const uint32_t a = s_a;

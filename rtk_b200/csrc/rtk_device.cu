@@ -889,6 +889,7 @@ struct build_bufs {
 	uint32_t *ctr;
 	uint2 *leaf_list;
 	unsigned char *node_level;
+	unsigned char *nleaf;
 	double *d_cost;
 	uint32_t cap, nblocks;
 	size_t act_cap, small_cap;
@@ -938,10 +939,16 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 	B.ctr = A.take<uint32_t>(8 + RTKD_COLLAPSE_LEVELS);
 	B.leaf_list = A.take<uint2>(n);
 	B.node_level = A.take<unsigned char>(B.cap);
+	B.nleaf = A.take<unsigned char>(2 * (size_t)n + 2);
 	B.d_cost = A.take<double>(1);
 }
 
-// binned-SAH binary tree (k_sah.cuh): one host synchronisation per level of large nodes
+// binned-SAH binary tree (k_sah.cuh).  The level loop runs on the device's word: k_sah_plan leaves the
+// level's node and chunk counts in device memory, the level's kernels are launched with upper-bound grids
+// (at most 2^level nodes, never more than n / RTK_SAH_SMALL; chunks <= n / RTK_SAH_CHUNK + nodes) and blocks
+// beyond the counts return at once.  The host looks at the counters only after the first
+// ceil(log2(n / RTK_SAH_SMALL)) levels -- no tree is done before that -- and then every second level
+// (round 1 read them back after every level: 13 round trips per 1M-triangle build).
 static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, build_bufs &B, uint32_t n)
 {
 	RTK_NVTX("rtk_b200 build: binned SAH levels");
@@ -950,24 +957,35 @@ static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, 
 	RTK_LAUNCH(k_sah_root, 1, 32, st, h, (const uint32_t*)B.d_bounds, n); CK_LAUNCH();
 	RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();
 	uint32_t hc[8];
-	CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
-	uint32_t n_act = hc[1], chunks = hc[5], depth = 0;
+	memset(hc, 0, sizeof(hc));
+	uint32_t blind = 0;
+	for (uint32_t m = n; m > RTK_SAH_SMALL; m = (m + 1) / 2) blind++;
+	const uint32_t max_chunks = n / RTK_SAH_CHUNK + 1;
+	uint32_t depth = 0;
 	int src_buf = 0;
-	while (n_act) {
-		if (n_act > B.act_cap) { rtkd_set_error("SAH active list overflow"); return RTKD_ERR_MEMORY; }
-		CK(cudaMemsetAsync(h.counters + 1, 0, sizeof(uint32_t), st));
-		RTK_LAUNCH(k_sah_bins_clear, n_act, 128, st, h, n_act); CK_LAUNCH();
-		RTK_LAUNCH(k_sah_bin_large, chunks, 256, st, h, n_act, src_buf); CK_LAUNCH();
-		RTK_LAUNCH(k_sah_split_large, (n_act + 3) / 4, 128, st, h, n_act, depth, src_buf ^ 1); CK_LAUNCH();
-		RTK_LAUNCH(k_sah_partition_large, chunks, 256, st, h, n_act, src_buf); CK_LAUNCH();
+	bool done = n <= RTK_SAH_SMALL;
+	while (!done) {
+		const unsigned long long pow2 = depth < 40 ? 1ull << depth : ~0ull;
+		const uint32_t act_bound = (uint32_t)(pow2 < B.act_cap ? pow2 : B.act_cap);
+		const uint32_t chunk_bound = max_chunks + act_bound;
+		RTK_LAUNCH(k_sah_bins_clear, act_bound, 128, st, h); CK_LAUNCH();
+		RTK_LAUNCH(k_sah_bin_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
+		RTK_LAUNCH(k_sah_split_large, (act_bound + 3) / 4, 128, st, h, depth, src_buf ^ 1); CK_LAUNCH();
+		RTK_LAUNCH(k_sah_partition_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
 		uint32_t *tmp = h.act_in; h.act_in = h.act_out; h.act_out = tmp;
 		RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();
-		CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		n_act = hc[1]; chunks = hc[5];
 		src_buf ^= 1;
 		depth++;
+		if (depth >= blind && ((depth - blind) & 1u) == 0) {
+			CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			done = hc[6] == 0;
+			if (depth > 4096) { rtkd_set_error("SAH builder does not terminate"); return RTKD_ERR_MEMORY; }
+		}
+	}
+	if (n <= RTK_SAH_SMALL) {
+		CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
 	}
 	if (hc[2] > B.small_cap || hc[3]) { rtkd_set_error("SAH builder ran out of list space (flags %u)", hc[3]); return RTKD_ERR_MEMORY; }
 	if (hc[2]) { RTK_LAUNCH(k_sah_small, hc[2], RTK_SAH_SMALL_THREADS, st, h, hc[2]); CK_LAUNCH(); }
@@ -1095,6 +1113,11 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		CK(cudaMemcpyAsync(B.ctr, h_ctr, sizeof(h_ctr), cudaMemcpyHostToDevice, st));
 		CK(cudaMemcpyAsync(B.work[0], &w0, sizeof(w0), cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(B.d_cost, 0, sizeof(double), st));
+		{
+			// leaves below every binary node that could be absorbed whole (k_count_leaves)
+			const uint32_t bound = use_sah ? (uint32_t)(2 * (size_t)n + 2) : n - 1;
+			RTK_LAUNCH(k_count_leaves, (bound + 255) / 256, 256, st, t, use_sah ? (const uint32_t*)B.h.counters : (const uint32_t*)NULL, n - 1, B.nleaf); CK_LAUNCH();
+		}
 		// levels are launched with an upper bound on their width (8^L, capped) and read their
 		// true item count on the device; the host looks at the counters every 4 levels
 		unsigned long long bound = 1;
@@ -1107,7 +1130,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 				a.work_out = B.work[(level & 1) ^ 1]; a.n_out = B.ctr + 8 + level + 1;
 				a.node_alloc = B.ctr; a.node_cap = B.cap; a.leaf_count = B.ctr + 1; a.leaf_list = B.leaf_list; a.sah_cost = B.d_cost;
 				a.node_level = B.node_level; a.level = (uint32_t)level;
-				a.nodes = B.wide; a.n = (int)n; a.err = B.ctr + 2;
+				a.nodes = B.wide; a.n = (int)n; a.err = B.ctr + 2; a.nleaf = B.nleaf;
 				uint32_t width = (uint32_t)(bound < B.cap ? bound : B.cap);
 				RTK_LAUNCH(k_collapse, (width + 127) / 128, 128, st, a, t); CK_LAUNCH();
 				bound = bound * 8 < B.cap ? bound * 8 : B.cap;

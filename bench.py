@@ -484,7 +484,9 @@ def roofline_block(lib, workload_key, info, per_ray, bytes_per_ray, n, trace_ms,
     achieved = bytes_per_ray * n / (trace_ms * 1e-3) / 1e9
     prof = profile_summary(workload_key, info.num_wide_nodes)
     compulsory = 32.0 * n + 16.0 * n + float(info.device_bytes) * (1.0 if in_l2 else 0.0)
-    dram_bytes = prof["dram_bytes"] if prof else None
+    # the capture may have been taken with another ray count: DRAM traffic of this kernel is per ray (rays in, hits out,
+    # scene misses), so it is scaled to the launch this run timed
+    dram_bytes = prof["dram_bytes"] * (n / prof["rays"]) if prof else None
     blk = {"bound": "l2" if in_l2 else "hbm", "kernel": "k_trace", "achieved": achieved, "peak": g256.value, "unit": "GB/s",
            "frac": achieved / g256.value if g256.value else None,
            "traffic": dram_bytes,
@@ -493,7 +495,12 @@ def roofline_block(lib, workload_key, info, per_ray, bytes_per_ray, n, trace_ms,
                           "(rtk_cuda_measure_gather_bandwidth; %s); 128-byte records reach %.0f GB/s, a coalesced stream over "
                           "64 MiB %.0f GB/s, over 4 GiB (HBM) %.0f GB/s" % (probe_bytes >> 20, "inside the L2" if in_l2 else "far beyond the L2",
                                                                           g128.value, stream_l2.value, hbm_read.value),
-           "limiter": "instruction issue" if in_l2 else "memory latency / HBM gathers",
+           "limiter": ("instruction issue: %.0f %% of the issue slots busy, %.0f warp instructions per ray at %.1f of 32 threads each, ALU pipe %.0f %%; "
+                       "L2 hit rate %.0f %%, L2 throughput %.0f %%, DRAM %.0f %% of the measured HBM peak (ncu, %s)"
+                       % (prof["issue_active_pct"], prof["warp_instructions_per_ray"], prof["threads_per_instruction"], prof["pipe_alu_pct"],
+                          prof["l2_hit_rate_pct"], prof.get("l2_throughput_pct") or 0.0,
+                          100.0 * prof["dram_bytes"] / (prof["duration_ms"] * 1e-3) / 1e9 / hbm_peak, prof["source"])) if prof else
+                      ("instruction issue (no ncu capture of this tree at hand)" if in_l2 else "instruction issue and memory latency (no ncu capture of this tree at hand)"),
            "issue_active_pct": prof.get("issue_active_pct") if prof else None,
            "warp_instructions_per_ray": prof.get("warp_instructions_per_ray") if prof else None,
            "dram": {"bytes_per_launch": dram_bytes, "compulsory_bytes_per_launch": compulsory,

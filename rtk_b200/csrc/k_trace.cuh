@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 		const bool is_node = has_ray && cur_ref != RTK_REF_EMPTY && !rtk_ref_is_leaf(cur_ref);
 		if (__any_sync(FULL, is_node)) {
 			uint32_t hitbits = 0;                 // bit (child index) for the children of this lane
-			uint32_t ok = 0xffffffffu;            // best ordering key of this lane ...
+			uint32_t ok = 0x7fffffffu;            // best ordering key of this lane (a signed comparison, see below) ...
 			uint32_t okref = RTK_REF_EMPTY;       // ... and the child it belongs to
 			float key[CPL];
 			uint32_t ref[CPL];
@@ -428,14 +428,19 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 						kn = rc.kz == 0 ? tnx : (rc.kz == 1 ? tny : tnz);
 						kf = rc.kz == 0 ? tfx : (rc.kz == 1 ? tfy : tfz);
 					} else { kn = tn; kf = tf; }
-					const bool hit = ref[j] != RTK_REF_EMPTY && tn <= tf && kn <= best_t && kf >= rc.min_t;
+					// an empty slot is an inverted box (lo = +RTK_INF, hi = -RTK_INF): tn <= tf already fails for it, so
+					// the slot's reference needs no test of its own (measured: 9.84 -> 9.69 ms per 16.7M C3 rays)
+					const bool hit = tn <= tf && kn <= best_t && kf >= rc.min_t;
 					key[j] = kn;
 					if (hit) {
 						hitbits |= 1u << k;
 						// nearest hit child: entry distance with the child number in the low 3 bits
 						// (the reference tags 2 bits the same way, rtk.c:496)
-						const uint32_t kk = (__float_as_uint(rtk_fmax(tn, 0.0f)) & ~7u) | (uint32_t)k;
-						if (kk < ok) { ok = kk; okref = ref[j]; }
+						// compared as SIGNED integers: a negative entry distance (the origin is inside the box) sorts
+						// before every positive one without being clamped to zero first (9.69 -> 9.55 ms per 16.7M C3 rays;
+						// the order among children that contain the origin is irrelevant to the result)
+						const uint32_t kk = (__float_as_uint(tn) & ~7u) | (uint32_t)k;
+						if ((int)kk < (int)ok) { ok = kk; okref = ref[j]; }
 					}
 				}
 				if (STATS) st_nodes++;
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(RTK_TRACE_THREADS, RTK_TRACE_MINB) k_trace(rtk
 			uint32_t om = ok, gm = hitbits;
 #pragma unroll
 			for (int o = 1; o < LANES; o <<= 1) {
-				om = rtk_umin(om, __shfl_xor_sync(FULL, om, o));
+				om = (uint32_t)rtk_imin((int)om, (int)__shfl_xor_sync(FULL, om, o));
 				if (CPL > 1) gm |= __shfl_xor_sync(FULL, gm, o);
 			}
 			if (CPL == 1) gm = (__ballot_sync(FULL, hitbits != 0) >> (g * LANES)) & 0xffu;

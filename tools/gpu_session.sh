@@ -75,8 +75,8 @@ run_stage() {
 	numa)
 		# host link ceilings and the row path under the three placement policies of the batch arrays
 		N="$1"
-		for v in 1 0 2; do RTK_B200_NUMA=$v timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 3 2>&1 | grep -E "rows  |compact|host link, $N" | sed "s/^/NUMA=$v /"; done
-		for m in 4 8; do RTK_B200_HOST_MIX=$m timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 3 2>&1 | grep -E "rows  " | sed "s/^/MIX=$m /"; done ;;
+		for v in 1 0; do RTK_B200_NUMA=$v timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 3 2>&1 | grep -E "rows  |compact|host link, $N" | sed "s/^/NUMA=$v /"; done
+		RTK_B200_HOST_MIX=0 timeout 900 python tools/prof_e2e.py C3 $((16777216 * N)) $N 3 2>&1 | grep -E "rows  " | sed "s/^/MIX=0 /" ;;
 	*) echo "unknown stage $stage" ;;
 	esac
 }

@@ -34,7 +34,7 @@ static size_t g_l2_setaside = 0;    // L2 bytes set aside for persisting lines
 static int g_l2_persist = 0;        // RTK_B200_L2_PERSIST=1: persisting L2 window over nodes + leaf slots.  Off by default --
                                     // measured on C3/C4: k_trace gains nothing (1705 vs 1704 Mrays/s), while k_resolve, whose
                                     // corner gathers lose the set-aside part of the L2, goes from 0.47 to 1.10 ms per batch
-static int g_host_mix = -1;         // RTK_B200_HOST_MIX: every k-th chunk of a direct batch takes the staged route (-1: 2 x devices)
+static int g_host_mix = -1;         // RTK_B200_HOST_MIX: every k-th chunk of a direct batch takes the staged route (-1: 2 on one device, none on several)
 static int g_push_sms = 8;          // RTK_B200_PUSH_SMS: SMs the traversal grid leaves to the row-push kernel of the direct host path
 static __thread int t_reserve_extra = 0;   // set by the direct host pipeline around its traversal launches
 static int g_host_direct = 1;       // RTK_B200_HOST_DIRECT=0: rows always travel through pinned staging
@@ -1749,8 +1749,7 @@ static int host_stage_c(host_stage &G, host_buf &B, const batch_job &J)
 //            host's memory system, a resource all devices share.
 //
 // staged_every = 0: every chunk direct; 1: every chunk staged (pageable arrays); k > 1: every k-th chunk
-// staged, so that link and host threads both work: one device alone is fastest at k = 2, and the staged
-// share shrinks with the number of devices that share the host.
+// staged, so that link and host threads both work (one device alone: k = 2; several devices: all direct).
 static int pipeline_rows(dev_ctx &X, batch_job &J, uint32_t *m_hits, unsigned char *m_mask, unsigned staged_every)
 {
 	static const char *what = "rtk_trace_rays";
@@ -1869,10 +1868,13 @@ static void run_job(dev_ctx &X, batch_job &J)
 		m_mask = J.mask ? (unsigned char*)host_mapped(J.mask, J.first + J.n) : NULL;
 		direct = m_hits && (!J.mask || m_mask);
 	}
-	// direct and staged chunks are mixed when the arrays allow direct writes: every (2 x devices in the batch)-th
-	// chunk is staged (RTK_B200_HOST_MIX=k: every k-th; 0: none), i.e. about half a device's rows for the host threads
+	// direct and staged chunks are mixed when the arrays allow direct writes and ONE device runs the batch: every
+	// second chunk is staged (measured on a 16-vCPU host: 18.1 ms all direct, 17.5 every 2nd, 17.1 every 3rd, 20.0
+	// every 4th chunk staged per 16.7M rays).  With several devices the host threads are the scarcer resource
+	// (8 devices: 80.6 ms all direct against 84.0 with every 16th chunk staged): all direct.  RTK_B200_HOST_MIX=k
+	// forces every k-th chunk onto the staged route, 0 none.
 	unsigned staged_every = 1;
-	if (direct) staged_every = g_host_mix >= 0 ? (unsigned)g_host_mix : 2u * (unsigned)(J.ndev > 0 ? J.ndev : 1);
+	if (direct) staged_every = g_host_mix >= 0 ? (unsigned)g_host_mix : (J.ndev > 1 ? 0u : 2u);
 	if (rc == RTKD_OK) rc = stage_prepare(X.stage, J.n, J.mode == 0 && staged_every != 0);
 	if (rc == RTKD_OK) rc = stage_rays(X.stage, J.n);
 	if (rc == RTKD_OK) {

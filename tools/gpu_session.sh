@@ -47,6 +47,17 @@ run_stage() {
 				bench.py --gpus $N --steps 30 --warmup 3 --gather $g $legs "$@" > $OUT/${TAG}_scale_${N}_${g}.json 2> $OUT/${TAG}_scale_${N}_${g}.err
 			echo "scale $N $g exit $?"; tail -c 400 $OUT/${TAG}_scale_${N}_${g}.err; head -c 600 $OUT/${TAG}_scale_${N}_${g}.json; echo
 		done ;;
+	scale8final|benchn)
+		# the driver's own command line at N ranks: bench.py defaults (peer-memory gather, all legs)
+		N="${1:-8}"
+		timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 \
+			bench.py --gpus $N --steps 30 --warmup 3 > $OUT/${TAG}_bench_n$N.json 2> $OUT/${TAG}_bench_n$N.err
+		echo "bench $N exit $?"; tail -c 300 $OUT/${TAG}_bench_n$N.err; head -c 400 $OUT/${TAG}_bench_n$N.json; echo ;;
+	sanitize)
+		# compute-sanitizer memcheck over the GPU cases that exercise the kernels added in round 2 (one tool per call)
+		timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_gpu_parity.py -x -q \
+			-k "known_answer or direct_rows or blob_validation or two_streams or probes or configs_reduced or refit" > $OUT/${TAG}_sanitizer.log 2>&1
+		echo "sanitizer exit $?"; grep -E "ERROR SUMMARY|passed|failed|Invalid|error" $OUT/${TAG}_sanitizer.log | tail -8 ;;
 	e2e)
 		# one process, N devices: rows direct / staged, compact, link ceilings
 		N="$1"

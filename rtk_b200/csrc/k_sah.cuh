@@ -49,8 +49,6 @@ struct rtkd_sah {
 	int4 *split;                  // per active node: axis (-1: equal split), bin, n_left, first child
 	uint32_t *cursor;             // per active node: left / right write cursors
 	uint32_t node_cap;
-	uint32_t *small_end;          // [level + 1] = entries of small_list after `level` levels of large nodes ([0] = 0)
-	uint32_t plan_level;          // the level k_sah_plan is closing (it writes small_end[plan_level])
 	uint32_t act_cap, small_cap;  // capacities of act_in / act_out and small_list (never reached: see carve(); guarded all the same)
 };
 
@@ -325,10 +323,7 @@ __global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, const uint32_t *a
 	// counters[6] / [5]: nodes and chunks of the level about to run (the kernels of the level read them on the
 	// device: the host launches upper-bound grids and does not wait for them); counters[1] starts the next list
 	__syncthreads();
-	if (threadIdx.x == 0) {
-		s.chunk_base[n_act] = s_carry; s.counters[5] = s_carry; s.counters[6] = n_act; s.counters[1] = 0;
-		s.small_end[s.plan_level] = s.counters[2];        // small subtrees known so far: complete and final
-	}
+	if (threadIdx.x == 0) { s.chunk_base[n_act] = s_carry; s.counters[5] = s_carry; s.counters[6] = n_act; s.counters[1] = 0; }
 }
 
 RTK_DEV uint32_t rtk_sah_find_node(const uint32_t *chunk_base, uint32_t n_act, uint32_t chunk)
@@ -640,11 +635,7 @@ RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *
 // One CTA per small subtree.  Phase 1: the whole CTA splits nodes above RTK_SAH_WARP_MAX
 // triangles; phase 2: the warps take the remaining subtrees from a shared queue and finish them
 // independently with warp-level synchronisation only.
-// The small subtrees a level of large nodes emitted are final as soon as that level's partition has run, so
-// they are finished WHILE the next large levels run: after level L the plan kernel snapshots the length of the
-// small list into small_end[L + 1] (small_end[0] = 0), and this kernel, launched on a second stream with an
-// upper-bound grid, takes entries [small_end[level], small_end[level + 1]).
-__global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s, uint32_t level)
+__global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s, uint32_t n_small)
 {
 	__shared__ float4 s_lo[RTK_SAH_SMALL], s_hi[RTK_SAH_SMALL];
 	__shared__ uint32_t s_gid[RTK_SAH_SMALL];
@@ -657,12 +648,9 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 	__shared__ rtk_sah_choice s_choice[1 + RTK_SAH_SMALL_WARPS];
 	__shared__ uint32_t s_child[1 + RTK_SAH_SMALL_WARPS], s_wl[RTK_SAH_SMALL_WARPS], s_wr[RTK_SAH_SMALL_WARPS];
 
-	const uint32_t list_begin = s.small_end[level], list_end = s.small_end[level + 1];
+	if (blockIdx.x >= n_small) return;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	// the grid is an upper bound (the host does not know how many subtrees a level emitted): CTAs stride over the list
-	for (uint32_t item = list_begin + blockIdx.x; item < list_end; item += gridDim.x) {
-	__syncthreads();                                          // the previous subtree's shared state is done with
-	const uint32_t entry = s.small_list[item];
+	const uint32_t entry = s.small_list[blockIdx.x];
 	const uint32_t root = entry & 0x7fffffffu;
 	const uint32_t *src = (entry >> 31) ? s.idx1 : s.idx0;
 	const uint32_t gfirst = (uint32_t)s.first[root];
@@ -737,7 +725,6 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < total; i += RTK_SAH_SMALL_THREADS) s.idx_final[gfirst + i] = s_gid[s_perm[0][i]];
-	}   // subtrees of this CTA
 }
 
 // final leaf order as original triangle numbers

@@ -39,7 +39,6 @@ static int g_push_sms = 8;          // RTK_B200_PUSH_SMS: SMs the traversal grid
 static __thread int t_reserve_extra = 0;   // set by the direct host pipeline around its traversal launches
 static int g_host_direct = 1;       // RTK_B200_HOST_DIRECT=0: rows always travel through pinned staging
 static size_t g_min_share = (size_t)1 << 18;   // a device joins a host batch only for at least this many rays (RTK_B200_HOST_MIN_SHARE_LOG2)
-static int g_sah_overlap = 1;       // RTK_B200_SAH_OVERLAP=0: small subtrees on the build's own stream (no second stream)
 static int g_stack_limit = 0;       // test hook (rtkd_debug_limit_stack): spill entries per ray, 0 = sized from the tree
 static uint64_t g_next_id = 1;
 
@@ -116,8 +115,6 @@ struct dev_ctx {
 	pthread_t thread; bool thread_up, quit;
 	pthread_mutex_t jm; pthread_cond_t jc;
 	batch_job *job; bool job_done;
-	cudaStream_t aux_st;                // second stream of the SAH build (small subtrees beside the large levels)
-	cudaEvent_t aux_ev, aux_join;
 };
 static dev_ctx g_ctx[RTKD_MAX_DEVICES];
 static int g_ndev = 0;
@@ -209,7 +206,6 @@ static int init_devices_locked(const int *devices, int n)
 		if (g_trace_lanes == 8) g_trace_pd = 0;
 	}
 	{ const char *e = getenv("RTK_B200_PUSH_SMS"); if (e && atoi(e) >= 0 && atoi(e) < sm) g_push_sms = atoi(e); }
-	{ const char *e = getenv("RTK_B200_SAH_OVERLAP"); if (e) g_sah_overlap = atoi(e) != 0; }
 	{ const char *e = getenv("RTK_B200_HOST_MIX"); if (e && atoi(e) >= 0) g_host_mix = atoi(e); }
 	{ const char *e = getenv("RTK_B200_HOST_DIRECT"); if (e) g_host_direct = atoi(e) != 0; }
 	{ const char *e = getenv("RTK_B200_HOST_MIN_SHARE_LOG2"); if (e && atoi(e) >= 7 && atoi(e) <= 30) g_min_share = (size_t)1 << atoi(e); }
@@ -274,10 +270,7 @@ extern "C" void rtkd_shutdown(void)
 	}
 	for (int i = 0; i < n; i++) {
 		dev_ctx &X = g_ctx[i];
-		if (cudaSetDevice(X.device) == cudaSuccess) {
-			cudaDeviceSynchronize(); stage_shutdown(X);
-			if (X.aux_st) { cudaStreamDestroy(X.aux_st); cudaEventDestroy(X.aux_ev); cudaEventDestroy(X.aux_join); X.aux_st = NULL; }
-		}
+		if (cudaSetDevice(X.device) == cudaSuccess) { cudaDeviceSynchronize(); stage_shutdown(X); }
 		pthread_mutex_destroy(&X.lock); pthread_mutex_destroy(&X.jm); pthread_cond_destroy(&X.jc);
 	}
 	if (n) cudaSetDevice(g_ctx[0].device);
@@ -903,7 +896,6 @@ struct build_bufs {
 };
 
 #define RTKD_COLLAPSE_LEVELS 80
-#define RTKD_SAH_LEVELS 4096         // levels of large nodes the SAH builder can run (peeling splits: one per level)
 
 static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 {
@@ -929,7 +921,6 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 		B.h.counters = A.take<uint32_t>(8);
 		B.h.act_in = A.take<uint32_t>(B.act_cap); B.h.act_out = A.take<uint32_t>(B.act_cap);
 		B.h.small_list = A.take<uint32_t>(B.small_cap);
-		B.h.small_end = A.take<uint32_t>(RTKD_SAH_LEVELS + 2);
 		B.h.chunk_base = A.take<uint32_t>(B.act_cap + 1);
 		B.h.bins = A.take<uint32_t>(B.act_cap * RTK_SAH_NODEBINS);
 		B.h.split = A.take<int4>(B.act_cap); B.h.cursor = A.take<uint32_t>(2 * B.act_cap);
@@ -958,23 +949,13 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 // beyond the counts return at once.  The host looks at the counters only after the first
 // ceil(log2(n / RTK_SAH_SMALL)) levels -- no tree is done before that -- and then every second level
 // (round 1 read them back after every level: 13 round trips per 1M-triangle build).
-static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, build_bufs &B, uint32_t n, int aux_index)
+static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, build_bufs &B, uint32_t n)
 {
 	RTK_NVTX("rtk_b200 build: binned SAH levels");
 	rtkd_sah &h = B.h;
 	RTK_LAUNCH(k_sah_prim_bounds, (n + 255) / 256, 256, st, tri, svals, n, (float4*)h.pb, h.idx0); CK_LAUNCH();
-	CK(cudaMemsetAsync(h.small_end, 0, sizeof(uint32_t) * (RTKD_SAH_LEVELS + 2), st));
 	RTK_LAUNCH(k_sah_root, 1, 32, st, h, (const uint32_t*)B.d_bounds, n); CK_LAUNCH();
-	h.plan_level = 1;                                          // "level -1": a scene that is one small subtree
 	RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();
-	// the small subtrees are finished on a second stream while the next large levels run on `st`
-	dev_ctx &X = g_ctx[aux_index];
-	if (!X.aux_st) {
-		CK(cudaStreamCreateWithFlags(&X.aux_st, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&X.aux_ev, cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&X.aux_join, cudaEventDisableTiming));
-	}
-	cudaStream_t st2 = g_sah_overlap ? X.aux_st : st;
 	uint32_t hc[8];
 	memset(hc, 0, sizeof(hc));
 	uint32_t blind = 0;
@@ -983,9 +964,7 @@ static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, 
 	uint32_t depth = 0;
 	int src_buf = 0;
 	bool done = n <= RTK_SAH_SMALL;
-	if (done) { RTK_LAUNCH(k_sah_small, 1, RTK_SAH_SMALL_THREADS, st, h, 0u); CK_LAUNCH(); }
 	while (!done) {
-		if (depth + 2 > RTKD_SAH_LEVELS) { rtkd_set_error("SAH builder: more than %d levels of large nodes", RTKD_SAH_LEVELS); return RTKD_ERR_MEMORY; }
 		const unsigned long long pow2 = depth < 40 ? 1ull << depth : ~0ull;
 		const uint32_t act_bound = (uint32_t)(pow2 < B.act_cap ? pow2 : B.act_cap);
 		const uint32_t chunk_bound = max_chunks + act_bound;
@@ -994,26 +973,23 @@ static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, 
 		RTK_LAUNCH(k_sah_split_large, (act_bound + 3) / 4, 128, st, h, depth, src_buf ^ 1); CK_LAUNCH();
 		RTK_LAUNCH(k_sah_partition_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
 		uint32_t *tmp = h.act_in; h.act_in = h.act_out; h.act_out = tmp;
-		h.plan_level = depth + 2;                              // small_end[depth + 2] = list length after this level
 		RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();
-		// this level's small subtrees: at most two per large node
-		if (st2 != st) { CK(cudaEventRecord(X.aux_ev, st)); CK(cudaStreamWaitEvent(st2, X.aux_ev, 0)); }
-		{
-			const uint32_t small_bound = 2 * act_bound, resident = (uint32_t)g_sm_count * 8;
-			RTK_LAUNCH(k_sah_small, small_bound < resident ? small_bound : resident, RTK_SAH_SMALL_THREADS, st2, h, depth + 1); CK_LAUNCH();
-		}
 		src_buf ^= 1;
 		depth++;
 		if (depth >= blind && ((depth - blind) & 1u) == 0) {
 			CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
 			done = hc[6] == 0;
+			if (depth > 4096) { rtkd_set_error("SAH builder does not terminate"); return RTKD_ERR_MEMORY; }
 		}
 	}
-	if (st2 != st) { CK(cudaEventRecord(X.aux_join, st2)); CK(cudaStreamWaitEvent(st, X.aux_join, 0)); }
+	if (n <= RTK_SAH_SMALL) {
+		CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+	}
+	if (hc[2] > B.small_cap || hc[3]) { rtkd_set_error("SAH builder ran out of list space (flags %u)", hc[3]); return RTKD_ERR_MEMORY; }
+	if (hc[2]) { RTK_LAUNCH(k_sah_small, hc[2], RTK_SAH_SMALL_THREADS, st, h, hc[2]); CK_LAUNCH(); }
 	RTK_LAUNCH(k_sah_compose, (n + 255) / 256, 256, st, (const uint32_t*)h.idx_final, svals, n, B.order); CK_LAUNCH();
-	// list overflows and pool exhaustion (also of the small subtrees, which may still be running): the flags
-	// are read with the first counters of the collapse
 	return RTKD_OK;
 }
 
@@ -1111,7 +1087,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	// binary tree: binned SAH over the Morton-ordered triangles, or the radix tree itself
 	rtkd_bvh2 t = B.t;
 	if (use_sah) {
-		int r = build_sah(st, tri, svals, B, n, s->dev_index);
+		int r = build_sah(st, tri, svals, B, n);
 		if (r) return r;
 		t.left = B.h.left; t.right = B.h.right; t.first = B.h.first; t.last = B.h.last; t.blo = B.h.blo; t.bhi = B.h.bhi;
 		svals = B.order;
@@ -1146,9 +1122,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		// true item count on the device; the host looks at the counters every 4 levels
 		unsigned long long bound = 1;
 		int level = 0;
-		bool done = false, sah_checked = false;
-		uint32_t h_sah[8];
-		memset(h_sah, 0, sizeof(h_sah));
+		bool done = false;
 		while (!done) {
 			for (int k = 0; k < 4 && level < RTKD_COLLAPSE_LEVELS - 1; k++, level++) {
 				rtkd_collapse_args a;
@@ -1162,12 +1136,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 				bound = bound * 8 < B.cap ? bound * 8 : B.cap;
 			}
 			CK(cudaMemcpyAsync(h_ctr, B.ctr, sizeof(h_ctr), cudaMemcpyDeviceToHost, st));
-			if (use_sah && !sah_checked) CK(cudaMemcpyAsync(h_sah, B.h.counters, sizeof(h_sah), cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
-			if (use_sah && !sah_checked) {
-				sah_checked = true;
-				if (h_sah[3] || h_sah[2] > B.small_cap) { rtkd_set_error("SAH builder ran out of node or list space (flags %u)", h_sah[3]); return RTKD_ERR_MEMORY; }
-			}
 			done = h_ctr[8 + level] == 0 || level >= RTKD_COLLAPSE_LEVELS - 1;
 		}
 		for (depth = 0; depth < RTKD_COLLAPSE_LEVELS && h_ctr[8 + depth]; depth++) { }

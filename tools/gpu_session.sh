@@ -31,11 +31,7 @@ run_stage() {
 			python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --parity-rays 0 --legs e2e > $OUT/${TAG}_launch_ncu.log 2>&1
 		echo "launch list exit $?" ;;
 	build)
-		for v in 1 0; do
-			RTK_B200_SAH_OVERLAP=$v timeout 600 python tools/build_profile.py --config C3 --rebuilds 4 2>&1 | tail -3 | sed "s/^/C3 overlap=$v /"
-			RTK_B200_SAH_OVERLAP=$v timeout 600 python tools/build_profile.py --config C4 --rebuilds 3 2>&1 | tail -2 | sed "s/^/C4 overlap=$v /"
-			RTK_B200_SAH_OVERLAP=$v timeout 600 python tools/build_profile.py --config C2 --rebuilds 3 2>&1 | tail -2 | sed "s/^/C2 overlap=$v /"
-		done ;;
+		for w in C3 C4 C2; do timeout 600 python tools/build_profile.py --config $w --rebuilds 3 2>&1 | tail -3 | sed "s/^/$w /"; done ;;
 	buildncu)
 		timeout 600 python tools/prof_build.py ${1:-C3} sah > $OUT/${TAG}_pb_plain.log 2>&1 &&
 		timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/${TAG}_launches_build_${1:-C3}.csv \

@@ -2099,7 +2099,11 @@ __global__ void __launch_bounds__(256) k_validate_blob(const float4 *nodes, uint
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < num_nodes * RTK_WIDE) {
 		const uint32_t ref = __float_as_uint(nodes[2ull * i].w), parent = i / RTK_WIDE;
-		if (ref != RTK_REF_EMPTY) {
+		if (ref == RTK_REF_EMPTY) {
+			// the traversal never looks at the reference of an empty slot: it relies on the slot's box being inverted
+			const float4 lo = nodes[2ull * i], hi = nodes[2ull * i + 1];
+			if (!(lo.x > hi.x && lo.y > hi.y && lo.z > hi.z)) atomicOr(bad, 8u);
+		} else {
 			if (rtk_ref_is_leaf(ref)) {
 				const uint32_t first = rtk_leaf_first(ref);
 				if ((first & 7u) || first + RTK_LEAF_MAX > num_tv) atomicOr(bad, 1u);
@@ -2166,7 +2170,8 @@ extern "C" rtkd_scene *rtkd_blob_read(const void *payload, size_t payload_size)
 		cudaFree(d_bad);
 	}
 	if (e != cudaSuccess || bad) {
-		if (bad) rtkd_set_error("scene blob is corrupt (%s)", (bad & 2u) ? "child reference outside the tree" : (bad & 1u) ? "leaf reference outside the triangle slots" : "triangle number outside the scene");
+		if (bad) rtkd_set_error("scene blob is corrupt (%s)", (bad & 2u) ? "child reference outside the tree" : (bad & 1u) ? "leaf reference outside the triangle slots" :
+		                        (bad & 8u) ? "empty child slot without an inverted box" : "triangle number outside the scene");
 		else rtkd_set_error("scene upload failed: %s", cudaGetErrorString(e));
 		rtkd_scene_free(s);
 		return NULL;

@@ -1221,6 +1221,14 @@ def case_blob_validation(lib, orc):
     r, err, _ = attempt(cycle, "cycle")
     assert r == C.c_size_t(-1).value and "child reference" in err, err
 
+    def fake_empty(v):
+        # an "empty" reference on a slot that still carries a real box: the traversal would follow it as a leaf
+        node0 = v[128 + off_nodes:128 + off_nodes + 256].view(np.uint32)
+        k = [j for j in range(8) if node0[8 * j + 3] != 0xffffffff]
+        node0[8 * k[-1] + 3] = 0xffffffff
+    r, err, _ = attempt(fake_empty, "empty slot with a box")
+    assert r == C.c_size_t(-1).value and "empty child slot" in err, err
+
     off_tv0 = int(good[128:256].view(np.uint64)[11])
 
     def bad_prim(v):

@@ -92,6 +92,11 @@ struct host_buf {
 struct host_stage {
 	size_t chunk, blocks, meta_bytes;
 	host_buf b[RTKD_HOST_BUFS];
+	// pageable rays: chunks are copied into pinned bounce buffers by the host worker pool first (cudaMemcpyAsync from
+	// pageable memory stages through ONE driver thread at ~10 GB/s and blocks the caller meanwhile)
+	unsigned char *h_up[RTKD_HOST_RING];
+	cudaEvent_t up_read[RTKD_HOST_RING];
+	bool up_used[RTKD_HOST_RING];
 	cudaStream_t up;                    // upload stream
 	cudaStream_t push;                  // direct host path: the stream of the row-push kernel
 	cudaEvent_t uploaded[RTKD_HOST_RING];
@@ -1573,6 +1578,7 @@ struct batch_job {
 	size_t first, n;                    // this device's range of them
 	int mode;                           // 0: rtk_hit rows + mask, 1: compact records (hits = rtk_cuda_hit16[])
 	int ndev;                           // devices that share this batch
+	bool rays_pinned;                   // the caller's ray array is page-locked
 	long long found;                    // rays that hit (mode 0)
 	int rc;
 	char err[320];
@@ -1603,10 +1609,12 @@ static void stage_shutdown(dev_ctx &X)
 		}
 		if (G.up) cudaStreamDestroy(G.up);
 		if (G.push) cudaStreamDestroy(G.push);
+		for (int k = 0; k < RTKD_HOST_RING; k++) if (G.up_read[k]) cudaEventDestroy(G.up_read[k]);
 		for (int k = 0; k < RTKD_HOST_RING; k++) if (G.uploaded[k]) cudaEventDestroy(G.uploaded[k]);
 	}
 	if (G.d_rays) cudaFree(G.d_rays);
 	if (G.d_count) cudaFree(G.d_count);
+	for (int k = 0; k < RTKD_HOST_RING; k++) if (G.h_up[k]) cudaFreeHost(G.h_up[k]);
 	if (G.sm_st) cudaStreamDestroy(G.sm_st);
 	cudaFree(G.sm_d_rays); cudaFree(G.sm_d_h16); cudaFree(G.sm_d_rows); cudaFree(G.sm_d_mask);
 	cudaFreeHost(G.sm_h_rows); cudaFreeHost(G.sm_h_mask);
@@ -1641,6 +1649,7 @@ static int stage_prepare(host_stage &G, size_t want, bool staged)
 		CK(cudaStreamCreateWithFlags(&G.up, cudaStreamNonBlocking));
 		CK(cudaStreamCreateWithFlags(&G.push, cudaStreamNonBlocking));
 		for (int k = 0; k < RTKD_HOST_RING; k++) CK(cudaEventCreateWithFlags(&G.uploaded[k], cudaEventDisableTiming));
+		for (int k = 0; k < RTKD_HOST_RING; k++) CK(cudaEventCreateWithFlags(&G.up_read[k], cudaEventDisableTiming));
 		CK(cudaMalloc(&G.d_count, 64));
 		G.streams = true;
 	}
@@ -1692,8 +1701,21 @@ static int pipe_uploads(host_stage &G, const batch_job &J, size_t it, size_t nch
 	int rc = RTKD_OK;
 	for (; uploads < nchunks && uploads <= it + RTKD_HOST_AHEAD && rc == RTKD_OK; uploads++) {
 		const size_t off = uploads * G.chunk, cnt = J.n - off < G.chunk ? J.n - off : G.chunk;
-		PIPE_CK(cudaMemcpyAsync(G.d_rays + 2 * off, J.rays + 32 * (J.first + off), 32 * cnt, cudaMemcpyHostToDevice, G.up), what);
-		if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(G.uploaded[uploads % RTKD_HOST_RING], G.up), what);
+		const char *src = J.rays + 32 * (J.first + off);
+		const int k = (int)(uploads % RTKD_HOST_RING);
+		if (!J.rays_pinned) {
+			// pageable rays: the worker pool copies the chunk into a pinned bounce buffer, the copy engine takes it from there
+			if (!G.h_up[k] && cudaMallocHost(&G.h_up[k], 32 * G.chunk) != cudaSuccess) { cudaGetLastError(); G.h_up[k] = NULL; }
+			if (G.h_up[k]) {
+				if (G.up_used[k]) PIPE_CK(cudaEventSynchronize(G.up_read[k]), what);       // the upload that last read this buffer
+				if (rc) break;
+				rtkd_place_wait(rtkd_copy_submit(G.h_up[k], src, 32 * cnt));
+				src = (const char*)G.h_up[k];
+			}
+		}
+		PIPE_CK(cudaMemcpyAsync(G.d_rays + 2 * off, src, 32 * cnt, cudaMemcpyHostToDevice, G.up), what);
+		if (rc == RTKD_OK && !J.rays_pinned && G.h_up[k]) { PIPE_CK(cudaEventRecord(G.up_read[k], G.up), what); G.up_used[k] = true; }
+		if (rc == RTKD_OK) PIPE_CK(cudaEventRecord(G.uploaded[k], G.up), what);
 	}
 	return rc;
 }
@@ -1875,6 +1897,7 @@ static void run_job(dev_ctx &X, batch_job &J)
 	// forces every k-th chunk onto the staged route, 0 none.
 	unsigned staged_every = 1;
 	if (direct) staged_every = g_host_mix >= 0 ? (unsigned)g_host_mix : (J.ndev > 1 ? 0u : 2u);
+	J.rays_pinned = rc == RTKD_OK && host_mapped(J.rays + 32 * J.first, 32 * J.n) != NULL;
 	if (rc == RTKD_OK) rc = stage_prepare(X.stage, J.n, J.mode == 0 && staged_every != 0);
 	if (rc == RTKD_OK) rc = stage_rays(X.stage, J.n);
 	if (rc == RTKD_OK) {

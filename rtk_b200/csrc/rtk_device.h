@@ -165,6 +165,7 @@ typedef struct rtkd_place_desc {
 } rtkd_place_desc;
 int  rtkd_place_submit(const rtkd_place_desc *d);   /* returns a ticket (or -1: done synchronously) */
 void rtkd_place_wait(int ticket);
+int  rtkd_copy_submit(void *dst, const void *src, size_t bytes);   /* parallel memcpy on the placement pool; ticket for rtkd_place_wait, or -1 (done) */
 int  rtkd_place_threads(void);
 
 /* serialisation of the device layout into a relocatable blob (payload after the 128-byte

@@ -23,10 +23,14 @@
 
 typedef struct place_job {
 	rtkd_place_desc d;
+	/* kind 1: a plain parallel copy (pageable rays into the pinned bounce buffer of the upload stream) */
+	int kind;
+	char *cdst; const char *csrc; size_t cbytes;
 	size_t next_slice, num_slices, slice_blocks;
 	size_t done_slices;
 	int active;
 } place_job;
+#define COPY_SLICE ((size_t)1 << 18)
 
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_work = PTHREAD_COND_INITIALIZER;
@@ -76,7 +80,10 @@ static void *place_worker(void *arg)
 		}
 		if (!job) { pthread_cond_wait(&g_work, &g_mu); continue; }
 		pthread_mutex_unlock(&g_mu);
-		place_slice(&job->d, slice * job->slice_blocks, (slice + 1) * job->slice_blocks);
+		if (job->kind == 1) {
+			const size_t off = slice * COPY_SLICE, len = job->cbytes - off < COPY_SLICE ? job->cbytes - off : COPY_SLICE;
+			memcpy(job->cdst + off, job->csrc + off, len);
+		} else place_slice(&job->d, slice * job->slice_blocks, (slice + 1) * job->slice_blocks);
 		pthread_mutex_lock(&g_mu);
 		if (++job->done_slices == job->num_slices) pthread_cond_broadcast(&g_done);
 	}
@@ -136,12 +143,37 @@ int rtkd_place_submit(const rtkd_place_desc *d)
 	}
 	place_job *job = &g_jobs[ticket];
 	job->d = *d;
+	job->kind = 0;
 	size_t nblocks = (d->nrays + PLACE_BLOCK - 1) / PLACE_BLOCK;
 	job->slice_blocks = 256;                               /* 32 Ki rays per slice */
 	job->num_slices = (nblocks + job->slice_blocks - 1) / job->slice_blocks;
 	job->next_slice = 0; job->done_slices = 0;
 	job->active = 1;
 	if (job->num_slices == 0) job->active = 0, ticket = -1;
+	pthread_cond_broadcast(&g_work);
+	pthread_mutex_unlock(&g_mu);
+	return ticket;
+}
+
+/* parallel memcpy on the same worker pool; returns a ticket for rtkd_place_wait (or -1: done synchronously) */
+int rtkd_copy_submit(void *dst, const void *src, size_t bytes)
+{
+	if (!bytes) return -1;
+	pthread_mutex_lock(&g_mu);
+	pool_start();
+	int ticket = -1;
+	for (int j = 0; j < PLACE_MAX_JOBS; j++) if (!g_jobs[j].active) { ticket = j; break; }
+	if (ticket < 0 || g_nthreads == 0 || bytes < 2 * COPY_SLICE) {
+		pthread_mutex_unlock(&g_mu);
+		memcpy(dst, src, bytes);
+		return -1;
+	}
+	place_job *job = &g_jobs[ticket];
+	job->kind = 1;
+	job->cdst = (char*)dst; job->csrc = (const char*)src; job->cbytes = bytes;
+	job->num_slices = (bytes + COPY_SLICE - 1) / COPY_SLICE;
+	job->next_slice = 0; job->done_slices = 0;
+	job->active = 1;
 	pthread_cond_broadcast(&g_work);
 	pthread_mutex_unlock(&g_mu);
 	return ticket;

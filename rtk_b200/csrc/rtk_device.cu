@@ -1592,6 +1592,8 @@ static void stage_release(host_stage &G)
 		cudaFreeHost(B.h_meta); cudaFreeHost(B.h_rows);
 		B.d_h16 = NULL; B.d_rows = B.d_base = NULL; B.d_mask = NULL; B.h_meta = B.h_rows = NULL;
 	}
+	// the bounce buffers of pageable uploads are sized by the chunk as well
+	for (int k = 0; k < RTKD_HOST_RING; k++) { if (G.h_up[k]) cudaFreeHost(G.h_up[k]); G.h_up[k] = NULL; G.up_used[k] = false; }
 	G.ready = G.staged = false;
 }
 
@@ -1614,7 +1616,6 @@ static void stage_shutdown(dev_ctx &X)
 	}
 	if (G.d_rays) cudaFree(G.d_rays);
 	if (G.d_count) cudaFree(G.d_count);
-	for (int k = 0; k < RTKD_HOST_RING; k++) if (G.h_up[k]) cudaFreeHost(G.h_up[k]);
 	if (G.sm_st) cudaStreamDestroy(G.sm_st);
 	cudaFree(G.sm_d_rays); cudaFree(G.sm_d_h16); cudaFree(G.sm_d_rows); cudaFree(G.sm_d_mask);
 	cudaFreeHost(G.sm_h_rows); cudaFreeHost(G.sm_h_mask);

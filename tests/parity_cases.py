@@ -935,9 +935,14 @@ def case_host_batch_chunks(lib, orc, nrays=30000, chunk_log2=12):
     sc = lib.build_scene(s["meshes"])
     old = os.environ.pop("RTK_B200_HOST_CHUNK_LOG2", None)
     try:
+        # a small pageable batch first: the staging of the host path (bounce buffers of the upload included) is
+        # sized by the chunk and has to grow with the next, larger batch
+        small = min(nrays, 4500)
+        _, m0, n0 = sc.trace_rays(np.ascontiguousarray(rays[:small]))
         hits1 = np.zeros(nrays, dtype=api.HIT_DTYPE)
         hits1.view(np.uint8)[:] = 0x5A
         _, mask1, n1 = sc.trace_rays(rays, hits=hits1)
+        assert np.array_equal(m0, mask1[:small]) and n0 == int(mask1[:small].sum())
         os.environ["RTK_B200_HOST_CHUNK_LOG2"] = str(chunk_log2)
         hits2 = np.zeros(nrays, dtype=api.HIT_DTYPE)
         hits2.view(np.uint8)[:] = 0x5A

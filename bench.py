@@ -759,7 +759,7 @@ def e2e_legs(lib, api, sc, scene, rays_all, steps, ndev, check16=None):
         p_s = time.perf_counter() - t0
         mm = p_mask.astype(bool)
         out["e2e_pageable"] = {"value": m / p_s / 1e6, "unit": UNIT, "ms_per_step": p_s * 1e3, "rays_per_step": m, "devices": ndev,
-                               "api": "rtk_trace_rays with pageable arrays: pinned staging + host placement threads",
+                               "api": "rtk_trace_rays with pageable (malloc) arrays: rays through pinned bounce buffers, rows through pinned staging + host placement threads",
                                "rows_equal_pinned_path": bool(got == int(h_mask[:m].sum()) and p_hits[mm].tobytes() == h_hits[:m][mm].tobytes())}
     finally:
         pin.free()

@@ -72,6 +72,12 @@ run_stage() {
 	mix)
 		for m in 0 2 3 4; do RTK_B200_HOST_MIX=$m timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows  " | sed "s/^/MIX=$m /"; done
 		for r in 6 12; do RTK_B200_PUSH_SMS=$r RTK_B200_HOST_MIX=2 timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows  " | sed "s/^/MIX=2 PUSH_SMS=$r /"; done ;;
+	buildvariants)
+		# device build time of variant libraries: "buildvariants main hyb ..."
+		for v in "$@"; do
+			lib=rtk_b200/librtk_b200_$v.so; [ "$v" = main ] && lib=rtk_b200/librtk_b200.so
+			for w in C3 C4 C2; do RTK_LIB=$lib timeout 300 python tools/prof_build.py $w sah 2>&1 | tail -1 | sed "s/^/$v /"; done
+		done ;;
 	hostab)
 		for v in 1 0; do RTK_B200_HOST_DIRECT=$v timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows|compact" | sed "s/^/HOST_DIRECT=$v /"; done
 		for r in 2 8; do RTK_B200_PUSH_SMS=$r timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows " | sed "s/^/PUSH_SMS=$r /"; done ;;

@@ -838,6 +838,7 @@ def main():
         workload["triangles"] = int(len(scene["tris"]))
         rays = gen_rays(scene, min(args.rays, args.ref_sample), 0, args.workload, gen_threads)
         workload["rays_per_gpu"] = args.rays
+        workload["gather"] = (args.gather if world > 1 else None)      # the same `config` object as the repo's arm prints
         run_reference(args, workload, scene, rays)
         return 0
 

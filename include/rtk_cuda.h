@@ -137,10 +137,12 @@ int  rtk_cuda_measure_host_link(int num_devices, size_t bytes_per_device, int di
  * only where hit_mask[i] != 0; rows of rays that missed are left untouched,
  * the miss rule of rtk.c:571-576.  hit_mask may be NULL.  The batch runs as a
  * pipeline over 1M-ray chunks: rays go up, only the rows of rays that hit
- * (plus one mask byte per ray) come back, and a few library threads
- * (RTK_B200_HOST_THREADS, default 3/4 of the CPUs, at most 16) copy each row to hits[i] -- unless hits
- * and hit_mask are page-locked (see rtk_cuda_host_alloc), in which case the device writes the rows
- * straight into them.  With several devices in use the batch is split over all of them.
+ * (plus one mask byte per ray) come back.  With page-locked hits / hit_mask arrays
+ * (rtk_cuda_host_alloc[_batch], cudaHostAlloc, cudaHostRegister ...) the device writes the rows
+ * straight into them; with pageable (malloc'ed) arrays rays and rows travel through pinned
+ * staging, moved by a few library threads (RTK_B200_HOST_THREADS, default 3/4 of the CPUs, at
+ * most 16) -- about 60 % of the speed.  With several devices in use (rtk_cuda_init_devices) the
+ * batch is split over all of them.  Thread-safe; batches of different host threads queue per device.
  * Returns the number of hits, or (size_t)-1 on error. */
 size_t rtk_trace_rays(const rtk_scene *scene, const rtk_ray *rays, rtk_hit *hits, uint8_t *hit_mask, size_t n);
 

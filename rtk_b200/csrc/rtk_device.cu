@@ -1710,7 +1710,10 @@ static int pipe_uploads(host_stage &G, const batch_job &J, size_t it, size_t nch
 			if (G.h_up[k]) {
 				if (G.up_used[k]) PIPE_CK(cudaEventSynchronize(G.up_read[k]), what);       // the upload that last read this buffer
 				if (rc) break;
-				rtkd_place_wait(rtkd_copy_submit(G.h_up[k], src, 32 * cnt));
+				// one device: the worker pool copies the chunk in parallel; several devices: every device's own
+				// driving thread copies its chunk (the pool has the rows to place, and there are already ndev copiers)
+				if (J.ndev > 1) memcpy(G.h_up[k], src, 32 * cnt);
+				else rtkd_place_wait(rtkd_copy_submit(G.h_up[k], src, 32 * cnt));
 				src = (const char*)G.h_up[k];
 			}
 		}

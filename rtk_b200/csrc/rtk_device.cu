@@ -233,8 +233,8 @@ static int init_devices_locked(const int *devices, int n)
 	__atomic_store_n(&g_ndev, n, __ATOMIC_RELEASE);
 	// one worker per further device; they sleep on a condition variable between batches
 	for (int i = 1; i < n; i++) {
+		// a device without a worker still takes part: the caller's thread runs its share after its own
 		if (pthread_create(&g_ctx[i].thread, NULL, ctx_worker, &g_ctx[i]) == 0) g_ctx[i].thread_up = true;
-		else { rtkd_set_error("cannot start the worker thread of device %d", devices[i]); return RTKD_ERR_MEMORY; }
 	}
 	return RTKD_OK;
 }
@@ -1955,14 +1955,17 @@ static long long run_batch(rtkd_scene *s, const void *rays, void *hits, unsigned
 	for (int k = 0; k < used; k++) pthread_mutex_lock(&g_ctx[k].lock);      // ascending order: no deadlock between batches
 	for (int k = 1; k < used; k++) {
 		dev_ctx &X = g_ctx[k];
+		if (!X.thread_up) continue;                          // no worker (thread creation failed at start-up): run it here, below
 		pthread_mutex_lock(&X.jm);
 		X.job = &J[k]; X.job_done = false;
 		pthread_cond_broadcast(&X.jc);
 		pthread_mutex_unlock(&X.jm);
 	}
 	run_job(g_ctx[0], J[0]);
+	for (int k = 1; k < used; k++) if (!g_ctx[k].thread_up) run_job(g_ctx[k], J[k]);
 	for (int k = 1; k < used; k++) {
 		dev_ctx &X = g_ctx[k];
+		if (!X.thread_up) continue;
 		pthread_mutex_lock(&X.jm);
 		while (!X.job_done) pthread_cond_wait(&X.jc, &X.jm);
 		X.job = NULL;

@@ -128,3 +128,25 @@ def test_no_device_fails_loudly():
         "    print('ok', e)\n" % ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_c_example_links_and_fails_loudly_without_a_device(tmp_path):
+    """examples/trace_batch.c is the reference user's program after the switch: plain C against
+    include/*.h, linked with librtk_b200.so.  Without a CUDA device it must say so and exit non-zero (no CPU path)."""
+    import shutil
+    lib = os.path.join(ROOT, "rtk_b200", "librtk_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("librtk_b200.so not built")
+    exe = str(tmp_path / "trace_batch")
+    subprocess.run(["gcc", "-Wall", "-Werror", "-std=gnu11", os.path.join(ROOT, "examples", "trace_batch.c"), "-I", os.path.join(ROOT, "include"),
+                    "-L", os.path.dirname(lib), "-lrtk_b200", "-Wl,-rpath," + os.path.dirname(lib), "-o", exe], check=True)
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = shutil.which("nvidia-smi") is not None
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    if has_gpu:
+        assert r.returncode == 0 and "rays hit" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr, r.stdout + r.stderr

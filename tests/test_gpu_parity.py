@@ -337,3 +337,21 @@ def test_full_size_c4_and_one_c5_band(gpu_lib, orc):
     pc.assert_same(got[pick[:512]], orc.trace_brute(s["tris"], r_last[:512]), "C5 bounce 3 vs CPU oracle")
     assert gpu_lib.rtk_cuda_scene_status(sc.ptr) == 0
     sc.free()
+
+
+def test_c_example_program(tmp_path):
+    """examples/trace_batch.c, compiled with gcc against include/*.h and run on the device: a 64 x 64 grid of quads at
+    z = 1, 2^20 rays along +z of which those over the grid must hit at t = 1"""
+    import os
+    import subprocess
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    lib_dir = os.path.join(root, "rtk_b200")
+    exe = str(tmp_path / "trace_batch")
+    subprocess.run(["gcc", "-Wall", "-std=gnu11", os.path.join(root, "examples", "trace_batch.c"), "-I", os.path.join(root, "include"),
+                    "-L", lib_dir, "-lrtk_b200", "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    # x, y in [-0.1, 1.1): the grid covers [0, 1]^2 -> (1/1.2)^2 of the rays (edges included), and ray 600000 is over it
+    found = int(r.stdout.split()[0])
+    assert abs(found / (1 << 20) - (1 / 1.2) ** 2) < 0.01, r.stdout
+    assert "ray 600000: hit t=1 " in r.stdout and "rtk_trace_ray agrees: t=1" in r.stdout, r.stdout

@@ -351,7 +351,7 @@ def test_c_example_program(tmp_path):
                     "-L", lib_dir, "-lrtk_b200", "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
-    # x, y in [-0.1, 1.1): the grid covers [0, 1]^2 -> (1/1.2)^2 of the rays (edges included), and ray 600000 is over it
+    # x, y in [-0.1, 1.1): the grid covers [0, 1]^2 -> (1/1.2)^2 of the rays (edges included), and ray 524800 is over it
     found = int(r.stdout.split()[0])
     assert abs(found / (1 << 20) - (1 / 1.2) ** 2) < 0.01, r.stdout
-    assert "ray 600000: hit t=1 " in r.stdout and "rtk_trace_ray agrees: t=1" in r.stdout, r.stdout
+    assert "ray 524800: hit t=1 " in r.stdout and "rtk_trace_ray agrees: t=1" in r.stdout, r.stdout

@@ -395,32 +395,54 @@ struct rtkd_collapse_args {
 	float4 *nodes;
 	int n;                       // triangles
 	uint32_t *err;
-	const unsigned char *nleaf;  // [binary node] from k_count_leaves
+	const int4 *rec;             // [binary node] (left, right, area of left, area of right) from k_collapse_prep
+	const unsigned char *nleaf2; // [binary node] leaves below left | leaves below right << 4
 };
 
-// nleaf[c] for every binary node c: the number of leaves (maximal subtrees of at most RTK_LEAF_MAX triangles)
-// below c when c must be opened and that number is at most RTK_WIDE, else 0.  k_collapse asks this of every
-// slot each time it opens one; walking the subtree there (a local-memory stack per thread, up to a dozen walks
-// per wide node) had doubled the kernel's time -- one pass over the binary nodes up front, walks only where at
-// most RTK_LEAF_MAX * RTK_WIDE triangles hang below, costs a tenth of that.
-__global__ void k_count_leaves(rtkd_bvh2 t, const uint32_t *num_nodes_dev, uint32_t num_nodes_host, unsigned char *nleaf)
+#define RTK_BIDX(c, n) ((c) >= 0 ? (c) : ((n) - 1) + ~(c))
+
+// number of leaves (maximal subtrees of at most RTK_LEAF_MAX triangles) below binary node c when c must be
+// opened and that number is at most RTK_WIDE, else 0.  Only subtrees of at most RTK_WIDE * RTK_LEAF_MAX
+// triangles can qualify, so the walk is short.
+RTK_DEV int rtk_count_leaves(const rtkd_bvh2 &t, int c0)
+{
+	if (c0 < 0) return 0;
+	const int span = t.last[c0] - t.first[c0] + 1;
+	if (span <= RTK_LEAF_MAX || span > RTK_LEAF_MAX * RTK_WIDE) return 0;
+	int todo[2 * RTK_WIDE + 2], ntodo = 0, leaves = 0;
+	todo[ntodo++] = c0;
+	while (ntodo > 0 && leaves + ntodo <= RTK_WIDE) {
+		const int c1 = todo[--ntodo];
+		if (c1 >= 0 && (t.last[c1] - t.first[c1] + 1) > RTK_LEAF_MAX) { todo[ntodo++] = t.left[c1]; todo[ntodo++] = t.right[c1]; }
+		else leaves++;
+	}
+	return ntodo == 0 ? leaves : 0;
+}
+
+// What k_collapse wants to know when it opens binary node c, gathered into ONE 16-byte record (+ one byte) per node:
+// both children, the half area of each child that can itself be opened (-1: a leaf) and the number of leaves below
+// it.  k_collapse is one thread per wide node walking a chain of dependent loads; it used to take two rounds per
+// opening (the children of c, then box / range / leaf count of each child from five arrays) and measured 17 us for
+// the root alone, 276 us for the eight levels of a 1M-triangle tree.  This pass is one thread per binary node, all
+// of them independent.  (Round 1 counted the leaves inside k_collapse with a local-memory stack per thread: that had
+// doubled the kernel's time.)
+__global__ void k_collapse_prep(rtkd_bvh2 t, const uint32_t *num_nodes_dev, uint32_t num_nodes_host, int n, int4 *rec, unsigned char *nleaf2)
 {
 	const uint32_t c0 = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t num = num_nodes_dev ? *num_nodes_dev : num_nodes_host;
 	if (c0 >= num) return;
-	unsigned char out = 0;
-	const int span = t.last[c0] - t.first[c0] + 1;
-	if (span > RTK_LEAF_MAX && span <= RTK_LEAF_MAX * RTK_WIDE) {
-		int todo[2 * RTK_WIDE + 2], ntodo = 0, leaves = 0;
-		todo[ntodo++] = (int)c0;
-		while (ntodo > 0 && leaves + ntodo <= RTK_WIDE) {
-			const int c1 = todo[--ntodo];
-			if (c1 >= 0 && (t.last[c1] - t.first[c1] + 1) > RTK_LEAF_MAX) { todo[ntodo++] = t.left[c1]; todo[ntodo++] = t.right[c1]; }
-			else leaves++;
-		}
-		if (ntodo == 0) out = (unsigned char)leaves;
+	if (c0 != 0 && t.last[c0] - t.first[c0] + 1 <= RTK_LEAF_MAX) return;   // becomes a leaf: never opened (the root always is)
+	const int ch[2] = { t.left[c0], t.right[c0] };
+	float area[2];
+	int nl[2];
+	for (int k = 0; k < 2; k++) {
+		const int c = ch[k];
+		const bool openable = c >= 0 && (t.last[c] - t.first[c] + 1) > RTK_LEAF_MAX;
+		area[k] = openable ? rtk_half_area(t.blo[c], t.bhi[c]) : -1.0f;
+		nl[k] = openable ? rtk_count_leaves(t, c) : 0;
 	}
-	nleaf[c0] = out;
+	rec[c0] = make_int4(ch[0], ch[1], __float_as_int(area[0]), __float_as_int(area[1]));
+	nleaf2[c0] = (unsigned char)(nl[0] | (nl[1] << 4));
 }
 
 __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
@@ -428,22 +450,17 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 	uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= *a.n_in) return;
 	const int n = a.n;
-	int root = (int)a.work_in[w].x;
-	uint32_t dst = a.work_in[w].y;
+	const int root = (int)a.work_in[w].x;
+	const uint32_t dst = a.work_in[w].y;
 	int slot[RTK_WIDE];
-	float area[RTK_WIDE];
+	float area[RTK_WIDE];       // half area of a slot that can be opened, -1 for a leaf
+	int nleaf[RTK_WIDE];        // leaves below an openable slot when that is at most RTK_WIDE, else 0
 	int ns = 2;
-	slot[0] = t.left[root]; slot[1] = t.right[root];
-#define RTK_OPENABLE(c) ((c) >= 0 && (t.last[c] - t.first[c] + 1) > RTK_LEAF_MAX)
-#define RTK_BIDX(c) ((c) >= 0 ? (c) : (n - 1) + ~(c))
-	// nleaf[k]: number of leaves (maximal subtrees of at most RTK_LEAF_MAX triangles) below an openable
-	// slot when that is at most RTK_WIDE, else 0.  Only subtrees of at most RTK_WIDE * RTK_LEAF_MAX
-	// triangles can qualify, so the walk is short.
-	int nleaf[RTK_WIDE];
-#define RTK_COUNT_LEAVES(k) do { nleaf[k] = area[k] >= 0.0f ? (int)a.nleaf[slot[k]] : 0; } while (0)
-	for (int k = 0; k < 2; k++) {
-		area[k] = RTK_OPENABLE(slot[k]) ? rtk_half_area(t.blo[slot[k]], t.bhi[slot[k]]) : -1.0f;
-		RTK_COUNT_LEAVES(k);
+	{
+		const int4 r = a.rec[root];
+		const int q = a.nleaf2[root];
+		slot[0] = r.x; slot[1] = r.y; area[0] = __int_as_float(r.z); area[1] = __int_as_float(r.w);
+		nleaf[0] = q & 15; nleaf[1] = q >> 4;
 	}
 	while (ns < RTK_WIDE) {
 		// A subtree whose leaves ALL fit into the free slots is absorbed whole, largest area first: the
@@ -455,48 +472,61 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 		for (int k = 0; k < ns; k++) if (nleaf[k] && nleaf[k] <= RTK_WIDE - ns + 1 && area[k] > ba) { ba = area[k]; best = k; }
 		if (best < 0) for (int k = 0; k < ns; k++) if (area[k] > ba) { ba = area[k]; best = k; }
 		if (best < 0) break;
-		int c = slot[best];
-		int l = t.left[c], r = t.right[c];
-		slot[best] = l; slot[ns] = r;
-		area[best] = RTK_OPENABLE(l) ? rtk_half_area(t.blo[l], t.bhi[l]) : -1.0f;
-		area[ns] = RTK_OPENABLE(r) ? rtk_half_area(t.blo[r], t.bhi[r]) : -1.0f;
-		RTK_COUNT_LEAVES(best); RTK_COUNT_LEAVES(ns);
+		const int c = slot[best];
+		const int4 r = a.rec[c];                        // the one dependent load of an opening
+		const int q = a.nleaf2[c];
+		slot[best] = r.x; slot[ns] = r.y;
+		area[best] = __int_as_float(r.z); area[ns] = __int_as_float(r.w);
+		nleaf[best] = q & 15; nleaf[ns] = q >> 4;
 		ns++;
 	}
-#undef RTK_COUNT_LEAVES
+	// one allocation per kind for the whole node (it used to be two returning atomics per child, one after the
+	// other): the children of a node get consecutive numbers, its leaves consecutive slots
+	uint32_t n_open = 0, n_leafs = 0;
+	for (int k = 0; k < ns; k++) { if (area[k] >= 0.0f) n_open++; else n_leafs++; }
+	uint32_t idx = n_open ? atomicAdd(a.node_alloc, n_open) : 0u;
+	uint32_t o = n_open ? atomicAdd(a.n_out, n_open) : 0u;
+	uint32_t lslot = n_leafs ? atomicAdd(a.leaf_count, n_leafs) : 0u;
+	// boxes and ranges of the slots: independent loads, all in flight before the first store
+	float4 lo[RTK_WIDE], hi[RTK_WIDE];
+	uint32_t first[RTK_WIDE], count[RTK_WIDE];
+#pragma unroll
+	for (int k = 0; k < RTK_WIDE; k++) {
+		lo[k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, 0.0f);
+		hi[k] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
+		first[k] = 0; count[k] = 0;
+		if (k < ns) {
+			const int c = slot[k];
+			lo[k] = t.blo[RTK_BIDX(c, n)]; hi[k] = t.bhi[RTK_BIDX(c, n)];
+			if (!(area[k] >= 0.0f)) {
+				first[k] = c >= 0 ? (uint32_t)t.first[c] : (uint32_t)~c;
+				count[k] = c >= 0 ? (uint32_t)(t.last[c] - t.first[c] + 1) : 1u;
+			}
+		}
+	}
+	if (idx + n_open > a.node_cap) { atomicOr(a.err, 1u); idx = 0; }
+	if (lslot + n_leafs > RTK_MAX_LEAVES) { atomicOr(a.err, 2u); lslot = 0; }
 	float4 *node = a.nodes + 16ull * dst;
 	double cost = 0.0;
+#pragma unroll
 	for (int k = 0; k < RTK_WIDE; k++) {
-		if (k >= ns) {
-			node[2 * k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, __uint_as_float(RTK_REF_EMPTY));
-			node[2 * k + 1] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
-			continue;
+		uint32_t ref = RTK_REF_EMPTY;
+		if (k < ns) {
+			if (area[k] >= 0.0f) {
+				a.work_out[o++] = make_uint2((uint32_t)slot[k], idx);
+				a.node_level[idx] = (unsigned char)(a.level + 1u);
+				ref = idx++;
+			} else {
+				// every leaf owns an 8-triangle slot of the traversal arrays: 128 aligned bytes per array
+				a.leaf_list[lslot] = make_uint2(first[k], count[k]);
+				ref = rtk_leaf_ref(lslot * RTK_LEAF_MAX, count[k]);
+				lslot++;
+			}
+			cost += (double)rtk_half_area(lo[k], hi[k]);       // node step or one 8-lane triangle round: cost 1
 		}
-		int c = slot[k];
-		float4 lo = t.blo[RTK_BIDX(c)], hi = t.bhi[RTK_BIDX(c)];
-		uint32_t ref;
-		if (RTK_OPENABLE(c)) {
-			uint32_t idx = atomicAdd(a.node_alloc, 1u);
-			if (idx >= a.node_cap) { atomicOr(a.err, 1u); idx = 0; }
-			uint32_t o = atomicAdd(a.n_out, 1u);
-			a.work_out[o] = make_uint2((uint32_t)c, idx);
-			a.node_level[idx] = (unsigned char)(a.level + 1u);
-			ref = idx;
-		} else {
-			uint32_t first = c >= 0 ? (uint32_t)t.first[c] : (uint32_t)~c;
-			uint32_t count = c >= 0 ? (uint32_t)(t.last[c] - t.first[c] + 1) : 1u;
-			// every leaf owns an 8-triangle slot of the traversal arrays: 128 aligned bytes per array
-			uint32_t slot = atomicAdd(a.leaf_count, 1u);
-			if (slot >= RTK_MAX_LEAVES) { atomicOr(a.err, 2u); slot = 0; }
-			a.leaf_list[slot] = make_uint2(first, count);
-			ref = rtk_leaf_ref(slot * RTK_LEAF_MAX, count);
-		}
-		cost += (double)rtk_half_area(lo, hi);       // node step or one 8-lane triangle round: cost 1
-		lo.w = __uint_as_float(ref); hi.w = 0.0f;
-		node[2 * k] = lo; node[2 * k + 1] = hi;
+		node[2 * k] = make_float4(lo[k].x, lo[k].y, lo[k].z, __uint_as_float(ref));
+		node[2 * k + 1] = make_float4(hi[k].x, hi[k].y, hi[k].z, 0.0f);
 	}
-#undef RTK_OPENABLE
-#undef RTK_BIDX
 	atomicAdd(a.sah_cost, cost);
 }
 

@@ -33,6 +33,10 @@
 #define RTK_SAH_MAX_DEPTH 64          // RTK_BVH_MAX_DEPTH, rtk.c:5
 #define RTK_SAH_BINWORDS 8            // lo xyz, hi xyz, count, pad
 #define RTK_SAH_NODEBINS (3 * RTK_SAH_BINS * RTK_SAH_BINWORDS)
+// word w of bin b of axis a.  Word-major: the 32 bins of one word are 32 consecutive words, so the lanes of a warp
+// that update different bins hit different shared-memory banks (bin-major, 8 words per bin, put every bin on one of
+// 4 banks: an 8-way conflict on each of the 21 atomics of a triangle), and the sweep's lane-per-bin reads coalesce
+#define RTK_SAH_BIN_AT(a, b, w) ((((a) * RTK_SAH_BINWORDS + (w)) * RTK_SAH_BINS) + (b))
 
 struct rtkd_sah {
 	const float4 *pb;             // [2n] AABBs in Morton order: pb[2j] = lo, pb[2j+1] = hi
@@ -67,7 +71,7 @@ RTK_DEV void rtk_sah_bins_clear(uint32_t *bins, int tid, int nthreads)
 {
 	const uint32_t pinf = rtk_f2ord(+RTK_INF_F), ninf = rtk_f2ord(-RTK_INF_F);
 	for (int i = tid; i < RTK_SAH_NODEBINS; i += nthreads) {
-		int w = i & 7;
+		int w = (i / RTK_SAH_BINS) & 7;
 		bins[i] = w < 3 ? pinf : (w < 6 ? ninf : 0u);
 	}
 }
@@ -82,10 +86,10 @@ RTK_DEV void rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, f
 	uint32_t ol[3] = { rtk_f2ord(lo.x), rtk_f2ord(lo.y), rtk_f2ord(lo.z) };
 	uint32_t oh[3] = { rtk_f2ord(hi.x), rtk_f2ord(hi.y), rtk_f2ord(hi.z) };
 	for (int a = 0; a < 3; a++) {
-		uint32_t *p = bins + (a * RTK_SAH_BINS + b[a]) * RTK_SAH_BINWORDS;
-		atomicMin(p + 0, ol[0]); atomicMin(p + 1, ol[1]); atomicMin(p + 2, ol[2]);
-		atomicMax(p + 3, oh[0]); atomicMax(p + 4, oh[1]); atomicMax(p + 5, oh[2]);
-		atomicAdd(p + 6, 1u);
+		uint32_t *p = bins + RTK_SAH_BIN_AT(a, b[a], 0);
+		atomicMin(p + 0 * RTK_SAH_BINS, ol[0]); atomicMin(p + 1 * RTK_SAH_BINS, ol[1]); atomicMin(p + 2 * RTK_SAH_BINS, ol[2]);
+		atomicMax(p + 3 * RTK_SAH_BINS, oh[0]); atomicMax(p + 4 * RTK_SAH_BINS, oh[1]); atomicMax(p + 5 * RTK_SAH_BINS, oh[2]);
+		atomicAdd(p + 6 * RTK_SAH_BINS, 1u);
 	}
 }
 
@@ -116,16 +120,16 @@ RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 n
 			const uint32_t x1 = __reduce_max_sync(FULL, valid ? oh[1] : 0u);
 			const uint32_t x2 = __reduce_max_sync(FULL, valid ? oh[2] : 0u);
 			if (lane == leader) {
-				uint32_t *p = bins + (a * RTK_SAH_BINS + lb) * RTK_SAH_BINWORDS;
-				atomicMin(p + 0, m0); atomicMin(p + 1, m1); atomicMin(p + 2, m2);
-				atomicMax(p + 3, x0); atomicMax(p + 4, x1); atomicMax(p + 5, x2);
-				atomicAdd(p + 6, (uint32_t)__popc(vm));
+				uint32_t *p = bins + RTK_SAH_BIN_AT(a, lb, 0);
+				atomicMin(p + 0 * RTK_SAH_BINS, m0); atomicMin(p + 1 * RTK_SAH_BINS, m1); atomicMin(p + 2 * RTK_SAH_BINS, m2);
+				atomicMax(p + 3 * RTK_SAH_BINS, x0); atomicMax(p + 4 * RTK_SAH_BINS, x1); atomicMax(p + 5 * RTK_SAH_BINS, x2);
+				atomicAdd(p + 6 * RTK_SAH_BINS, (uint32_t)__popc(vm));
 			}
 		} else if (valid) {
-			uint32_t *p = bins + (a * RTK_SAH_BINS + b[a]) * RTK_SAH_BINWORDS;
-			atomicMin(p + 0, ol[0]); atomicMin(p + 1, ol[1]); atomicMin(p + 2, ol[2]);
-			atomicMax(p + 3, oh[0]); atomicMax(p + 4, oh[1]); atomicMax(p + 5, oh[2]);
-			atomicAdd(p + 6, 1u);
+			uint32_t *p = bins + RTK_SAH_BIN_AT(a, b[a], 0);
+			atomicMin(p + 0 * RTK_SAH_BINS, ol[0]); atomicMin(p + 1 * RTK_SAH_BINS, ol[1]); atomicMin(p + 2 * RTK_SAH_BINS, ol[2]);
+			atomicMax(p + 3 * RTK_SAH_BINS, oh[0]); atomicMax(p + 4 * RTK_SAH_BINS, oh[1]); atomicMax(p + 5 * RTK_SAH_BINS, oh[2]);
+			atomicAdd(p + 6 * RTK_SAH_BINS, 1u);
 		}
 	}
 }
@@ -158,10 +162,10 @@ RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 n
 		int b[3] = { (int)(first_code & 255u), (int)((first_code >> 8) & 255u), (int)((first_code >> 16) & 255u) };
 		uint32_t cnt = (uint32_t)__popc(vm);
 		for (int a = 0; a < 3; a++) {
-			uint32_t *p = bins + (a * RTK_SAH_BINS + b[a]) * RTK_SAH_BINWORDS;
-			atomicMin(p + 0, rtk_f2ord(v[0])); atomicMin(p + 1, rtk_f2ord(v[1])); atomicMin(p + 2, rtk_f2ord(v[2]));
-			atomicMax(p + 3, rtk_f2ord(v[3])); atomicMax(p + 4, rtk_f2ord(v[4])); atomicMax(p + 5, rtk_f2ord(v[5]));
-			atomicAdd(p + 6, cnt);
+			uint32_t *p = bins + RTK_SAH_BIN_AT(a, b[a], 0);
+			atomicMin(p + 0 * RTK_SAH_BINS, rtk_f2ord(v[0])); atomicMin(p + 1 * RTK_SAH_BINS, rtk_f2ord(v[1])); atomicMin(p + 2 * RTK_SAH_BINS, rtk_f2ord(v[2]));
+			atomicMax(p + 3 * RTK_SAH_BINS, rtk_f2ord(v[3])); atomicMax(p + 4 * RTK_SAH_BINS, rtk_f2ord(v[4])); atomicMax(p + 5 * RTK_SAH_BINS, rtk_f2ord(v[5]));
+			atomicAdd(p + 6 * RTK_SAH_BINS, cnt);
 		}
 	}
 }
@@ -187,10 +191,10 @@ RTK_DEV rtk_sah_choice rtk_sah_sweep_warp(const uint32_t *bins, float4 plo, floa
 	uint32_t best_nl = 0;
 	float bl[6] = { 0, 0, 0, 0, 0, 0 }, br[6] = { 0, 0, 0, 0, 0, 0 };
 	for (int axis = 0; axis < 3; axis++) {
-		const uint32_t *p = bins + (axis * RTK_SAH_BINS + lane) * RTK_SAH_BINWORDS;
-		float lo[3] = { rtk_ord2f(p[0]), rtk_ord2f(p[1]), rtk_ord2f(p[2]) };
-		float hi[3] = { rtk_ord2f(p[3]), rtk_ord2f(p[4]), rtk_ord2f(p[5]) };
-		uint32_t cnt = p[6];
+		const uint32_t *p = bins + RTK_SAH_BIN_AT(axis, lane, 0);
+		float lo[3] = { rtk_ord2f(p[0 * RTK_SAH_BINS]), rtk_ord2f(p[1 * RTK_SAH_BINS]), rtk_ord2f(p[2 * RTK_SAH_BINS]) };
+		float hi[3] = { rtk_ord2f(p[3 * RTK_SAH_BINS]), rtk_ord2f(p[4 * RTK_SAH_BINS]), rtk_ord2f(p[5 * RTK_SAH_BINS]) };
+		uint32_t cnt = p[6 * RTK_SAH_BINS];
 		float Llo[3] = { lo[0], lo[1], lo[2] }, Lhi[3] = { hi[0], hi[1], hi[2] };
 		float Rlo[3] = { lo[0], lo[1], lo[2] }, Rhi[3] = { hi[0], hi[1], hi[2] };
 		uint32_t nl = cnt;
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf)
 	__syncthreads();
 	uint32_t *g = s.bins + (size_t)a * RTK_SAH_NODEBINS;
 	for (int i = threadIdx.x; i < RTK_SAH_NODEBINS; i += 256) {
-		int w = i & 7;
+		int w = (i / RTK_SAH_BINS) & 7;
 		uint32_t v = s_bins[i];
 		if (w < 3) { if (v != rtk_f2ord(+RTK_INF_F)) atomicMin(g + i, v); }
 		else if (w < 6) { if (v != rtk_f2ord(-RTK_INF_F)) atomicMax(g + i, v); }
@@ -448,6 +452,14 @@ __global__ void __launch_bounds__(128) k_sah_split_large(rtkd_sah s, uint32_t de
 __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, int src_buf)
 {
 	__shared__ uint32_t s_a, s_cntl[8], s_basel, s_baser;
+	// the bins of the NEXT level's nodes are cleared here (counters[1] is final once k_sah_split_large has run; this
+	// level's bins have been read): a launch less per level.  There are never more than twice as many nodes on the
+	// next level as there are blocks in this grid (the host launches at least one block per node of this level).
+	{
+		const uint32_t n_next = rtk_umin(s.counters[1], s.act_cap);
+		for (uint32_t a2 = 2 * blockIdx.x; a2 < 2 * blockIdx.x + 2 && a2 < n_next; a2++)
+			rtk_sah_bins_clear(s.bins + (size_t)a2 * RTK_SAH_NODEBINS, threadIdx.x, 256);
+	}
 	if (blockIdx.x >= s.counters[5]) return;
 	const uint32_t n_act = s.counters[6];
 	if (threadIdx.x == 0) s_a = rtk_sah_find_node(s.chunk_base, n_act, blockIdx.x);

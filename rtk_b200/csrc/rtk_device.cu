@@ -31,6 +31,7 @@ static int g_reserved_sms = 0;      // SMs the persistent traversal grid leaves 
 static size_t g_l2_bytes = 0;
 static size_t g_l2_window_max = 0;  // largest access-policy window the device accepts (0: no L2 persistence)
 static size_t g_l2_setaside = 0;    // L2 bytes set aside for persisting lines
+static int g_sah_sort_bits = 32;    // RTK_B200_SAH_SORT_BITS (8, 16, 24 or 32): Morton bits the SAH builder's input order is sorted by
 static int g_l2_persist = 0;        // RTK_B200_L2_PERSIST=1: persisting L2 window over nodes + leaf slots.  Off by default --
                                     // measured on C3/C4: k_trace gains nothing (1705 vs 1704 Mrays/s), while k_resolve, whose
                                     // corner gathers lose the set-aside part of the L2, goes from 0.47 to 1.10 ms per batch
@@ -211,6 +212,7 @@ static int init_devices_locked(const int *devices, int n)
 		if (g_trace_lanes == 8) g_trace_pd = 0;
 	}
 	{ const char *e = getenv("RTK_B200_PUSH_SMS"); if (e && atoi(e) >= 0 && atoi(e) < sm) g_push_sms = atoi(e); }
+	{ const char *e = getenv("RTK_B200_SAH_SORT_BITS"); if (e && atoi(e) >= 8 && atoi(e) <= 32 && atoi(e) % 8 == 0) g_sah_sort_bits = atoi(e); }
 	{ const char *e = getenv("RTK_B200_HOST_MIX"); if (e && atoi(e) >= 0) g_host_mix = atoi(e); }
 	{ const char *e = getenv("RTK_B200_HOST_DIRECT"); if (e) g_host_direct = atoi(e) != 0; }
 	{ const char *e = getenv("RTK_B200_HOST_MIN_SHARE_LOG2"); if (e && atoi(e) >= 7 && atoi(e) <= 30) g_min_share = (size_t)1 << atoi(e); }
@@ -894,7 +896,8 @@ struct build_bufs {
 	uint32_t *ctr;
 	uint2 *leaf_list;
 	unsigned char *node_level;
-	unsigned char *nleaf;
+	unsigned char *nleaf;          // [binary node] leaf counts of its two children, 4 bits each (k_collapse_prep)
+	int4 *rec;                     // [binary node] children and their areas
 	double *d_cost;
 	uint32_t cap, nblocks;
 	size_t act_cap, small_cap;
@@ -945,6 +948,7 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 	B.leaf_list = A.take<uint2>(n);
 	B.node_level = A.take<unsigned char>(B.cap);
 	B.nleaf = A.take<unsigned char>(2 * (size_t)n + 2);
+	B.rec = A.take<int4>(use_sah ? 2 * (size_t)n + 2 : (size_t)n);
 	B.d_cost = A.take<double>(1);
 }
 
@@ -973,7 +977,7 @@ static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, 
 		const unsigned long long pow2 = depth < 40 ? 1ull << depth : ~0ull;
 		const uint32_t act_bound = (uint32_t)(pow2 < B.act_cap ? pow2 : B.act_cap);
 		const uint32_t chunk_bound = max_chunks + act_bound;
-		RTK_LAUNCH(k_sah_bins_clear, act_bound, 128, st, h); CK_LAUNCH();
+		if (depth == 0) { RTK_LAUNCH(k_sah_bins_clear, act_bound, 128, st, h); CK_LAUNCH(); }      // later levels: cleared by the partition kernel of the level above
 		RTK_LAUNCH(k_sah_bin_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
 		RTK_LAUNCH(k_sah_split_large, (act_bound + 3) / 4, 128, st, h, depth, src_buf ^ 1); CK_LAUNCH();
 		RTK_LAUNCH(k_sah_partition_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
@@ -1076,7 +1080,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 	// neighbours apart); the SAH builder only wants spatial locality in its input order, for which
 	// the upper 31 bits (10 per axis) are plenty -- half the passes
 	int src = 0;
-	for (int shift = use_sah ? 32 : 0; shift < 64; shift += 8) {
+	for (int shift = use_sah ? 64 - g_sah_sort_bits : 0; shift < 64; shift += 8) {
 		RTK_LAUNCH(k_radix_hist, B.nblocks, RTK_SORT_THREADS, st, (const unsigned long long*)B.keys[src], n, shift, B.counts, B.nblocks); CK_LAUNCH();
 		RTK_LAUNCH(k_radix_scan, 256, 256, st, B.counts, B.nblocks, B.totals); CK_LAUNCH();
 		RTK_LAUNCH(k_radix_scatter, B.nblocks, RTK_SORT_THREADS, st, (const unsigned long long*)B.keys[src], (const uint32_t*)B.vals[src],
@@ -1119,9 +1123,9 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 		CK(cudaMemcpyAsync(B.work[0], &w0, sizeof(w0), cudaMemcpyHostToDevice, st));
 		CK(cudaMemsetAsync(B.d_cost, 0, sizeof(double), st));
 		{
-			// leaves below every binary node that could be absorbed whole (k_count_leaves)
+			// one record per binary node: its children, their areas and the leaves below them (k_collapse_prep)
 			const uint32_t bound = use_sah ? (uint32_t)(2 * (size_t)n + 2) : n - 1;
-			RTK_LAUNCH(k_count_leaves, (bound + 255) / 256, 256, st, t, use_sah ? (const uint32_t*)B.h.counters : (const uint32_t*)NULL, n - 1, B.nleaf); CK_LAUNCH();
+			RTK_LAUNCH(k_collapse_prep, (bound + 255) / 256, 256, st, t, use_sah ? (const uint32_t*)B.h.counters : (const uint32_t*)NULL, n - 1, (int)n, B.rec, B.nleaf); CK_LAUNCH();
 		}
 		// levels are launched with an upper bound on their width (8^L, capped) and read their
 		// true item count on the device; the host looks at the counters every 4 levels
@@ -1135,7 +1139,7 @@ extern "C" int rtkd_build(rtkd_scene *s, int mode, void *stream)
 				a.work_out = B.work[(level & 1) ^ 1]; a.n_out = B.ctr + 8 + level + 1;
 				a.node_alloc = B.ctr; a.node_cap = B.cap; a.leaf_count = B.ctr + 1; a.leaf_list = B.leaf_list; a.sah_cost = B.d_cost;
 				a.node_level = B.node_level; a.level = (uint32_t)level;
-				a.nodes = B.wide; a.n = (int)n; a.err = B.ctr + 2; a.nleaf = B.nleaf;
+				a.nodes = B.wide; a.n = (int)n; a.err = B.ctr + 2; a.rec = B.rec; a.nleaf2 = B.nleaf;
 				uint32_t width = (uint32_t)(bound < B.cap ? bound : B.cap);
 				RTK_LAUNCH(k_collapse, (width + 127) / 128, 128, st, a, t); CK_LAUNCH();
 				bound = bound * 8 < B.cap ? bound * 8 : B.cap;

@@ -78,6 +78,15 @@ run_stage() {
 			lib=rtk_b200/librtk_b200_$v.so; [ "$v" = main ] && lib=rtk_b200/librtk_b200.so
 			for w in C3 C4 C2; do RTK_LIB=$lib timeout 300 python tools/prof_build.py $w sah 2>&1 | tail -1 | sed "s/^/$v /"; done
 		done ;;
+	sortbits)
+		# Morton bits the SAH builder's input is sorted by (one radix pass per 8): device build time
+		for b in 32 24 16; do for w in C3 C4; do RTK_B200_SAH_SORT_BITS=$b timeout 300 python tools/prof_build.py $w sah 2>&1 | tail -1 | sed "s/^/SORT_BITS=$b /"; done; done ;;
+	buildfull)
+		# ncu --set full of the build's heavy kernels (first build of the run)
+		timeout 600 python tools/prof_build.py ${1:-C3} sah > $OUT/${TAG}_pbf_plain.log 2>&1 &&
+		timeout 1200 ncu --set full --clock-control none -k regex:'k_sah_small|k_sah_bin_large|k_collapse|k_sah_partition_large|k_radix_scatter' -c 40 -f -o $OUT/${TAG}_build_${1:-C3} \
+			python tools/prof_build.py ${1:-C3} sah > $OUT/${TAG}_pbf_ncu.log 2>&1
+		echo "build ncu exit $?"; tail -1 $OUT/${TAG}_pbf_plain.log ;;
 	hostab)
 		for v in 1 0; do RTK_B200_HOST_DIRECT=$v timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows|compact" | sed "s/^/HOST_DIRECT=$v /"; done
 		for r in 2 8; do RTK_B200_PUSH_SMS=$r timeout 600 python tools/prof_e2e.py C3 16777216 1 5 2>&1 | grep -E "rows " | sed "s/^/PUSH_SMS=$r /"; done ;;

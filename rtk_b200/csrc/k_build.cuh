@@ -447,22 +447,22 @@ __global__ void k_collapse_prep(rtkd_bvh2 t, const uint32_t *num_nodes_dev, uint
 
 __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 {
-	uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= *a.n_in) return;
+	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool valid = w < *a.n_in;          // lanes without a node stay for the warp-wide allocation below
 	const int n = a.n;
-	const int root = (int)a.work_in[w].x;
-	const uint32_t dst = a.work_in[w].y;
+	const int root = valid ? (int)a.work_in[w].x : 0;
+	const uint32_t dst = valid ? a.work_in[w].y : 0u;
 	int slot[RTK_WIDE];
 	float area[RTK_WIDE];       // half area of a slot that can be opened, -1 for a leaf
 	int nleaf[RTK_WIDE];        // leaves below an openable slot when that is at most RTK_WIDE, else 0
-	int ns = 2;
-	{
+	int ns = valid ? 2 : 0;
+	if (valid) {
 		const int4 r = a.rec[root];
 		const int q = a.nleaf2[root];
 		slot[0] = r.x; slot[1] = r.y; area[0] = __int_as_float(r.z); area[1] = __int_as_float(r.w);
 		nleaf[0] = q & 15; nleaf[1] = q >> 4;
 	}
-	while (ns < RTK_WIDE) {
+	while (valid && ns < RTK_WIDE) {
 		// A subtree whose leaves ALL fit into the free slots is absorbed whole, largest area first: the
 		// wide node it would have become -- with few children, near the bottom of the tree, where most
 		// nodes are -- disappears (a third fewer wide nodes, 3 % fewer node visits per ray on the
@@ -480,13 +480,32 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 		nleaf[best] = q & 15; nleaf[ns] = q >> 4;
 		ns++;
 	}
-	// one allocation per kind for the whole node (it used to be two returning atomics per child, one after the
-	// other): the children of a node get consecutive numbers, its leaves consecutive slots
+	// One allocation per kind for the whole WARP (it used to be two returning atomics per child, one after the
+	// other; then one set per node -- still thousands of atomics on the same three addresses from the threads of
+	// a level, which finish together): the children of a node get consecutive numbers, its leaves consecutive slots.
 	uint32_t n_open = 0, n_leafs = 0;
 	for (int k = 0; k < ns; k++) { if (area[k] >= 0.0f) n_open++; else n_leafs++; }
-	uint32_t idx = n_open ? atomicAdd(a.node_alloc, n_open) : 0u;
-	uint32_t o = n_open ? atomicAdd(a.n_out, n_open) : 0u;
-	uint32_t lslot = n_leafs ? atomicAdd(a.leaf_count, n_leafs) : 0u;
+	__syncwarp();
+	const int lane = threadIdx.x & 31;
+	const uint32_t mine = n_open | (n_leafs << 16);          // at most 8 each: the warp's sums fit 16 bits
+	uint32_t incl = mine;
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+		if (lane >= d) incl += y;
+	}
+	const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+	uint32_t base_idx = 0, base_o = 0, base_l = 0;
+	if (lane == 31) {
+		if (tot & 0xffffu) { base_idx = atomicAdd(a.node_alloc, tot & 0xffffu); base_o = atomicAdd(a.n_out, tot & 0xffffu); }
+		if (tot >> 16) base_l = atomicAdd(a.leaf_count, tot >> 16);
+	}
+	base_idx = __shfl_sync(0xffffffffu, base_idx, 31);
+	base_o = __shfl_sync(0xffffffffu, base_o, 31);
+	base_l = __shfl_sync(0xffffffffu, base_l, 31);
+	const uint32_t excl = incl - mine;
+	uint32_t idx = base_idx + (excl & 0xffffu);
+	uint32_t o = base_o + (excl & 0xffffu);
+	uint32_t lslot = base_l + (excl >> 16);
 	// boxes and ranges of the slots: independent loads, all in flight before the first store
 	float4 lo[RTK_WIDE], hi[RTK_WIDE];
 	uint32_t first[RTK_WIDE], count[RTK_WIDE];
@@ -510,6 +529,7 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 	double cost = 0.0;
 #pragma unroll
 	for (int k = 0; k < RTK_WIDE; k++) {
+		if (!valid) break;
 		uint32_t ref = RTK_REF_EMPTY;
 		if (k < ns) {
 			if (area[k] >= 0.0f) {
@@ -527,7 +547,9 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 		node[2 * k] = make_float4(lo[k].x, lo[k].y, lo[k].z, __uint_as_float(ref));
 		node[2 * k + 1] = make_float4(hi[k].x, hi[k].y, hi[k].z, 0.0f);
 	}
-	atomicAdd(a.sah_cost, cost);
+	__syncwarp();
+	for (int d = 16; d > 0; d >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, d);
+	if (lane == 0 && cost != 0.0) atomicAdd(a.sah_cost, cost);
 }
 
 // scene with a single triangle: a root node with one leaf child

@@ -45,11 +45,12 @@ struct rtkd_sah {
 	int *left, *right, *first, *last;
 	float4 *blo, *bhi;
 	uint32_t *ndepth;
-	uint32_t *counters;           // [0] node_alloc [1] n_act_out [2] n_small [3] err [4] max depth [5] chunks, [6] nodes of the level
+	uint32_t *counters;           // [0] node_alloc [1] n_act_out [2] n_small [3] err [4] unused [5] chunks, [6] nodes of the level
 	uint32_t *act_in, *act_out;   // large nodes of this / the next level
 	uint32_t *small_list;         // node id | (buffer << 31)
 	uint32_t *chunk_base;         // [n_act + 1] exclusive scan of chunk counts
-	uint32_t *bins;               // [n_act][3][32][8]
+	uint32_t *bins;               // [n_act][3][8][32]
+	uint32_t *binpack;            // [n] the three bins of the triangle at each position of the level's permutation (large levels)
 	int4 *split;                  // per active node: axis (-1: equal split), bin, n_left, first child
 	uint32_t *cursor;             // per active node: left / right write cursors
 	uint32_t node_cap;
@@ -94,63 +95,77 @@ RTK_DEV void rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, f
 }
 
 #if RTK_SAH_BIN_HYBRID
-// Uniformity is decided per axis, and a uniform axis is reduced with the hardware warp reductions
-// (REDUX) instead of a shuffle tree (measured in round 2: 2.13 -> 2.07 ms at 1M triangles, 15.36 -> 15.10 at 10M;
-// RTK_SAH_BIN_HYBRID=0 is the all-or-nothing test of round 1).  A first version that walked
-// ALL distinct bins of an axis with REDUX was 2.7x faster on the top level (23 vs 61 us) but 3x
-// slower on the deep large levels, where a warp's 32 triangles spread over many bins.
-RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
+#ifndef RTK_SAH_REDUX_MIN
+#define RTK_SAH_REDUX_MIN 6          // lanes that must share a bin before the warp reduces them with REDUX
+#endif
+// Per axis, the lanes of a warp that fall into the same bin are reduced with the hardware warp reductions (REDUX)
+// and ONE lane issues the 7 atomics, as long as such a group has at least RTK_SAH_REDUX_MIN lanes; smaller groups
+// update the bins lane by lane.  Morton-neighbours share bins: on the upper levels a warp is one group (round 2:
+// 2.13 -> 2.07 ms at 1M triangles against the shuffle tree of round 1) or two or three -- a warp that straddles a
+// bin boundary used to fall back to 32 lanes fighting over two addresses, which made levels 1-4 the slowest.  A
+// version that walked ALL distinct bins with REDUX was 3x slower on the deep levels, where a warp's triangles
+// spread over many bins: the walk stops after two small groups.
+RTK_DEV uint32_t rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
 {
 	const uint32_t FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const uint32_t vm = __ballot_sync(FULL, valid);
-	if (vm == 0) return;
-	const int leader = __ffs((int)vm) - 1;
+	if (vm == 0) return 0u;
 	const int b[3] = { rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x), rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y), rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z) };
 	const uint32_t ol[3] = { rtk_f2ord(lo.x), rtk_f2ord(lo.y), rtk_f2ord(lo.z) };
 	const uint32_t oh[3] = { rtk_f2ord(hi.x), rtk_f2ord(hi.y), rtk_f2ord(hi.z) };
 #pragma unroll
 	for (int a = 0; a < 3; a++) {
-		const int lb = __shfl_sync(FULL, b[a], leader);
-		if (__all_sync(FULL, !valid || b[a] == lb)) {
-			const uint32_t m0 = __reduce_min_sync(FULL, valid ? ol[0] : 0xffffffffu);
-			const uint32_t m1 = __reduce_min_sync(FULL, valid ? ol[1] : 0xffffffffu);
-			const uint32_t m2 = __reduce_min_sync(FULL, valid ? ol[2] : 0xffffffffu);
-			const uint32_t x0 = __reduce_max_sync(FULL, valid ? oh[0] : 0u);
-			const uint32_t x1 = __reduce_max_sync(FULL, valid ? oh[1] : 0u);
-			const uint32_t x2 = __reduce_max_sync(FULL, valid ? oh[2] : 0u);
+		uint32_t rem = vm, solo = 0;
+		int small = 0;
+		while (rem && small < 2) {                      // warp-uniform
+			const int leader = __ffs((int)rem) - 1;
+			const int lb = __shfl_sync(FULL, b[a], leader);
+			const uint32_t grp = __ballot_sync(FULL, valid && b[a] == lb) & rem;
+			rem &= ~grp;
+			if (__popc(grp) < RTK_SAH_REDUX_MIN) { solo |= grp; small++; continue; }
+			const bool in = (grp >> lane) & 1u;
+			const uint32_t m0 = __reduce_min_sync(FULL, in ? ol[0] : 0xffffffffu);
+			const uint32_t m1 = __reduce_min_sync(FULL, in ? ol[1] : 0xffffffffu);
+			const uint32_t m2 = __reduce_min_sync(FULL, in ? ol[2] : 0xffffffffu);
+			const uint32_t x0 = __reduce_max_sync(FULL, in ? oh[0] : 0u);
+			const uint32_t x1 = __reduce_max_sync(FULL, in ? oh[1] : 0u);
+			const uint32_t x2 = __reduce_max_sync(FULL, in ? oh[2] : 0u);
 			if (lane == leader) {
 				uint32_t *p = bins + RTK_SAH_BIN_AT(a, lb, 0);
 				atomicMin(p + 0 * RTK_SAH_BINS, m0); atomicMin(p + 1 * RTK_SAH_BINS, m1); atomicMin(p + 2 * RTK_SAH_BINS, m2);
 				atomicMax(p + 3 * RTK_SAH_BINS, x0); atomicMax(p + 4 * RTK_SAH_BINS, x1); atomicMax(p + 5 * RTK_SAH_BINS, x2);
-				atomicAdd(p + 6 * RTK_SAH_BINS, (uint32_t)__popc(vm));
+				atomicAdd(p + 6 * RTK_SAH_BINS, (uint32_t)__popc(grp));
 			}
-		} else if (valid) {
+		}
+		if (((solo | rem) >> lane) & 1u) {
 			uint32_t *p = bins + RTK_SAH_BIN_AT(a, b[a], 0);
 			atomicMin(p + 0 * RTK_SAH_BINS, ol[0]); atomicMin(p + 1 * RTK_SAH_BINS, ol[1]); atomicMin(p + 2 * RTK_SAH_BINS, ol[2]);
 			atomicMax(p + 3 * RTK_SAH_BINS, oh[0]); atomicMax(p + 4 * RTK_SAH_BINS, oh[1]); atomicMax(p + 5 * RTK_SAH_BINS, oh[2]);
 			atomicAdd(p + 6 * RTK_SAH_BINS, 1u);
 		}
 	}
+	return (uint32_t)(b[0] | (b[1] << 8) | (b[2] << 16));
 }
 #else
 // Warp-cooperative variant (all 32 lanes call it; `valid` masks lanes without a triangle).  In
 // the upper levels a warp's 32 Morton-neighbours almost always fall into the same bin on every
 // axis: then the warp reduces its boxes with shuffles and one lane issues the 21 atomics instead
 // of 32 lanes fighting over the same 21 addresses.
-RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
+RTK_DEV uint32_t rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
 {
 	const uint32_t FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	int b0 = rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x), b1 = rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y), b2 = rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z);
 	uint32_t code = valid ? (uint32_t)(b0 | (b1 << 8) | (b2 << 16)) : 0xffffffffu;
 	uint32_t vm = __ballot_sync(FULL, valid);
-	if (vm == 0) return;
+	if (vm == 0) return 0u;
+	const uint32_t packed = (uint32_t)(b0 | (b1 << 8) | (b2 << 16));
 	uint32_t first_code = __shfl_sync(FULL, code, __ffs(vm) - 1);
 	bool uniform = __all_sync(FULL, !valid || code == first_code);
 	if (!uniform) {
 		if (valid) rtk_sah_bin_add(bins, lo, hi, nlo, nhi);
-		return;
+		return packed;
 	}
 	float v[6] = { valid ? lo.x : +RTK_INF_F, valid ? lo.y : +RTK_INF_F, valid ? lo.z : +RTK_INF_F,
 	               valid ? hi.x : -RTK_INF_F, valid ? hi.y : -RTK_INF_F, valid ? hi.z : -RTK_INF_F };
@@ -168,6 +183,7 @@ RTK_DEV void rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 n
 			atomicAdd(p + 6 * RTK_SAH_BINS, cnt);
 		}
 	}
+	return packed;
 }
 #endif
 
@@ -175,57 +191,79 @@ struct rtk_sah_choice {
 	int axis, bin;               // axis < 0: no valid split
 	uint32_t n_left;
 	float llo[3], lhi[3], rlo[3], rhi[3];
+	float cost;                  // only meaningful between rtk_sah_sweep_axis and rtk_sah_pick_axis
 };
 
-// The sweep of rtk.c:909-945 with one warp: lane i owns bin i.  Returns the same choice in
-// every lane.  Ties go to the lower axis, then the lower bin (the reference's strict '<' in
-// axis-major, bin-minor order, rtk.c:938).
+// One axis of the sweep of rtk.c:909-945 with one warp: lane i owns bin i and prices the split after it.
+// Returns the cost (RTK_INF_F: not a valid split), the triangles on the left and the two boxes.
+RTK_DEV float rtk_sah_axis_candidate(const uint32_t *bins, int axis, uint32_t count, float rcp_parent, uint32_t &nl_out, float (&L)[6], float (&R)[6])
+{
+	const uint32_t FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const uint32_t *p = bins + RTK_SAH_BIN_AT(axis, lane, 0);
+	float lo[3] = { rtk_ord2f(p[0 * RTK_SAH_BINS]), rtk_ord2f(p[1 * RTK_SAH_BINS]), rtk_ord2f(p[2 * RTK_SAH_BINS]) };
+	float hi[3] = { rtk_ord2f(p[3 * RTK_SAH_BINS]), rtk_ord2f(p[4 * RTK_SAH_BINS]), rtk_ord2f(p[5 * RTK_SAH_BINS]) };
+	uint32_t cnt = p[6 * RTK_SAH_BINS];
+	float Llo[3] = { lo[0], lo[1], lo[2] }, Lhi[3] = { hi[0], hi[1], hi[2] };
+	float Rlo[3] = { lo[0], lo[1], lo[2] }, Rhi[3] = { hi[0], hi[1], hi[2] };
+	uint32_t nl = cnt;
+	for (int o = 1; o < 32; o <<= 1) {
+		for (int k = 0; k < 3; k++) {
+			float a = __shfl_up_sync(FULL, Llo[k], o), b = __shfl_up_sync(FULL, Lhi[k], o);
+			float c = __shfl_down_sync(FULL, Rlo[k], o), d = __shfl_down_sync(FULL, Rhi[k], o);
+			if (lane >= o) { Llo[k] = rtk_fmin(Llo[k], a); Lhi[k] = rtk_fmax(Lhi[k], b); }
+			if (lane + o < 32) { Rlo[k] = rtk_fmin(Rlo[k], c); Rhi[k] = rtk_fmax(Rhi[k], d); }
+		}
+		uint32_t e = __shfl_up_sync(FULL, nl, o);
+		if (lane >= o) nl += e;
+	}
+	// split after bin `lane`: left = bins 0..lane (mine), right = bins lane+1..31 (neighbour's suffix)
+	for (int k = 0; k < 3; k++) {
+		L[k] = Llo[k]; L[3 + k] = Lhi[k];
+		R[k] = __shfl_down_sync(FULL, Rlo[k], 1);
+		R[3 + k] = __shfl_down_sync(FULL, Rhi[k], 1);
+	}
+	nl_out = nl;
+	const uint32_t nr = count - nl;
+	if (!(lane < RTK_SAH_BINS - 1 && nl > 0 && nr > 0)) return RTK_INF_F;
+	float lx = L[3] - L[0], ly = L[4] - L[1], lz = L[5] - L[2];
+	float rx = R[3] - R[0], ry = R[4] - R[1], rz = R[5] - R[2];
+	float area_l = 2.0f * (lx * ly + ly * lz + lz * lx);                // rtk.c:729-733
+	float area_r = 2.0f * (rx * ry + ry * rz + rz * rx);
+	float cost_l = (float)((nl + RTK_LEAF_MAX - 1u) / RTK_LEAF_MAX), cost_r = (float)((nr + RTK_LEAF_MAX - 1u) / RTK_LEAF_MAX);  // rtk.c:934-935
+	return 1.0f + (area_l * cost_l + area_r * cost_r) * rcp_parent;     // rtk.c:936, split cost 1
+}
+
+RTK_DEV float rtk_sah_rcp_parent(float4 plo, float4 phi)
+{
+	float px = phi.x - plo.x, py = phi.y - plo.y, pz = phi.z - plo.z;
+	return 1.0f / (2.0f * (px * py + py * pz + pz * px));          // rtk.c:880
+}
+
+RTK_DEV void rtk_sah_choice_none(rtk_sah_choice &c, float4 plo, float4 phi, uint32_t count)
+{
+	c.axis = -1; c.bin = 0; c.n_left = count / 2; c.cost = RTK_INF_F;
+	for (int k = 0; k < 3; k++) { c.llo[k] = c.rlo[k] = k == 0 ? plo.x : (k == 1 ? plo.y : plo.z); c.lhi[k] = c.rhi[k] = k == 0 ? phi.x : (k == 1 ? phi.y : phi.z); }
+}
+
+// The whole sweep with one warp.  Returns the same choice in every lane.  Ties go to the lower axis, then the
+// lower bin (the reference's strict '<' in axis-major, bin-minor order, rtk.c:938).
 RTK_DEV rtk_sah_choice rtk_sah_sweep_warp(const uint32_t *bins, float4 plo, float4 phi, uint32_t count)
 {
 	const uint32_t FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
-	float px = phi.x - plo.x, py = phi.y - plo.y, pz = phi.z - plo.z;
-	float rcp_parent = 1.0f / (2.0f * (px * py + py * pz + pz * px));          // rtk.c:880
+	const float rcp_parent = rtk_sah_rcp_parent(plo, phi);
 	float best_cost = RTK_INF_F;
 	int best_axis = -1;
 	uint32_t best_nl = 0;
 	float bl[6] = { 0, 0, 0, 0, 0, 0 }, br[6] = { 0, 0, 0, 0, 0, 0 };
 	for (int axis = 0; axis < 3; axis++) {
-		const uint32_t *p = bins + RTK_SAH_BIN_AT(axis, lane, 0);
-		float lo[3] = { rtk_ord2f(p[0 * RTK_SAH_BINS]), rtk_ord2f(p[1 * RTK_SAH_BINS]), rtk_ord2f(p[2 * RTK_SAH_BINS]) };
-		float hi[3] = { rtk_ord2f(p[3 * RTK_SAH_BINS]), rtk_ord2f(p[4 * RTK_SAH_BINS]), rtk_ord2f(p[5 * RTK_SAH_BINS]) };
-		uint32_t cnt = p[6 * RTK_SAH_BINS];
-		float Llo[3] = { lo[0], lo[1], lo[2] }, Lhi[3] = { hi[0], hi[1], hi[2] };
-		float Rlo[3] = { lo[0], lo[1], lo[2] }, Rhi[3] = { hi[0], hi[1], hi[2] };
-		uint32_t nl = cnt;
-		for (int o = 1; o < 32; o <<= 1) {
-			for (int k = 0; k < 3; k++) {
-				float a = __shfl_up_sync(FULL, Llo[k], o), b = __shfl_up_sync(FULL, Lhi[k], o);
-				float c = __shfl_down_sync(FULL, Rlo[k], o), d = __shfl_down_sync(FULL, Rhi[k], o);
-				if (lane >= o) { Llo[k] = rtk_fmin(Llo[k], a); Lhi[k] = rtk_fmax(Lhi[k], b); }
-				if (lane + o < 32) { Rlo[k] = rtk_fmin(Rlo[k], c); Rhi[k] = rtk_fmax(Rhi[k], d); }
-			}
-			uint32_t e = __shfl_up_sync(FULL, nl, o);
-			if (lane >= o) nl += e;
-		}
-		// split after bin `lane`: left = bins 0..lane (mine), right = bins lane+1..31 (neighbour's suffix)
-		float r[6];
-		for (int k = 0; k < 3; k++) {
-			r[k] = __shfl_down_sync(FULL, Rlo[k], 1);
-			r[3 + k] = __shfl_down_sync(FULL, Rhi[k], 1);
-		}
-		uint32_t nr = count - nl;
-		if (lane < RTK_SAH_BINS - 1 && nl > 0 && nr > 0) {
-			float lx = Lhi[0] - Llo[0], ly = Lhi[1] - Llo[1], lz = Lhi[2] - Llo[2];
-			float rx = r[3] - r[0], ry = r[4] - r[1], rz = r[5] - r[2];
-			float area_l = 2.0f * (lx * ly + ly * lz + lz * lx);                // rtk.c:729-733
-			float area_r = 2.0f * (rx * ry + ry * rz + rz * rx);
-			float cost_l = (float)((nl + RTK_LEAF_MAX - 1u) / RTK_LEAF_MAX), cost_r = (float)((nr + RTK_LEAF_MAX - 1u) / RTK_LEAF_MAX);  // rtk.c:934-935
-			float cost = 1.0f + (area_l * cost_l + area_r * cost_r) * rcp_parent;     // rtk.c:936, split cost 1
-			if (cost < best_cost) {
-				best_cost = cost; best_axis = axis; best_nl = nl;
-				for (int k = 0; k < 3; k++) { bl[k] = Llo[k]; bl[3 + k] = Lhi[k]; br[k] = r[k]; br[3 + k] = r[3 + k]; }
-			}
+		float L[6], R[6];
+		uint32_t nl;
+		const float cost = rtk_sah_axis_candidate(bins, axis, count, rcp_parent, nl, L, R);
+		if (cost < best_cost) {
+			best_cost = cost; best_axis = axis; best_nl = nl;
+			for (int k = 0; k < 6; k++) { bl[k] = L[k]; br[k] = R[k]; }
 		}
 	}
 	// warp argmin over (cost, axis, bin)
@@ -234,13 +272,9 @@ RTK_DEV rtk_sah_choice rtk_sah_sweep_warp(const uint32_t *bins, float4 plo, floa
 	uint32_t key = (best_axis >= 0 && best_cost == m) ? (uint32_t)(best_axis * 32 + lane) : 0xffffffffu;
 	for (int o = 16; o > 0; o >>= 1) key = rtk_umin(key, __shfl_xor_sync(FULL, key, o));
 	rtk_sah_choice c;
-	if (key == 0xffffffffu) {
-		c.axis = -1; c.bin = 0; c.n_left = count / 2;
-		for (int k = 0; k < 3; k++) { c.llo[k] = c.rlo[k] = k == 0 ? plo.x : (k == 1 ? plo.y : plo.z); c.lhi[k] = c.rhi[k] = k == 0 ? phi.x : (k == 1 ? phi.y : phi.z); }
-		return c;
-	}
+	if (key == 0xffffffffu) { rtk_sah_choice_none(c, plo, phi, count); return c; }
 	int src = (int)(key & 31u);
-	c.axis = (int)(key >> 5); c.bin = src;
+	c.axis = (int)(key >> 5); c.bin = src; c.cost = m;
 	// the winning lane may hold a different axis as its own best: only `src` is read
 	c.n_left = __shfl_sync(FULL, best_nl, src);
 	for (int k = 0; k < 3; k++) {
@@ -248,6 +282,38 @@ RTK_DEV rtk_sah_choice rtk_sah_sweep_warp(const uint32_t *bins, float4 plo, floa
 		c.rlo[k] = __shfl_sync(FULL, br[k], src); c.rhi[k] = __shfl_sync(FULL, br[3 + k], src);
 	}
 	return c;
+}
+
+// One axis of the sweep with one warp, for callers that give each axis its own warp (the three scans are the
+// longest dependency chain of a split).  The best split of the axis -- lowest cost, then lowest bin -- in every lane;
+// axis < 0 when the axis has no valid split.  rtk_sah_pick_axis then takes the lowest cost, lower axis on ties:
+// the same choice as rtk_sah_sweep_warp.
+RTK_DEV rtk_sah_choice rtk_sah_sweep_axis(const uint32_t *bins, int axis, float4 plo, float4 phi, uint32_t count)
+{
+	const uint32_t FULL = 0xffffffffu;
+	float L[6], R[6];
+	uint32_t nl;
+	const float cost = rtk_sah_axis_candidate(bins, axis, count, rtk_sah_rcp_parent(plo, phi), nl, L, R);
+	float m = cost;
+	for (int o = 16; o > 0; o >>= 1) m = rtk_fmin(m, __shfl_xor_sync(FULL, m, o));
+	const uint32_t hit = __ballot_sync(FULL, cost < RTK_INF_F && cost == m);
+	rtk_sah_choice c;
+	if (!hit) { rtk_sah_choice_none(c, plo, phi, count); return c; }
+	const int src = __ffs((int)hit) - 1;
+	c.axis = axis; c.bin = src; c.cost = m;
+	c.n_left = __shfl_sync(FULL, nl, src);
+	for (int k = 0; k < 3; k++) {
+		c.llo[k] = __shfl_sync(FULL, L[k], src); c.lhi[k] = __shfl_sync(FULL, L[3 + k], src);
+		c.rlo[k] = __shfl_sync(FULL, R[k], src); c.rhi[k] = __shfl_sync(FULL, R[3 + k], src);
+	}
+	return c;
+}
+
+RTK_DEV rtk_sah_choice rtk_sah_pick_axis(const rtk_sah_choice *cand)
+{
+	int best = 0;                                        // all three invalid: any of them is the "no split" choice
+	for (int a = 1; a < 3; a++) if (cand[a].axis >= 0 && (cand[best].axis < 0 || cand[a].cost < cand[best].cost)) best = a;
+	return cand[best];
 }
 
 // depth rule of rtk.c:1429-1443: if the remaining levels cannot bring the node down to
@@ -382,7 +448,11 @@ __global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf)
 			if (valid[u]) { lo[u] = s.pb[2ull * j[u]]; hi[u] = s.pb[2ull * j[u] + 1]; }
 		}
 #pragma unroll
-		for (int u = 0; u < 4; u++) rtk_sah_bin_add_warp(s_bins, lo[u], hi[u], nlo, nhi, valid[u]);
+		for (int u = 0; u < 4; u++) {
+			// the partition kernel of this level reads the bins back (coalesced) instead of gathering the boxes again
+			const uint32_t packed = rtk_sah_bin_add_warp(s_bins, lo[u], hi[u], nlo, nhi, valid[u]);
+			if (valid[u]) s.binpack[base + u * 256 + threadIdx.x] = packed;
+		}
 	}
 	__syncthreads();
 	uint32_t *g = s.bins + (size_t)a * RTK_SAH_NODEBINS;
@@ -396,10 +466,12 @@ __global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf)
 }
 
 // children of a split node: allocate, fill, classify for the next step
+// `local_alloc`: a shared-memory cursor into node numbers the caller has reserved (k_sah_small), or NULL to take two
+// from the global counter
 RTK_DEV void rtk_sah_emit_children(rtkd_sah &s, uint32_t node, const rtk_sah_choice &c, uint32_t depth,
-                                   int child_buf, uint32_t &child0)
+                                   int child_buf, uint32_t &child0, uint32_t *local_alloc = NULL)
 {
-	uint32_t ch = atomicAdd(&s.counters[0], 2u);
+	uint32_t ch = local_alloc ? atomicAdd(local_alloc, 2u) : atomicAdd(&s.counters[0], 2u);
 	if (ch + 2 > s.node_cap) { atomicOr(&s.counters[3], 1u); ch = 0; }
 	child0 = ch;
 	const uint32_t first = (uint32_t)s.first[node], last = (uint32_t)s.last[node];
@@ -422,26 +494,27 @@ RTK_DEV void rtk_sah_emit_children(rtkd_sah &s, uint32_t node, const rtk_sah_cho
 			}
 		}
 	}
-	atomicMax(&s.counters[4], depth + 1);
 }
 
-// one warp per active large node
-__global__ void __launch_bounds__(128) k_sah_split_large(rtkd_sah s, uint32_t depth, int dst_buf)
+// one block of three warps per active large node: a warp per axis
+__global__ void __launch_bounds__(96) k_sah_split_large(rtkd_sah s, uint32_t depth, int dst_buf)
 {
-	const uint32_t a = blockIdx.x * 4 + (threadIdx.x >> 5);
+	__shared__ rtk_sah_choice s_cand[3];
+	const uint32_t a = blockIdx.x;
 	if (a >= s.counters[6]) return;
-	const int lane = threadIdx.x & 31;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t node = s.act_in[a];
 	const uint32_t count = (uint32_t)(s.last[node] - s.first[node] + 1);
-	rtk_sah_choice c = rtk_sah_sweep_warp(s.bins + (size_t)a * RTK_SAH_NODEBINS, s.blo[node], s.bhi[node], count);
-	if (rtk_sah_must_halve(count, depth) && c.axis >= 0) {
-		// forced equal split (rtk.c:1440-1443): position halves, children keep the parent's box
-		float4 plo = s.blo[node], phi = s.bhi[node];
-		c.axis = -1; c.n_left = count / 2;
-		c.llo[0] = c.rlo[0] = plo.x; c.llo[1] = c.rlo[1] = plo.y; c.llo[2] = c.rlo[2] = plo.z;
-		c.lhi[0] = c.rhi[0] = phi.x; c.lhi[1] = c.rhi[1] = phi.y; c.lhi[2] = c.rhi[2] = phi.z;
-	}
-	if (lane == 0) {
+	const float4 plo = s.blo[node], phi = s.bhi[node];
+	const rtk_sah_choice mine = rtk_sah_sweep_axis(s.bins + (size_t)a * RTK_SAH_NODEBINS, warp, plo, phi, count);
+	if (lane == 0) s_cand[warp] = mine;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		rtk_sah_choice c = rtk_sah_pick_axis(s_cand);
+		if (rtk_sah_must_halve(count, depth) && c.axis >= 0) {
+			// forced equal split (rtk.c:1440-1443): position halves, children keep the parent's box
+			rtk_sah_choice_none(c, plo, phi, count);
+		}
 		uint32_t ch;
 		rtk_sah_emit_children(s, node, c, depth, dst_buf, ch);
 		s.split[a] = make_int4(c.axis, c.bin, (int)c.n_left, (int)ch);
@@ -470,45 +543,41 @@ __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, int src
 	const uint32_t first = (uint32_t)s.first[node], last = (uint32_t)s.last[node];
 	const uint32_t begin = first + (blockIdx.x - s.chunk_base[a]) * RTK_SAH_CHUNK;
 	const uint32_t end = rtk_umin(begin + RTK_SAH_CHUNK, last + 1);
-	const float4 nlo = s.blo[node], nhi = s.bhi[node];
 	const uint32_t *src = src_buf ? s.idx1 : s.idx0;
 	uint32_t *dst = src_buf ? s.idx0 : s.idx1;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const float amin = sp.x == 0 ? nlo.x : (sp.x == 1 ? nlo.y : nlo.z);
-	const float amax = sp.x == 0 ? nhi.x : (sp.x == 1 ? nhi.y : nhi.z);
 	// The whole 2048-triangle chunk in one pass: every thread classifies its 8 triangles (all index
 	// loads, then all box gathers, in flight together), the block scans the per-thread counts and
 	// reserves its left / right ranges with ONE pair of atomics (it used to take a pair, and three
-	// barriers, per 256 triangles).  The order inside a side is irrelevant to the tree.
+	// barriers, per 256 triangles).  The order inside a side is irrelevant to the tree but not to the next level's
+	// speed: a thread takes PER CONSECUTIVE positions, so thread order is position order and the partition is
+	// stable -- the Morton order survives inside each side of a chunk, and with it the warps whose triangles share
+	// a bin (with positions dealt out round-robin, every level interleaved the order 8 ways and the binning of
+	// levels 1-4 took twice as long as that of the sorted level 0).
 	constexpr int PER = RTK_SAH_CHUNK / 256;
 	uint32_t j[PER];
 	uint32_t vmask = 0, lmask = 0;
 #pragma unroll
 	for (int u = 0; u < PER; u++) {
-		const uint32_t p = begin + u * 256 + threadIdx.x;
+		const uint32_t p = begin + threadIdx.x * PER + u;
 		j[u] = 0;
 		if (p < end) { vmask |= 1u << u; j[u] = src[p]; }
 	}
 	if (sp.x < 0) {
 #pragma unroll
 		for (int u = 0; u < PER; u++) {
-			const uint32_t p = begin + u * 256 + threadIdx.x;
+			const uint32_t p = begin + threadIdx.x * PER + u;
 			if (((vmask >> u) & 1u) && (p - first) < (uint32_t)sp.z) lmask |= 1u << u;      // equal split by position
 		}
 	} else {
-		float l[PER], h[PER];
+		// the triangle's bin on the split axis, as k_sah_bin_large computed it for this position (rtk.c:973-977
+		// recomputes it from the box: a gather of 32 bytes per triangle that this level has already done once)
+		const int sh = 8 * sp.x;
 #pragma unroll
 		for (int u = 0; u < PER; u++) {
-			l[u] = 0.0f; h[u] = 0.0f;
-			if ((vmask >> u) & 1u) {
-				const float4 lo = s.pb[2ull * j[u]], hi = s.pb[2ull * j[u] + 1];
-				l[u] = sp.x == 0 ? lo.x : (sp.x == 1 ? lo.y : lo.z);
-				h[u] = sp.x == 0 ? hi.x : (sp.x == 1 ? hi.y : hi.z);
-			}
+			const uint32_t p = begin + threadIdx.x * PER + u;
+			if (((vmask >> u) & 1u) && (int)((s.binpack[p] >> sh) & 0xffu) <= sp.y) lmask |= 1u << u;
 		}
-#pragma unroll
-		for (int u = 0; u < PER; u++)
-			if (((vmask >> u) & 1u) && rtk_sah_bin(l[u], h[u], amin, amax) <= sp.y) lmask |= 1u << u;   // rtk.c:973-977
 	}
 	const uint32_t cl = (uint32_t)__popc(lmask), cr = (uint32_t)__popc(vmask & ~lmask);
 	// exclusive scan of (cl, cr) over the block: packed in one word (a chunk holds at most 2048)
@@ -562,7 +631,7 @@ struct rtk_sah_task { uint32_t node, begin, count, depth; float lo[3], hi[3]; };
 template <bool WARP>
 RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *bins, const float4 *s_lo, const float4 *s_hi,
                                   unsigned short *perm0, unsigned short *perm1, rtk_sah_choice *s_choice, uint32_t *s_child,
-                                  uint32_t *wl, uint32_t *wr, int tid, int nthreads, rtk_sah_task &a, rtk_sah_task &b)
+                                  uint32_t *wl, uint32_t *wr, int tid, int nthreads, uint32_t *node_alloc, rtk_sah_task &a, rtk_sah_task &b)
 {
 #define RTK_SYNC() do { if (WARP) __syncwarp(); else __syncthreads(); } while (0)
 	const int lane = tid & 31, warp = tid >> 5;
@@ -584,15 +653,26 @@ RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *
 		}
 	}
 	RTK_SYNC();
-	if (warp == 0) {
+	if (WARP) {
 		rtk_sah_choice c = rtk_sah_sweep_warp(bins, nlo, nhi, t.count);
-		if (rtk_sah_must_halve(t.count, t.depth) && c.axis >= 0) {
-			c.axis = -1; c.n_left = t.count / 2;
-			for (int k = 0; k < 3; k++) { c.llo[k] = c.rlo[k] = t.lo[k]; c.lhi[k] = c.rhi[k] = t.hi[k]; }
-		}
+		if (rtk_sah_must_halve(t.count, t.depth) && c.axis >= 0) rtk_sah_choice_none(c, nlo, nhi, t.count);
 		if (lane == 0) {
 			uint32_t ch;
-			rtk_sah_emit_children(s, t.node, c, t.depth, -1, ch);
+			rtk_sah_emit_children(s, t.node, c, t.depth, -1, ch, node_alloc);
+			*s_choice = c; *s_child = ch;
+		}
+	} else {
+		// a warp per axis (s_choice[1..3] belong to the warps' own splits of phase 2: free during phase 1)
+		if (warp < 3) {
+			const rtk_sah_choice mine = rtk_sah_sweep_axis(bins, warp, nlo, nhi, t.count);
+			if (lane == 0) s_choice[1 + warp] = mine;
+		}
+		__syncthreads();
+		if (tid == 0) {
+			rtk_sah_choice c = rtk_sah_pick_axis(s_choice + 1);
+			if (rtk_sah_must_halve(t.count, t.depth) && c.axis >= 0) rtk_sah_choice_none(c, nlo, nhi, t.count);
+			uint32_t ch;
+			rtk_sah_emit_children(s, t.node, c, t.depth, -1, ch, node_alloc);
 			*s_choice = c; *s_child = ch;
 		}
 	}
@@ -658,6 +738,7 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 	__shared__ rtk_sah_task s_wq[64];
 	__shared__ rtk_sah_task s_wstack[RTK_SAH_SMALL_WARPS][12];
 	__shared__ int s_sp, s_nwq, s_wq_next;
+	__shared__ uint32_t s_node_next, s_node_end;
 	__shared__ rtk_sah_choice s_choice[1 + RTK_SAH_SMALL_WARPS];
 	__shared__ uint32_t s_child[1 + RTK_SAH_SMALL_WARPS], s_wl[RTK_SAH_SMALL_WARPS], s_wr[RTK_SAH_SMALL_WARPS];
 
@@ -681,6 +762,15 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 		t.lo[0] = lo.x; t.lo[1] = lo.y; t.lo[2] = lo.z; t.hi[0] = hi.x; t.hi[1] = hi.y; t.hi[2] = hi.z;
 		s_stack[0] = t;
 		s_sp = 1; s_nwq = 0; s_wq_next = 0;
+		// Node numbers for the whole subtree in ONE global atomic: a subtree of `total` triangles has at most
+		// 2 * total - 2 nodes below its root.  (One returning atomic per split -- 125 000 of them on one address
+		// for 1M triangles -- serialised the CTAs of this kernel on the L2.)  The reservations of all subtrees
+		// plus the nodes of the large levels never exceed 2n - 1, so node_cap = 2n + 2 holds them; numbers that
+		// stay unused are marked as empty ranges below (k_collapse_prep skips them, nothing refers to them).
+		const uint32_t need = total > RTK_LEAF_MAX ? 2u * total - 2u : 0u;
+		uint32_t base = need ? atomicAdd(&s.counters[0], need) : 0u;
+		if (base + need > s.node_cap) { atomicOr(&s.counters[3], 1u); base = 0; }
+		s_node_next = base; s_node_end = base + need;
 	}
 	__syncthreads();
 
@@ -697,7 +787,7 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 		}
 		rtk_sah_task a, b;
 		rtk_sah_split_shared<false>(s, t, s_bins[0], s_lo, s_hi, s_perm[0], s_perm[1], &s_choice[0], &s_child[0],
-		                            s_wl, s_wr, tid, RTK_SAH_SMALL_THREADS, a, b);
+		                            s_wl, s_wr, tid, RTK_SAH_SMALL_THREADS, &s_node_next, a, b);
 		if (tid == 0) {
 			// the larger child is pushed first so that the stack stays logarithmic
 			int sp = s_sp;
@@ -727,7 +817,7 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 			if (t.count <= RTK_LEAF_MAX) continue;
 			rtk_sah_task a, b;
 			rtk_sah_split_shared<true>(s, t, s_bins[1 + warp], s_lo, s_hi, s_perm[0], s_perm[1], &s_choice[1 + warp], &s_child[1 + warp],
-			                           NULL, NULL, lane, 32, a, b);
+			                           NULL, NULL, lane, 32, &s_node_next, a, b);
 			if (lane == 0) {
 				if (a.count >= b.count) { st[sp] = a; st[sp + 1] = b; }
 				else { st[sp] = b; st[sp + 1] = a; }
@@ -738,6 +828,9 @@ __global__ void __launch_bounds__(RTK_SAH_SMALL_THREADS) k_sah_small(rtkd_sah s,
 	}
 	__syncthreads();
 	for (uint32_t i = tid; i < total; i += RTK_SAH_SMALL_THREADS) s.idx_final[gfirst + i] = s_gid[s_perm[0][i]];
+	for (uint32_t id = s_node_next + tid; id < s_node_end; id += RTK_SAH_SMALL_THREADS) {
+		s.first[id] = 0; s.last[id] = -1; s.left[id] = -1; s.right[id] = -1;      // reserved, not used: an empty range
+	}
 }
 
 // final leaf order as original triangle numbers

@@ -31,7 +31,8 @@ static int g_reserved_sms = 0;      // SMs the persistent traversal grid leaves 
 static size_t g_l2_bytes = 0;
 static size_t g_l2_window_max = 0;  // largest access-policy window the device accepts (0: no L2 persistence)
 static size_t g_l2_setaside = 0;    // L2 bytes set aside for persisting lines
-static int g_sah_sort_bits = 32;    // RTK_B200_SAH_SORT_BITS (8, 16, 24 or 32): Morton bits the SAH builder's input order is sorted by
+static int g_sah_sort_bits = 24;    // RTK_B200_SAH_SORT_BITS (8, 16, 24 or 32): Morton bits the SAH builder's input order is sorted by (8 per axis:
+                                    // the order only buys locality, the tree does not depend on it; 32 -> 24 bits: 1.69 -> 1.65 ms at 1M triangles, 12.4 -> 12.1 at 10M)
 static int g_l2_persist = 0;        // RTK_B200_L2_PERSIST=1: persisting L2 window over nodes + leaf slots.  Off by default --
                                     // measured on C3/C4: k_trace gains nothing (1705 vs 1704 Mrays/s), while k_resolve, whose
                                     // corner gathers lose the set-aside part of the L2, goes from 0.47 to 1.10 ms per batch
@@ -931,6 +932,7 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 		B.h.small_list = A.take<uint32_t>(B.small_cap);
 		B.h.chunk_base = A.take<uint32_t>(B.act_cap + 1);
 		B.h.bins = A.take<uint32_t>(B.act_cap * RTK_SAH_NODEBINS);
+		B.h.binpack = A.take<uint32_t>(n);
 		B.h.split = A.take<int4>(B.act_cap); B.h.cursor = A.take<uint32_t>(2 * B.act_cap);
 		B.h.node_cap = (uint32_t)cap2;
 		B.h.act_cap = (uint32_t)B.act_cap; B.h.small_cap = (uint32_t)B.small_cap;
@@ -979,7 +981,7 @@ static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, 
 		const uint32_t chunk_bound = max_chunks + act_bound;
 		if (depth == 0) { RTK_LAUNCH(k_sah_bins_clear, act_bound, 128, st, h); CK_LAUNCH(); }      // later levels: cleared by the partition kernel of the level above
 		RTK_LAUNCH(k_sah_bin_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
-		RTK_LAUNCH(k_sah_split_large, (act_bound + 3) / 4, 128, st, h, depth, src_buf ^ 1); CK_LAUNCH();
+		RTK_LAUNCH(k_sah_split_large, act_bound, 96, st, h, depth, src_buf ^ 1); CK_LAUNCH();
 		RTK_LAUNCH(k_sah_partition_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
 		uint32_t *tmp = h.act_in; h.act_in = h.act_out; h.act_out = tmp;
 		RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();

@@ -480,6 +480,24 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 		nleaf[best] = q & 15; nleaf[ns] = q >> 4;
 		ns++;
 	}
+	// boxes and ranges of the slots: independent loads, issued before the allocation below so that they are in
+	// flight while the warp waits for its atomics
+	float4 lo[RTK_WIDE], hi[RTK_WIDE];
+	uint32_t first[RTK_WIDE], count[RTK_WIDE];
+#pragma unroll
+	for (int k = 0; k < RTK_WIDE; k++) {
+		lo[k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, 0.0f);
+		hi[k] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
+		first[k] = 0; count[k] = 0;
+		if (k < ns) {
+			const int c = slot[k];
+			lo[k] = t.blo[RTK_BIDX(c, n)]; hi[k] = t.bhi[RTK_BIDX(c, n)];
+			if (!(area[k] >= 0.0f)) {
+				first[k] = c >= 0 ? (uint32_t)t.first[c] : (uint32_t)~c;
+				count[k] = c >= 0 ? (uint32_t)(t.last[c] - t.first[c] + 1) : 1u;
+			}
+		}
+	}
 	// One allocation per kind for the whole WARP (it used to be two returning atomics per child, one after the
 	// other; then one set per node -- still thousands of atomics on the same three addresses from the threads of
 	// a level, which finish together): the children of a node get consecutive numbers, its leaves consecutive slots.
@@ -506,23 +524,6 @@ __global__ void k_collapse(rtkd_collapse_args a, rtkd_bvh2 t)
 	uint32_t idx = base_idx + (excl & 0xffffu);
 	uint32_t o = base_o + (excl & 0xffffu);
 	uint32_t lslot = base_l + (excl >> 16);
-	// boxes and ranges of the slots: independent loads, all in flight before the first store
-	float4 lo[RTK_WIDE], hi[RTK_WIDE];
-	uint32_t first[RTK_WIDE], count[RTK_WIDE];
-#pragma unroll
-	for (int k = 0; k < RTK_WIDE; k++) {
-		lo[k] = make_float4(+RTK_INF_F, +RTK_INF_F, +RTK_INF_F, 0.0f);
-		hi[k] = make_float4(-RTK_INF_F, -RTK_INF_F, -RTK_INF_F, 0.0f);
-		first[k] = 0; count[k] = 0;
-		if (k < ns) {
-			const int c = slot[k];
-			lo[k] = t.blo[RTK_BIDX(c, n)]; hi[k] = t.bhi[RTK_BIDX(c, n)];
-			if (!(area[k] >= 0.0f)) {
-				first[k] = c >= 0 ? (uint32_t)t.first[c] : (uint32_t)~c;
-				count[k] = c >= 0 ? (uint32_t)(t.last[c] - t.first[c] + 1) : 1u;
-			}
-		}
-	}
 	if (idx + n_open > a.node_cap) { atomicOr(a.err, 1u); idx = 0; }
 	if (lslot + n_leafs > RTK_MAX_LEAVES) { atomicOr(a.err, 2u); lslot = 0; }
 	float4 *node = a.nodes + 16ull * dst;

@@ -30,6 +30,9 @@
 #endif
 #define RTK_SAH_SMALL 512
 #define RTK_SAH_CHUNK 2048
+#ifndef RTK_SAH_COMPACT_MIN
+#define RTK_SAH_COMPACT_MIN 32768    // large nodes of at least this many triangles are binned a warp per 32 consecutive positions
+#endif
 #define RTK_SAH_MAX_DEPTH 64          // RTK_BVH_MAX_DEPTH, rtk.c:5
 #define RTK_SAH_BINWORDS 8            // lo xyz, hi xyz, count, pad
 #define RTK_SAH_NODEBINS (3 * RTK_SAH_BINS * RTK_SAH_BINWORDS)
@@ -49,6 +52,7 @@ struct rtkd_sah {
 	uint32_t *act_in, *act_out;   // large nodes of this / the next level
 	uint32_t *small_list;         // node id | (buffer << 31)
 	uint32_t *chunk_base;         // [n_act + 1] exclusive scan of chunk counts
+	uint32_t *chunk_node;         // [chunks] the active node each chunk belongs to
 	uint32_t *bins;               // [n_act][3][8][32]
 	uint32_t *binpack;            // [n] the three bins of the triangle at each position of the level's permutation (large levels)
 	int4 *split;                  // per active node: axis (-1: equal split), bin, n_left, first child
@@ -78,7 +82,7 @@ RTK_DEV void rtk_sah_bins_clear(uint32_t *bins, int tid, int nthreads)
 }
 
 // add one AABB to the three axes' bins (shared or global memory)
-RTK_DEV void rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi)
+RTK_DEV uint32_t rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi)
 {
 	int b[3];
 	b[0] = rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x);
@@ -92,6 +96,7 @@ RTK_DEV void rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nlo, f
 		atomicMax(p + 3 * RTK_SAH_BINS, oh[0]); atomicMax(p + 4 * RTK_SAH_BINS, oh[1]); atomicMax(p + 5 * RTK_SAH_BINS, oh[2]);
 		atomicAdd(p + 6 * RTK_SAH_BINS, 1u);
 	}
+	return (uint32_t)(b[0] | (b[1] << 8) | (b[2] << 16));
 }
 
 #if RTK_SAH_BIN_HYBRID
@@ -386,7 +391,14 @@ __global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, const uint32_t *a
 		uint32_t woff = 0;
 		for (int w = 0; w < warp; w++) woff += s_warp[w];
 		uint32_t carry = s_carry;
-		if (a < n_act) s.chunk_base[a] = carry + woff + x - v;
+		if (a < n_act) {
+			// the map from chunk to node, so that the level's blocks find their node with one load (a binary search
+			// over chunk_base by one thread of each block -- a dozen dependent loads with the rest of the block
+			// waiting -- was a third of the binning kernel's time on the deep levels)
+			const uint32_t c0 = carry + woff + x - v;
+			s.chunk_base[a] = c0;
+			for (uint32_t c = 0; c < v; c++) s.chunk_node[c0 + c] = a;
+		}
 		__syncthreads();
 		if (threadIdx.x == 1023) s_carry = carry + woff + x;
 		__syncthreads();
@@ -395,16 +407,6 @@ __global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, const uint32_t *a
 	// device: the host launches upper-bound grids and does not wait for them); counters[1] starts the next list
 	__syncthreads();
 	if (threadIdx.x == 0) { s.chunk_base[n_act] = s_carry; s.counters[5] = s_carry; s.counters[6] = n_act; s.counters[1] = 0; }
-}
-
-RTK_DEV uint32_t rtk_sah_find_node(const uint32_t *chunk_base, uint32_t n_act, uint32_t chunk)
-{
-	uint32_t lo = 0, hi = n_act;          // largest a with chunk_base[a] <= chunk
-	while (hi - lo > 1) {
-		uint32_t mid = (lo + hi) >> 1;
-		if (chunk_base[mid] <= chunk) lo = mid; else hi = mid;
-	}
-	return lo;
 }
 
 __global__ void k_sah_bins_clear(rtkd_sah s)
@@ -416,29 +418,37 @@ __global__ void k_sah_bins_clear(rtkd_sah s)
 __global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf)
 {
 	__shared__ uint32_t s_bins[RTK_SAH_NODEBINS];
-	__shared__ uint32_t s_a;
 	if (blockIdx.x >= s.counters[5]) return;                 // the grid is an upper bound on the level's chunks
-	const uint32_t n_act = s.counters[6];
-	if (threadIdx.x == 0) s_a = rtk_sah_find_node(s.chunk_base, n_act, blockIdx.x);
+	const uint32_t a = s.chunk_node[blockIdx.x];
 	rtk_sah_bins_clear(s_bins, threadIdx.x, 256);
 	__syncthreads();
-	const uint32_t a = s_a;
 	const uint32_t node = s.act_in[a];
 	const uint32_t first = (uint32_t)s.first[node], last = (uint32_t)s.last[node];
 	const uint32_t begin = first + (blockIdx.x - s.chunk_base[a]) * RTK_SAH_CHUNK;
 	const uint32_t end = rtk_umin(begin + RTK_SAH_CHUNK, last + 1);
 	const float4 nlo = s.blo[node], nhi = s.bhi[node];
 	const uint32_t *idx = src_buf ? s.idx1 : s.idx0;
-	// four 256-triangle rows at a time: the index loads, then the dependent box gathers, are all in
+	// four triangles per thread at a time: the index loads, then the dependent box gathers, are all in
 	// flight together before the first bin is touched (the kernel was bound by that two-load latency
 	// chain, 8 times per chunk).  The trip count is warp-uniform.
-	for (uint32_t base = begin; base < end; base += 256 * 4) {
-		uint32_t j[4];
+	// Two ways of dealing the chunk's positions to the lanes.  Large nodes (the upper levels): a warp takes 32
+	// consecutive positions, Morton neighbours, which share bins -- the warp reduces each group with REDUX.  Smaller
+	// nodes: the bins are narrower than such a cluster but not by much, groups of 4-8 lanes are too small for the
+	// reductions to pay and too large for the shared-memory atomics (same-address updates serialise); there a lane
+	// takes positions 64 apart from its neighbours' and the warp's triangles mostly fall into different bins
+	// (measured per level at 1M triangles, consecutive / spread: 24 / 26 us on the root, 27 / 46 on level 1, 36 / 30
+	// on level 7).
+	const bool compact = last - first + 1 >= RTK_SAH_COMPACT_MIN;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (uint32_t it = 0; it < RTK_SAH_CHUNK / 1024; it++) {
+		if (begin + it * 1024 >= end && compact) break;
+		uint32_t j[4], pos[4];
 		bool valid[4];
 		float4 lo[4], hi[4];
 #pragma unroll
 		for (int u = 0; u < 4; u++) {
-			const uint32_t p = base + u * 256 + threadIdx.x;
+			const uint32_t p = compact ? begin + it * 1024 + u * 256 + threadIdx.x : begin + lane * (RTK_SAH_CHUNK / 32) + warp * 8 + it * 4 + u;
+			pos[u] = p;
 			valid[u] = p < end;
 			j[u] = valid[u] ? idx[p] : 0u;
 		}
@@ -450,8 +460,10 @@ __global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf)
 #pragma unroll
 		for (int u = 0; u < 4; u++) {
 			// the partition kernel of this level reads the bins back (coalesced) instead of gathering the boxes again
-			const uint32_t packed = rtk_sah_bin_add_warp(s_bins, lo[u], hi[u], nlo, nhi, valid[u]);
-			if (valid[u]) s.binpack[base + u * 256 + threadIdx.x] = packed;
+			uint32_t packed = 0;
+			if (compact) packed = rtk_sah_bin_add_warp(s_bins, lo[u], hi[u], nlo, nhi, valid[u]);
+			else if (valid[u]) packed = rtk_sah_bin_add(s_bins, lo[u], hi[u], nlo, nhi);
+			if (valid[u]) s.binpack[pos[u]] = packed;
 		}
 	}
 	__syncthreads();
@@ -524,7 +536,7 @@ __global__ void __launch_bounds__(96) k_sah_split_large(rtkd_sah s, uint32_t dep
 
 __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, int src_buf)
 {
-	__shared__ uint32_t s_a, s_cntl[8], s_basel, s_baser;
+	__shared__ uint32_t s_cntl[8], s_basel, s_baser;
 	// the bins of the NEXT level's nodes are cleared here (counters[1] is final once k_sah_split_large has run; this
 	// level's bins have been read): a launch less per level.  There are never more than twice as many nodes on the
 	// next level as there are blocks in this grid (the host launches at least one block per node of this level).
@@ -534,10 +546,7 @@ __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, int src
 			rtk_sah_bins_clear(s.bins + (size_t)a2 * RTK_SAH_NODEBINS, threadIdx.x, 256);
 	}
 	if (blockIdx.x >= s.counters[5]) return;
-	const uint32_t n_act = s.counters[6];
-	if (threadIdx.x == 0) s_a = rtk_sah_find_node(s.chunk_base, n_act, blockIdx.x);
-	__syncthreads();
-	const uint32_t a = s_a;
+	const uint32_t a = s.chunk_node[blockIdx.x];
 	const uint32_t node = s.act_in[a];
 	const int4 sp = s.split[a];
 	const uint32_t first = (uint32_t)s.first[node], last = (uint32_t)s.last[node];
@@ -647,9 +656,16 @@ RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *
 			rtk_sah_bin_add_warp(bins, s_lo[k], s_hi[k], nlo, nhi, valid);
 		}
 	} else {
-		for (uint32_t i = tid; i < t.count; i += nthreads) {
-			uint32_t k = perm0[t.begin + i];
-			rtk_sah_bin_add(bins, s_lo[k], s_hi[k], nlo, nhi);
+		// transposed walk: the lanes of a warp take triangles count/32 apart.  Neighbours in the (Morton-like) order
+		// share bins, and 32 lanes updating 2 or 3 addresses serialise in the shared-memory atomics; triangles
+		// from 32 different stretches of the range mostly fall into different bins.
+		const uint32_t rows = (t.count + 31u) / 32u;
+		for (uint32_t i = tid; i < rows * 32u; i += nthreads) {
+			const uint32_t e = (i & 31u) * rows + (i >> 5);
+			if (e < t.count) {
+				const uint32_t k = perm0[t.begin + e];
+				rtk_sah_bin_add(bins, s_lo[k], s_hi[k], nlo, nhi);
+			}
 		}
 	}
 	RTK_SYNC();

@@ -931,6 +931,7 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 		B.h.act_in = A.take<uint32_t>(B.act_cap); B.h.act_out = A.take<uint32_t>(B.act_cap);
 		B.h.small_list = A.take<uint32_t>(B.small_cap);
 		B.h.chunk_base = A.take<uint32_t>(B.act_cap + 1);
+		B.h.chunk_node = A.take<uint32_t>((size_t)n / RTK_SAH_CHUNK + 1 + B.act_cap);
 		B.h.bins = A.take<uint32_t>(B.act_cap * RTK_SAH_NODEBINS);
 		B.h.binpack = A.take<uint32_t>(n);
 		B.h.split = A.take<int4>(B.act_cap); B.h.cursor = A.take<uint32_t>(2 * B.act_cap);

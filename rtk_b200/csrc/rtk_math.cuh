@@ -18,6 +18,10 @@ struct rtk_ray_ctx {
 	float min_t;
 };
 
+#ifndef RTK_TRI_SUB_FIRST
+#define RTK_TRI_SUB_FIRST 1     // 1: the triangle test subtracts the (unpermuted) origin before the axis permutation
+#endif
+
 RTK_DEV float rtk_fast_rcp(float x)
 {
 #ifdef RTK_SIMT_EMU
@@ -45,9 +49,13 @@ RTK_DEV void rtk_ray_setup(rtk_ray_ctx &r, float ox, float oy, float oz, float d
 	r.sx = __fdiv_rn(-dkx, dkz);      // rtk.c:561
 	r.sy = __fdiv_rn(-dky, dkz);      // rtk.c:562
 	r.sz = __fdiv_rn(1.0f, dkz);      // rtk.c:563
+#if RTK_TRI_SUB_FIRST
+	r.ox = ox; r.oy = oy; r.oz = oz;  // unpermuted: rtk_tri_test translates first, then permutes
+#else
 	r.ox = rtk_sel3(ox, oy, oz, kx);  // rtk.c:564-566
 	r.oy = rtk_sel3(ox, oy, oz, ky);
 	r.oz = rtk_sel3(ox, oy, oz, kz);
+#endif
 	r.min_t = min_t;
 
 	// Conservative box test (DESIGN.md "node test").  The triangle test rounds in fp32, so it
@@ -119,12 +127,16 @@ RTK_DEV void rtk_ray_node_ctx(rtk_ray_ctx &r, float4 q0, float4 q1, float4 q2, f
 RTK_DEV void rtk_ray_tri_ctx(rtk_ray_ctx &r, float4 q0, float4 q1)
 {
 	const int kz = (int)(__float_as_uint(q1.w) & 3u);
+	r.kz = kz;
+#if RTK_TRI_SUB_FIRST
+	r.ox = q0.x; r.oy = q0.y; r.oz = q0.z;
+#else
 	const int kx = kz == 2 ? 0 : kz + 1;
 	const int ky = kx == 2 ? 0 : kx + 1;
-	r.kz = kz;
 	r.ox = rtk_sel3(q0.x, q0.y, q0.z, kx);                  // rtk.c:564-566
 	r.oy = rtk_sel3(q0.x, q0.y, q0.z, ky);
 	r.oz = rtk_sel3(q0.x, q0.y, q0.z, kz);
+#endif
 	r.sx = q1.x; r.sy = q1.y; r.sz = q1.z;
 	r.min_t = q0.w;
 }
@@ -137,6 +149,13 @@ RTK_DEV bool rtk_tri_test(const rtk_ray_ctx &r, float4 p0, float4 p1, float4 p2,
                           float &t_out, float &u_out, float &v_out)
 {
 	const int kz = r.kz;
+#if RTK_TRI_SUB_FIRST
+	// translate (rtk.c:256-280) BEFORE the axis permutation: component-wise, so the same nine differences, and the
+	// origin needs no permutation of its own
+	p0.x = __fsub_rn(p0.x, r.ox); p0.y = __fsub_rn(p0.y, r.oy); p0.z = __fsub_rn(p0.z, r.oz);
+	p1.x = __fsub_rn(p1.x, r.ox); p1.y = __fsub_rn(p1.y, r.oy); p1.z = __fsub_rn(p1.z, r.oz);
+	p2.x = __fsub_rn(p2.x, r.ox); p2.y = __fsub_rn(p2.y, r.oy); p2.z = __fsub_rn(p2.z, r.oz);
+#endif
 	// axis permutation (the reference's pshufb, rtk.c:232-243)
 	float a0x = kz == 0 ? p0.y : (kz == 1 ? p0.z : p0.x);
 	float a0y = kz == 0 ? p0.z : (kz == 1 ? p0.x : p0.y);
@@ -147,10 +166,12 @@ RTK_DEV bool rtk_tri_test(const rtk_ray_ctx &r, float4 p0, float4 p1, float4 p2,
 	float a2x = kz == 0 ? p2.y : (kz == 1 ? p2.z : p2.x);
 	float a2y = kz == 0 ? p2.z : (kz == 1 ? p2.x : p2.y);
 	float a2z = kz == 0 ? p2.x : (kz == 1 ? p2.y : p2.z);
+#if !RTK_TRI_SUB_FIRST
 	// translate, rtk.c:256-280
 	a0x = __fsub_rn(a0x, r.ox); a0y = __fsub_rn(a0y, r.oy); a0z = __fsub_rn(a0z, r.oz);
 	a1x = __fsub_rn(a1x, r.ox); a1y = __fsub_rn(a1y, r.oy); a1z = __fsub_rn(a1z, r.oz);
 	a2x = __fsub_rn(a2x, r.ox); a2y = __fsub_rn(a2y, r.oy); a2z = __fsub_rn(a2z, r.oz);
+#endif
 	// shear, rtk.c:284-292 (separate multiply and add)
 	float x0 = __fadd_rn(a0x, __fmul_rn(r.sx, a0z));
 	float y0 = __fadd_rn(a0y, __fmul_rn(r.sy, a0z));

@@ -84,9 +84,11 @@ WORKLOADS = {
 # write by construction, not a counter
 BUILD_BYTES_PER_TRI = {
     "decode (36 + 12 idx in, 48 out)": 96, "scene bounds": 48, "morton (48 in, 12 out)": 60,
-    "radix sort, 4 passes x (hist 8 + scatter 20 in + 12 out)": 160, "prim bounds (48 in, 36 out)": 84,
-    "binned SAH, large levels (~13 x 76 on the shrinking large set, measured average 5.5 full passes)": 420,
-    "small subtrees (36 in, 4 out)": 40, "collapse + leaf emission (~64 + 52 in, ~80 + 51 out)": 247,
+    "radix sort, 3 passes x (hist 8 + scatter 20 in + 12 out)": 120, "prim bounds (48 in, 36 out)": 84,
+    "binned SAH, large levels (~13 x 52: binning 4 + 32 in, 4 out; partition 8 in, 4 out; on the shrinking large set, "
+    "measured average 5.5 full passes)": 286,
+    "small subtrees (36 in, 4 out)": 40, "collapse records (0.4 binary nodes per triangle x (40 in, 17 out))": 23,
+    "collapse + leaf emission (~64 + 52 in, ~80 + 51 out)": 247,
 }
 
 

@@ -124,6 +124,36 @@ def case_config(lib, orc, name, scale, nrays, mode=None):
     return int(m.sum())
 
 
+# (scene, build mode) -> wide nodes, leaves, depth, SAH cost.  The builders are deterministic functions of the triangle
+# SET (bins, counts and boxes do not depend on the order the triangles arrive in), so these numbers only move when
+# the algorithm does: a guard for the restructurings of the build kernels, which must leave the trees alone.
+TREE_STATS = {
+    ("terrain 200x100", 1): (1353, 5217, 6, 9.980880375670187),
+    ("terrain 200x100", 0): (1638, 7828, 7, 24.284567995333656),
+    ("soup 30000", 1): (771, 3853, 5, 30.131097424911744),
+    ("soup 30000", 0): (1473, 5396, 6, 32.72317522549396),
+    ("terrain 40x30", 1): (74, 310, 4, 6.014886789363808),
+    ("terrain 40x30", 0): (104, 474, 5, 11.919080584366526),
+}
+
+
+def case_tree_stats(lib):
+    made = {"terrain 200x100": lambda: scenes.terrain(200, 100), "soup 30000": lambda: scenes.soup(30000),
+            "terrain 40x30": lambda: scenes.terrain(40, 30)}
+    try:
+        for (name, mode), (nodes, leaves, depth, cost) in TREE_STATS.items():
+            sc = lib.build_scene(made[name]()["meshes"], mode=mode)
+            try:
+                i = sc.info()
+                got = (int(i.num_wide_nodes), int(i.num_leaves), int(i.wide_depth))
+                assert got == (nodes, leaves, depth), f"{name}, mode {mode}: tree {got}, expected {(nodes, leaves, depth)}"
+                assert abs(i.sah_cost - cost) <= 1e-9 * cost, f"{name}, mode {mode}: SAH cost {i.sah_cost!r}, expected {cost!r}"
+            finally:
+                sc.free()
+    finally:
+        lib.rtk_cuda_set_build_mode(api.RTK_CUDA_BUILD_SAH)     # the library's default
+
+
 def case_edge_scenes(lib, orc):
     ray = np.zeros(4, dtype=api.RAY_DTYPE)
     ray["o"] = [(0.25, 0.25, 0), (0.25, 0.25, 0), (5, 5, 0), (0.25, 0.25, 2)]

@@ -15,6 +15,10 @@ def test_configs_small(emu_lib, orc, name, scale, nrays):
     assert pc.case_config(emu_lib, orc, name, scale, nrays) > 0
 
 
+def test_trees_are_what_they_were(emu_lib):
+    pc.case_tree_stats(emu_lib)
+
+
 def test_edge_scenes(emu_lib, orc):
     pc.case_edge_scenes(emu_lib, orc)
 

@@ -31,6 +31,11 @@ def test_build_modes(gpu_lib, orc, mode):
     gpu_lib.rtk_cuda_set_build_mode(api.RTK_CUDA_BUILD_LBVH)
 
 
+def test_trees_are_what_they_were(gpu_lib):
+    """the device builds the trees the emulator builds from the same sources (and built before the build kernels were restructured)"""
+    pc.case_tree_stats(gpu_lib)
+
+
 def test_edge_scenes(gpu_lib, orc):
     pc.case_edge_scenes(gpu_lib, orc)
 

@@ -25,9 +25,6 @@
 #include "k_build.cuh"
 
 #define RTK_SAH_BINS 32
-#ifndef RTK_SAH_BIN_HYBRID
-#define RTK_SAH_BIN_HYBRID 1
-#endif
 #define RTK_SAH_SMALL 512
 #define RTK_SAH_CHUNK 2048
 #ifndef RTK_SAH_COMPACT_MIN
@@ -48,11 +45,13 @@ struct rtkd_sah {
 	int *left, *right, *first, *last;
 	float4 *blo, *bhi;
 	uint32_t *ndepth;
-	uint32_t *counters;           // [0] node_alloc [1] n_act_out [2] n_small [3] err [4] unused [5] chunks, [6] nodes of the level
+	uint32_t *counters;           // [0] node_alloc [2] n_small [3] err; [8 + 2 * (level & 1)] large nodes, [9 + 2 * (level & 1)] chunks of a level
 	uint32_t *act_in, *act_out;   // large nodes of this / the next level
 	uint32_t *small_list;         // node id | (buffer << 31)
-	uint32_t *chunk_base;         // [n_act + 1] exclusive scan of chunk counts
-	uint32_t *chunk_node;         // [chunks] the active node each chunk belongs to
+	uint32_t *chunk_base;         // [n_act] first chunk of each active node of this level
+	uint32_t *chunk_node;         // [chunks] the active node each chunk of this level belongs to
+	uint32_t *chunk_base_out, *chunk_node_out;   // the same for the next level (filled by k_sah_split_large)
+	uint32_t chunk_cap;           // capacity of chunk_node
 	uint32_t *bins;               // [n_act][3][8][32]
 	uint32_t *binpack;            // [n] the three bins of the triangle at each position of the level's permutation (large levels)
 	int4 *split;                  // per active node: axis (-1: equal split), bin, n_left, first child
@@ -60,6 +59,9 @@ struct rtkd_sah {
 	uint32_t node_cap;
 	uint32_t act_cap, small_cap;  // capacities of act_in / act_out and small_list (never reached: see carve(); guarded all the same)
 };
+
+#define RTK_SAH_LEVEL_NODES(s, par) ((s).counters[8 + 2 * (par)])
+#define RTK_SAH_LEVEL_CHUNKS(s, par) ((s).counters[9 + 2 * (par)])
 
 // bin of a triangle on one axis, rtk.c:892-902
 RTK_DEV int rtk_sah_bin(float lo, float hi, float nmin, float nmax)
@@ -99,7 +101,6 @@ RTK_DEV uint32_t rtk_sah_bin_add(uint32_t *bins, float4 lo, float4 hi, float4 nl
 	return (uint32_t)(b[0] | (b[1] << 8) | (b[2] << 16));
 }
 
-#if RTK_SAH_BIN_HYBRID
 #ifndef RTK_SAH_REDUX_MIN
 #define RTK_SAH_REDUX_MIN 6          // lanes that must share a bin before the warp reduces them with REDUX
 #endif
@@ -152,45 +153,6 @@ RTK_DEV uint32_t rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, floa
 	}
 	return (uint32_t)(b[0] | (b[1] << 8) | (b[2] << 16));
 }
-#else
-// Warp-cooperative variant (all 32 lanes call it; `valid` masks lanes without a triangle).  In
-// the upper levels a warp's 32 Morton-neighbours almost always fall into the same bin on every
-// axis: then the warp reduces its boxes with shuffles and one lane issues the 21 atomics instead
-// of 32 lanes fighting over the same 21 addresses.
-RTK_DEV uint32_t rtk_sah_bin_add_warp(uint32_t *bins, float4 lo, float4 hi, float4 nlo, float4 nhi, bool valid)
-{
-	const uint32_t FULL = 0xffffffffu;
-	const int lane = threadIdx.x & 31;
-	int b0 = rtk_sah_bin(lo.x, hi.x, nlo.x, nhi.x), b1 = rtk_sah_bin(lo.y, hi.y, nlo.y, nhi.y), b2 = rtk_sah_bin(lo.z, hi.z, nlo.z, nhi.z);
-	uint32_t code = valid ? (uint32_t)(b0 | (b1 << 8) | (b2 << 16)) : 0xffffffffu;
-	uint32_t vm = __ballot_sync(FULL, valid);
-	if (vm == 0) return 0u;
-	const uint32_t packed = (uint32_t)(b0 | (b1 << 8) | (b2 << 16));
-	uint32_t first_code = __shfl_sync(FULL, code, __ffs(vm) - 1);
-	bool uniform = __all_sync(FULL, !valid || code == first_code);
-	if (!uniform) {
-		if (valid) rtk_sah_bin_add(bins, lo, hi, nlo, nhi);
-		return packed;
-	}
-	float v[6] = { valid ? lo.x : +RTK_INF_F, valid ? lo.y : +RTK_INF_F, valid ? lo.z : +RTK_INF_F,
-	               valid ? hi.x : -RTK_INF_F, valid ? hi.y : -RTK_INF_F, valid ? hi.z : -RTK_INF_F };
-	for (int o = 16; o > 0; o >>= 1) {
-		for (int k = 0; k < 3; k++) v[k] = rtk_fmin(v[k], __shfl_xor_sync(FULL, v[k], o));
-		for (int k = 3; k < 6; k++) v[k] = rtk_fmax(v[k], __shfl_xor_sync(FULL, v[k], o));
-	}
-	if (lane == 0) {
-		int b[3] = { (int)(first_code & 255u), (int)((first_code >> 8) & 255u), (int)((first_code >> 16) & 255u) };
-		uint32_t cnt = (uint32_t)__popc(vm);
-		for (int a = 0; a < 3; a++) {
-			uint32_t *p = bins + RTK_SAH_BIN_AT(a, b[a], 0);
-			atomicMin(p + 0 * RTK_SAH_BINS, rtk_f2ord(v[0])); atomicMin(p + 1 * RTK_SAH_BINS, rtk_f2ord(v[1])); atomicMin(p + 2 * RTK_SAH_BINS, rtk_f2ord(v[2]));
-			atomicMax(p + 3 * RTK_SAH_BINS, rtk_f2ord(v[3])); atomicMax(p + 4 * RTK_SAH_BINS, rtk_f2ord(v[4])); atomicMax(p + 5 * RTK_SAH_BINS, rtk_f2ord(v[5]));
-			atomicAdd(p + 6 * RTK_SAH_BINS, cnt);
-		}
-	}
-	return packed;
-}
-#endif
 
 struct rtk_sah_choice {
 	int axis, bin;               // axis < 0: no valid split
@@ -345,80 +307,42 @@ __global__ void k_sah_prim_bounds(const float4 *tri_orig, const uint32_t *svals,
 	idx0[j] = j;
 }
 
-// root node from the scene bounds
+// root node from the scene bounds; one warp (the lanes fill the root's chunk table)
 __global__ void k_sah_root(rtkd_sah s, const uint32_t *bounds, uint32_t n)
 {
-	if (threadIdx.x || blockIdx.x) return;
+	if (blockIdx.x) return;
+	const uint32_t chunks = n > RTK_SAH_SMALL ? (n + RTK_SAH_CHUNK - 1) / RTK_SAH_CHUNK : 0u;
+	for (uint32_t c = threadIdx.x; c < chunks && c < s.chunk_cap; c += blockDim.x) s.chunk_node[c] = 0;
+	if (threadIdx.x) return;
 	s.first[0] = 0; s.last[0] = (int)n - 1; s.left[0] = -1; s.right[0] = -1; s.ndepth[0] = 0;
 	s.blo[0] = make_float4(rtk_ord2f(bounds[0]), rtk_ord2f(bounds[1]), rtk_ord2f(bounds[2]), 0.0f);
 	s.bhi[0] = make_float4(rtk_ord2f(bounds[3]), rtk_ord2f(bounds[4]), rtk_ord2f(bounds[5]), 0.0f);
-	s.counters[0] = 1; s.counters[1] = 0; s.counters[2] = 0; s.counters[3] = 0; s.counters[4] = 0;
-	s.counters[5] = 0; s.counters[6] = 0;
-	if (n > RTK_SAH_SMALL) { s.act_in[0] = 0; s.counters[1] = 1; }
+	for (int k = 0; k < 12; k++) s.counters[k] = 0;
+	s.counters[0] = 1;
+	if (n > RTK_SAH_SMALL) { s.act_in[0] = 0; s.chunk_base[0] = 0; RTK_SAH_LEVEL_NODES(s, 0) = 1; RTK_SAH_LEVEL_CHUNKS(s, 0) = chunks; }
 	else { s.small_list[0] = 0; s.counters[2] = 1; }
 }
 
 // ---------------------------------------------------------------------------------------------
-// large nodes, one level
+// large nodes, one level.  `par` = level & 1 selects the level's pair of counters (nodes, chunks); the kernels of a
+// level are launched with upper-bound grids and read the pair on the device.  k_sah_split_large builds the NEXT
+// level's node list, chunk table (chunk -> node, node -> first chunk) and counters with atomics as it emits the
+// children -- the order of the nodes within a level is irrelevant -- so there is no planning kernel between the
+// levels (a single-block scan, 4.6 us x 14 levels of a 1M-triangle build).  k_sah_bin_large zeroes the next pair
+// before that: its level's predecessor, which used the pair, has finished.
 // ---------------------------------------------------------------------------------------------
 
-// chunk table of the level about to run: chunk_base[a] = first chunk of active node a.  Single
-// block; reads the number of active nodes from counters[1] and leaves it in counters[6], the chunk
-// total in counters[5].
-__global__ void __launch_bounds__(1024) k_sah_plan(rtkd_sah s, const uint32_t *act)
+__global__ void k_sah_bins_clear(rtkd_sah s, int par)
 {
-	__shared__ uint32_t s_warp[32];
-	__shared__ uint32_t s_carry;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t n_act = s.counters[1];
-	if (threadIdx.x == 0) s_carry = 0;
-	__syncthreads();
-	for (uint32_t base = 0; base < n_act; base += 1024) {
-		uint32_t a = base + threadIdx.x;
-		uint32_t v = 0;
-		if (a < n_act) {
-			uint32_t node = act[a];
-			uint32_t cnt = (uint32_t)(s.last[node] - s.first[node] + 1);
-			v = (cnt + RTK_SAH_CHUNK - 1) / RTK_SAH_CHUNK;
-		}
-		uint32_t x = v;
-		for (int o = 1; o < 32; o <<= 1) {
-			uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-			if (lane >= o) x += y;
-		}
-		if (lane == 31) s_warp[warp] = x;
-		__syncthreads();
-		uint32_t woff = 0;
-		for (int w = 0; w < warp; w++) woff += s_warp[w];
-		uint32_t carry = s_carry;
-		if (a < n_act) {
-			// the map from chunk to node, so that the level's blocks find their node with one load (a binary search
-			// over chunk_base by one thread of each block -- a dozen dependent loads with the rest of the block
-			// waiting -- was a third of the binning kernel's time on the deep levels)
-			const uint32_t c0 = carry + woff + x - v;
-			s.chunk_base[a] = c0;
-			for (uint32_t c = 0; c < v; c++) s.chunk_node[c0 + c] = a;
-		}
-		__syncthreads();
-		if (threadIdx.x == 1023) s_carry = carry + woff + x;
-		__syncthreads();
-	}
-	// counters[6] / [5]: nodes and chunks of the level about to run (the kernels of the level read them on the
-	// device: the host launches upper-bound grids and does not wait for them); counters[1] starts the next list
-	__syncthreads();
-	if (threadIdx.x == 0) { s.chunk_base[n_act] = s_carry; s.counters[5] = s_carry; s.counters[6] = n_act; s.counters[1] = 0; }
-}
-
-__global__ void k_sah_bins_clear(rtkd_sah s)
-{
-	if (blockIdx.x >= s.counters[6]) return;
+	if (blockIdx.x >= RTK_SAH_LEVEL_NODES(s, par)) return;
 	rtk_sah_bins_clear(s.bins + (size_t)blockIdx.x * RTK_SAH_NODEBINS, threadIdx.x, blockDim.x);
 }
 
-__global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf)
+__global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf, int par)
 {
 	__shared__ uint32_t s_bins[RTK_SAH_NODEBINS];
-	if (blockIdx.x >= s.counters[5]) return;                 // the grid is an upper bound on the level's chunks
+	if (blockIdx.x == 0 && threadIdx.x == 0) { RTK_SAH_LEVEL_NODES(s, par ^ 1) = 0; RTK_SAH_LEVEL_CHUNKS(s, par ^ 1) = 0; }
+	if (blockIdx.x >= RTK_SAH_LEVEL_CHUNKS(s, par)) return;  // the grid is an upper bound on the level's chunks
 	const uint32_t a = s.chunk_node[blockIdx.x];
 	rtk_sah_bins_clear(s_bins, threadIdx.x, 256);
 	__syncthreads();
@@ -480,8 +404,10 @@ __global__ void __launch_bounds__(256) k_sah_bin_large(rtkd_sah s, int src_buf)
 // children of a split node: allocate, fill, classify for the next step
 // `local_alloc`: a shared-memory cursor into node numbers the caller has reserved (k_sah_small), or NULL to take two
 // from the global counter
+// For a child that stays large (child_buf >= 0 only) `large[k]` receives its index in the next level's node list,
+// its first chunk and its number of chunks (the caller fills the chunk -> node map with all its threads).
 RTK_DEV void rtk_sah_emit_children(rtkd_sah &s, uint32_t node, const rtk_sah_choice &c, uint32_t depth,
-                                   int child_buf, uint32_t &child0, uint32_t *local_alloc = NULL)
+                                   int child_buf, uint32_t &child0, uint32_t *local_alloc = NULL, int par_next = 0, uint4 *large = NULL)
 {
 	uint32_t ch = local_alloc ? atomicAdd(local_alloc, 2u) : atomicAdd(&s.counters[0], 2u);
 	if (ch + 2 > s.node_cap) { atomicOr(&s.counters[3], 1u); ch = 0; }
@@ -498,8 +424,13 @@ RTK_DEV void rtk_sah_emit_children(rtkd_sah &s, uint32_t node, const rtk_sah_cho
 		s.left[id] = -1; s.right[id] = -1; s.ndepth[id] = depth + 1;
 		if (child_buf >= 0) {
 			if (cnt > RTK_SAH_SMALL) {
-				const uint32_t at = atomicAdd(&s.counters[1], 1u);
-				if (at < s.act_cap) s.act_out[at] = id; else atomicOr(&s.counters[3], 2u);
+				const uint32_t v = (cnt + RTK_SAH_CHUNK - 1) / RTK_SAH_CHUNK;
+				const uint32_t at = atomicAdd(&RTK_SAH_LEVEL_NODES(s, par_next), 1u);
+				const uint32_t c0 = atomicAdd(&RTK_SAH_LEVEL_CHUNKS(s, par_next), v);
+				if (at < s.act_cap && c0 + v <= s.chunk_cap) {
+					s.act_out[at] = id; s.chunk_base_out[at] = c0;
+					large[k] = make_uint4(at, c0, v, 0u);
+				} else atomicOr(&s.counters[3], 2u);
 			} else {
 				const uint32_t at = atomicAdd(&s.counters[2], 1u);
 				if (at < s.small_cap) s.small_list[at] = id | ((uint32_t)child_buf << 31); else atomicOr(&s.counters[3], 4u);
@@ -509,11 +440,12 @@ RTK_DEV void rtk_sah_emit_children(rtkd_sah &s, uint32_t node, const rtk_sah_cho
 }
 
 // one block of three warps per active large node: a warp per axis
-__global__ void __launch_bounds__(96) k_sah_split_large(rtkd_sah s, uint32_t depth, int dst_buf)
+__global__ void __launch_bounds__(96) k_sah_split_large(rtkd_sah s, uint32_t depth, int dst_buf, int par)
 {
 	__shared__ rtk_sah_choice s_cand[3];
+	__shared__ uint4 s_large[2];
 	const uint32_t a = blockIdx.x;
-	if (a >= s.counters[6]) return;
+	if (a >= RTK_SAH_LEVEL_NODES(s, par)) return;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t node = s.act_in[a];
 	const uint32_t count = (uint32_t)(s.last[node] - s.first[node] + 1);
@@ -528,24 +460,31 @@ __global__ void __launch_bounds__(96) k_sah_split_large(rtkd_sah s, uint32_t dep
 			rtk_sah_choice_none(c, plo, phi, count);
 		}
 		uint32_t ch;
-		rtk_sah_emit_children(s, node, c, depth, dst_buf, ch);
+		s_large[0] = make_uint4(0u, 0u, 0u, 0u); s_large[1] = make_uint4(0u, 0u, 0u, 0u);
+		rtk_sah_emit_children(s, node, c, depth, dst_buf, ch, NULL, par ^ 1, s_large);
 		s.split[a] = make_int4(c.axis, c.bin, (int)c.n_left, (int)ch);
 		s.cursor[2 * a] = 0; s.cursor[2 * a + 1] = 0;
 	}
+	__syncthreads();
+	// chunk -> node map of the children that stay large (up to n / 4096 entries each on the upper levels)
+	for (int k = 0; k < 2; k++) {
+		const uint4 lg = s_large[k];
+		for (uint32_t i = threadIdx.x; i < lg.z; i += 96) s.chunk_node_out[lg.y + i] = lg.x;
+	}
 }
 
-__global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, int src_buf)
+__global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, int src_buf, int par)
 {
 	__shared__ uint32_t s_cntl[8], s_basel, s_baser;
-	// the bins of the NEXT level's nodes are cleared here (counters[1] is final once k_sah_split_large has run; this
+	// the bins of the NEXT level's nodes are cleared here (their number is final once k_sah_split_large has run; this
 	// level's bins have been read): a launch less per level.  There are never more than twice as many nodes on the
 	// next level as there are blocks in this grid (the host launches at least one block per node of this level).
 	{
-		const uint32_t n_next = rtk_umin(s.counters[1], s.act_cap);
+		const uint32_t n_next = rtk_umin(RTK_SAH_LEVEL_NODES(s, par ^ 1), s.act_cap);
 		for (uint32_t a2 = 2 * blockIdx.x; a2 < 2 * blockIdx.x + 2 && a2 < n_next; a2++)
 			rtk_sah_bins_clear(s.bins + (size_t)a2 * RTK_SAH_NODEBINS, threadIdx.x, 256);
 	}
-	if (blockIdx.x >= s.counters[5]) return;
+	if (blockIdx.x >= RTK_SAH_LEVEL_CHUNKS(s, par)) return;
 	const uint32_t a = s.chunk_node[blockIdx.x];
 	const uint32_t node = s.act_in[a];
 	const int4 sp = s.split[a];
@@ -625,9 +564,6 @@ __global__ void __launch_bounds__(256) k_sah_partition_large(rtkd_sah s, int src
 #define RTK_SAH_SMALL_THREADS 128
 #endif
 #define RTK_SAH_SMALL_WARPS (RTK_SAH_SMALL_THREADS / 32)
-#ifndef RTK_SAH_COOP_MIN
-#define RTK_SAH_COOP_MIN 100000          // CTA-wide small-subtree splits of at least this many triangles bin warp-cooperatively (measured: 192 is 3 % slower than never)
-#endif
 #ifndef RTK_SAH_WARP_MAX
 #define RTK_SAH_WARP_MAX 64           // subtrees of at most this many triangles are finished by one warp
 #endif
@@ -647,15 +583,7 @@ RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *
 	const float4 nlo = make_float4(t.lo[0], t.lo[1], t.lo[2], 0.0f), nhi = make_float4(t.hi[0], t.hi[1], t.hi[2], 0.0f);
 	rtk_sah_bins_clear(bins, tid, nthreads);
 	RTK_SYNC();
-	if (!WARP && t.count >= RTK_SAH_COOP_MIN) {
-		// many triangles per bin: neighbours share bins, reduce per warp first (warp-uniform loop)
-		for (uint32_t base = 0; base < t.count; base += nthreads) {
-			const uint32_t i = base + tid;
-			const bool valid = i < t.count;
-			const uint32_t k = valid ? perm0[t.begin + i] : 0u;
-			rtk_sah_bin_add_warp(bins, s_lo[k], s_hi[k], nlo, nhi, valid);
-		}
-	} else {
+	{
 		// transposed walk: the lanes of a warp take triangles count/32 apart.  Neighbours in the (Morton-like) order
 		// share bins, and 32 lanes updating 2 or 3 addresses serialise in the shared-memory atomics; triangles
 		// from 32 different stretches of the range mostly fall into different bins.
@@ -669,14 +597,14 @@ RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *
 		}
 	}
 	RTK_SYNC();
+	rtk_sah_choice c;
+	uint32_t child = 0;
 	if (WARP) {
-		rtk_sah_choice c = rtk_sah_sweep_warp(bins, nlo, nhi, t.count);
+		// every lane holds the choice; only the child number travels (a shuffle, not a round trip through shared memory)
+		c = rtk_sah_sweep_warp(bins, nlo, nhi, t.count);
 		if (rtk_sah_must_halve(t.count, t.depth) && c.axis >= 0) rtk_sah_choice_none(c, nlo, nhi, t.count);
-		if (lane == 0) {
-			uint32_t ch;
-			rtk_sah_emit_children(s, t.node, c, t.depth, -1, ch, node_alloc);
-			*s_choice = c; *s_child = ch;
-		}
+		if (lane == 0) rtk_sah_emit_children(s, t.node, c, t.depth, -1, child, node_alloc);
+		child = __shfl_sync(0xffffffffu, child, 0);
 	} else {
 		// a warp per axis (s_choice[1..3] belong to the warps' own splits of phase 2: free during phase 1)
 		if (warp < 3) {
@@ -685,16 +613,16 @@ RTK_DEV void rtk_sah_split_shared(rtkd_sah &s, const rtk_sah_task &t, uint32_t *
 		}
 		__syncthreads();
 		if (tid == 0) {
-			rtk_sah_choice c = rtk_sah_pick_axis(s_choice + 1);
-			if (rtk_sah_must_halve(t.count, t.depth) && c.axis >= 0) rtk_sah_choice_none(c, nlo, nhi, t.count);
+			rtk_sah_choice pick = rtk_sah_pick_axis(s_choice + 1);
+			if (rtk_sah_must_halve(t.count, t.depth) && pick.axis >= 0) rtk_sah_choice_none(pick, nlo, nhi, t.count);
 			uint32_t ch;
-			rtk_sah_emit_children(s, t.node, c, t.depth, -1, ch, node_alloc);
-			*s_choice = c; *s_child = ch;
+			rtk_sah_emit_children(s, t.node, pick, t.depth, -1, ch, node_alloc);
+			*s_choice = pick; *s_child = ch;
 		}
+		__syncthreads();
+		c = *s_choice;
+		child = *s_child;
 	}
-	RTK_SYNC();
-	const rtk_sah_choice c = *s_choice;
-	const uint32_t child = *s_child;
 	// stable partition of perm0[begin, begin+count) into perm1, then copy back
 	const float amin = c.axis <= 0 ? nlo.x : (c.axis == 1 ? nlo.y : nlo.z);
 	const float amax = c.axis <= 0 ? nhi.x : (c.axis == 1 ? nhi.y : nhi.z);

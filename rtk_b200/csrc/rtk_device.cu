@@ -927,11 +927,12 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 		B.h.idx0 = A.take<uint32_t>(n); B.h.idx1 = A.take<uint32_t>(n); B.h.idx_final = A.take<uint32_t>(n);
 		B.h.left = A.take<int>(cap2); B.h.right = A.take<int>(cap2); B.h.first = A.take<int>(cap2); B.h.last = A.take<int>(cap2);
 		B.h.blo = A.take<float4>(cap2); B.h.bhi = A.take<float4>(cap2); B.h.ndepth = A.take<uint32_t>(cap2);
-		B.h.counters = A.take<uint32_t>(8);
+		B.h.counters = A.take<uint32_t>(16);
 		B.h.act_in = A.take<uint32_t>(B.act_cap); B.h.act_out = A.take<uint32_t>(B.act_cap);
 		B.h.small_list = A.take<uint32_t>(B.small_cap);
-		B.h.chunk_base = A.take<uint32_t>(B.act_cap + 1);
-		B.h.chunk_node = A.take<uint32_t>((size_t)n / RTK_SAH_CHUNK + 1 + B.act_cap);
+		B.h.chunk_cap = (uint32_t)((size_t)n / RTK_SAH_CHUNK + 1 + B.act_cap);
+		B.h.chunk_base = A.take<uint32_t>(B.act_cap + 1); B.h.chunk_base_out = A.take<uint32_t>(B.act_cap + 1);
+		B.h.chunk_node = A.take<uint32_t>(B.h.chunk_cap); B.h.chunk_node_out = A.take<uint32_t>(B.h.chunk_cap);
 		B.h.bins = A.take<uint32_t>(B.act_cap * RTK_SAH_NODEBINS);
 		B.h.binpack = A.take<uint32_t>(n);
 		B.h.split = A.take<int4>(B.act_cap); B.h.cursor = A.take<uint32_t>(2 * B.act_cap);
@@ -955,20 +956,19 @@ static void carve(build_arena &A, build_bufs &B, uint32_t n, bool use_sah)
 	B.d_cost = A.take<double>(1);
 }
 
-// binned-SAH binary tree (k_sah.cuh).  The level loop runs on the device's word: k_sah_plan leaves the
-// level's node and chunk counts in device memory, the level's kernels are launched with upper-bound grids
-// (at most 2^level nodes, never more than n / RTK_SAH_SMALL; chunks <= n / RTK_SAH_CHUNK + nodes) and blocks
-// beyond the counts return at once.  The host looks at the counters only after the first
-// ceil(log2(n / RTK_SAH_SMALL)) levels -- no tree is done before that -- and then every second level
-// (round 1 read them back after every level: 13 round trips per 1M-triangle build).
+// binned-SAH binary tree (k_sah.cuh).  The level loop runs on the device's word: the split kernel of a level
+// leaves the next level's node list, chunk table and counts in device memory (no planning kernel in between), the
+// level's kernels are launched with upper-bound grids (at most 2^level nodes, never more than n / RTK_SAH_SMALL;
+// chunks <= n / RTK_SAH_CHUNK + nodes) and blocks beyond the counts return at once.  The host looks at the counters
+// only after the first ceil(log2(n / RTK_SAH_SMALL)) levels -- no tree is done before that -- and then every second
+// level (round 1 read them back after every level: 13 round trips per 1M-triangle build).
 static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, build_bufs &B, uint32_t n)
 {
 	RTK_NVTX("rtk_b200 build: binned SAH levels");
 	rtkd_sah &h = B.h;
 	RTK_LAUNCH(k_sah_prim_bounds, (n + 255) / 256, 256, st, tri, svals, n, (float4*)h.pb, h.idx0); CK_LAUNCH();
 	RTK_LAUNCH(k_sah_root, 1, 32, st, h, (const uint32_t*)B.d_bounds, n); CK_LAUNCH();
-	RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();
-	uint32_t hc[8];
+	uint32_t hc[16];
 	memset(hc, 0, sizeof(hc));
 	uint32_t blind = 0;
 	for (uint32_t m = n; m > RTK_SAH_SMALL; m = (m + 1) / 2) blind++;
@@ -980,18 +980,21 @@ static int build_sah(cudaStream_t st, const float4 *tri, const uint32_t *svals, 
 		const unsigned long long pow2 = depth < 40 ? 1ull << depth : ~0ull;
 		const uint32_t act_bound = (uint32_t)(pow2 < B.act_cap ? pow2 : B.act_cap);
 		const uint32_t chunk_bound = max_chunks + act_bound;
-		if (depth == 0) { RTK_LAUNCH(k_sah_bins_clear, act_bound, 128, st, h); CK_LAUNCH(); }      // later levels: cleared by the partition kernel of the level above
-		RTK_LAUNCH(k_sah_bin_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
-		RTK_LAUNCH(k_sah_split_large, act_bound, 96, st, h, depth, src_buf ^ 1); CK_LAUNCH();
-		RTK_LAUNCH(k_sah_partition_large, chunk_bound, 256, st, h, src_buf); CK_LAUNCH();
-		uint32_t *tmp = h.act_in; h.act_in = h.act_out; h.act_out = tmp;
-		RTK_LAUNCH(k_sah_plan, 1, 1024, st, h, (const uint32_t*)h.act_in); CK_LAUNCH();
+		const int par = (int)(depth & 1u);
+		if (depth == 0) { RTK_LAUNCH(k_sah_bins_clear, act_bound, 128, st, h, par); CK_LAUNCH(); }      // later levels: cleared by the partition kernel of the level above
+		RTK_LAUNCH(k_sah_bin_large, chunk_bound, 256, st, h, src_buf, par); CK_LAUNCH();
+		RTK_LAUNCH(k_sah_split_large, act_bound, 96, st, h, depth, src_buf ^ 1, par); CK_LAUNCH();
+		RTK_LAUNCH(k_sah_partition_large, chunk_bound, 256, st, h, src_buf, par); CK_LAUNCH();
+		// the lists the split kernel has filled are the next level's
+		{ uint32_t *tmp = h.act_in; h.act_in = h.act_out; h.act_out = tmp; }
+		{ uint32_t *tmp = h.chunk_base; h.chunk_base = h.chunk_base_out; h.chunk_base_out = tmp; }
+		{ uint32_t *tmp = h.chunk_node; h.chunk_node = h.chunk_node_out; h.chunk_node_out = tmp; }
 		src_buf ^= 1;
 		depth++;
 		if (depth >= blind && ((depth - blind) & 1u) == 0) {
 			CK(cudaMemcpyAsync(hc, h.counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
 			CK(cudaStreamSynchronize(st));
-			done = hc[6] == 0;
+			done = hc[8 + 2 * (depth & 1u)] == 0;             // large nodes of the level that would run next
 			if (depth > 4096) { rtkd_set_error("SAH builder does not terminate"); return RTKD_ERR_MEMORY; }
 		}
 	}

@@ -147,7 +147,8 @@ def case_tree_stats(lib):
                 i = sc.info()
                 got = (int(i.num_wide_nodes), int(i.num_leaves), int(i.wide_depth))
                 assert got == (nodes, leaves, depth), f"{name}, mode {mode}: tree {got}, expected {(nodes, leaves, depth)}"
-                assert abs(i.sah_cost - cost) <= 1e-9 * cost, f"{name}, mode {mode}: SAH cost {i.sah_cost!r}, expected {cost!r}"
+                # the areas are x*y + y*z + z*x: nvcc contracts them into FMAs, the emulator build does not
+                assert abs(i.sah_cost - cost) <= 1e-6 * cost, f"{name}, mode {mode}: SAH cost {i.sah_cost!r}, expected {cost!r}"
             finally:
                 sc.free()
     finally:

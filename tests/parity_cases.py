@@ -911,6 +911,18 @@ def case_pathological(lib, orc):
     neg[::3, :, 2] = -0.0
     cases["signed zeros"] = neg
     cases["two far clusters"] = np.concatenate([rng.random((n // 2, 3, 3)), rng.random((n // 2, 3, 3)) + 1e6])
+    # the same kind of trouble above the size one CTA finishes on its own (512 triangles): the level-by-level part of
+    # the SAH builder with no valid split at all (position halves), with splits that peel a sliver off a geometric
+    # progression level after level (unbalanced node lists, one-chunk and many-chunk nodes side by side), and with
+    # two clusters that separate at the root
+    m = 3000
+    cases["3000 triangles at one place"] = np.repeat(np.repeat(rng.random((1, 1, 3)), 3, 1), m, 0)
+    prog = np.zeros((m, 3, 3))
+    x = 1.01 ** np.arange(m)
+    prog[:, :, 0] = x[:, None] * (1 + 0.004 * rng.random((m, 3)))
+    prog[:, :, 1:] = rng.random((m, 3, 2)) * x[:, None, None] * 0.01
+    cases["geometric progression along x"] = prog
+    cases["two far clusters of 1500"] = np.concatenate([rng.random((m // 2, 3, 3)), rng.random((m // 2, 3, 3)) + 1e6])
     total = 0
     for mode in (api.RTK_CUDA_BUILD_LBVH, api.RTK_CUDA_BUILD_SAH):
         for name, tris in cases.items():

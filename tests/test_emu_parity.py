@@ -166,3 +166,26 @@ def test_multi_device_in_one_process():
     env = dict(os.environ, SIMT_DEVICES="3", RTK_B200_HOST_MIN_SHARE_LOG2="14", RTK_B200_HOST_CHUNK_LOG2="12")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "multi-device ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("bits", ["8", "32"])
+def test_sah_tree_does_not_depend_on_the_input_order(bits):
+    """RTK_B200_SAH_SORT_BITS only changes the ORDER the SAH builder meets the triangles in (8 / 24 / 32 Morton bits); bins,
+    counts and boxes are functions of the triangle sets, so the pinned trees must come out whatever the order.  A
+    process of its own: the knob is read at initialisation."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    code = (
+        "import sys\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r}); sys.path.insert(0, {os.path.join(root, 'tests', 'emu')!r})\n"
+        "import build_emu, parity_cases as pc\n"
+        "from rtk_b200 import api\n"
+        "lib = api.Library(build_emu.build())\n"
+        "assert lib.rtk_cuda_init(0) == 0, lib.last_error()\n"
+        "pc.case_tree_stats(lib)\n"
+        "print('trees ok')\n"
+    )
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RTK_B200_SAH_SORT_BITS=bits), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "trees ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
